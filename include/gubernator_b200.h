@@ -1,0 +1,198 @@
+/*
+ * gubernator_b200.h — C ABI of the B200-native rate-limit evaluation path.
+ *
+ * This is the drop-in boundary for mailgun/gubernator v2.4.0's WorkerPool (the only thing `gubernator.go` calls on
+ * the hot path).  Every entry point names the reference interface it replaces (file:line under the reference repo).
+ * The reference-side cgo binding is shown in INTEGRATION.md and go/workerpool_b200.go.
+ *
+ * Model.  A `gub_table` is one GPU's shard of the key space: a device-resident open-addressed hash table of 64-byte
+ * bucket-state slots (TokenBucketItem / LeakyBucketItem + CacheItem.ExpireAt, store.go:29-43, cache.go:29-41),
+ * replacing the per-worker LRUCache (lrucache.go:32) of every Worker in the pool (workers.go:54-61).  One
+ * `gub_submit*` call evaluates a whole batch of pre-hashed requests on the GPU with exactly the results the
+ * reference produces when it applies the same requests one after another in index order (the order of the loop at
+ * gubernator.go:203) under a frozen clock `now_ms`.
+ *
+ * Strings never cross this ABI on the fast path: a request carries XXH64(Name+"_"+UniqueKey, seed 0) — the hash
+ * workers.go:153 already computes per request — and the FNV-1 64 hash replicated_hash.go:108 computes for peer
+ * routing.  Together they form the 120-bit key fingerprint stored in the slot (see DESIGN.md for the residual
+ * collision probability).  gub_hash_keys() computes both from packed key bytes.
+ *
+ * Threading: all calls on one gub_table are serialised internally (a mutex), mirroring "each worker owns its cache"
+ * (workers.go:19-25); use one long call per batch, never one per request.  Ownership: the caller owns every buffer it
+ * passes for the duration of the call only; the library owns all device memory.  Errors: 0 = ok, negative = failure
+ * with text in gub_last_error(); per-request errors come back in-band in gub_resp.err_code exactly as the reference
+ * returns them in RateLimitResp.Error (gubernator.go:210,215,255), the shim maps codes to the reference strings.
+ */
+#ifndef GUBERNATOR_B200_H
+#define GUBERNATOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GUB_ABI_VERSION 1
+
+/* Algorithm, Status, Behavior: gubernator.proto:56-135 */
+enum { GUB_TOKEN_BUCKET = 0, GUB_LEAKY_BUCKET = 1 };
+enum { GUB_UNDER_LIMIT = 0, GUB_OVER_LIMIT = 1 };
+enum {
+  GUB_BEHAVIOR_NO_BATCHING = 1,
+  GUB_BEHAVIOR_GLOBAL = 2,
+  GUB_BEHAVIOR_DURATION_IS_GREGORIAN = 4,
+  GUB_BEHAVIOR_RESET_REMAINING = 8,
+  GUB_BEHAVIOR_MULTI_REGION = 16,
+  GUB_BEHAVIOR_DRAIN_OVER_LIMIT = 32,
+  /* RateLimitReqState.IsOwner (gubernator.go:56): gates metricOverLimitCounter only (algorithms.go:164,184,242) */
+  GUB_REQ_IS_OWNER = 0x100
+};
+
+/* gub_resp.err_code: in-band per-request errors */
+enum {
+  GUB_OK = 0,
+  GUB_ERR_UNIQUE_KEY_EMPTY = 1,   /* gubernator.go:208-211 (raised by the host layer, never by the device) */
+  GUB_ERR_NAMESPACE_EMPTY = 2,    /* gubernator.go:213-216 (host layer) */
+  GUB_ERR_INVALID_ALGORITHM = 3,  /* workers.go:318 */
+  GUB_ERR_GREGORIAN_WEEKS = 4,    /* interval.go:93,134 */
+  GUB_ERR_GREGORIAN_INVALID = 5,  /* interval.go:107,147 */
+  GUB_ERR_TABLE_FULL = 6          /* no reference analogue: the LRU would have evicted (lrucache.go:98) */
+};
+
+/* One RateLimitReq (gubernator.proto:137-183) after HashKey() (client.go:39-41) and hashing.  64 bytes. */
+typedef struct {
+  uint64_t key_xxh64;  /* XXH64(Name + "_" + UniqueKey, seed 0)      workers.go:153-155 */
+  uint64_t key_fnv1;   /* FNV-1 64 of the same string                replicated_hash.go:108 */
+  int64_t hits;
+  int64_t limit;
+  int64_t duration;    /* ms, or a Gregorian interval id 0..5 when DURATION_IS_GREGORIAN */
+  int64_t burst;
+  int64_t created_at;  /* epoch ms; must already be defaulted (gubernator.go:218-220) */
+  uint32_t algorithm;
+  uint32_t behavior;   /* Behavior bits | GUB_REQ_IS_OWNER */
+} gub_req;
+
+/* One RateLimitResp (gubernator.proto:190-203).  32 bytes.  All other fields are zero when err_code != 0. */
+typedef struct {
+  uint32_t status;
+  uint32_t err_code;
+  int64_t limit;
+  int64_t remaining;
+  int64_t reset_time;
+} gub_resp;
+
+/* The frozen clock of one batch.  now_ms is what clock.Now()/MillisecondNow() return for every request of the batch
+ * (lrucache.go:106-108, algorithms.go:128,219,339-344,442); the Gregorian tables are GregorianExpiration(now, d) and
+ * GregorianDuration(now, d) for d = 0..5 (interval.go:84-148), computed on the host by gub_clock_fill(). */
+typedef struct {
+  int64_t now_ms;
+  int64_t greg_expire[6];
+  int64_t greg_duration[6];
+} gub_clock;
+
+/* One CacheItem with its bucket value flattened (cache.go:29-41, store.go:29-43). */
+typedef struct {
+  uint64_t key_xxh64;
+  uint64_t key_fnv1;     /* on output only the top 56 bits are meaningful (low 8 bits read back as zero) */
+  int32_t algorithm;     /* GUB_TOKEN_BUCKET | GUB_LEAKY_BUCKET: also the dynamic type of CacheItem.Value */
+  int32_t status;        /* TokenBucketItem.Status */
+  int64_t limit;
+  int64_t duration;
+  int64_t remaining;     /* TokenBucketItem.Remaining */
+  double remaining_f;    /* LeakyBucketItem.Remaining */
+  int64_t stamp;         /* TokenBucketItem.CreatedAt | LeakyBucketItem.UpdatedAt */
+  int64_t burst;         /* LeakyBucketItem.Burst */
+  int64_t expire_at;     /* CacheItem.ExpireAt */
+} gub_item;
+
+/* Mirrors metricOverLimitCounter (gubernator.go:74), metricCacheAccess hit/miss (lrucache.go:52) + table stats */
+typedef struct {
+  uint64_t over_limit;
+  uint64_t cache_hit;
+  uint64_t cache_miss;
+  uint64_t inserts;        /* slots claimed for new keys */
+  uint64_t table_full;     /* requests answered GUB_ERR_TABLE_FULL */
+  uint64_t requests;       /* decisions evaluated */
+  uint64_t batches;
+  uint64_t dup_groups;     /* keys that occurred more than once within a batch */
+  uint64_t heavy_groups;   /* of those, keys handled by the block-cooperative path */
+  uint64_t serial_fallbacks; /* heavy groups that had to be walked serially */
+} gub_counters;
+
+typedef struct {
+  uint64_t capacity_slots; /* table size in 64-byte slots (>= 2x expected live keys); replaces Config.CacheSize (config.go:86) */
+  uint32_t max_batch;      /* largest batch evaluated by one launch sequence; larger submits are chunked in order. 0 = 65536 */
+  int32_t device;          /* CUDA device ordinal */
+} gub_config;
+
+typedef struct gub_table gub_table;
+
+/* ---- lifecycle: NewWorkerPool (workers.go:125) / WorkerPool.Close (workers.go:157) ------------------------- */
+int gub_create(const gub_config* cfg, gub_table** out);
+void gub_destroy(gub_table* t);
+const char* gub_last_error(void);
+int gub_abi_version(void);
+
+/* ---- the hot path: WorkerPool.GetRateLimit (workers.go:261-324) for a whole batch -------------------------- */
+/* Host buffers: copies requests H2D, evaluates, copies responses D2H, returns when `out` is filled. */
+int gub_submit(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out);
+/* Device buffers (already resident in this GPU's HBM); enqueued on `stream` (a cudaStream_t), returns immediately. */
+int gub_submit_device(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
+/* Pipelined host path: up to gub_pipeline_depth() submissions may be in flight; each uses library-owned pinned
+ * staging.  gub_submit_async returns a ticket; gub_wait(ticket) blocks until that batch's responses are in `out`. */
+int gub_pipeline_depth(gub_table* t);
+int gub_submit_async(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out, int* ticket);
+int gub_wait(gub_table* t, int ticket);
+
+/* Gregorian tables for a batch clock: GregorianDuration / GregorianExpiration (interval.go:84-148), UTC. */
+int gub_clock_fill(int64_t now_ms, gub_clock* out);
+
+/* ---- WorkerPool.AddCacheItem (workers.go:537), WorkerPool.Load (workers.go:329), UpdatePeerGlobals
+ *      (gubernator.go:425-459): upsert whole items.  Duplicate keys within one call: last one wins. ------------ */
+int gub_add_items(gub_table* t, const gub_item* items, size_t n);
+/* WorkerPool.GetCacheItem (workers.go:583) -> LRUCache.GetItem (lrucache.go:111): expired entries are misses. */
+int gub_get_items(gub_table* t, const uint64_t* key_xxh64, const uint64_t* key_fnv1, size_t n, int64_t now_ms,
+                  gub_item* out, uint8_t* found);
+/* WorkerPool.Store (workers.go:451) -> Cache.Each (lrucache.go:76): every stored item, in no particular order.
+ * Writes at most `cap` items; *n_out receives the total number stored. */
+int gub_scan(gub_table* t, gub_item* out, size_t cap, size_t* n_out);
+/* Cache.Size (lrucache.go:159) */
+int gub_size(gub_table* t, size_t* n_out);
+/* Reclaims slots whose item has expired (ExpireAt < now_ms) or was removed; the reference does this lazily on access
+ * (lrucache.go:115) and by LRU eviction (lrucache.go:98,138).  *removed may be NULL. */
+int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
+int gub_get_counters(gub_table* t, gub_counters* out);
+
+/* ---- key hashing: client.go:39-41 HashKey + workers.go:153 + replicated_hash.go:108 -------------------------
+ * keys are packed back to back in `bytes`; key i is bytes[offsets[i] .. offsets[i+1]).  Host implementation. */
+int gub_hash_keys(const char* bytes, const uint64_t* offsets, size_t n, uint64_t* xxh64_out, uint64_t* fnv1_out);
+uint64_t gub_xxh64(const void* data, size_t len, uint64_t seed);
+uint64_t gub_fnv1_64(const void* data, size_t len);
+uint64_t gub_fnv1a_64(const void* data, size_t len);
+
+/* ---- ReplicatedConsistentHash (replicated_hash.go:36-119): which shard (GPU / peer) owns a key -------------- */
+typedef struct gub_ring gub_ring;
+gub_ring* gub_ring_create(int hash_kind /* 0 fnv1 (replicated_hash.go:33), 1 fnv1a (config.go:429) */, int replicas /* 0 = 512 */);
+void gub_ring_destroy(gub_ring* r);
+int gub_ring_add(gub_ring* r, const char* grpc_address);                 /* Add, replicated_hash.go:78-91 */
+int gub_ring_size(const gub_ring* r);                                    /* Size, :94 */
+int gub_ring_get(const gub_ring* r, const char* key, size_t len);        /* Get, :104-119; -1 when empty */
+int gub_ring_get_by_hash(const gub_ring* r, uint64_t key_hash);
+size_t gub_ring_points(const gub_ring* r, uint64_t* hashes, int32_t* peers, size_t cap);
+
+/* ---- multi-GPU routing (replaces the peer forwarding of gubernator.go:257-283 / peer_client.go:284 inside one
+ *      NVSwitch domain).  All pointers are device pointers on the table's GPU; work is enqueued on `stream`.
+ *  gub_route_device: stable partition of a batch by owning shard: out_reqs holds the requests grouped by owner
+ *      (owner 0 first), each group in original index order; perm[j] = original index of out_reqs[j];
+ *      counts[g] = number of requests owned by shard g (device array of n_shards uint32).
+ *  gub_unroute_device: resp_out[perm[j]] = resp_in[j]. */
+int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs,
+                     uint32_t* d_perm, uint32_t* d_counts, void* stream);
+int gub_unroute_device(gub_table* t, const gub_resp* d_resp_in, const uint32_t* d_perm, size_t n, gub_resp* d_resp_out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUBERNATOR_B200_H */

@@ -1,0 +1,122 @@
+"""Seeded synthetic request generators shared by the CPU and GPU parity tests and by bench.py."""
+import numpy as np
+
+import oracle_py as O
+
+T0 = 1_700_000_000_000
+
+
+def make_clock(now_ms, clock_dtype=None):
+    """gub_clock for a batch, built from the ORACLE's Gregorian functions (tests only)."""
+    from _host_math import CLOCK_DTYPE
+    clk = np.zeros(1, dtype=clock_dtype or CLOCK_DTYPE)
+    clk["now_ms"] = now_ms
+    for d in range(6):
+        clk["greg_expire"][0][d] = O.gregorian_expiration(now_ms, d)[0]
+        clk["greg_duration"][0][d] = O.gregorian_duration(now_ms, d)[0]
+    return clk
+
+
+_KEY_CACHE = {}
+
+
+def key_hashes(ids, name="bench"):
+    """(xxh64, fnv1) of Name + "_" + "k%09d" % id for each id (BASELINE.md synthetic keys)."""
+    ids = np.asarray(ids, dtype=np.int64)
+    xx = np.zeros(len(ids), dtype=np.uint64)
+    fv = np.zeros(len(ids), dtype=np.uint64)
+    for j, i in enumerate(ids.tolist()):
+        k = (name, i)
+        v = _KEY_CACHE.get(k)
+        if v is None:
+            s = f"{name}_k{i:09d}".encode()
+            v = (O.xxh64(s), O.fnv1_64(s))
+            if len(_KEY_CACHE) < 2_000_000:
+                _KEY_CACHE[k] = v
+        xx[j], fv[j] = v
+    return xx, fv
+
+
+def adversarial_batch(rng, n, n_keys, now_ms, uniform_run_prob=0.3, p_weird=0.15):
+    """Few keys, many duplicates, every behaviour / edge the reference's algorithms branch on.
+
+    Runs of identical requests are mixed with fully random ones so that both the run planner and the serial paths are
+    exercised.  Per key the algorithm is mostly fixed (switching resets the bucket) but sometimes switches."""
+    reqs = np.zeros(n, dtype=O.HREQ_DTYPE)
+    ids = rng.integers(0, n_keys, n)
+    xx, fv = key_hashes(ids, name="adv")
+    reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
+    limits = np.array([0, 1, 2, 5, 10, 100, 2000, -3, 1 << 40])
+    durs = np.array([0, 1, 5, 1000, 30000, 60000, 3600000, -50])
+    hits_c = np.array([0, 1, 1, 1, 2, 3, 7, 100, -1, -2, 1 << 41])
+    bursts = np.array([0, 0, 0, 5, 20, 3000])
+    behs = np.array([0, 0, 0, 0, O.RESET_REMAINING, O.DRAIN_OVER_LIMIT, O.DRAIN_OVER_LIMIT, O.NO_BATCHING | O.GLOBAL,
+                     O.DURATION_IS_GREGORIAN])
+    i = 0
+    # a per-key "usual" parameter set
+    usual = {}
+    while i < n:
+        kid = int(ids[i])
+        if kid not in usual:
+            usual[kid] = dict(limit=int(rng.choice(limits[1:7])), duration=int(rng.choice(durs[3:7])),
+                              burst=int(rng.choice(bursts)), algorithm=int(rng.integers(0, 2)), hits=int(rng.choice([1, 1, 1, 2, 3])),
+                              behavior=int(rng.choice([0, 0, O.DRAIN_OVER_LIMIT])))
+        u = usual[kid]
+        r = dict(u)
+        r["created_at"] = now_ms + int(rng.choice([0, 0, 0, 1, -1, 2]))
+        if rng.random() < p_weird:
+            r["limit"] = int(rng.choice(limits)); r["duration"] = int(rng.choice(durs)); r["hits"] = int(rng.choice(hits_c))
+            r["burst"] = int(rng.choice(bursts)); r["behavior"] = int(rng.choice(behs))
+            if rng.random() < 0.2:
+                r["algorithm"] = int(rng.choice([0, 1, 1 - u["algorithm"], 2, 7]))
+            if r["behavior"] & O.DURATION_IS_GREGORIAN:
+                r["duration"] = int(rng.choice([0, 0, 1, 2, 3, 4, 5, 6, 99, -1]))
+            if rng.random() < 0.15:
+                r["created_at"] = now_ms + int(rng.choice([-100000, -3600001, 50000, 10**9]))
+        owner = O.REQ_IS_OWNER if rng.random() < 0.8 else 0
+
+        def put(j):
+            reqs[j]["hits"] = r["hits"]; reqs[j]["limit"] = r["limit"]; reqs[j]["duration"] = r["duration"]
+            reqs[j]["burst"] = r["burst"]; reqs[j]["created_at"] = r["created_at"]; reqs[j]["algorithm"] = r["algorithm"]
+            reqs[j]["behavior"] = r["behavior"] | owner
+        put(i)
+        i += 1
+        if rng.random() < uniform_run_prob:
+            # repeat the identical request on later occurrences of the same key (contiguous in key order, not in index order)
+            reps = int(rng.integers(1, 40))
+            j = i
+            while reps > 0 and j < n:
+                if ids[j] == kid:
+                    put(j)
+                    reps -= 1
+                j += 1
+    return reqs
+
+
+def bench_batch(rng, n, n_keys, created_at, zipf_s=None, mixed=False, perm_seed=12345, name="bench"):
+    """BASELINE.md synthetic traffic: hits=1, limit=100, duration=60000, burst=0; uniform or Zipf(s) ids; algorithm fixed
+    per key (odd id -> LEAKY) when `mixed`."""
+    if zipf_s is None:
+        ids = rng.integers(0, n_keys, n)
+    else:
+        ids = zipf_ids(rng, n, n_keys, zipf_s, perm_seed)
+    reqs = np.zeros(n, dtype=O.HREQ_DTYPE)
+    reqs["key_xxh64"], reqs["key_fnv1"] = key_hashes(ids, name=name)
+    reqs["hits"] = 1; reqs["limit"] = 100; reqs["duration"] = 60000; reqs["burst"] = 0
+    reqs["created_at"] = created_at
+    reqs["algorithm"] = (ids & 1) if mixed else 0
+    reqs["behavior"] = O.REQ_IS_OWNER
+    return reqs, ids
+
+
+def zipf_ids(rng, n, n_keys, s, perm_seed=12345):
+    """Bounded Zipf(s) over ranks 1..n_keys by inverse-CDF on the continuous approximation, then rank -> id through a
+    fixed multiplicative permutation (so hot keys are spread over the id space)."""
+    u = rng.random(n)
+    a = 1.0 - s
+    # CDF(x) ~ (x^a - 1) / (K^a - 1) for the density x^-s on [1, K+1)
+    K = float(n_keys) + 1.0
+    x = (u * (K ** a - 1.0) + 1.0) ** (1.0 / a)
+    rank = np.minimum(np.floor(x).astype(np.int64) - 1, n_keys - 1)
+    mult = 0x9E3779B97F4A7C15 | 1
+    return ((rank.astype(np.uint64) * np.uint64(mult & 0xFFFFFFFFFFFFFFFF) + np.uint64(perm_seed)) % np.uint64(n_keys)).astype(np.int64)
