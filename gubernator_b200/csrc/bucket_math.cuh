@@ -11,11 +11,12 @@
 
 #include "../../include/gubernator_b200.h"
 
+#include <emmintrin.h>  // host-side CVTTSD2SI (the host compilation of this header is what tests run on CPU)
+
 #if defined(__CUDACC__)
 #define GUB_HD __host__ __device__ __forceinline__
 #else
 #define GUB_HD inline
-#include <emmintrin.h>
 #endif
 
 namespace gub {

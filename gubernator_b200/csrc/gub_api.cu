@@ -1,0 +1,519 @@
+// gub_api.cu — the C ABI (include/gubernator_b200.h) over the kernels in gub_kernels.cuh.
+//
+// This is the layer that sits where gubernator's WorkerPool sits (workers.go:54-61): gub_create = NewWorkerPool,
+// gub_submit* = GetRateLimit for a whole batch, gub_add_items = AddCacheItem/Load, gub_scan = Store, gub_destroy = Close.
+// There is no CPU fallback: every entry point that evaluates requests launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gubernator_b200.h"
+#include "gub_kernels.cuh"
+
+extern "C" uint64_t gub_ring_version_(const gub_ring* r);
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return -1; }
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                                    \
+  } while (0)
+
+constexpr int PIPE_DEPTH = 4;
+
+struct PipeSlot {
+  gub_req* d_req = nullptr;
+  gub_resp* d_resp = nullptr;
+  size_t cap = 0;
+  cudaEvent_t in_done = nullptr, out_done = nullptr;
+  bool busy = false;
+};
+
+uint32_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t)p; }
+
+}  // namespace
+
+struct gub_table {
+  int device = 0;
+  std::mutex mu;
+  gub::Slot* table = nullptr;
+  uint64_t capacity = 0;
+  uint32_t max_batch = 0;
+  // per-batch scratch
+  gub::AuxEntry* aux = nullptr; uint32_t aux_entries = 0;
+  uint32_t *ent = nullptr, *ticket = nullptr, *lists = nullptr, *list_ent = nullptr, *heavy_ent = nullptr, *bitmaps = nullptr, *order = nullptr;
+  uint32_t bitmap_words = 0, max_lists = 0, max_heavy = 0;
+  gub::BatchCtr* ctr = nullptr;
+  unsigned long long* counters = nullptr;
+  uint32_t epoch = 0;
+  // ordering between streams that touch the shared scratch
+  cudaEvent_t last_done = nullptr;
+  bool have_last = false;
+  // host path
+  cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
+  cudaEvent_t compute_done[PIPE_DEPTH] = {};
+  PipeSlot pipe[PIPE_DEPTH];
+  int next_slot = 0;
+  // maintenance scratch
+  unsigned long long* d_scalar = nullptr;
+  // route
+  uint64_t* d_ring_pts = nullptr; int32_t* d_ring_peers = nullptr; uint32_t ring_npts = 0; const gub_ring* ring_cached = nullptr; uint64_t ring_version = 0;
+  uint8_t* d_owner = nullptr; uint32_t* d_tile_counts = nullptr;
+  size_t owner_cap = 0, tiles_cap = 0;
+  // optional per-kernel timing (bench.py's roofline leg): events bracket every kernel of the batch path
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;   // 4 events per pending chunk
+  size_t prof_pending = 0;            // chunks recorded and not yet accumulated
+  double prof_ms[3] = {0, 0, 0};
+  uint64_t prof_launches = 0;
+};
+
+namespace {
+
+// Folds finished per-kernel event triples into the running totals.  force: wait for everything pending.
+int prof_flush(gub_table* t, bool force) {
+  if (!force && t->prof_pending < 1024) return 0;
+  for (size_t c = 0; c < t->prof_pending; c++) {
+    cudaEvent_t* pe = &t->prof_ev[c * 4];
+    CK(cudaEventSynchronize(pe[3]));
+    for (int k = 0; k < 3; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, pe[k], pe[k + 1])); t->prof_ms[k] += ms; }
+    t->prof_launches++;
+  }
+  t->prof_pending = 0;
+  return 0;
+}
+
+int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
+  if (t->epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
+    CK(cudaMemsetAsync(t->aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), st));
+    t->epoch = 0;
+  }
+  t->epoch++;
+  gub::BatchArgs A;
+  A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = t->epoch;
+  A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.ent = t->ent; A.ticket = t->ticket; A.lists = t->lists;
+  A.list_ent = t->list_ent; A.heavy_ent = t->heavy_ent; A.bitmaps = t->bitmaps; A.bitmap_words = t->bitmap_words;
+  A.max_lists = t->max_lists; A.max_heavy = t->max_heavy; A.order = t->order; A.ctr = t->ctr; A.counters = t->counters;
+  A.clk = *clk;
+  const uint32_t blocks = (n + 255) / 256;
+  cudaEvent_t* pe = nullptr;
+  if (t->prof) {
+    if (prof_flush(t, false)) return -1;
+    if (t->prof_ev.size() < (t->prof_pending + 1) * 4) {
+      for (int k = 0; k < 4; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); t->prof_ev.push_back(e); }
+    }
+    pe = &t->prof_ev[t->prof_pending * 4];
+    t->prof_pending++;
+    CK(cudaEventRecord(pe[0], st));
+  }
+  gub::k_group<<<blocks, 256, 0, st>>>(A);
+  if (pe) CK(cudaEventRecord(pe[1], st));
+  gub::k_single<<<blocks, 256, 0, st>>>(A);
+  if (pe) CK(cudaEventRecord(pe[2], st));
+  // heavy groups: one block each (at most n/(INLINE+1)); light groups: one thread each (at most n/2)
+  const uint32_t heavy_blocks = std::min<uint32_t>(296u, std::max<uint32_t>(1u, n / (gub::INLINE + 1)));
+  const uint32_t light_blocks = std::max<uint32_t>(1u, (n / 2 + gub::HEAVY_THREADS - 1) / gub::HEAVY_THREADS);
+  gub::k_multi<<<heavy_blocks + light_blocks, gub::HEAVY_THREADS, 0, st>>>(A, heavy_blocks);
+  if (pe) CK(cudaEventRecord(pe[3], st));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
+  if (t->have_last) CK(cudaStreamWaitEvent(st, t->last_done, 0));
+  for (size_t off = 0; off < n; off += t->max_batch) {
+    const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
+    if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st)) return -1;
+  }
+  CK(cudaEventRecord(t->last_done, st));
+  t->have_last = true;
+  return 0;
+}
+
+int ensure_slot(PipeSlot& s, size_t n) {
+  if (s.cap >= n) return 0;
+  if (s.d_req) cudaFree(s.d_req);
+  if (s.d_resp) cudaFree(s.d_resp);
+  s.d_req = nullptr; s.d_resp = nullptr; s.cap = 0;
+  CK(cudaMalloc(&s.d_req, n * sizeof(gub_req)));
+  CK(cudaMalloc(&s.d_resp, n * sizeof(gub_resp)));
+  s.cap = n;
+  return 0;
+}
+
+gub::DevItem to_dev(const gub_item& it) {
+  gub::DevItem d;
+  std::memset(&d, 0, sizeof d);
+  d.key = it.key_xxh64 < 2 ? it.key_xxh64 + 2 : it.key_xxh64;
+  d.tag = it.key_fnv1 >> 8;
+  const bool leaky = it.algorithm == GUB_LEAKY_BUCKET;
+  d.flags = gub::F_LIVE | (leaky ? gub::F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? gub::F_OVER : 0u);
+  d.w[0] = (uint64_t)it.limit; d.w[1] = (uint64_t)it.duration;
+  if (leaky) std::memcpy(&d.w[2], &it.remaining_f, 8); else d.w[2] = (uint64_t)it.remaining;
+  d.w[3] = (uint64_t)it.stamp; d.w[4] = leaky ? (uint64_t)it.burst : 0; d.w[5] = (uint64_t)it.expire_at;
+  return d;
+}
+gub_item from_dev(const gub::DevItem& d) {
+  gub_item it;
+  std::memset(&it, 0, sizeof it);
+  it.key_xxh64 = d.key; it.key_fnv1 = d.tag << 8;
+  const bool leaky = (d.flags & gub::F_LEAKY) != 0;
+  it.algorithm = leaky ? GUB_LEAKY_BUCKET : GUB_TOKEN_BUCKET;
+  it.status = (d.flags & gub::F_OVER) ? GUB_OVER_LIMIT : GUB_UNDER_LIMIT;
+  it.limit = (int64_t)d.w[0]; it.duration = (int64_t)d.w[1];
+  if (leaky) std::memcpy(&it.remaining_f, &d.w[2], 8); else it.remaining = (int64_t)d.w[2];
+  it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5];
+  return it;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gub_last_error(void) { return g_err.c_str(); }
+int gub_abi_version(void) { return GUB_ABI_VERSION; }
+
+void gub_destroy(gub_table* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+  void* ptrs[] = {t->table, t->aux, t->ent, t->ticket, t->lists, t->list_ent, t->heavy_ent, t->bitmaps, t->order, t->ctr, t->counters,
+                  t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& s : t->pipe) {
+    if (s.d_req) cudaFree(s.d_req);
+    if (s.d_resp) cudaFree(s.d_resp);
+    if (s.in_done) cudaEventDestroy(s.in_done);
+    if (s.out_done) cudaEventDestroy(s.out_done);
+  }
+  for (auto& e : t->compute_done) if (e) cudaEventDestroy(e);
+  for (auto& e : t->prof_ev) cudaEventDestroy(e);
+  if (t->last_done) cudaEventDestroy(t->last_done);
+  if (t->s_h2d) cudaStreamDestroy(t->s_h2d);
+  if (t->s_compute) cudaStreamDestroy(t->s_compute);
+  if (t->s_d2h) cudaStreamDestroy(t->s_d2h);
+  delete t;
+}
+
+int gub_create(const gub_config* cfg, gub_table** out) {
+  if (!cfg || !out) return fail("gub_create: null argument");
+  *out = nullptr;
+  if (cfg->capacity_slots < 64) return fail("gub_create: capacity_slots must be >= 64");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("gub_create: no such CUDA device");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail("gub_create: this library is built for sm_100a (B200) only");
+  gub_table* t = new gub_table();
+  t->device = cfg->device;
+  t->capacity = cfg->capacity_slots;
+  t->max_batch = cfg->max_batch ? cfg->max_batch : 65536u;
+  if (t->max_batch < 1024) t->max_batch = 1024;
+  if (t->max_batch > 262144u) t->max_batch = 262144u;
+  t->max_batch = (t->max_batch + 31u) & ~31u;
+  const uint32_t B = t->max_batch;
+  t->aux_entries = next_pow2((uint64_t)B * 4);
+  t->bitmap_words = B / 32;
+  t->max_lists = B / 2 + 1;
+  t->max_heavy = B / (gub::INLINE + 1) + 1;
+#define ALLOC(ptr, bytes)                                                    \
+  do {                                                                       \
+    cudaError_t e__ = cudaMalloc((void**)&(ptr), (bytes));                   \
+    if (e__ != cudaSuccess) {                                                \
+      fail(std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(e__)); \
+      gub_destroy(t);                                                        \
+      return -1;                                                             \
+    }                                                                        \
+    cudaMemset((ptr), 0, (bytes));                                           \
+  } while (0)
+  ALLOC(t->table, t->capacity * sizeof(gub::Slot));
+  ALLOC(t->aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
+  ALLOC(t->ent, (size_t)B * 4);
+  ALLOC(t->ticket, (size_t)B * 4);
+  ALLOC(t->lists, (size_t)t->max_lists * gub::INLINE * 4);
+  ALLOC(t->list_ent, (size_t)t->max_lists * 4);
+  ALLOC(t->heavy_ent, (size_t)t->max_heavy * 4);
+  ALLOC(t->bitmaps, (size_t)t->max_heavy * t->bitmap_words * 4);
+  ALLOC(t->order, (size_t)B * 4);
+  ALLOC(t->ctr, 2 * sizeof(gub::BatchCtr));
+  ALLOC(t->counters, gub::C_COUNT * sizeof(unsigned long long));
+  ALLOC(t->d_scalar, 4 * sizeof(unsigned long long));
+#undef ALLOC
+  CK(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&t->s_compute, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&t->last_done, cudaEventDisableTiming));
+  for (int i = 0; i < PIPE_DEPTH; i++) {
+    CK(cudaEventCreateWithFlags(&t->pipe[i].in_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&t->pipe[i].out_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&t->compute_done[i], cudaEventDisableTiming));
+  }
+  CK(cudaDeviceSynchronize());
+  *out = t;
+  return 0;
+}
+
+int gub_submit_device(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
+  if (!t || !clk || (n && (!d_reqs || !d_out))) return fail("gub_submit_device: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  return launch_batch(t, d_reqs, n, clk, d_out, (cudaStream_t)stream);
+}
+
+int gub_pipeline_depth(gub_table*) { return PIPE_DEPTH; }
+
+int gub_submit_async(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out, int* ticket) {
+  if (!t || !clk || !ticket || (n && (!reqs || !out))) return fail("gub_submit_async: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  const int si = t->next_slot;
+  t->next_slot = (t->next_slot + 1) % PIPE_DEPTH;
+  PipeSlot& s = t->pipe[si];
+  if (s.busy) { CK(cudaEventSynchronize(s.out_done)); s.busy = false; }
+  *ticket = si;
+  if (n == 0) { CK(cudaEventRecord(s.out_done, t->s_d2h)); s.busy = true; return 0; }
+  if (ensure_slot(s, n)) return -1;
+  CK(cudaMemcpyAsync(s.d_req, reqs, n * sizeof(gub_req), cudaMemcpyHostToDevice, t->s_h2d));
+  CK(cudaEventRecord(s.in_done, t->s_h2d));
+  CK(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
+  if (launch_batch(t, s.d_req, n, clk, s.d_resp, t->s_compute)) return -1;
+  CK(cudaEventRecord(t->compute_done[si], t->s_compute));
+  CK(cudaStreamWaitEvent(t->s_d2h, t->compute_done[si], 0));
+  CK(cudaMemcpyAsync(out, s.d_resp, n * sizeof(gub_resp), cudaMemcpyDeviceToHost, t->s_d2h));
+  CK(cudaEventRecord(s.out_done, t->s_d2h));
+  s.busy = true;
+  return 0;
+}
+
+int gub_wait(gub_table* t, int ticket) {
+  if (!t || ticket < 0 || ticket >= PIPE_DEPTH) return fail("gub_wait: bad ticket");
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    if (!t->pipe[ticket].busy) return 0;
+    ev = t->pipe[ticket].out_done;
+  }
+  CK(cudaSetDevice(t->device));
+  CK(cudaEventSynchronize(ev));
+  std::lock_guard<std::mutex> lk(t->mu);
+  t->pipe[ticket].busy = false;
+  return 0;
+}
+
+int gub_submit(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out) {
+  int ticket = -1;
+  if (gub_submit_async(t, reqs, n, clk, out, &ticket)) return -1;
+  return gub_wait(t, ticket);
+}
+
+void* gub_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+  return p;
+}
+void gub_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int gub_add_items(gub_table* t, const gub_item* items, size_t n) {
+  if (!t || (n && !items)) return fail("gub_add_items: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  // last one wins for duplicate keys (sequential AddCacheItem calls would overwrite in order)
+  std::vector<gub::DevItem> dev;
+  dev.reserve(n);
+  std::unordered_map<uint64_t, size_t> seen;
+  seen.reserve(n * 2);
+  for (size_t i = 0; i < n; i++) {
+    if (items[i].algorithm != GUB_TOKEN_BUCKET && items[i].algorithm != GUB_LEAKY_BUCKET) continue;  // Value would be nil (gubernator.go:434-451)
+    gub::DevItem d = to_dev(items[i]);
+    const uint64_t h = d.key ^ (d.tag * 0x9E3779B97F4A7C15ULL);
+    auto it = seen.find(h);
+    if (it != seen.end() && dev[it->second].key == d.key && dev[it->second].tag == d.tag) dev[it->second] = d;
+    else { seen[h] = dev.size(); dev.push_back(d); }
+  }
+  if (dev.empty()) return 0;
+  CK(cudaDeviceSynchronize());
+  gub::DevItem* d_items = nullptr;
+  CK(cudaMalloc(&d_items, dev.size() * sizeof(gub::DevItem)));
+  cudaError_t e = cudaMemcpy(d_items, dev.data(), dev.size() * sizeof(gub::DevItem), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(t->d_scalar, 0, 8);
+  uint32_t failed = 0;
+  if (e == cudaSuccess) {
+    gub::k_add_items<<<(unsigned)((dev.size() + 255) / 256), 256>>>(t->table, t->capacity, d_items, (uint32_t)dev.size(), t->counters,
+                                                                    reinterpret_cast<uint32_t*>(t->d_scalar));
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&failed, t->d_scalar, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_items);
+  if (e != cudaSuccess) return fail(std::string("gub_add_items: ") + cudaGetErrorString(e));
+  if (failed) return fail("gub_add_items: table full for " + std::to_string(failed) + " items");
+  return 0;
+}
+
+int gub_get_items(gub_table* t, const uint64_t* kx, const uint64_t* kf, size_t n, int64_t now_ms, gub_item* out, uint8_t* found) {
+  if (!t || (n && (!kx || !kf || !out || !found))) return fail("gub_get_items: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  uint64_t *d_kx = nullptr, *d_kf = nullptr; gub::DevItem* d_out = nullptr; uint8_t* d_found = nullptr;
+  std::vector<gub::DevItem> host(n);
+  cudaError_t e = cudaMalloc(&d_kx, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_kf, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, n * sizeof(gub::DevItem));
+  if (e == cudaSuccess) e = cudaMalloc(&d_found, n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_kx, kx, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_kf, kf, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    gub::k_get_items<<<(unsigned)((n + 255) / 256), 256>>>(t->table, t->capacity, d_kx, d_kf, (uint32_t)n, now_ms, d_out, d_found);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(host.data(), d_out, n * sizeof(gub::DevItem), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(found, d_found, n, cudaMemcpyDeviceToHost);
+  cudaFree(d_kx); cudaFree(d_kf); cudaFree(d_out); cudaFree(d_found);
+  if (e != cudaSuccess) return fail(std::string("gub_get_items: ") + cudaGetErrorString(e));
+  for (size_t i = 0; i < n; i++) { out[i] = from_dev(host[i]); out[i].key_xxh64 = kx[i]; out[i].key_fnv1 = kf[i]; }
+  return 0;
+}
+
+int gub_scan(gub_table* t, gub_item* out, size_t cap, size_t* n_out) {
+  if (!t || !n_out || (cap && !out)) return fail("gub_scan: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  gub::DevItem* d_out = nullptr;
+  if (cap) CK(cudaMalloc(&d_out, cap * sizeof(gub::DevItem)));
+  unsigned long long total = 0;
+  cudaError_t e = cudaMemset(t->d_scalar, 0, 8);
+  if (e == cudaSuccess) {
+    gub::k_scan<<<148 * 8, 256>>>(t->table, t->capacity, d_out, (unsigned long long)cap, t->d_scalar);
+    e = cudaDeviceSynchronize();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&total, t->d_scalar, 8, cudaMemcpyDeviceToHost);
+  std::vector<gub::DevItem> host(std::min<size_t>(cap, (size_t)total));
+  if (e == cudaSuccess && !host.empty()) e = cudaMemcpy(host.data(), d_out, host.size() * sizeof(gub::DevItem), cudaMemcpyDeviceToHost);
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) return fail(std::string("gub_scan: ") + cudaGetErrorString(e));
+  for (size_t i = 0; i < host.size(); i++) out[i] = from_dev(host[i]);
+  *n_out = (size_t)total;
+  return 0;
+}
+
+int gub_size(gub_table* t, size_t* n_out) { return gub_scan(t, nullptr, 0, n_out); }
+
+int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed) {
+  if (!t) return fail("gub_sweep: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(t->d_scalar, 0, 8));
+  gub::k_sweep<<<148 * 8, 256>>>(t->table, t->capacity, now_ms, t->d_scalar);
+  CK(cudaDeviceSynchronize());
+  unsigned long long r = 0;
+  CK(cudaMemcpy(&r, t->d_scalar, 8, cudaMemcpyDeviceToHost));
+  if (removed) *removed = (size_t)r;
+  return 0;
+}
+
+int gub_get_counters(gub_table* t, gub_counters* out) {
+  if (!t || !out) return fail("gub_get_counters: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long c[gub::C_COUNT];
+  CK(cudaMemcpy(c, t->counters, sizeof c, cudaMemcpyDeviceToHost));
+  out->over_limit = c[gub::C_OVER]; out->cache_hit = c[gub::C_HIT]; out->cache_miss = c[gub::C_MISS];
+  out->inserts = c[gub::C_INSERTS]; out->table_full = c[gub::C_FULL]; out->requests = c[gub::C_REQUESTS];
+  out->batches = c[gub::C_BATCHES]; out->dup_groups = c[gub::C_DUP_GROUPS]; out->heavy_groups = c[gub::C_HEAVY_GROUPS];
+  out->serial_fallbacks = c[gub::C_SERIAL];
+  return 0;
+}
+
+int gub_set_profiling(gub_table* t, int on) {
+  if (!t) return fail("gub_set_profiling: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  if (prof_flush(t, true)) return -1;
+  t->prof = on != 0;
+  return 0;
+}
+
+int gub_get_profile(gub_table* t, double kernel_ms[3], uint64_t* launches, int reset) {
+  if (!t || !kernel_ms || !launches) return fail("gub_get_profile: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  if (prof_flush(t, true)) return -1;
+  for (int k = 0; k < 3; k++) kernel_ms[k] = t->prof_ms[k];
+  *launches = t->prof_launches;
+  if (reset) { t->prof_ms[0] = t->prof_ms[1] = t->prof_ms[2] = 0; t->prof_launches = 0; }
+  return 0;
+}
+
+// ---- multi-GPU routing ----------------------------------------------------------------------------------------
+static int ensure_ring(gub_table* t, const gub_ring* ring) {
+  const uint64_t ver = gub_ring_version_(ring);
+  if (t->ring_cached == ring && t->ring_version == ver && t->d_ring_pts) return 0;
+  const size_t npts = gub_ring_points(ring, nullptr, nullptr, 0);
+  if (npts == 0) return fail("gub_route_device: ring is empty");
+  if (gub_ring_size(ring) > gub::MAX_SHARDS) return fail("gub_route_device: at most 16 shards");
+  std::vector<uint64_t> hs(npts); std::vector<int32_t> ps(npts);
+  gub_ring_points(ring, hs.data(), ps.data(), npts);
+  CK(cudaDeviceSynchronize());
+  if (t->d_ring_pts) cudaFree(t->d_ring_pts);
+  if (t->d_ring_peers) cudaFree(t->d_ring_peers);
+  t->d_ring_pts = nullptr; t->d_ring_peers = nullptr;
+  CK(cudaMalloc(&t->d_ring_pts, npts * 8));
+  CK(cudaMalloc(&t->d_ring_peers, npts * 4));
+  CK(cudaMemcpy(t->d_ring_pts, hs.data(), npts * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(t->d_ring_peers, ps.data(), npts * 4, cudaMemcpyHostToDevice));
+  t->ring_npts = (uint32_t)npts; t->ring_cached = ring; t->ring_version = ver;
+  return 0;
+}
+
+int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs, uint32_t* d_perm,
+                     uint32_t* d_counts, void* stream) {
+  if (!t || !ring || !d_counts || (n && (!d_reqs || !d_out_reqs || !d_perm))) return fail("gub_route_device: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  if (ensure_ring(t, ring)) return -1;
+  const uint32_t nshards = (uint32_t)gub_ring_size(ring);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { CK(cudaMemsetAsync(d_counts, 0, nshards * 4, st)); return 0; }
+  if (n > 0x7FFFFFFFull) return fail("gub_route_device: batch too large");
+  const uint32_t ntiles = (uint32_t)((n + gub::ROUTE_TILE - 1) / gub::ROUTE_TILE);
+  if (!t->d_owner || t->owner_cap < n) { if (t->d_owner) { CK(cudaDeviceSynchronize()); cudaFree(t->d_owner); } CK(cudaMalloc(&t->d_owner, n)); t->owner_cap = n; }
+  const size_t tc = (size_t)ntiles * gub::MAX_SHARDS;
+  if (!t->d_tile_counts || t->tiles_cap < tc) { if (t->d_tile_counts) { CK(cudaDeviceSynchronize()); cudaFree(t->d_tile_counts); } CK(cudaMalloc(&t->d_tile_counts, tc * 4)); t->tiles_cap = tc; }
+  gub::k_route_count<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, nshards, t->d_owner,
+                                            t->d_tile_counts, ntiles);
+  gub::k_route_scan<<<1, 1024, 0, st>>>(t->d_tile_counts, nshards * ntiles, nshards, ntiles, d_counts);
+  gub::k_route_scatter<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_owner, t->d_tile_counts, ntiles, nshards, d_out_reqs, d_perm);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gub_unroute_device(gub_table* t, const gub_resp* d_resp_in, const uint32_t* d_perm, size_t n, gub_resp* d_resp_out, void* stream) {
+  if (!t || (n && (!d_resp_in || !d_perm || !d_resp_out))) return fail("gub_unroute_device: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  gub::k_unroute<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_resp_in, d_perm, (uint32_t)n, d_resp_out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

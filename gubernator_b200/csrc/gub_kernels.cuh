@@ -1,0 +1,612 @@
+// gub_kernels.cuh — sm_100a kernels of the rate-limit evaluation path.
+//
+// Replaces, for a whole batch at a time, WorkerPool.GetRateLimit -> Worker.handleGetRateLimit -> LRUCache.GetItem ->
+// tokenBucket/leakyBucket (workers.go:261-324, lrucache.go:111, algorithms.go:37-493 of mailgun/gubernator v2.4.0).
+//
+// Data layout in HBM
+//   table    : capacity x 64-byte slots, open addressing with linear probing from home = mulhi(key, capacity):
+//              w0 key (XXH64, remapped off the two sentinels)   w1 tag(FNV-1 >> 8) << 8 | flags
+//              w2 limit  w3 duration  w4 remaining (int64 | float64 bits)  w5 stamp  w6 burst  w7 expire_at
+//   requests : n x 64 B gub_req (AoS, what the Go shim fills), responses: n x 32 B gub_resp
+//
+// Why three kernels.  The reference applies same-key requests strictly in index order (gubernator.go:203), and the
+// updates do not commute, so a batch must first be grouped by key:
+//   k_group  : every request claims/joins a per-batch hash entry for its key and draws a ticket; the 2nd arrival
+//              allocates an inline member list, the (INLINE+1)th a per-group bitmap.            (L2-resident scratch)
+//   k_single : keys seen once in the batch (the vast majority of groups) are probed + updated right away, one thread
+//              each: one 64 B random HBM read + one write-back.  Members of multi-hit keys record themselves
+//              (list slot by ticket, or a bit in the group's bitmap).
+//   k_multi  : light groups (<= INLINE members): one thread sorts the member indices and walks them in order.
+//              heavy groups: one thread block per key: rank every member by prefix popcount over the bitmap (index
+//              order falls out for free), split the run into segments of identical requests, let one thread plan each
+//              segment with plan_run() (closed forms for the subtract and fixed-point regimes) and all threads
+//              evaluate and scatter the responses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bucket_math.cuh"
+
+namespace gub {
+
+constexpr uint64_t KEY_EMPTY = 0ull;
+constexpr uint64_t KEY_TOMB = 1ull;
+constexpr int MAX_PROBE = 512;       // window [home, home + MAX_PROBE): inserts never leave it, so lookups may stop there
+constexpr int INLINE = 16;           // members of a light group
+constexpr int HEAVY_THREADS = 256;
+constexpr int MAX_SEG = 96;          // uniform segments of a heavy group planned in parallel; more => serial walk
+constexpr int MAX_PIECES = 16;
+
+struct __align__(64) Slot { uint64_t w[8]; };
+
+struct __align__(16) AuxEntry {
+  unsigned long long word;  // [63:48] epoch  [47:24] key tag  [23:0] member count
+  uint32_t lid;             // inline list id (valid once count >= 2)
+  uint32_t hg;              // heavy group id (valid once count > INLINE)
+};
+__host__ __device__ inline uint32_t aux_count(unsigned long long w) { return (uint32_t)(w & 0xFFFFFFull); }
+__host__ __device__ inline uint32_t aux_epoch(unsigned long long w) { return (uint32_t)(w >> 48); }
+__host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint32_t)((w >> 24) & 0xFFFFFFull); }
+
+struct BatchCtr { uint32_t nlists, nheavy, order_bump, _pad; };
+
+enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_HEAVY_GROUPS, C_SERIAL, C_COUNT };
+
+struct BatchArgs {
+  Slot* table;
+  uint64_t capacity;
+  const gub_req* reqs;
+  gub_resp* out;
+  uint32_t n;
+  uint32_t epoch;          // 1..65535
+  AuxEntry* aux;
+  uint32_t aux_mask;       // entries - 1 (power of two)
+  uint32_t* ent;           // [n] aux entry of request i
+  uint32_t* ticket;        // [n] arrival ticket of request i within its group
+  uint32_t* lists;         // [max_lists * INLINE]
+  uint32_t* list_ent;      // [max_lists]
+  uint32_t* heavy_ent;     // [max_heavy]
+  uint32_t* bitmaps;       // [max_heavy * bitmap_words], all zero between batches
+  uint32_t bitmap_words;   // max_batch / 32
+  uint32_t max_lists, max_heavy;
+  uint32_t* order;         // [max_batch] rank-ordered member indices of heavy groups
+  BatchCtr* ctr;           // [2], indexed by epoch parity
+  unsigned long long* counters;  // [C_COUNT]
+  gub_clock clk;
+};
+
+__device__ __forceinline__ uint64_t remap_key(uint64_t k) { return k < 2 ? k + 2 : k; }
+
+// ---- slot access ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slot_load(const Slot* s, ulonglong2& a, ulonglong2& b, ulonglong2& c, ulonglong2& d) {
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s);
+  a = __ldcg(p); b = __ldcg(p + 1); c = __ldcg(p + 2); d = __ldcg(p + 3);  // 4 x 128-bit, L2-only (no reuse in L1)
+}
+__device__ __forceinline__ void bucket_from(Bucket& bk, const ulonglong2& a, const ulonglong2& b, const ulonglong2& c, const ulonglong2& d) {
+  bk.key = a.x; bk.tag = a.y >> 8; bk.flags = (uint32_t)(a.y & 0xFF);
+  bk.limit = (int64_t)b.x; bk.duration = (int64_t)b.y; bk.rem = c.x; bk.stamp = (int64_t)c.y;
+  bk.burst = (int64_t)d.x; bk.expire = (int64_t)d.y;
+}
+
+struct Cursor {  // one key's slot while requests are applied to it
+  Bucket b, old;
+  int64_t slot;      // slot index when found, else first free slot in the probe window (or -1)
+  uint64_t home;
+  bool found;
+};
+
+// Looks `key` up.  On a hit the slot is loaded into cur.b.  On a miss cur.b is an empty (not live) bucket and cur.slot
+// is the first reusable slot (tombstone or empty) seen, if any.
+__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag) {
+  uint64_t idx = __umul64hi(key, cap);
+  cur.home = idx; cur.found = false; cur.slot = -1;
+#pragma unroll 1
+  for (int p = 0; p < MAX_PROBE; p++) {
+    ulonglong2 a, b, c, d;
+    slot_load(table + idx, a, b, c, d);
+    if (a.x == key && (a.y >> 8) == tag) {
+      bucket_from(cur.b, a, b, c, d);
+      cur.old = cur.b; cur.slot = (int64_t)idx; cur.found = true;
+      return;
+    }
+    if (a.x == KEY_EMPTY) { if (cur.slot < 0) cur.slot = (int64_t)idx; break; }
+    if (a.x == KEY_TOMB && cur.slot < 0) cur.slot = (int64_t)idx;
+    idx = (idx + 1 == cap) ? 0 : idx + 1;
+  }
+  cur.b.key = key; cur.b.tag = tag; cur.b.flags = 0; cur.b.limit = 0; cur.b.duration = 0; cur.b.rem = 0; cur.b.stamp = 0;
+  cur.b.burst = 0; cur.b.expire = 0;
+  cur.old = cur.b;
+}
+
+// Writes cur.b back.  Returns false when a new key needed a slot and the probe window had none (table full).
+__device__ __forceinline__ bool cursor_close(Cursor& cur, Slot* table, uint64_t cap, uint32_t& inserts) {
+  const Bucket& b = cur.b;
+  const uint64_t w1 = (b.tag << 8) | (uint64_t)(b.flags & 0xFF);
+  if (cur.found) {
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(table + cur.slot);
+    if (b.flags != cur.old.flags) __stcg(p, make_ulonglong2(b.key, w1));
+    if (b.limit != cur.old.limit || b.duration != cur.old.duration) __stcg(p + 1, make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration));
+    if (b.rem != cur.old.rem || b.stamp != cur.old.stamp) __stcg(p + 2, make_ulonglong2(b.rem, (uint64_t)b.stamp));
+    if (b.burst != cur.old.burst || b.expire != cur.old.expire) __stcg(p + 3, make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire));
+    return true;
+  }
+  if (!(b.flags & F_LIVE)) return true;  // nothing was created
+  // claim a slot inside the probe window, starting at the first reusable one seen
+  if (cur.slot < 0) return false;
+  uint64_t idx = (uint64_t)cur.slot;
+  uint64_t dist = idx >= cur.home ? idx - cur.home : idx + cap - cur.home;
+#pragma unroll 1
+  for (; dist < (uint64_t)MAX_PROBE; dist++) {
+    unsigned long long* w0 = reinterpret_cast<unsigned long long*>(&table[idx].w[0]);
+    unsigned long long seen = __ldcg(w0);
+    if (seen == KEY_EMPTY || seen == KEY_TOMB) {
+      if (atomicCAS(w0, seen, (unsigned long long)b.key) == seen) {
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(table + idx);
+        // w0 is already the key; writing the pair again stores the same value
+        __stcg(p, make_ulonglong2(b.key, w1));
+        __stcg(p + 1, make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration));
+        __stcg(p + 2, make_ulonglong2(b.rem, (uint64_t)b.stamp));
+        __stcg(p + 3, make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire));
+        cur.slot = (int64_t)idx; cur.found = true; cur.old = cur.b;
+        inserts++;
+        return true;
+      }
+    }
+    idx = (idx + 1 == cap) ? 0 : idx + 1;
+  }
+  return false;
+}
+
+__device__ __forceinline__ gub_req load_req(const gub_req* p) {
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+  ulonglong2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  gub_req r;
+  r.key_xxh64 = a.x; r.key_fnv1 = a.y; r.hits = (int64_t)b.x; r.limit = (int64_t)b.y; r.duration = (int64_t)c.x;
+  r.burst = (int64_t)c.y; r.created_at = (int64_t)d.x; r.algorithm = (uint32_t)(d.y & 0xFFFFFFFFull); r.behavior = (uint32_t)(d.y >> 32);
+  return r;
+}
+__device__ __forceinline__ void store_resp(gub_resp* p, const gub_resp& r) {
+  ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+  __stcs(q, make_ulonglong2((uint64_t)r.status | ((uint64_t)r.err_code << 32), (uint64_t)r.limit));
+  __stcs(q + 1, make_ulonglong2((uint64_t)r.remaining, (uint64_t)r.reset_time));
+}
+
+struct Tally { uint32_t over, hit, miss, inserts, full; };
+
+__device__ __forceinline__ void tally_flush_warp(const Tally& t, unsigned long long* counters) {
+  uint32_t over = __reduce_add_sync(0xFFFFFFFFu, t.over), hit = __reduce_add_sync(0xFFFFFFFFu, t.hit),
+           miss = __reduce_add_sync(0xFFFFFFFFu, t.miss), ins = __reduce_add_sync(0xFFFFFFFFu, t.inserts),
+           full = __reduce_add_sync(0xFFFFFFFFu, t.full);
+  if ((threadIdx.x & 31) == 0) {
+    if (over) atomicAdd(counters + C_OVER, (unsigned long long)over);
+    if (hit) atomicAdd(counters + C_HIT, (unsigned long long)hit);
+    if (miss) atomicAdd(counters + C_MISS, (unsigned long long)miss);
+    if (ins) atomicAdd(counters + C_INSERTS, (unsigned long long)ins);
+    if (full) atomicAdd(counters + C_FULL, (unsigned long long)full);
+  }
+}
+
+// Applies the requests reqs[idx[0..cnt)] (ascending batch order) one after another, keeping the current key's slot in
+// registers and switching slots only when the key changes (it never does unless two keys collide on the 24-bit group tag).
+template <typename IdxFn>
+__device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, IdxFn idx_of, Tally& t) {
+  Cursor cur;
+  bool open = false;
+  uint64_t ck = 0, ct = 0;
+#pragma unroll 1
+  for (uint32_t j = 0; j < cnt; j++) {
+    const uint32_t i = idx_of(j);
+    const gub_req rq = load_req(A.reqs + i);
+    const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
+    if (!open || key != ck || tag != ct) {
+      if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;  // state of the previous key is lost: counted
+      cursor_open(cur, A.table, A.capacity, key, tag);
+      open = true; ck = key; ct = tag;
+    }
+    Delta d = {0, 0, 0};
+    gub_resp r = apply_one(cur.b, rq, A.clk, d);
+    if (!cur.found && (cur.b.flags & F_LIVE)) {
+      // a new key: claim its slot now so that a full table is reported on the request that created the item
+      if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); cur.b.flags = 0; t.full++; }
+    }
+    t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+    store_resp(A.out + i, r);
+  }
+  if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
+}
+
+// ---- kernel 1: group the batch by key -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_group(const BatchArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const uint64_t key = remap_key(__ldg(&A.reqs[i].key_xxh64));
+  const uint32_t tag = (uint32_t)(key >> 40);  // 24 bits, disjoint from the position bits below
+  uint32_t pos = (uint32_t)(key ^ (key >> 29)) & A.aux_mask;
+  const unsigned long long fresh = ((unsigned long long)A.epoch << 48) | ((unsigned long long)tag << 24) | 1ull;
+  uint32_t my_ticket;
+#pragma unroll 1
+  for (;;) {
+    unsigned long long cur = A.aux[pos].word;
+    if (aux_epoch(cur) != A.epoch) {  // stale entry from an earlier batch == empty
+      const unsigned long long old = atomicCAS(&A.aux[pos].word, cur, fresh);
+      if (old == cur) { my_ticket = 0; break; }
+      cur = old;  // somebody else just claimed it for this batch: fall through and compare tags
+    }
+    if (aux_epoch(cur) == A.epoch && aux_tag(cur) == tag) {
+      my_ticket = aux_count(atomicAdd(&A.aux[pos].word, 1ull));
+      break;
+    }
+    pos = (pos + 1) & A.aux_mask;
+  }
+  A.ent[i] = pos;
+  A.ticket[i] = my_ticket;
+  BatchCtr* ctr = A.ctr + (A.epoch & 1);
+  if (my_ticket == 1) {  // the key repeats: give the group an inline member list
+    const uint32_t lid = atomicAdd(&ctr->nlists, 1u);
+    A.aux[pos].lid = lid;
+    A.list_ent[lid] = pos;
+  }
+  if (my_ticket == INLINE) {  // too many for a list: give it a bitmap
+    const uint32_t hg = atomicAdd(&ctr->nheavy, 1u);
+    A.aux[pos].hg = hg;
+    A.heavy_ent[hg] = pos;
+  }
+}
+
+// ---- kernel 2: singletons are evaluated; members of repeated keys register themselves ------------------------
+__global__ void __launch_bounds__(256) k_single(const BatchArgs A) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  Tally t = {0, 0, 0, 0, 0};
+  if (i == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
+    BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
+    nxt->nlists = 0; nxt->nheavy = 0; nxt->order_bump = 0;
+    atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
+    atomicAdd(A.counters + C_BATCHES, 1ull);
+  }
+  if (i < A.n) {
+    const uint32_t pos = A.ent[i];
+    const AuxEntry e = A.aux[pos];
+    const uint32_t cnt = aux_count(e.word);
+    if (cnt == 1) {
+      serial_walk(A, 1u, [i](uint32_t) { return i; }, t);
+    } else if (cnt <= (uint32_t)INLINE) {
+      A.lists[(size_t)e.lid * INLINE + A.ticket[i]] = i;
+    } else {
+      atomicOr(&A.bitmaps[(size_t)e.hg * A.bitmap_words + (i >> 5)], 1u << (i & 31));
+    }
+  }
+  tally_flush_warp(t, A.counters);
+}
+
+// ---- kernel 3: repeated keys -----------------------------------------------------------------------------------
+__device__ __forceinline__ void light_group(const BatchArgs& A, uint32_t lid, Tally& t) {
+  const uint32_t pos = A.list_ent[lid];
+  const uint32_t cnt = aux_count(A.aux[pos].word);
+  if (cnt > (uint32_t)INLINE) return;  // promoted to a heavy group
+  uint32_t idx[INLINE];
+  const uint32_t* lst = A.lists + (size_t)lid * INLINE;
+#pragma unroll
+  for (int j = 0; j < INLINE; j++) idx[j] = (j < (int)cnt) ? lst[j] : 0xFFFFFFFFu;
+  // insertion sort by batch index (tickets are arrival order, not index order)
+#pragma unroll 1
+  for (uint32_t a = 1; a < cnt; a++) {
+    const uint32_t v = idx[a];
+    int b = (int)a - 1;
+    while (b >= 0 && idx[b] > v) { idx[b + 1] = idx[b]; b--; }
+    idx[b + 1] = v;
+  }
+  serial_walk(A, cnt, [&idx](uint32_t j) { return idx[j]; }, t);
+}
+
+struct HeavyShared {
+  uint32_t warp_sums[HEAVY_THREADS / 32];
+  uint32_t obase;
+  uint32_t nseg;
+  uint32_t np;
+  uint32_t covered;
+  uint32_t seg[MAX_SEG];
+  Piece pieces[MAX_PIECES];
+};
+
+__device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tally& t) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t pos = A.heavy_ent[hg];
+  const uint32_t cnt = aux_count(A.aux[pos].word);
+  uint32_t* bm = A.bitmaps + (size_t)hg * A.bitmap_words;
+  const uint32_t nw = (A.n + 31) >> 5;
+  const uint32_t wpt = (nw + HEAVY_THREADS - 1) / HEAVY_THREADS;  // contiguous words per thread => ranks are ordered by thread
+  const uint32_t w0 = tid * wpt, w1 = min(nw, w0 + wpt);
+  BatchCtr* ctr = A.ctr + (A.epoch & 1);
+
+  if (tid == 0) { S.obase = atomicAdd(&ctr->order_bump, cnt); S.nseg = 0; }
+  // 1. rank = prefix popcount over the group's bitmap
+  uint32_t local = 0;
+  for (uint32_t w = w0; w < w1; w++) local += __popc(bm[w]);
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
+  if ((tid & 31) == 31) S.warp_sums[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t base = incl - local;
+  for (uint32_t w = 0; w < (tid >> 5); w++) base += S.warp_sums[w];
+  const uint32_t obase = S.obase;
+  // 2. materialise the members in index order and give the bitmap back zeroed
+  uint32_t r = base;
+  for (uint32_t w = w0; w < w1; w++) {
+    uint32_t bits = bm[w];
+    if (bits) bm[w] = 0;
+    while (bits) { const uint32_t bit = __ffs(bits) - 1; bits &= bits - 1; A.order[obase + r++] = (w << 5) + bit; }
+  }
+  __syncthreads();
+  const uint32_t* ord = A.order + obase;
+  // 3. segment boundaries: ranks whose request differs from the previous member's
+  for (uint32_t k = tid; k < cnt; k += HEAVY_THREADS) {
+    bool boundary = (k == 0);
+    if (!boundary) {
+      const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
+      boundary = !req_same(a, b);
+    }
+    if (boundary) { const uint32_t s = atomicAdd(&S.nseg, 1u); if (s < (uint32_t)MAX_SEG) S.seg[s] = k; }
+  }
+  __syncthreads();
+  const uint32_t nseg = S.nseg;
+  if (nseg > (uint32_t)MAX_SEG) {  // too irregular to plan: one thread walks the group in order
+    if (tid == 0) {
+      serial_walk(A, cnt, [ord](uint32_t j) { return ord[j]; }, t);
+      atomicAdd(A.counters + C_SERIAL, 1ull);
+    }
+    __syncthreads();
+    return;
+  }
+  if (tid == 0) {  // tiny insertion sort of the segment starts
+    for (uint32_t a = 1; a < nseg; a++) {
+      const uint32_t v = S.seg[a];
+      int b = (int)a - 1;
+      while (b >= 0 && S.seg[b] > v) { S.seg[b + 1] = S.seg[b]; b--; }
+      S.seg[b + 1] = v;
+    }
+  }
+  __syncthreads();
+  // 4. per segment: thread 0 plans, everybody evaluates
+  Cursor cur;
+  bool open = false;
+  uint64_t ck = 0, ct = 0;
+#pragma unroll 1
+  for (uint32_t s = 0; s < nseg; s++) {
+    const uint32_t lo = S.seg[s], hi = (s + 1 < nseg) ? S.seg[s + 1] : cnt, m = hi - lo;
+    if (tid == 0) {
+      const gub_req rq = load_req(A.reqs + ord[lo]);
+      const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
+      if (!open || key != ck || tag != ct) {
+        if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
+        cursor_open(cur, A.table, A.capacity, key, tag);
+        open = true; ck = key; ct = tag;
+      }
+      Delta d = {0, 0, 0};
+      uint32_t np = 0, covered;
+      const bool was_found = cur.found;
+      Bucket before = cur.b;
+      covered = plan_run(cur.b, rq, m, A.clk, d, S.pieces, MAX_PIECES, &np);
+      bool full = false;
+      if (!was_found && (cur.b.flags & F_LIVE)) {
+        if (!cursor_close(cur, A.table, A.capacity, t.inserts)) full = true;
+      }
+      if (full) {  // no slot for a new key: every request of the segment reports it, nothing is stored
+        cur.b = before; cur.b.flags = 0;
+        S.pieces[0].start = 0; S.pieces[0].kind = P_FIXED; S.pieces[0].resp = mk_err(GUB_ERR_TABLE_FULL);
+        np = 1; covered = m; t.full += m;
+      } else {
+        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+        // ranks the piece buffer could not hold (no regular regime, e.g. RESET_REMAINING flip-flops): walk them
+        for (uint32_t k = covered; k < m; k++) {
+          Delta d2 = {0, 0, 0};
+          const gub_resp rr = apply_one(cur.b, rq, A.clk, d2);
+          t.over += d2.over; t.hit += d2.hit; t.miss += d2.miss;
+          store_resp(A.out + ord[lo + k], rr);
+        }
+      }
+      S.np = np; S.covered = covered;
+    }
+    __syncthreads();
+    const uint32_t np = S.np, covered = S.covered;
+    for (uint32_t k = tid; k < covered; k += HEAVY_THREADS) {
+      uint32_t pi = 0;
+      while (pi + 1 < np && S.pieces[pi + 1].start <= k) pi++;
+      store_resp(A.out + ord[lo + k], eval_piece(S.pieces[pi], k));
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
+}
+
+// Blocks [0, heavy_blocks) take heavy groups (one block per group, grid-stride); the rest take light groups, one thread each.
+__global__ void __launch_bounds__(HEAVY_THREADS) k_multi(const BatchArgs A, uint32_t heavy_blocks) {
+  __shared__ HeavyShared S;
+  Tally t = {0, 0, 0, 0, 0};
+  const BatchCtr ctr = A.ctr[A.epoch & 1];
+  if (blockIdx.x < heavy_blocks) {
+    const uint32_t nheavy = min(ctr.nheavy, A.max_heavy);
+    for (uint32_t hg = blockIdx.x; hg < nheavy; hg += heavy_blocks) {
+      heavy_group(A, hg, S, t);
+      __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.nlists);
+      atomicAdd(A.counters + C_HEAVY_GROUPS, (unsigned long long)ctr.nheavy);
+    }
+  } else {
+    const uint32_t nlists = min(ctr.nlists, A.max_lists);
+    const uint32_t stride = (gridDim.x - heavy_blocks) * blockDim.x;
+    for (uint32_t lid = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x; lid < nlists; lid += stride) light_group(A, lid, t);
+  }
+  tally_flush_warp(t, A.counters);
+}
+
+// ---- maintenance kernels -------------------------------------------------------------------------------------
+// Upsert whole items: WorkerPool.AddCacheItem / Load / UpdatePeerGlobals.  Keys are unique within one launch.
+struct DevItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags; uint32_t _pad; };
+
+__global__ void k_add_items(Slot* table, uint64_t cap, const DevItem* items, uint32_t n, unsigned long long* counters, uint32_t* failed) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DevItem it = items[i];
+  Cursor cur;
+  cursor_open(cur, table, cap, it.key, it.tag);
+  cur.b.key = it.key; cur.b.tag = it.tag; cur.b.flags = it.flags;
+  cur.b.limit = (int64_t)it.w[0]; cur.b.duration = (int64_t)it.w[1]; cur.b.rem = it.w[2]; cur.b.stamp = (int64_t)it.w[3];
+  cur.b.burst = (int64_t)it.w[4]; cur.b.expire = (int64_t)it.w[5];
+  uint32_t ins = 0;
+  if (!cursor_close(cur, table, cap, ins)) atomicAdd(failed, 1u);
+  if (ins) atomicAdd(counters + C_INSERTS, (unsigned long long)ins);
+}
+
+__global__ void k_get_items(const Slot* table, uint64_t cap, const uint64_t* keys, const uint64_t* fnv, uint32_t n, int64_t now_ms,
+                            DevItem* out, uint8_t* found) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Cursor cur;
+  cursor_open(cur, table, cap, remap_key(keys[i]), fnv[i] >> 8);
+  const bool ok = cur.found && (cur.b.flags & F_LIVE) && !(cur.b.expire < now_ms);  // lrucache.go:111-128
+  found[i] = ok ? 1 : 0;
+  DevItem o;
+  o.key = keys[i]; o.tag = cur.b.tag; o.flags = cur.b.flags; o._pad = 0;
+  o.w[0] = (uint64_t)cur.b.limit; o.w[1] = (uint64_t)cur.b.duration; o.w[2] = cur.b.rem; o.w[3] = (uint64_t)cur.b.stamp;
+  o.w[4] = (uint64_t)cur.b.burst; o.w[5] = (uint64_t)cur.b.expire;
+  out[i] = o;
+}
+
+// Cache.Each: every live item (expired ones included until something removes them, like the reference's map walk).
+__global__ void k_scan(const Slot* table, uint64_t cap, DevItem* out, unsigned long long out_cap, unsigned long long* n_out) {
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2*>(table + s));
+    if (a.x > KEY_TOMB && (a.y & F_LIVE)) {
+      const unsigned long long k = atomicAdd(n_out, 1ull);
+      if (k < out_cap) {
+        ulonglong2 a2, b, c, d;
+        slot_load(table + s, a2, b, c, d);
+        DevItem o;
+        o.key = a.x; o.tag = a.y >> 8; o.flags = (uint32_t)(a.y & 0xFF); o._pad = 0;
+        o.w[0] = b.x; o.w[1] = b.y; o.w[2] = c.x; o.w[3] = c.y; o.w[4] = d.x; o.w[5] = d.y;
+        out[k] = o;
+      }
+    }
+  }
+}
+
+// Frees slots whose item is gone (removed, or ExpireAt < now): the batch path only ever marks them not-live.
+__global__ void k_sweep(Slot* table, uint64_t cap, int64_t now_ms, unsigned long long* removed) {
+  unsigned long long mine = 0;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2*>(table + s));
+    if (a.x > KEY_TOMB) {
+      bool dead = !(a.y & F_LIVE);
+      if (!dead) dead = (int64_t)__ldcs(&table[s].w[7]) < now_ms;
+      if (dead) { table[s].w[0] = KEY_TOMB; mine++; }
+    }
+  }
+  if (mine) atomicAdd(removed, mine);
+}
+
+// ---- multi-GPU routing ----------------------------------------------------------------------------------------
+// Owner of a key = first ring point >= FNV-1(key), wrapping (replicated_hash.go:104-119).  Stable partition of the
+// batch by owner: per-tile counts -> exclusive scan over (owner, tile) -> ordered scatter.
+constexpr int ROUTE_TILE = 1024;  // requests per block
+constexpr int MAX_SHARDS = 16;
+
+__device__ __forceinline__ uint32_t ring_owner(const uint64_t* pts, const int32_t* peers, uint32_t npts, uint64_t h) {
+  uint32_t lo = 0, hi = npts;
+  while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (pts[mid] >= h) hi = mid; else lo = mid + 1; }
+  if (lo == npts) lo = 0;
+  return (uint32_t)peers[lo];
+}
+
+__global__ void __launch_bounds__(256) k_route_count(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32_t* peers, uint32_t npts,
+                                                     uint32_t nshards, uint8_t* owner, uint32_t* tile_counts /* [nshards][ntiles] */, uint32_t ntiles) {
+  __shared__ uint32_t cnt[MAX_SHARDS];
+  if (threadIdx.x < MAX_SHARDS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * ROUTE_TILE;
+  for (uint32_t k = threadIdx.x; k < ROUTE_TILE; k += blockDim.x) {
+    const uint32_t i = base + k;
+    if (i < n) {
+      const uint32_t o = ring_owner(pts, peers, npts, __ldg(&reqs[i].key_fnv1));
+      owner[i] = (uint8_t)o;
+      atomicAdd(&cnt[o], 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nshards) tile_counts[threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// one block: exclusive scan of tile_counts in (owner-major, tile-minor) order; also totals per owner
+__global__ void __launch_bounds__(1024) k_route_scan(uint32_t* tile_counts, uint32_t total, uint32_t nshards, uint32_t ntiles, uint32_t* counts) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < total; base += blockDim.x) {
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t v = k < total ? tile_counts[k] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((threadIdx.x & 31) >= (uint32_t)o) incl += u; }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t off = carry;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); w++) off += warp_sums[w];
+    if (k < total) tile_counts[k] = off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = off + incl;
+    __syncthreads();
+  }
+  // totals: owner g covers tile_counts[g*ntiles .. (g+1)*ntiles)
+  if (threadIdx.x < nshards) {
+    const uint32_t start = tile_counts[threadIdx.x * ntiles];
+    const uint32_t end = (threadIdx.x + 1 < nshards) ? tile_counts[(threadIdx.x + 1) * ntiles] : carry;
+    counts[threadIdx.x] = end - start;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_route_scatter(const gub_req* reqs, uint32_t n, const uint8_t* owner, const uint32_t* tile_offsets,
+                                                       uint32_t ntiles, uint32_t nshards, gub_req* out_reqs, uint32_t* perm) {
+  // ranks inside the tile are computed warp by warp in index order so the partition is stable
+  __shared__ uint32_t run[MAX_SHARDS];
+  if (threadIdx.x < MAX_SHARDS) run[threadIdx.x] = (threadIdx.x < nshards) ? tile_offsets[threadIdx.x * ntiles + blockIdx.x] : 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * ROUTE_TILE;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (uint32_t chunk = 0; chunk < ROUTE_TILE; chunk += blockDim.x) {
+    // within a chunk of blockDim.x consecutive requests, warps take turns in order
+    for (uint32_t w = 0; w < nwarps; w++) {
+      if (w == warp) {
+        const uint32_t i = base + chunk + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t o = valid ? owner[i] : 0xFFu;
+        const uint32_t peers_mask = __match_any_sync(0xFFFFFFFFu, o);
+        const uint32_t rank = __popc(peers_mask & ((1u << lane) - 1u));
+        const uint32_t leader = __ffs(peers_mask) - 1;
+        uint32_t start = 0;
+        if (valid && lane == leader) { start = run[o]; run[o] = start + __popc(peers_mask); }
+        start = __shfl_sync(0xFFFFFFFFu, start, leader);
+        if (valid) {
+          const uint32_t dst = start + rank;
+          const ulonglong2* src = reinterpret_cast<const ulonglong2*>(reqs + i);
+          ulonglong2* d2 = reinterpret_cast<ulonglong2*>(out_reqs + dst);
+          d2[0] = __ldg(src); d2[1] = __ldg(src + 1); d2[2] = __ldg(src + 2); d2[3] = __ldg(src + 3);
+          perm[dst] = i;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void k_unroute(const gub_resp* in, const uint32_t* perm, uint32_t n, gub_resp* out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const ulonglong2* s = reinterpret_cast<const ulonglong2*>(in + j);
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(out + perm[j]);
+  d[0] = s[0]; d[1] = s[1];
+}
+
+}  // namespace gub

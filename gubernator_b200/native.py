@@ -1,0 +1,274 @@
+"""ctypes binding of libgubernator_b200.so (include/gubernator_b200.h).  No fallbacks: a missing library is an error."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgubernator_b200.so")
+
+TOKEN_BUCKET, LEAKY_BUCKET = 0, 1
+UNDER_LIMIT, OVER_LIMIT = 0, 1
+NO_BATCHING, GLOBAL, DURATION_IS_GREGORIAN, RESET_REMAINING, MULTI_REGION, DRAIN_OVER_LIMIT = 1, 2, 4, 8, 16, 32
+REQ_IS_OWNER = 0x100
+ERR_UNIQUE_KEY_EMPTY, ERR_NAMESPACE_EMPTY, ERR_INVALID_ALGORITHM, ERR_GREGORIAN_WEEKS, ERR_GREGORIAN_INVALID, ERR_TABLE_FULL = 1, 2, 3, 4, 5, 6
+
+REQ_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("hits", "<i8"), ("limit", "<i8"), ("duration", "<i8"),
+                      ("burst", "<i8"), ("created_at", "<i8"), ("algorithm", "<u4"), ("behavior", "<u4")])
+RESP_DTYPE = np.dtype([("status", "<u4"), ("err_code", "<u4"), ("limit", "<i8"), ("remaining", "<i8"), ("reset_time", "<i8")])
+CLOCK_DTYPE = np.dtype([("now_ms", "<i8"), ("greg_expire", "<i8", (6,)), ("greg_duration", "<i8", (6,))])
+ITEM_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("algorithm", "<i4"), ("status", "<i4"), ("limit", "<i8"),
+                       ("duration", "<i8"), ("remaining", "<i8"), ("remaining_f", "<f8"), ("stamp", "<i8"), ("burst", "<i8"),
+                       ("expire_at", "<i8")])
+COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups",
+                  "heavy_groups", "serial_fallbacks")
+assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 80
+
+EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device",
+           "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
+           "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys",
+           "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
+           "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device"]
+
+
+class Config(C.Structure):
+    _fields_ = [("capacity_slots", C.c_uint64), ("max_batch", C.c_uint32), ("device", C.c_int32)]
+
+
+class GubError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GubError(f"{LIB_PATH} is missing: build it with `python -m gubernator_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, i64, sz, i32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_size_t, C.c_int
+        L.gub_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+        L.gub_destroy.argtypes = [vp]; L.gub_destroy.restype = None
+        L.gub_last_error.restype = C.c_char_p
+        L.gub_submit.argtypes = [vp, vp, sz, vp, vp]
+        L.gub_submit_device.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.gub_pipeline_depth.argtypes = [vp]
+        L.gub_submit_async.argtypes = [vp, vp, sz, vp, vp, C.POINTER(i32)]
+        L.gub_wait.argtypes = [vp, i32]
+        L.gub_host_alloc.argtypes = [sz]; L.gub_host_alloc.restype = vp
+        L.gub_host_free.argtypes = [vp]; L.gub_host_free.restype = None
+        L.gub_clock_fill.argtypes = [i64, vp]
+        L.gub_add_items.argtypes = [vp, vp, sz]
+        L.gub_get_items.argtypes = [vp, vp, vp, sz, i64, vp, vp]
+        L.gub_scan.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        L.gub_size.argtypes = [vp, C.POINTER(sz)]
+        L.gub_sweep.argtypes = [vp, i64, C.POINTER(sz)]
+        L.gub_get_counters.argtypes = [vp, vp]
+        L.gub_set_profiling.argtypes = [vp, i32]
+        L.gub_get_profile.argtypes = [vp, vp, vp, i32]
+        L.gub_hash_keys.argtypes = [vp, vp, sz, vp, vp]
+        L.gub_xxh64.argtypes = [C.c_char_p, sz, u64]; L.gub_xxh64.restype = u64
+        L.gub_fnv1_64.argtypes = [C.c_char_p, sz]; L.gub_fnv1_64.restype = u64
+        L.gub_fnv1a_64.argtypes = [C.c_char_p, sz]; L.gub_fnv1a_64.restype = u64
+        L.gub_ring_create.argtypes = [i32, i32]; L.gub_ring_create.restype = vp
+        L.gub_ring_destroy.argtypes = [vp]; L.gub_ring_destroy.restype = None
+        L.gub_ring_add.argtypes = [vp, C.c_char_p]
+        L.gub_ring_size.argtypes = [vp]
+        L.gub_ring_get.argtypes = [vp, C.c_char_p, sz]
+        L.gub_ring_get_by_hash.argtypes = [vp, u64]
+        L.gub_ring_points.argtypes = [vp, vp, vp, sz]; L.gub_ring_points.restype = sz
+        L.gub_route_device.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+        L.gub_unroute_device.argtypes = [vp, vp, vp, sz, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GubError(f"{what}: {lib().gub_last_error().decode()}")
+
+
+def xxh64(b: bytes, seed=0):
+    return lib().gub_xxh64(b, len(b), seed)
+
+
+def fnv1_64(b: bytes):
+    return lib().gub_fnv1_64(b, len(b))
+
+
+def fnv1a_64(b: bytes):
+    return lib().gub_fnv1a_64(b, len(b))
+
+
+def hash_keys(keys):
+    """keys: list of bytes -> (xxh64 array, fnv1 array); one library call over the packed bytes."""
+    n = len(keys)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    if n:
+        offs[1:] = np.cumsum([len(k) for k in keys])
+    blob = b"".join(keys)
+    xx = np.zeros(n, dtype=np.uint64)
+    fv = np.zeros(n, dtype=np.uint64)
+    buf = C.create_string_buffer(blob, len(blob) + 1)
+    _check(lib().gub_hash_keys(C.addressof(buf), offs.ctypes.data, n, xx.ctypes.data, fv.ctypes.data), "gub_hash_keys")
+    return xx, fv
+
+
+def clock_fill(now_ms):
+    clk = np.zeros(1, dtype=CLOCK_DTYPE)
+    _check(lib().gub_clock_fill(int(now_ms), clk.ctypes.data), "gub_clock_fill")
+    return clk
+
+
+Clock = clock_fill
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from gub_host_alloc."""
+
+    def __init__(self, n, dtype):
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        self.ptr = lib().gub_host_alloc(max(self.nbytes, 64))
+        if not self.ptr:
+            raise GubError("gub_host_alloc failed")
+        buf = (C.c_char * max(self.nbytes, 64)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().gub_host_free(self.ptr)
+            self.ptr = None
+
+
+class Table:
+    """One GPU's shard: the device-resident bucket table + batch evaluation (WorkerPool replacement)."""
+
+    def __init__(self, capacity_slots, max_batch=65536, device=0):
+        cfg = Config(int(capacity_slots), int(max_batch), int(device))
+        h = C.c_void_p()
+        _check(lib().gub_create(C.byref(cfg), C.byref(h)), "gub_create")
+        self._h = h
+        self.device = device
+        self.capacity = int(capacity_slots)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gub_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- hot path
+    def submit(self, reqs: np.ndarray, clk: np.ndarray, out: np.ndarray = None):
+        assert reqs.dtype == REQ_DTYPE and reqs.flags.c_contiguous
+        if out is None:
+            out = np.zeros(len(reqs), dtype=RESP_DTYPE)
+        _check(lib().gub_submit(self._h, reqs.ctypes.data, len(reqs), clk.ctypes.data, out.ctypes.data), "gub_submit")
+        return out
+
+    def submit_async(self, reqs_ptr, n, clk: np.ndarray, out_ptr):
+        ticket = C.c_int(-1)
+        _check(lib().gub_submit_async(self._h, reqs_ptr, n, clk.ctypes.data, out_ptr, C.byref(ticket)), "gub_submit_async")
+        return ticket.value
+
+    def wait(self, ticket):
+        _check(lib().gub_wait(self._h, ticket), "gub_wait")
+
+    def submit_device(self, d_reqs_ptr, n, clk: np.ndarray, d_out_ptr, stream=0):
+        _check(lib().gub_submit_device(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_submit_device")
+
+    # ---- maintenance
+    def add_items(self, items: np.ndarray):
+        assert items.dtype == ITEM_DTYPE and items.flags.c_contiguous
+        _check(lib().gub_add_items(self._h, items.ctypes.data, len(items)), "gub_add_items")
+
+    def get_items(self, key_xxh64, key_fnv1, now_ms):
+        kx = np.ascontiguousarray(key_xxh64, dtype=np.uint64)
+        kf = np.ascontiguousarray(key_fnv1, dtype=np.uint64)
+        out = np.zeros(len(kx), dtype=ITEM_DTYPE)
+        found = np.zeros(len(kx), dtype=np.uint8)
+        _check(lib().gub_get_items(self._h, kx.ctypes.data, kf.ctypes.data, len(kx), int(now_ms), out.ctypes.data, found.ctypes.data), "gub_get_items")
+        return out, found.astype(bool)
+
+    def size(self):
+        n = C.c_size_t(0)
+        _check(lib().gub_size(self._h, C.byref(n)), "gub_size")
+        return n.value
+
+    def scan(self):
+        n = self.size()
+        out = np.zeros(max(n, 1), dtype=ITEM_DTYPE)
+        m = C.c_size_t(0)
+        _check(lib().gub_scan(self._h, out.ctypes.data, len(out), C.byref(m)), "gub_scan")
+        return out[:min(m.value, len(out))]
+
+    def sweep(self, now_ms):
+        n = C.c_size_t(0)
+        _check(lib().gub_sweep(self._h, int(now_ms), C.byref(n)), "gub_sweep")
+        return n.value
+
+    def counters(self):
+        c = np.zeros(len(COUNTER_FIELDS), dtype=np.uint64)
+        _check(lib().gub_get_counters(self._h, c.ctypes.data), "gub_get_counters")
+        return {k: int(v) for k, v in zip(COUNTER_FIELDS, c)}
+
+    def set_profiling(self, on):
+        _check(lib().gub_set_profiling(self._h, 1 if on else 0), "gub_set_profiling")
+
+    def get_profile(self, reset=True):
+        ms = np.zeros(3, dtype=np.float64)
+        n = C.c_uint64(0)
+        _check(lib().gub_get_profile(self._h, ms.ctypes.data, C.byref(n), 1 if reset else 0), "gub_get_profile")
+        return dict(k_group_ms=float(ms[0]), k_single_ms=float(ms[1]), k_multi_ms=float(ms[2]), launches=int(n.value))
+
+    # ---- multi-GPU routing
+    def route_device(self, ring, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream=0):
+        _check(lib().gub_route_device(self._h, ring._r, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream), "gub_route_device")
+
+    def unroute_device(self, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream=0):
+        _check(lib().gub_unroute_device(self._h, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream), "gub_unroute_device")
+
+
+class Ring:
+    """ReplicatedConsistentHash (replicated_hash.go:36-119)."""
+
+    def __init__(self, hash_kind=0, replicas=512):
+        self._r = C.c_void_p(lib().gub_ring_create(hash_kind, replicas))
+        self.peers = []
+
+    def add(self, addr: str):
+        rc = lib().gub_ring_add(self._r, addr.encode())
+        if rc < 0:
+            raise GubError("gub_ring_add failed")
+        self.peers.append(addr)
+        return rc
+
+    def size(self):
+        return lib().gub_ring_size(self._r)
+
+    def get(self, key: str):
+        b = key.encode()
+        return lib().gub_ring_get(self._r, b, len(b))
+
+    def get_by_hash(self, h):
+        return lib().gub_ring_get_by_hash(self._r, int(h))
+
+    def points(self):
+        n = lib().gub_ring_points(self._r, None, None, 0)
+        hs = np.zeros(n, dtype=np.uint64)
+        ps = np.zeros(n, dtype=np.int32)
+        lib().gub_ring_points(self._r, hs.ctypes.data, ps.ctypes.data, n)
+        return hs, ps
+
+    def __del__(self):
+        try:
+            lib().gub_ring_destroy(self._r)
+        except Exception:
+            pass

@@ -1,0 +1,127 @@
+"""Python binding of the host service layer (include/gubernator_b200_host.h, csrc/host_v1.cpp): `V1Instance` mirrors the
+reference's V1Instance.GetRateLimits (gubernator.go:183) for a one-node cluster, evaluated on the GPU."""
+import ctypes as C
+from dataclasses import dataclass
+
+from . import native
+
+MAX_BATCH_SIZE = 1000  # gubernator.go:40
+
+
+class _Req(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("unique_key", C.c_char_p), ("hits", C.c_int64), ("limit", C.c_int64),
+                ("duration", C.c_int64), ("burst", C.c_int64), ("algorithm", C.c_int32), ("behavior", C.c_int32),
+                ("created_at", C.c_int64)]
+
+
+class _Resp(C.Structure):
+    _fields_ = [("status", C.c_int32), ("err_code", C.c_int32), ("limit", C.c_int64), ("remaining", C.c_int64),
+                ("reset_time", C.c_int64), ("error", C.c_char * 256)]
+
+
+@dataclass
+class RateLimitReq:  # gubernator.proto:137-183
+    name: str = ""
+    unique_key: str = ""
+    hits: int = 0
+    limit: int = 0
+    duration: int = 0
+    algorithm: int = 0
+    behavior: int = 0
+    burst: int = 0
+    created_at: int = 0
+
+
+@dataclass
+class RateLimitResp:  # gubernator.proto:190-203
+    status: int = 0
+    limit: int = 0
+    remaining: int = 0
+    reset_time: int = 0
+    error: str = ""
+
+
+_bound = False
+
+
+def _bind():
+    global _bound
+    L = native.lib()
+    if not _bound:
+        vp = C.c_void_p
+        L.gub_instance_create.argtypes = [vp, C.POINTER(vp)]
+        L.gub_instance_destroy.argtypes = [vp]; L.gub_instance_destroy.restype = None
+        L.gub_instance_set_clock.argtypes = [vp, C.c_int64]; L.gub_instance_set_clock.restype = None
+        L.gub_instance_now.argtypes = [vp]; L.gub_instance_now.restype = C.c_int64
+        L.gub_instance_get_rate_limits.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
+        L.gub_instance_get_rate_limits_unbounded.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
+        L.gub_instance_update_peer_global.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]
+        _bound = True
+    return L
+
+
+class V1Instance:
+    """V1Instance for a one-node cluster over one device table, with the frozen-clock hooks the reference's tests use."""
+
+    def __init__(self, capacity_slots=1 << 16, max_batch=65536, device=0, now_ms=None, table=None):
+        L = _bind()
+        self.table = table or native.Table(capacity_slots, max_batch, device)
+        h = C.c_void_p()
+        if L.gub_instance_create(self.table._h, C.byref(h)) != 0:
+            raise native.GubError("gub_instance_create failed")
+        self._h = h
+        if now_ms is not None:
+            self.set_now(now_ms)
+
+    # holster clock.Freeze / Advance
+    def set_now(self, now_ms):
+        _bind().gub_instance_set_clock(self._h, int(now_ms))
+
+    def now(self):
+        return _bind().gub_instance_now(self._h)
+
+    def advance(self, ms):
+        self.set_now(self.now() + int(ms))
+
+    def get_rate_limits(self, reqs, unbounded=False):
+        """reqs: list of RateLimitReq or dicts.  Returns list of dicts like the oracle binding (status, limit, remaining,
+        reset_time, error).  Raises ValueError for more than 1000 requests (gubernator.go:189-193)."""
+        L = _bind()
+        n = len(reqs)
+        arr = (_Req * max(n, 1))()
+        for i, r in enumerate(reqs):
+            if not isinstance(r, dict):
+                r = r.__dict__
+            arr[i].name = r.get("name", "").encode()
+            arr[i].unique_key = r.get("unique_key", "").encode()
+            arr[i].hits = r.get("hits", 0); arr[i].limit = r.get("limit", 0); arr[i].duration = r.get("duration", 0)
+            arr[i].burst = r.get("burst", 0); arr[i].algorithm = r.get("algorithm", 0); arr[i].behavior = r.get("behavior", 0)
+            arr[i].created_at = r.get("created_at", 0) or 0
+        out = (_Resp * max(n, 1))()
+        fn = L.gub_instance_get_rate_limits_unbounded if unbounded else L.gub_instance_get_rate_limits
+        rc = fn(self._h, arr, n, out)
+        if rc == -2:
+            raise ValueError("Requests.RateLimits list too large; max size is '1000'")
+        if rc != 0:
+            raise native.GubError("GetRateLimits: " + L.gub_last_error().decode())
+        return [dict(status=o.status, limit=o.limit, remaining=o.remaining, reset_time=o.reset_time, error=o.error.decode(),
+                     err_code=o.err_code) for o in out[:n]]
+
+    def GetRateLimits(self, reqs):
+        return [RateLimitResp(o["status"], o["limit"], o["remaining"], o["reset_time"], o["error"]) for o in self.get_rate_limits(reqs)]
+
+    def update_peer_global(self, key: str, algorithm, duration, status, limit, remaining, reset_time):
+        rc = _bind().gub_instance_update_peer_global(self._h, key.encode(), algorithm, duration, status, limit, remaining, reset_time)
+        if rc != 0:
+            raise native.GubError("UpdatePeerGlobals: " + native.lib().gub_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _bind().gub_instance_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

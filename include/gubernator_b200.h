@@ -145,6 +145,11 @@ int gub_pipeline_depth(gub_table* t);
 int gub_submit_async(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out, int* ticket);
 int gub_wait(gub_table* t, int ticket);
 
+/* Page-locked host memory for request/response buffers: with these the H2D/D2H copies of gub_submit_async are truly
+ * asynchronous (a Go shim allocates its batch arenas here once).  Any other host memory works too, just slower. */
+void* gub_host_alloc(size_t bytes);
+void gub_host_free(void* p);
+
 /* Gregorian tables for a batch clock: GregorianDuration / GregorianExpiration (interval.go:84-148), UTC. */
 int gub_clock_fill(int64_t now_ms, gub_clock* out);
 
@@ -163,6 +168,11 @@ int gub_size(gub_table* t, size_t* n_out);
  * (lrucache.go:115) and by LRU eviction (lrucache.go:98,138).  *removed may be NULL. */
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
+
+/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_single / k_multi), the
+ * measurement counterpart of the reference's metricFuncTimeDuration summaries (gubernator.go:65-73).  Off by default. */
+int gub_set_profiling(gub_table* t, int on);
+int gub_get_profile(gub_table* t, double kernel_ms[3], uint64_t* launches, int reset);
 
 /* ---- key hashing: client.go:39-41 HashKey + workers.go:153 + replicated_hash.go:108 -------------------------
  * keys are packed back to back in `bytes`; key i is bytes[offsets[i] .. offsets[i+1]).  Host implementation. */

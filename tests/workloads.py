@@ -109,14 +109,84 @@ def bench_batch(rng, n, n_keys, created_at, zipf_s=None, mixed=False, perm_seed=
     return reqs, ids
 
 
+_ZIPF_CACHE = {}
+
+
 def zipf_ids(rng, n, n_keys, s, perm_seed=12345):
-    """Bounded Zipf(s) over ranks 1..n_keys by inverse-CDF on the continuous approximation, then rank -> id through a
-    fixed multiplicative permutation (so hot keys are spread over the id space)."""
-    u = rng.random(n)
-    a = 1.0 - s
-    # CDF(x) ~ (x^a - 1) / (K^a - 1) for the density x^-s on [1, K+1)
-    K = float(n_keys) + 1.0
-    x = (u * (K ** a - 1.0) + 1.0) ** (1.0 / a)
-    rank = np.minimum(np.floor(x).astype(np.int64) - 1, n_keys - 1)
-    mult = 0x9E3779B97F4A7C15 | 1
-    return ((rank.astype(np.uint64) * np.uint64(mult & 0xFFFFFFFFFFFFFFFF) + np.uint64(perm_seed)) % np.uint64(n_keys)).astype(np.int64)
+    """Bounded Zipf(s) over ranks 1..n_keys: exact inverse CDF for the first 2^20 ranks (cumulative table), the
+    midpoint-rule continuous tail beyond; then rank -> id through a fixed multiplicative permutation (so hot keys are
+    spread over the id space)."""
+    M = min(n_keys, 1 << 20)
+    key = (n_keys, s)
+    if key not in _ZIPF_CACHE:
+        head = np.cumsum(np.arange(1, M + 1, dtype=np.float64) ** (-s))
+        a = 1.0 - s
+        tail = ((n_keys + 0.5) ** a - (M + 0.5) ** a) / a if n_keys > M else 0.0
+        _ZIPF_CACHE[key] = (head, tail)
+    head, tail = _ZIPF_CACHE[key]
+    total = head[-1] + tail
+    u = rng.random(n) * total
+    rank = np.searchsorted(head, u, side="right").astype(np.int64)  # 0-based rank for the head
+    in_tail = u >= head[-1]
+    if in_tail.any():
+        a = 1.0 - s
+        x = ((u[in_tail] - head[-1]) * a + (M + 0.5) ** a) ** (1.0 / a)  # invert the tail integral
+        rank[in_tail] = np.clip(np.floor(x + 0.5).astype(np.int64) - 1, M, n_keys - 1)
+    rank = np.minimum(rank, n_keys - 1)
+    mult = 0x9E3779B97F4A7C15
+    with np.errstate(over="ignore"):
+        return ((rank.astype(np.uint64) * np.uint64(mult) + np.uint64(perm_seed)) % np.uint64(n_keys)).astype(np.int64)
+
+
+# ---- vectorised hashing of the BASELINE.md synthetic keys -----------------------------------------------------
+# Key string = "bench_k%09d" (16 bytes).  XXH64 (seed 0, the < 32-byte path) and FNV-1 64 over 16 bytes, in numpy
+# uint64 arithmetic (wrapping), so that 10^8 keys can be prepared in seconds.  Checked against the scalar
+# implementations in tests/test_workloads.py.
+_P1, _P2, _P3, _P4, _P5 = (np.uint64(x) for x in (0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9,
+                                                    0x85EBCA77C2B2AE63, 0x27D4EB2F165667C5))
+
+
+def _rotl(x, r):
+    return (x << np.uint64(r)) | (x >> np.uint64(64 - r))
+
+
+def bench_key_bytes(ids, prefix=b"bench_k"):
+    """uint8 [n, 16]: prefix + 9 decimal digits."""
+    ids = np.asarray(ids, dtype=np.int64)
+    out = np.empty((len(ids), 16), dtype=np.uint8)
+    out[:, :7] = np.frombuffer(prefix, dtype=np.uint8)
+    v = ids.copy()
+    for d in range(9):
+        out[:, 15 - d] = (v % 10 + 48).astype(np.uint8)
+        v //= 10
+    return out
+
+
+def bench_key_hashes(ids, prefix=b"bench_k"):
+    with np.errstate(over="ignore"):
+        b = bench_key_bytes(ids, prefix)
+        w = np.ascontiguousarray(b).view("<u8")  # [n, 2]
+        h = _P5 + np.uint64(16)
+        for j in range(2):
+            k = _rotl(w[:, j] * _P2, 31) * _P1
+            h = _rotl(h ^ k, 27) * _P1 + _P4
+        h = (h ^ (h >> np.uint64(33))) * _P2
+        h = (h ^ (h >> np.uint64(29))) * _P3
+        xx = h ^ (h >> np.uint64(32))
+        f = np.full(len(b), 0xCBF29CE484222325, dtype=np.uint64)
+        prime = np.uint64(0x100000001B3)
+        for j in range(16):
+            f = (f * prime) ^ b[:, j].astype(np.uint64)
+    return xx, f
+
+
+def bench_requests(ids, created_at, mixed=True, prefix=b"bench_k", dtype=None):
+    """BASELINE.md request records for the given key ids (hits=1, limit=100, duration=60 000, burst=0)."""
+    ids = np.asarray(ids, dtype=np.int64)
+    reqs = np.zeros(len(ids), dtype=dtype or O.HREQ_DTYPE)
+    reqs["key_xxh64"], reqs["key_fnv1"] = bench_key_hashes(ids, prefix)
+    reqs["hits"] = 1; reqs["limit"] = 100; reqs["duration"] = 60000
+    reqs["created_at"] = created_at
+    reqs["algorithm"] = (ids & 1) if mixed else 0
+    reqs["behavior"] = O.REQ_IS_OWNER
+    return reqs
