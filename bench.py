@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — rate-limit decisions/s of the B200 evaluation path on BASELINE.json's headline workload.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path (default)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU worker-pool path (oracle port) on the host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...        # N GPUs: key space sharded by the replicated-hash ring
+
+A "step" is one 65 536-request batch per GPU through the whole hot path (group -> probe -> bucket update -> response).
+Workload at N = 1: BASELINE config 3 — 100 M resident keys, Zipf s = 1.1, TOKEN/LEAKY 50/50 by key.  At N > 1:
+config 4 — the same key space sharded over the N GPUs by the 512-replica FNV-1 ring, requests routed to their owner
+with NCCL all-to-all and responses routed back (weak scaling: 65 536 requests ingested per GPU per step).
+
+Prints ONE JSON line (rank 0).  `value` = decisions/s with the request batches already resident in HBM (a pool of
+pre-generated batches larger than L2 is cycled; the 12.8 GB table is far larger than L2).  `e2e` = the same through
+the public host API (gub_submit_async with pinned host buffers: H2D of requests + D2H of responses inside the timed
+region).  `roofline` = algorithmic bytes of the dominant kernel / its CUDA-event time, vs MEASURED_PEAKS.json.
+`cpu_baseline` = the oracle's worker-pool port timed on this host's cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BATCH = 65536
+T0 = 1_700_000_000_000
+ALGO_BYTES_PER_DECISION = 224  # 64 slot read + 64 slot write-back + 64 request + 32 response
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--keys", type=int, default=int(os.environ.get("GUB_BENCH_KEYS", 100_000_000)))
+    ap.add_argument("--zipf", type=float, default=1.1)
+    ap.add_argument("--pool", type=int, default=32, help="distinct pre-generated batches cycled through (32 x 6 MiB > L2)")
+    ap.add_argument("--cpu-keys", type=int, default=int(os.environ.get("GUB_BENCH_CPU_KEYS", 10_000_000)))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---- helpers ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.dev = [], None, device_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def gen_batch(rng, n, n_keys, created_at, zipf_s, dtype):
+    from workloads import bench_requests, zipf_ids
+    ids = zipf_ids(rng, n, n_keys, zipf_s)
+    return bench_requests(ids, created_at, mixed=True, dtype=dtype), ids
+
+
+def batch_stats(ids):
+    _, counts = np.unique(ids, return_counts=True)
+    return dict(distinct=int(len(counts)), singles=int((counts == 1).sum()), multi_groups=int((counts > 1).sum()),
+                multi_requests=int(counts[counts > 1].sum()), top=int(counts.max()))
+
+
+# ---- reference arm: the reference's CPU path (oracle port; the Go reference cannot be built in this image) ----------
+def cpu_leg(n_keys, zipf_s, seconds, seed, steps=None, warmup=0):
+    import oracle_py as O
+    from workloads import bench_requests
+    cores = os.cpu_count() or 1
+    workers = cores
+    pool = O.Pool(workers=workers, cache_size=max(4 * n_keys, 1 << 20), now_ms=T0)
+    rng = np.random.default_rng(seed)
+    # warm pass: make every key resident, through the same worker-pool path
+    t_fill = time.perf_counter()
+    chunk = 1 << 20
+    for lo in range(0, n_keys, chunk):
+        ids = np.arange(lo, min(n_keys, lo + chunk), dtype=np.int64)
+        pool.submit_hashed(bench_requests(ids, T0), threads=cores)
+    t_fill = time.perf_counter() - t_fill
+    batches = [gen_batch(rng, BATCH, n_keys, T0 + 1 + b, zipf_s, O.HREQ_DTYPE)[0] for b in range(16)]
+    for w in range(max(warmup, 1)):
+        pool.set_now(T0 + 1 + w)
+        pool.submit_hashed(batches[w % len(batches)], threads=cores)
+    done, t_used, b = 0, 0.0, 0
+    while (steps is None and t_used < seconds) or (steps is not None and b < steps):
+        pool.set_now(T0 + 1 + b)
+        pool.submit_hashed(batches[b % len(batches)], threads=cores)
+        t_used += pool.last_mt_seconds
+        done += BATCH
+        b += 1
+    return dict(value=done / t_used, seconds=t_used, steps=b, cores=cores, fill_seconds=t_fill, keys=n_keys)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_leg(args.cpu_keys, args.zipf, args.cpu_seconds, 0xB200 + 3, steps=args.steps, warmup=args.warmup)
+    sample = (f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
+              f"{args.keys:,} to bound the warm pass), TOKEN/LEAKY 50/50, {r['cores']} worker threads")
+    line = {
+        "impl": "reference", "metric": "rate-limit decisions/sec", "value": r["value"], "unit": "decisions/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 3 shape on CPU: {sample}", "batch": BATCH, "keys": r["keys"], "zipf_s": args.zipf},
+        "cpu_baseline": {"value": r["value"], "unit": "decisions/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- this repo's arm --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import gubernator_b200 as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N = world
+    n_keys = args.keys
+    seed = 0xB200 + (3 if N == 1 else 4)
+    rng = np.random.default_rng(seed + 1000 * rank)
+
+    # table sized at load factor <= 0.5 for this shard's share of the key space (+25 % for ring imbalance)
+    shard_keys = n_keys if N == 1 else int(n_keys / N * 1.25)
+    capacity = max(2 * shard_keys, 1 << 16)
+    max_batch = BATCH if N == 1 else 262144
+    tab = g.Table(capacity, max_batch=max_batch, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    ring = None
+    if N > 1:
+        ring = g.Ring(0, 512)
+        for r in range(N):
+            ring.add(f"gpu:{r}")
+
+    def t2np(t, dtype):
+        return t.cpu().numpy().reshape(-1).view(dtype)
+
+    # ---- one step of the sharded path (N > 1): route -> all-to-all -> evaluate -> all-to-all back -> unroute
+    class Sharded:
+        def __init__(self, cap):
+            self.cap = cap
+            self.routed = torch.empty((cap, 64), dtype=torch.uint8, device=dev)
+            self.perm = torch.empty(cap, dtype=torch.int32, device=dev)
+            self.counts = torch.zeros(16, dtype=torch.int32, device=dev)
+            self.recv_cap = int(cap * 1.6) + 4096
+            self.recv = torch.empty((self.recv_cap, 64), dtype=torch.uint8, device=dev)
+            self.recv_resp = torch.empty((self.recv_cap, 32), dtype=torch.uint8, device=dev)
+            self.back = torch.empty((cap, 32), dtype=torch.uint8, device=dev)
+
+        def step(self, d_reqs, n, clk, d_out):
+            tab.route_device(ring, d_reqs.data_ptr(), n, self.routed.data_ptr(), self.perm.data_ptr(), self.counts.data_ptr(), stream)
+            send = self.counts[:N].clone()
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send)
+            send_l, recv_l = send.tolist(), recv.tolist()  # host sync: split sizes for the variable all-to-all
+            m = sum(recv_l)
+            if m > self.recv_cap:
+                raise RuntimeError("receive buffer too small")
+            dist.all_to_all_single(self.recv[:m], self.routed[:n], output_split_sizes=recv_l, input_split_sizes=send_l)
+            tab.submit_device(self.recv.data_ptr(), m, clk, self.recv_resp.data_ptr(), stream)
+            dist.all_to_all_single(self.back[:n], self.recv_resp[:m], output_split_sizes=send_l, input_split_sizes=recv_l)
+            tab.unroute_device(self.back.data_ptr(), self.perm.data_ptr(), n, d_out.data_ptr(), stream)
+            return m
+
+    sharded = Sharded(262144) if N > 1 else None
+
+    # ---- warm pass: make every key resident through the real path
+    t_fill = time.perf_counter()
+    clk0 = g.clock_fill(T0)
+    from workloads import bench_requests
+    chunk = 262144 if N > 1 else 1 << 20
+    d_chunk = torch.empty((chunk, 64), dtype=torch.uint8, device=dev)
+    d_chunk_out = torch.empty((chunk, 32), dtype=torch.uint8, device=dev)
+    my_lo = (n_keys * rank) // N
+    my_hi = (n_keys * (rank + 1)) // N
+    n_fill_steps = (n_keys // N + chunk - 1) // chunk  # identical on every rank (collectives inside)
+    for s in range(n_fill_steps):
+        lo = my_lo + s * chunk
+        hi = min(my_hi, lo + chunk)
+        ids = np.arange(lo, max(hi, lo), dtype=np.int64)
+        reqs = bench_requests(ids, T0, dtype=g.REQ_DTYPE)
+        n = len(reqs)
+        if n:
+            d_chunk[:n].copy_(torch.from_numpy(reqs.view(np.uint8).reshape(n, 64)), non_blocking=False)
+        if N == 1:
+            tab.submit_device(d_chunk.data_ptr(), n, clk0, d_chunk_out.data_ptr(), stream)
+        else:
+            sharded.step(d_chunk, n, clk0, d_chunk_out)
+    torch.cuda.synchronize()
+    t_fill = time.perf_counter() - t_fill
+    c0 = tab.counters()
+
+    # ---- pre-generated batch pool, resident in HBM
+    pool_n = max(2, args.pool)
+    host_batches, stats = [], []
+    for b in range(pool_n):
+        reqs, ids = gen_batch(rng, BATCH, n_keys, T0 + 1 + b, args.zipf, g.REQ_DTYPE)
+        host_batches.append(reqs)
+        stats.append(batch_stats(ids))
+    d_batches = [torch.from_numpy(r.view(np.uint8).reshape(BATCH, 64)).to(dev) for r in host_batches]
+    d_outs = [torch.empty((BATCH, 32), dtype=torch.uint8, device=dev) for _ in range(pool_n)]
+    clocks = [g.clock_fill(T0 + 1 + b) for b in range(args.steps + args.warmup + 8)]
+
+    def one_step(b):
+        k = b % pool_n
+        if N == 1:
+            tab.submit_device(d_batches[k].data_ptr(), BATCH, clocks[min(b, len(clocks) - 1)], d_outs[k].data_ptr(), stream)
+        else:
+            sharded.step(d_batches[k], BATCH, clocks[min(b, len(clocks) - 1)], d_outs[k])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for b in range(args.warmup):
+        one_step(b)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for b in range(args.steps):
+        one_step(args.warmup + b)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks_info = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = N * BATCH * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing leg (separate from the number above: events between kernels perturb the pipeline)
+    tab.set_profiling(True)
+    prof_steps = min(args.steps, 100)
+    for b in range(prof_steps):
+        one_step(args.warmup + args.steps + b)
+    barrier()
+    prof = tab.get_profile()
+    tab.set_profiling(False)
+
+    # ---- end-to-end leg through the host API with pinned buffers (N == 1 path; at N > 1 each rank ingests from its host)
+    e2e = None
+    if not args.no_e2e:
+        depth = 4
+        pin = [(g.native.PinnedArray(BATCH, g.REQ_DTYPE), g.native.PinnedArray(BATCH, g.RESP_DTYPE)) for _ in range(depth)]
+        for k in range(depth):
+            pin[k][0].array[:] = host_batches[k % pool_n]
+        if N == 1:
+            tickets = [None] * depth
+            e2e_steps = args.steps
+            for b in range(min(args.warmup, 8)):
+                tab.wait(tab.submit_async(pin[b % depth][0].ptr, BATCH, clocks[b], pin[b % depth][1].ptr))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for b in range(e2e_steps):
+                k = b % depth
+                if tickets[k] is not None:
+                    tab.wait(tickets[k])  # the response buffer of this slot has been read back
+                tickets[k] = tab.submit_async(pin[k][0].ptr, BATCH, clocks[min(b, len(clocks) - 1)], pin[k][1].ptr)
+            for k in range(depth):
+                if tickets[k] is not None:
+                    tab.wait(tickets[k])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        else:
+            # sharded e2e: per step copy the batch from pinned host memory, run the routed step, read responses back
+            h_in = [torch.from_numpy(host_batches[k % pool_n].view(np.uint8).reshape(BATCH, 64)).pin_memory() for k in range(depth)]
+            h_out = [torch.empty((BATCH, 32), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+            d_in = torch.empty((BATCH, 64), dtype=torch.uint8, device=dev)
+            d_o = torch.empty((BATCH, 32), dtype=torch.uint8, device=dev)
+            e2e_steps = args.steps
+            barrier()
+            t0 = time.perf_counter()
+            for b in range(e2e_steps):
+                k = b % depth
+                d_in.copy_(h_in[k], non_blocking=True)
+                sharded.step(d_in, BATCH, clocks[min(b, len(clocks) - 1)], d_o)
+                h_out[k].copy_(d_o, non_blocking=True)
+            barrier()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                tdt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+                dt = float(tdt.item())
+        e2e = {"value": N * BATCH * e2e_steps / dt, "unit": "decisions/s", "h2d_bytes_per_step": N * BATCH * 64,
+               "d2h_bytes_per_step": N * BATCH * 32, "api": "gub_submit_async (pinned host buffers, depth 4)" if N == 1 else
+               "pinned H2D + route/all-to-all/evaluate/all-to-all/unroute + D2H per step"}
+        for a, b_ in pin:
+            a.free(); b_.free()
+
+    c1 = tab.counters()
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = load_peaks()
+    kms = {"k_group": prof["k_group_ms"], "k_single": prof["k_single_ms"], "k_multi": prof["k_multi_ms"]}
+    launches = max(prof["launches"], 1)
+    dom = max(kms, key=kms.get)
+    st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
+    units = BATCH if N == 1 else BATCH  # per-GPU requests per launch (N > 1: expected share after routing)
+    alg = {  # algorithmic bytes per launch, by kernel
+        "k_group": 16.0 * units,
+        "k_single": ALGO_BYTES_PER_DECISION * st["singles"] + 12.0 * (units - st["singles"]),
+        "k_multi": (64 + 32) * st["multi_requests"] + 128.0 * st["multi_groups"],
+    }
+    dom_ms = kms[dom] / launches
+    path_ms = sum(kms.values()) / launches
+    achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": {k: v / launches for k, v in kms.items()},
+                "algorithmic_bytes_per_launch": alg,
+                "path": {"achieved": ALGO_BYTES_PER_DECISION * units / (path_ms * 1e-3) / 1e9 if path_ms > 0 else 0.0,
+                         "bytes_per_decision": ALGO_BYTES_PER_DECISION, "ms_per_batch_kernels_only": path_ms}}
+    roofline["path"]["frac"] = roofline["path"]["achieved"] / peak
+
+    cpu = None
+    if not args.no_cpu_baseline and N == 1:
+        r = cpu_leg(args.cpu_keys, args.zipf, args.cpu_seconds, seed)
+        cpu = {"value": r["value"], "unit": "decisions/s", "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
+                         f"{n_keys:,} to bound the warm pass), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
+
+    per_step_launches = 3 if N == 1 else 3 + 3 + 1  # group/single/multi (+ route count/scan/scatter + unroute)
+    line = {
+        "metric": "rate-limit decisions/sec", "value": value, "unit": "decisions/s", "n_gpus": N, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic",
+        "config": {"workload": ("BASELINE config 3: 100M keys, Zipf s=1.1, TOKEN/LEAKY 50/50, 1xB200" if N == 1 else
+                                f"BASELINE config 4: 100M keys sharded over {N}xB200 by replicated_hash (fnv1, 512 replicas), NCCL all-to-all routing, Zipf s=1.1"),
+                   "keys": n_keys, "batch_per_gpu": BATCH, "zipf_s": args.zipf, "table_slots_per_gpu": capacity,
+                   "cache": f"inputs cycle through {pool_n} resident batches ({pool_n * 6} MiB > L2); table {capacity * 64 / 1e9:.1f} GB >> L2",
+                   "batch_profile": st, "fill_seconds": t_fill, "resident_keys_after_fill": c0["inserts"]},
+        "clocks": clocks_info, "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "counters": {k: c1[k] - c0[k] for k in c1},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

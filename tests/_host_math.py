@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SO = os.path.join(HERE, "_host_math.so")
+SO = os.path.join(HERE, "libhostmath_test.so")
 SRC = [os.path.join(HERE, "host_math_harness.cpp"), os.path.join(ROOT, "gubernator_b200", "csrc", "bucket_math.cuh"),
        os.path.join(ROOT, "include", "gubernator_b200.h")]
 
