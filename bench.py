@@ -114,8 +114,11 @@ def gen_batch(rng, n, n_keys, created_at, zipf_s, dtype):
 
 def batch_stats(ids):
     _, counts = np.unique(ids, return_counts=True)
-    return dict(distinct=int(len(counts)), singles=int((counts == 1).sum()), multi_groups=int((counts > 1).sum()),
-                multi_requests=int(counts[counts > 1].sum()), top=int(counts.max()))
+    light = (counts > 1) & (counts <= 16)  # INLINE in gub_kernels.cuh
+    heavy = counts > 16
+    return dict(distinct=int(len(counts)), singles=int((counts == 1).sum()), light_groups=int(light.sum()),
+                light_requests=int(counts[light].sum()), heavy_groups=int(heavy.sum()), heavy_requests=int(counts[heavy].sum()),
+                top=int(counts.max()))
 
 
 # ---- reference arm: the reference's CPU path (oracle port; the Go reference cannot be built in this image) ----------
@@ -372,7 +375,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel
     peak, peak_src = load_peaks()
-    kms = {"k_group": prof["k_group_ms"], "k_single": prof["k_single_ms"], "k_multi": prof["k_multi_ms"]}
+    kms = {"k_group": prof["k_group_ms"], "k_single": prof["k_single_ms"], "k_light": prof["k_light_ms"], "k_heavy": prof["k_heavy_ms"]}
     launches = max(prof["launches"], 1)
     dom = max(kms, key=kms.get)
     st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
@@ -380,7 +383,8 @@ def run_b200(args):
     alg = {  # algorithmic bytes per launch, by kernel
         "k_group": 16.0 * units,
         "k_single": ALGO_BYTES_PER_DECISION * st["singles"] + 12.0 * (units - st["singles"]),
-        "k_multi": (64 + 32) * st["multi_requests"] + 128.0 * st["multi_groups"],
+        "k_light": (64 + 32) * st["light_requests"] + 128.0 * st["light_groups"],
+        "k_heavy": (64 + 32 + 4) * st["heavy_requests"] + 128.0 * st["heavy_groups"],
     }
     dom_ms = kms[dom] / launches
     path_ms = sum(kms.values()) / launches
@@ -399,7 +403,7 @@ def run_b200(args):
                "sample": f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
                          f"{n_keys:,} to bound the warm pass), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
 
-    per_step_launches = 3 if N == 1 else 3 + 3 + 1  # group/single/multi (+ route count/scan/scatter + unroute)
+    per_step_launches = 4 if N == 1 else 4 + 3 + 1  # group/single/light/heavy (+ route count/scan/scatter + unroute)
     line = {
         "metric": "rate-limit decisions/sec", "value": value, "unit": "decisions/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

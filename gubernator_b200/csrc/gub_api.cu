@@ -73,9 +73,9 @@ struct gub_table {
   size_t owner_cap = 0, tiles_cap = 0;
   // optional per-kernel timing (bench.py's roofline leg): events bracket every kernel of the batch path
   bool prof = false;
-  std::vector<cudaEvent_t> prof_ev;   // 4 events per pending chunk
+  std::vector<cudaEvent_t> prof_ev;   // 5 events per pending chunk
   size_t prof_pending = 0;            // chunks recorded and not yet accumulated
-  double prof_ms[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};
   uint64_t prof_launches = 0;
 };
 
@@ -85,9 +85,9 @@ namespace {
 int prof_flush(gub_table* t, bool force) {
   if (!force && t->prof_pending < 1024) return 0;
   for (size_t c = 0; c < t->prof_pending; c++) {
-    cudaEvent_t* pe = &t->prof_ev[c * 4];
-    CK(cudaEventSynchronize(pe[3]));
-    for (int k = 0; k < 3; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, pe[k], pe[k + 1])); t->prof_ms[k] += ms; }
+    cudaEvent_t* pe = &t->prof_ev[c * 5];
+    CK(cudaEventSynchronize(pe[4]));
+    for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, pe[k], pe[k + 1])); t->prof_ms[k] += ms; }
     t->prof_launches++;
   }
   t->prof_pending = 0;
@@ -110,22 +110,24 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   cudaEvent_t* pe = nullptr;
   if (t->prof) {
     if (prof_flush(t, false)) return -1;
-    if (t->prof_ev.size() < (t->prof_pending + 1) * 4) {
-      for (int k = 0; k < 4; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); t->prof_ev.push_back(e); }
+    if (t->prof_ev.size() < (t->prof_pending + 1) * 5) {
+      for (int k = 0; k < 5; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); t->prof_ev.push_back(e); }
     }
-    pe = &t->prof_ev[t->prof_pending * 4];
+    pe = &t->prof_ev[t->prof_pending * 5];
     t->prof_pending++;
     CK(cudaEventRecord(pe[0], st));
   }
-  gub::k_group<<<blocks, 256, 0, st>>>(A);
+  gub::k_group<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[1], st));
   gub::k_single<<<blocks, 256, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[2], st));
-  // heavy groups: one block each (at most n/(INLINE+1)); light groups: one thread each (at most n/2)
-  const uint32_t heavy_blocks = std::min<uint32_t>(296u, std::max<uint32_t>(1u, n / (gub::INLINE + 1)));
-  const uint32_t light_blocks = std::max<uint32_t>(1u, (n / 2 + gub::HEAVY_THREADS - 1) / gub::HEAVY_THREADS);
-  gub::k_multi<<<heavy_blocks + light_blocks, gub::HEAVY_THREADS, 0, st>>>(A, heavy_blocks);
+  // light groups: one thread each (at most n/2 of them); heavy groups: one block each (at most n/(INLINE+1))
+  const uint32_t light_blocks = std::max<uint32_t>(1u, (n / 2 + gub::LIGHT_THREADS - 1) / gub::LIGHT_THREADS);
+  const uint32_t heavy_blocks = std::min<uint32_t>(592u, std::max<uint32_t>(1u, n / (gub::INLINE + 1)));
+  gub::k_light<<<light_blocks, gub::LIGHT_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[3], st));
+  gub::k_heavy<<<heavy_blocks, gub::HEAVY_THREADS, 0, st>>>(A);
+  if (pe) CK(cudaEventRecord(pe[4], st));
   CK(cudaGetLastError());
   return 0;
 }
@@ -452,14 +454,14 @@ int gub_set_profiling(gub_table* t, int on) {
   return 0;
 }
 
-int gub_get_profile(gub_table* t, double kernel_ms[3], uint64_t* launches, int reset) {
+int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int reset) {
   if (!t || !kernel_ms || !launches) return fail("gub_get_profile: null argument");
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
   if (prof_flush(t, true)) return -1;
-  for (int k = 0; k < 3; k++) kernel_ms[k] = t->prof_ms[k];
+  for (int k = 0; k < 4; k++) kernel_ms[k] = t->prof_ms[k];
   *launches = t->prof_launches;
-  if (reset) { t->prof_ms[0] = t->prof_ms[1] = t->prof_ms[2] = 0; t->prof_launches = 0; }
+  if (reset) { for (int k = 0; k < 4; k++) t->prof_ms[k] = 0; t->prof_launches = 0; }
   return 0;
 }
 

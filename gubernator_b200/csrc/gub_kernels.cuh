@@ -16,7 +16,7 @@
 //   k_single : keys seen once in the batch (the vast majority of groups) are probed + updated right away, one thread
 //              each: one 64 B random HBM read + one write-back.  Members of multi-hit keys record themselves
 //              (list slot by ticket, or a bit in the group's bitmap).
-//   k_multi  : light groups (<= INLINE members): one thread sorts the member indices and walks them in order.
+//   k_light / k_heavy : light groups (<= INLINE members): one thread sorts the member indices and walks them in order.
 //              heavy groups: one thread block per key: rank every member by prefix popcount over the bitmap (index
 //              order falls out for free), split the run into segments of identical requests, let one thread plan each
 //              segment with plan_run() (closed forms for the subtract and fixed-point regimes) and all threads
@@ -173,16 +173,26 @@ __device__ __forceinline__ void store_resp(gub_resp* p, const gub_resp& r) {
 
 struct Tally { uint32_t over, hit, miss, inserts, full; };
 
-__device__ __forceinline__ void tally_flush_warp(const Tally& t, unsigned long long* counters) {
-  uint32_t over = __reduce_add_sync(0xFFFFFFFFu, t.over), hit = __reduce_add_sync(0xFFFFFFFFu, t.hit),
-           miss = __reduce_add_sync(0xFFFFFFFFu, t.miss), ins = __reduce_add_sync(0xFFFFFFFFu, t.inserts),
-           full = __reduce_add_sync(0xFFFFFFFFu, t.full);
+// Counter deltas are summed per block in shared memory first: a grid-wide atomicAdd per warp on five fixed addresses
+// serialises in L2 and costs more than the probes themselves.
+__device__ __forceinline__ void tally_flush_block(const Tally& t, unsigned long long* counters) {
+  __shared__ uint32_t s_tally[5];
+  if (threadIdx.x < 5) s_tally[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t over = __reduce_add_sync(0xFFFFFFFFu, t.over), hit = __reduce_add_sync(0xFFFFFFFFu, t.hit),
+                 miss = __reduce_add_sync(0xFFFFFFFFu, t.miss), ins = __reduce_add_sync(0xFFFFFFFFu, t.inserts),
+                 full = __reduce_add_sync(0xFFFFFFFFu, t.full);
   if ((threadIdx.x & 31) == 0) {
-    if (over) atomicAdd(counters + C_OVER, (unsigned long long)over);
-    if (hit) atomicAdd(counters + C_HIT, (unsigned long long)hit);
-    if (miss) atomicAdd(counters + C_MISS, (unsigned long long)miss);
-    if (ins) atomicAdd(counters + C_INSERTS, (unsigned long long)ins);
-    if (full) atomicAdd(counters + C_FULL, (unsigned long long)full);
+    if (over) atomicAdd(&s_tally[0], over);
+    if (hit) atomicAdd(&s_tally[1], hit);
+    if (miss) atomicAdd(&s_tally[2], miss);
+    if (ins) atomicAdd(&s_tally[3], ins);
+    if (full) atomicAdd(&s_tally[4], full);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 && s_tally[threadIdx.x]) {
+    const int slot[5] = {C_OVER, C_HIT, C_MISS, C_INSERTS, C_FULL};
+    atomicAdd(counters + slot[threadIdx.x], (unsigned long long)s_tally[threadIdx.x]);
   }
 }
 
@@ -193,10 +203,13 @@ __device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, Id
   Cursor cur;
   bool open = false;
   uint64_t ck = 0, ct = 0;
+  uint32_t i_next = idx_of(0);
+  gub_req rq_next = load_req(A.reqs + i_next);
 #pragma unroll 1
   for (uint32_t j = 0; j < cnt; j++) {
-    const uint32_t i = idx_of(j);
-    const gub_req rq = load_req(A.reqs + i);
+    const uint32_t i = i_next;
+    const gub_req rq = rq_next;
+    if (j + 1 < cnt) { i_next = idx_of(j + 1); rq_next = load_req(A.reqs + i_next); }  // overlap the next request's load with this update
     const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
     if (!open || key != ck || tag != ct) {
       if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;  // state of the previous key is lost: counted
@@ -216,40 +229,79 @@ __device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, Id
 }
 
 // ---- kernel 1: group the batch by key -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_group(const BatchArgs A) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.n) return;
-  const uint64_t key = remap_key(__ldg(&A.reqs[i].key_xxh64));
+// Each block first groups its own 256 requests in a shared-memory table, so a key that is hot in the batch costs one
+// global atomic per block instead of one per request (the top key of a Zipf(1.1) batch is ~11 % of it: thousands of
+// same-address L2 atomics otherwise).  Then one thread per distinct (block, key) joins the batch-wide table.
+constexpr int GROUP_THREADS = 256;
+constexpr int GROUP_SLOTS = 512;  // shared-memory table entries per block (load factor <= 0.5)
+
+// Joins `c` members to the batch-wide group of `key`; returns the first ticket of the joiner and the entry position.
+__device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, uint32_t c, uint32_t* pos_out) {
   const uint32_t tag = (uint32_t)(key >> 40);  // 24 bits, disjoint from the position bits below
   uint32_t pos = (uint32_t)(key ^ (key >> 29)) & A.aux_mask;
-  const unsigned long long fresh = ((unsigned long long)A.epoch << 48) | ((unsigned long long)tag << 24) | 1ull;
-  uint32_t my_ticket;
+  const unsigned long long fresh = ((unsigned long long)A.epoch << 48) | ((unsigned long long)tag << 24) | (unsigned long long)c;
+  uint32_t base;
 #pragma unroll 1
   for (;;) {
-    unsigned long long cur = A.aux[pos].word;
+    unsigned long long cur = __ldcg(&A.aux[pos].word);
     if (aux_epoch(cur) != A.epoch) {  // stale entry from an earlier batch == empty
       const unsigned long long old = atomicCAS(&A.aux[pos].word, cur, fresh);
-      if (old == cur) { my_ticket = 0; break; }
+      if (old == cur) { base = 0; break; }
       cur = old;  // somebody else just claimed it for this batch: fall through and compare tags
     }
     if (aux_epoch(cur) == A.epoch && aux_tag(cur) == tag) {
-      my_ticket = aux_count(atomicAdd(&A.aux[pos].word, 1ull));
+      base = aux_count(atomicAdd(&A.aux[pos].word, (unsigned long long)c));
       break;
     }
     pos = (pos + 1) & A.aux_mask;
   }
-  A.ent[i] = pos;
-  A.ticket[i] = my_ticket;
   BatchCtr* ctr = A.ctr + (A.epoch & 1);
-  if (my_ticket == 1) {  // the key repeats: give the group an inline member list
+  if (base <= 1 && base + c > 1) {  // this joiner holds ticket 1: the key repeats, give the group an inline member list
     const uint32_t lid = atomicAdd(&ctr->nlists, 1u);
     A.aux[pos].lid = lid;
     A.list_ent[lid] = pos;
   }
-  if (my_ticket == INLINE) {  // too many for a list: give it a bitmap
+  if (base <= (uint32_t)INLINE && base + c > (uint32_t)INLINE) {  // holds ticket INLINE: too many for a list, give it a bitmap
     const uint32_t hg = atomicAdd(&ctr->nheavy, 1u);
     A.aux[pos].hg = hg;
     A.heavy_ent[hg] = pos;
+  }
+  *pos_out = pos;
+  return base;
+}
+
+__global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
+  __shared__ unsigned long long s_key[GROUP_SLOTS];
+  __shared__ uint32_t s_cnt[GROUP_SLOTS];   // members in this block; later: first ticket of this block's members
+  __shared__ uint32_t s_pos[GROUP_SLOTS];   // batch-wide entry position
+  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
+  uint32_t sp = 0, local = 0;
+  if (i < A.n) {
+    const uint64_t key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
+    sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);          // top 9 bits -> GROUP_SLOTS
+#pragma unroll 1
+    for (;;) {
+      const unsigned long long old = atomicCAS(&s_key[sp], 0ull, (unsigned long long)key);
+      if (old == 0ull || old == key) break;
+      sp = (sp + 1) & (GROUP_SLOTS - 1);
+    }
+    local = atomicAdd(&s_cnt[sp], 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) {
+    const unsigned long long key = s_key[k];
+    if (key != 0ull) {
+      uint32_t pos;
+      s_cnt[k] = aux_join(A, key, s_cnt[k], &pos);
+      s_pos[k] = pos;
+    }
+  }
+  __syncthreads();
+  if (i < A.n) {
+    A.ent[i] = s_pos[sp];
+    A.ticket[i] = s_cnt[sp] + local;
   }
 }
 
@@ -275,7 +327,7 @@ __global__ void __launch_bounds__(256) k_single(const BatchArgs A) {
       atomicOr(&A.bitmaps[(size_t)e.hg * A.bitmap_words + (i >> 5)], 1u << (i & 31));
     }
   }
-  tally_flush_warp(t, A.counters);
+  tally_flush_block(t, A.counters);
 }
 
 // ---- kernel 3: repeated keys -----------------------------------------------------------------------------------
@@ -419,27 +471,31 @@ __device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tal
   if (tid == 0 && open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
 }
 
-// Blocks [0, heavy_blocks) take heavy groups (one block per group, grid-stride); the rest take light groups, one thread each.
-__global__ void __launch_bounds__(HEAVY_THREADS) k_multi(const BatchArgs A, uint32_t heavy_blocks) {
+// Light groups: one thread per repeated key with at most INLINE members.
+constexpr int LIGHT_THREADS = 128;
+__global__ void __launch_bounds__(LIGHT_THREADS) k_light(const BatchArgs A) {
+  Tally t = {0, 0, 0, 0, 0};
+  const uint32_t nlists = min(A.ctr[A.epoch & 1].nlists, A.max_lists);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < nlists; lid += stride) light_group(A, lid, t);
+  tally_flush_block(t, A.counters);
+}
+
+// Heavy groups: one thread block per hot key (grid-stride).
+__global__ void __launch_bounds__(HEAVY_THREADS, 2) k_heavy(const BatchArgs A) {
   __shared__ HeavyShared S;
   Tally t = {0, 0, 0, 0, 0};
   const BatchCtr ctr = A.ctr[A.epoch & 1];
-  if (blockIdx.x < heavy_blocks) {
-    const uint32_t nheavy = min(ctr.nheavy, A.max_heavy);
-    for (uint32_t hg = blockIdx.x; hg < nheavy; hg += heavy_blocks) {
-      heavy_group(A, hg, S, t);
-      __syncthreads();
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.nlists);
-      atomicAdd(A.counters + C_HEAVY_GROUPS, (unsigned long long)ctr.nheavy);
-    }
-  } else {
-    const uint32_t nlists = min(ctr.nlists, A.max_lists);
-    const uint32_t stride = (gridDim.x - heavy_blocks) * blockDim.x;
-    for (uint32_t lid = (blockIdx.x - heavy_blocks) * blockDim.x + threadIdx.x; lid < nlists; lid += stride) light_group(A, lid, t);
+  const uint32_t nheavy = min(ctr.nheavy, A.max_heavy);
+  for (uint32_t hg = blockIdx.x; hg < nheavy; hg += gridDim.x) {
+    heavy_group(A, hg, S, t);
+    __syncthreads();
   }
-  tally_flush_warp(t, A.counters);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.nlists);
+    atomicAdd(A.counters + C_HEAVY_GROUPS, (unsigned long long)ctr.nheavy);
+  }
+  tally_flush_block(t, A.counters);
 }
 
 // ---- maintenance kernels -------------------------------------------------------------------------------------

@@ -223,10 +223,10 @@ class Table:
         _check(lib().gub_set_profiling(self._h, 1 if on else 0), "gub_set_profiling")
 
     def get_profile(self, reset=True):
-        ms = np.zeros(3, dtype=np.float64)
+        ms = np.zeros(4, dtype=np.float64)
         n = C.c_uint64(0)
         _check(lib().gub_get_profile(self._h, ms.ctypes.data, C.byref(n), 1 if reset else 0), "gub_get_profile")
-        return dict(k_group_ms=float(ms[0]), k_single_ms=float(ms[1]), k_multi_ms=float(ms[2]), launches=int(n.value))
+        return dict(k_group_ms=float(ms[0]), k_single_ms=float(ms[1]), k_light_ms=float(ms[2]), k_heavy_ms=float(ms[3]), launches=int(n.value))
 
     # ---- multi-GPU routing
     def route_device(self, ring, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream=0):

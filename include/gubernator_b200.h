@@ -169,10 +169,10 @@ int gub_size(gub_table* t, size_t* n_out);
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
 
-/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_single / k_multi), the
+/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_single / k_light / k_heavy), the
  * measurement counterpart of the reference's metricFuncTimeDuration summaries (gubernator.go:65-73).  Off by default. */
 int gub_set_profiling(gub_table* t, int on);
-int gub_get_profile(gub_table* t, double kernel_ms[3], uint64_t* launches, int reset);
+int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int reset);
 
 /* ---- key hashing: client.go:39-41 HashKey + workers.go:153 + replicated_hash.go:108 -------------------------
  * keys are packed back to back in `bytes`; key i is bytes[offsets[i] .. offsets[i+1]).  Host implementation. */
