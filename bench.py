@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu-window", type=int, default=0,
+                    help="profile this many extra steps between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)")
     return ap.parse_args()
 
 
@@ -315,6 +317,14 @@ def run_b200(args):
     barrier()
     prof = tab.get_profile()
     tab.set_profiling(False)
+
+    if args.ncu_window > 0:  # the only launches an `ncu --profile-from-start off` run sees
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for b in range(args.ncu_window):
+            one_step(args.warmup + args.steps + prof_steps + b)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
     # ---- end-to-end leg through the host API with pinned buffers (N == 1 path; at N > 1 each rank ingests from its host)
     e2e = None
