@@ -385,16 +385,18 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel
     peak, peak_src = load_peaks()
-    kms = {"k_group": prof["k_group_ms"], "k_single": prof["k_single_ms"], "k_light": prof["k_light_ms"], "k_heavy": prof["k_heavy_ms"]}
+    kms = {"k_group": prof["k_group_ms"], "k_rank": prof["k_rank_ms"], "k_eval": prof["k_eval_ms"], "k_mixed": prof["k_mixed_ms"]}
     launches = max(prof["launches"], 1)
     dom = max(kms, key=kms.get)
     st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
     units = BATCH if N == 1 else BATCH  # per-GPU requests per launch (N > 1: expected share after routing)
-    alg = {  # algorithmic bytes per launch, by kernel
-        "k_group": 16.0 * units,
-        "k_single": ALGO_BYTES_PER_DECISION * st["singles"] + 12.0 * (units - st["singles"]),
-        "k_light": (64 + 32) * st["light_requests"] + 128.0 * st["light_groups"],
-        "k_heavy": (64 + 32 + 4) * st["heavy_requests"] + 128.0 * st["heavy_groups"],
+    multi_req = st["light_requests"] + st["heavy_requests"]
+    multi_grp = st["light_groups"] + st["heavy_groups"]
+    alg = {  # algorithmic bytes per launch, by kernel (Kernels)
+        "k_group": 16.0 * units,                                                        # 8 B key in, ent + meta out
+        "k_rank": ALGO_BYTES_PER_DECISION * st["singles"] + 140.0 * multi_req + 160.0 * multi_grp,  # singles: the whole 224 B; others: request + representative + rank; per key: slot read + snapshot
+        "k_eval": 200.0 * multi_req + 64.0 * multi_grp,                                # request + snapshot + response per member; one slot write-back per key
+        "k_mixed": 0.0,                                                                 # no non-uniform groups in this workload
     }
     dom_ms = kms[dom] / launches
     path_ms = sum(kms.values()) / launches
@@ -413,7 +415,7 @@ def run_b200(args):
                "sample": f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
                          f"{n_keys:,} to bound the warm pass), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
 
-    per_step_launches = 4 if N == 1 else 4 + 3 + 1  # group/single/light/heavy (+ route count/scan/scatter + unroute)
+    per_step_launches = 4 if N == 1 else 4 + 3 + 1  # group/rank/eval/mixed (+ route count/scan/scatter + unroute)
     line = {
         "metric": "rate-limit decisions/sec", "value": value, "unit": "decisions/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -398,4 +398,49 @@ GUB_HD uint32_t plan_run(Bucket& b, const gub_req& rq, uint32_t m, const gub_clo
   return rank;
 }
 
+// Response of the `target`-th (0-based) of a run of identical requests `rq` against bucket b, without materialising a
+// plan: walks the same regimes as plan_run() and stops at `target`.  On return b is the state after rank `target` and
+// d holds the counter deltas of ranks 0..target — so the caller holding the LAST rank of the run ends up with the run's
+// final state and total deltas, while every other member of the run computes only its own response.  This lets every
+// member of a hot key's run be evaluated by its own thread, in parallel, with no ordering structure beyond its rank.
+GUB_HD gub_resp run_to_rank(Bucket& b, const gub_req& rq, uint32_t target, const gub_clock& clk, Delta& d) {
+  uint32_t rank = 0;
+  for (;;) {
+    const Bucket before = b;
+    Delta d1 = {0, 0, 0};
+    const gub_resp resp = apply_one(b, rq, clk, d1);
+    d.over += d1.over; d.hit += d1.hit; d.miss += d1.miss;
+    if (rank == target) return resp;
+    rank++;
+    if (bucket_equal(before, b)) {  // fixed point: ranks rank..target repeat this response and these deltas
+      const uint32_t left = target - rank + 1;
+      d.over += d1.over * left; d.hit += d1.hit * left; d.miss += d1.miss * left;
+      return resp;
+    }
+    int64_t rate_i;
+    const uint64_t q = linear_steps(b, rq, clk, &rate_i);
+    if (q > 0) {
+      const uint64_t avail = (uint64_t)(target - rank) + 1;  // ranks rank..target
+      const uint64_t steps = q < avail ? q : avail;
+      const bool leaky = (b.flags & F_LEAKY) != 0;
+      const int64_t total = (int64_t)steps * rq.hits;  // <= Remaining: no overflow
+      int64_t shown;
+      if (leaky) {
+        const double rem = bits2f(b.rem) - i2f(total);  // exact: see linear_steps()
+        b.rem = f2bits(rem);
+        shown = f2i(rem);
+      } else {
+        shown = (int64_t)b.rem - total;
+        b.rem = (uint64_t)shown;
+      }
+      d.hit += (uint32_t)steps;
+      rank += (uint32_t)steps;
+      if (steps == avail) {  // the target is the last of these plain subtractions
+        return mk_resp(leaky ? (uint32_t)GUB_UNDER_LIMIT : ((b.flags & F_OVER) ? (uint32_t)GUB_OVER_LIMIT : (uint32_t)GUB_UNDER_LIMIT), rq.limit, shown,
+                       leaky ? wadd(rq.created_at, wmul(wsub(rq.limit, shown), rate_i)) : b.expire);
+      }
+    }
+  }
+}
+
 }  // namespace gub

@@ -52,8 +52,10 @@ struct gub_table {
   uint32_t max_batch = 0;
   // per-batch scratch
   gub::AuxEntry* aux = nullptr; uint32_t aux_entries = 0;
-  uint32_t *ent = nullptr, *ticket = nullptr, *lists = nullptr, *list_ent = nullptr, *heavy_ent = nullptr, *bitmaps = nullptr, *order = nullptr;
-  uint32_t bitmap_words = 0, max_lists = 0, max_heavy = 0;
+  uint32_t *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *presence = nullptr;
+  uint8_t* fragsize = nullptr;
+  ulonglong2* snap = nullptr;
+  uint32_t pres_words = 0, max_blocks = 0;
   gub::BatchCtr* ctr = nullptr;
   unsigned long long* counters = nullptr;
   uint32_t epoch = 0;
@@ -102,9 +104,9 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   t->epoch++;
   gub::BatchArgs A;
   A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = t->epoch;
-  A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.ent = t->ent; A.ticket = t->ticket; A.lists = t->lists;
-  A.list_ent = t->list_ent; A.heavy_ent = t->heavy_ent; A.bitmaps = t->bitmaps; A.bitmap_words = t->bitmap_words;
-  A.max_lists = t->max_lists; A.max_heavy = t->max_heavy; A.order = t->order; A.ctr = t->ctr; A.counters = t->counters;
+  A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
+  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank; A.snap = t->snap;
+  A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr; A.counters = t->counters;
   A.clk = *clk;
   const uint32_t blocks = (n + 255) / 256;
   cudaEvent_t* pe = nullptr;
@@ -119,14 +121,12 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   }
   gub::k_group<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[1], st));
-  gub::k_single<<<blocks, 256, 0, st>>>(A);
+  gub::k_rank<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[2], st));
-  // light groups: one thread each (at most n/2 of them); heavy groups: one block each (at most n/(INLINE+1))
-  const uint32_t light_blocks = std::max<uint32_t>(1u, (n / 2 + gub::LIGHT_THREADS - 1) / gub::LIGHT_THREADS);
-  const uint32_t heavy_blocks = std::min<uint32_t>(592u, std::max<uint32_t>(1u, n / (gub::INLINE + 1)));
-  gub::k_light<<<light_blocks, gub::LIGHT_THREADS, 0, st>>>(A);
+  gub::k_eval<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[3], st));
-  gub::k_heavy<<<heavy_blocks, gub::HEAVY_THREADS, 0, st>>>(A);
+  // non-uniform groups: one block each, grid-stride (normally there are none and the kernel returns at once)
+  gub::k_mixed<<<std::min<uint32_t>(592u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, 0, st>>>(A);
   if (pe) CK(cudaEventRecord(pe[4], st));
   CK(cudaGetLastError());
   return 0;
@@ -190,7 +190,7 @@ void gub_destroy(gub_table* t) {
   if (!t) return;
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {t->table, t->aux, t->ent, t->ticket, t->lists, t->list_ent, t->heavy_ent, t->bitmaps, t->order, t->ctr, t->counters,
+  void* ptrs[] = {t->table, t->aux, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->presence, t->fragsize, t->snap, t->ctr, t->counters,
                   t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : t->pipe) {
@@ -225,12 +225,11 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   t->max_batch = cfg->max_batch ? cfg->max_batch : 65536u;
   if (t->max_batch < 1024) t->max_batch = 1024;
   if (t->max_batch > 262144u) t->max_batch = 262144u;
-  t->max_batch = (t->max_batch + 31u) & ~31u;
+  t->max_batch = (t->max_batch + 255u) & ~255u;
   const uint32_t B = t->max_batch;
   t->aux_entries = next_pow2((uint64_t)B * 4);
-  t->bitmap_words = B / 32;
-  t->max_lists = B / 2 + 1;
-  t->max_heavy = B / (gub::INLINE + 1) + 1;
+  t->max_blocks = (B / gub::GROUP_THREADS + 31u) & ~31u;  // fragment-size row per group entry (multiple of 32 bytes)
+  t->pres_words = t->max_blocks / 32;
 #define ALLOC(ptr, bytes)                                                    \
   do {                                                                       \
     cudaError_t e__ = cudaMalloc((void**)&(ptr), (bytes));                   \
@@ -243,13 +242,14 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   } while (0)
   ALLOC(t->table, t->capacity * sizeof(gub::Slot));
   ALLOC(t->aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
+  ALLOC(t->presence, (size_t)t->aux_entries * t->pres_words * 4);
+  ALLOC(t->fragsize, (size_t)t->aux_entries * t->max_blocks);
+  ALLOC(t->snap, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
   ALLOC(t->ent, (size_t)B * 4);
-  ALLOC(t->ticket, (size_t)B * 4);
-  ALLOC(t->lists, (size_t)t->max_lists * gub::INLINE * 4);
-  ALLOC(t->list_ent, (size_t)t->max_lists * 4);
-  ALLOC(t->heavy_ent, (size_t)t->max_heavy * 4);
-  ALLOC(t->bitmaps, (size_t)t->max_heavy * t->bitmap_words * 4);
+  ALLOC(t->meta, (size_t)B * 4);
+  ALLOC(t->rank, (size_t)B * 4);
   ALLOC(t->order, (size_t)B * 4);
+  ALLOC(t->mixed_ent, ((size_t)B / 2 + 1) * 4);
   ALLOC(t->ctr, 2 * sizeof(gub::BatchCtr));
   ALLOC(t->counters, gub::C_COUNT * sizeof(unsigned long long));
   ALLOC(t->d_scalar, 4 * sizeof(unsigned long long));
@@ -440,7 +440,7 @@ int gub_get_counters(gub_table* t, gub_counters* out) {
   CK(cudaMemcpy(c, t->counters, sizeof c, cudaMemcpyDeviceToHost));
   out->over_limit = c[gub::C_OVER]; out->cache_hit = c[gub::C_HIT]; out->cache_miss = c[gub::C_MISS];
   out->inserts = c[gub::C_INSERTS]; out->table_full = c[gub::C_FULL]; out->requests = c[gub::C_REQUESTS];
-  out->batches = c[gub::C_BATCHES]; out->dup_groups = c[gub::C_DUP_GROUPS]; out->heavy_groups = c[gub::C_HEAVY_GROUPS];
+  out->batches = c[gub::C_BATCHES]; out->dup_groups = c[gub::C_DUP_GROUPS]; out->mixed_groups = c[gub::C_MIXED_GROUPS];
   out->serial_fallbacks = c[gub::C_SERIAL];
   return 0;
 }

@@ -9,18 +9,22 @@
 //              w2 limit  w3 duration  w4 remaining (int64 | float64 bits)  w5 stamp  w6 burst  w7 expire_at
 //   requests : n x 64 B gub_req (AoS, what the Go shim fills), responses: n x 32 B gub_resp
 //
-// Why three kernels.  The reference applies same-key requests strictly in index order (gubernator.go:203), and the
-// updates do not commute, so a batch must first be grouped by key:
-//   k_group  : every request claims/joins a per-batch hash entry for its key and draws a ticket; the 2nd arrival
-//              allocates an inline member list, the (INLINE+1)th a per-group bitmap.            (L2-resident scratch)
-//   k_single : keys seen once in the batch (the vast majority of groups) are probed + updated right away, one thread
-//              each: one 64 B random HBM read + one write-back.  Members of multi-hit keys record themselves
-//              (list slot by ticket, or a bit in the group's bitmap).
-//   k_light / k_heavy : light groups (<= INLINE members): one thread sorts the member indices and walks them in order.
-//              heavy groups: one thread block per key: rank every member by prefix popcount over the bitmap (index
-//              order falls out for free), split the run into segments of identical requests, let one thread plan each
-//              segment with plan_run() (closed forms for the subtract and fixed-point regimes) and all threads
-//              evaluate and scatter the responses.
+// The reference applies same-key requests strictly in index order (gubernator.go:203) and the updates do not commute,
+// so what every request needs is (a) how many requests of the batch share its key and (b) its RANK among them in index
+// order.  With those, a run of identical requests needs no ordering structure at all: every member evaluates
+// run_to_rank(bucket, request, rank) by itself (closed forms make that O(1)), and the member holding the last rank
+// writes the bucket back.  Only runs whose requests differ are materialised in rank order and walked segment by segment.
+//
+//   k_group  (256 consecutive requests per block) shared-memory grouping with index-ordered local ranks; one thread per
+//            distinct (block, key) "fragment" joins the batch-wide group entry (count += members), sets the block's bit
+//            in the group's presence bitmap and stores the fragment size.
+//   k_rank   keys seen once (most keys) are probed + updated + answered right here: one 64 B random HBM read, one
+//            write-back.  Members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank, and
+//            compare their request with the group's representative; any difference marks the group non-uniform.
+//   k_eval   members of uniform groups: probe, run_to_rank(), answer; the last rank writes the state back.
+//            members of non-uniform groups: order[base + rank] = index.
+//   k_mixed  one block per non-uniform group: split the ordered run into segments of identical requests, plan each with
+//            plan_run() on one thread, evaluate/scatter with all threads (serial walk when there are too many segments).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,25 +36,29 @@ namespace gub {
 constexpr uint64_t KEY_EMPTY = 0ull;
 constexpr uint64_t KEY_TOMB = 1ull;
 constexpr int MAX_PROBE = 512;       // window [home, home + MAX_PROBE): inserts never leave it, so lookups may stop there
-constexpr int INLINE = 16;           // members of a light group
-constexpr int HEAVY_THREADS = 256;
-constexpr int MAX_SEG = 96;          // uniform segments of a heavy group planned in parallel; more => serial walk
+constexpr int GROUP_THREADS = 256;   // requests per block in k_group / k_rank (a "fragment" is one key's members in one block)
+constexpr int GROUP_SLOTS = 512;     // shared-memory table entries per block (load factor <= 0.5)
+constexpr int MIXED_THREADS = 256;
+constexpr int MAX_SEG = 96;          // uniform segments of a non-uniform group planned in parallel; more => serial walk
 constexpr int MAX_PIECES = 16;
 
 struct __align__(64) Slot { uint64_t w[8]; };
 
-struct __align__(16) AuxEntry {
+struct __align__(32) AuxEntry {
   unsigned long long word;  // [63:48] epoch  [47:24] key tag  [23:0] member count
-  uint32_t lid;             // inline list id (valid once count >= 2)
-  uint32_t hg;              // heavy group id (valid once count > INLINE)
+  uint32_t rep;             // index of one member (the claimer's first): the request every other member is compared with
+  uint32_t flags;           // AUX_NONUNIFORM
+  uint32_t gbase;           // non-uniform groups: start of the group's region in `order`
+  uint32_t _pad[3];
 };
+constexpr uint32_t AUX_NONUNIFORM = 1u;
 __host__ __device__ inline uint32_t aux_count(unsigned long long w) { return (uint32_t)(w & 0xFFFFFFull); }
 __host__ __device__ inline uint32_t aux_epoch(unsigned long long w) { return (uint32_t)(w >> 48); }
 __host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint32_t)((w >> 24) & 0xFFFFFFull); }
 
-struct BatchCtr { uint32_t nlists, nheavy, order_bump, _pad; };
+struct BatchCtr { uint32_t n_mixed, order_bump, _pad0, _pad1; };
 
-enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_HEAVY_GROUPS, C_SERIAL, C_COUNT };
+enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_MIXED_GROUPS, C_SERIAL, C_COUNT };
 
 struct BatchArgs {
   Slot* table;
@@ -61,15 +69,15 @@ struct BatchArgs {
   uint32_t epoch;          // 1..65535
   AuxEntry* aux;
   uint32_t aux_mask;       // entries - 1 (power of two)
-  uint32_t* ent;           // [n] aux entry of request i
-  uint32_t* ticket;        // [n] arrival ticket of request i within its group
-  uint32_t* lists;         // [max_lists * INLINE]
-  uint32_t* list_ent;      // [max_lists]
-  uint32_t* heavy_ent;     // [max_heavy]
-  uint32_t* bitmaps;       // [max_heavy * bitmap_words], all zero between batches
-  uint32_t bitmap_words;   // max_batch / 32
-  uint32_t max_lists, max_heavy;
-  uint32_t* order;         // [max_batch] rank-ordered member indices of heavy groups
+  uint32_t* presence;      // [entries * pres_words] bit b set <=> block b holds a fragment of the group; all zero between batches
+  uint8_t* fragsize;       // [entries * max_blocks] fragment size - 1, valid where the presence bit is set
+  uint32_t pres_words, max_blocks;
+  uint32_t* ent;           // [n] group entry of request i
+  uint32_t* meta;          // [n] (shared-memory slot of the fragment << 16) | local rank
+  uint32_t* rank;          // [n] rank within the group (repeated keys only)
+  ulonglong2* snap;        // [entries * 6] repeated keys: the slot as k_rank found it (k_eval members all start from this)
+  uint32_t* order;         // [max_batch] rank-ordered member indices of non-uniform groups
+  uint32_t* mixed_ent;     // [max_batch / 2] entries of non-uniform groups
   BatchCtr* ctr;           // [2], indexed by epoch parity
   unsigned long long* counters;  // [C_COUNT]
   gub_clock clk;
@@ -157,6 +165,23 @@ __device__ __forceinline__ bool cursor_close(Cursor& cur, Slot* table, uint64_t 
   return false;
 }
 
+// A repeated key's slot as found before the batch touched it, parked in scratch by the group's rank-0 member so that
+// every member of the run starts from the same state while the last rank is already writing the table.
+__device__ __forceinline__ void snap_store(ulonglong2* sp, const Cursor& c) {
+  __stcg(sp + 0, make_ulonglong2(c.b.key, c.b.tag));
+  __stcg(sp + 1, make_ulonglong2((uint64_t)c.b.limit, (uint64_t)c.b.duration));
+  __stcg(sp + 2, make_ulonglong2(c.b.rem, (uint64_t)c.b.stamp));
+  __stcg(sp + 3, make_ulonglong2((uint64_t)c.b.burst, (uint64_t)c.b.expire));
+  __stcg(sp + 4, make_ulonglong2((uint64_t)c.b.flags | ((uint64_t)(c.found ? 1u : 0u) << 32), (uint64_t)c.slot));
+  __stcg(sp + 5, make_ulonglong2(c.home, 0ull));
+}
+__device__ __forceinline__ void snap_load(const ulonglong2* sp, Cursor& c) {
+  const ulonglong2 a = __ldcg(sp + 0), b = __ldcg(sp + 1), d = __ldcg(sp + 2), e = __ldcg(sp + 3), f = __ldcg(sp + 4), g = __ldcg(sp + 5);
+  c.b.key = a.x; c.b.tag = a.y; c.b.limit = (int64_t)b.x; c.b.duration = (int64_t)b.y; c.b.rem = d.x; c.b.stamp = (int64_t)d.y;
+  c.b.burst = (int64_t)e.x; c.b.expire = (int64_t)e.y; c.b.flags = (uint32_t)(f.x & 0xFFFFFFFFull); c.found = (f.x >> 32) != 0;
+  c.slot = (int64_t)f.y; c.home = g.x; c.old = c.b;
+}
+
 __device__ __forceinline__ gub_req load_req(const gub_req* p) {
   const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
   ulonglong2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
@@ -228,131 +253,226 @@ __device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, Id
   if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
 }
 
-// ---- kernel 1: group the batch by key -------------------------------------------------------------------------
-// Each block first groups its own 256 requests in a shared-memory table, so a key that is hot in the batch costs one
-// global atomic per block instead of one per request (the top key of a Zipf(1.1) batch is ~11 % of it: thousands of
-// same-address L2 atomics otherwise).  Then one thread per distinct (block, key) joins the batch-wide table.
-constexpr int GROUP_THREADS = 256;
-constexpr int GROUP_SLOTS = 512;  // shared-memory table entries per block (load factor <= 0.5)
-
-// Joins `c` members to the batch-wide group of `key`; returns the first ticket of the joiner and the entry position.
-__device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, uint32_t c, uint32_t* pos_out) {
+// ---- kernel 1: group the batch by key, rank members inside each block --------------------------------------------
+// Joins `c` members to the batch-wide group of `key`; returns the entry position.  *claimed = this call created the entry.
+__device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, uint32_t c, bool* claimed) {
   const uint32_t tag = (uint32_t)(key >> 40);  // 24 bits, disjoint from the position bits below
   uint32_t pos = (uint32_t)(key ^ (key >> 29)) & A.aux_mask;
   const unsigned long long fresh = ((unsigned long long)A.epoch << 48) | ((unsigned long long)tag << 24) | (unsigned long long)c;
-  uint32_t base;
+  *claimed = false;
 #pragma unroll 1
   for (;;) {
     unsigned long long cur = __ldcg(&A.aux[pos].word);
     if (aux_epoch(cur) != A.epoch) {  // stale entry from an earlier batch == empty
       const unsigned long long old = atomicCAS(&A.aux[pos].word, cur, fresh);
-      if (old == cur) { base = 0; break; }
+      if (old == cur) { *claimed = true; break; }
       cur = old;  // somebody else just claimed it for this batch: fall through and compare tags
     }
     if (aux_epoch(cur) == A.epoch && aux_tag(cur) == tag) {
-      base = aux_count(atomicAdd(&A.aux[pos].word, (unsigned long long)c));
+      atomicAdd(&A.aux[pos].word, (unsigned long long)c);
       break;
     }
     pos = (pos + 1) & A.aux_mask;
   }
-  BatchCtr* ctr = A.ctr + (A.epoch & 1);
-  if (base <= 1 && base + c > 1) {  // this joiner holds ticket 1: the key repeats, give the group an inline member list
-    const uint32_t lid = atomicAdd(&ctr->nlists, 1u);
-    A.aux[pos].lid = lid;
-    A.list_ent[lid] = pos;
-  }
-  if (base <= (uint32_t)INLINE && base + c > (uint32_t)INLINE) {  // holds ticket INLINE: too many for a list, give it a bitmap
-    const uint32_t hg = atomicAdd(&ctr->nheavy, 1u);
-    A.aux[pos].hg = hg;
-    A.heavy_ent[hg] = pos;
-  }
-  *pos_out = pos;
-  return base;
+  return pos;
 }
 
 __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ unsigned long long s_key[GROUP_SLOTS];
-  __shared__ uint32_t s_cnt[GROUP_SLOTS];   // members in this block; later: first ticket of this block's members
-  __shared__ uint32_t s_pos[GROUP_SLOTS];   // batch-wide entry position
+  __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block (running, in warp order)
+  __shared__ uint32_t s_pos[GROUP_SLOTS];  // batch-wide entry position
   for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
   __syncthreads();
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
-  uint32_t sp = 0, local = 0;
-  if (i < A.n) {
-    const uint64_t key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
-    sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);          // top 9 bits -> GROUP_SLOTS
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool valid = i < A.n;
+  uint32_t sp = 0xFFFFu;  // shared-memory slot of my key (0xFFFF: no request)
+  uint64_t key = 0;
+  if (valid) {
+    key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
+    sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
 #pragma unroll 1
     for (;;) {
       const unsigned long long old = atomicCAS(&s_key[sp], 0ull, (unsigned long long)key);
       if (old == 0ull || old == key) break;
       sp = (sp + 1) & (GROUP_SLOTS - 1);
     }
-    local = atomicAdd(&s_cnt[sp], 1u);
   }
   __syncthreads();
-  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) {
-    const unsigned long long key = s_key[k];
-    if (key != 0ull) {
-      uint32_t pos;
-      s_cnt[k] = aux_join(A, key, s_cnt[k], &pos);
-      s_pos[k] = pos;
+  // local rank in index order: warps take turns in order; inside a warp the lanes sharing a key are ranked by lane id
+  uint32_t local = 0;
+#pragma unroll 1
+  for (uint32_t w = 0; w < GROUP_THREADS / 32; w++) {
+    if (warp == w) {
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sp);
+      const uint32_t leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (valid && lane == leader) { base = s_cnt[sp]; s_cnt[sp] = base + __popc(peers); }
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      local = base + __popc(peers & ((1u << lane) - 1u));
     }
+    __syncthreads();
+  }
+  // the first member of each fragment joins the batch-wide group
+  if (valid && local == 0) {
+    const uint32_t c = s_cnt[sp];
+    bool claimed;
+    const uint32_t pos = aux_join(A, key, c, &claimed);
+    if (claimed) { A.aux[pos].rep = i; A.aux[pos].flags = 0; }
+    atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
+    A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(c - 1);
+    s_pos[sp] = pos;
   }
   __syncthreads();
-  if (i < A.n) {
+  if (valid) {
     A.ent[i] = s_pos[sp];
-    A.ticket[i] = s_cnt[sp] + local;
+    A.meta[i] = (sp << 16) | local;
   }
 }
 
-// ---- kernel 2: singletons are evaluated; members of repeated keys register themselves ------------------------
-__global__ void __launch_bounds__(256) k_single(const BatchArgs A) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- kernel 2: singletons are evaluated; members of repeated keys get their rank and check uniformity ------------
+// Requests that can make an identical run irregular for ever (no subtract regime, no fixed point) are sent down the
+// segment path, whose cost is linear in the run length: negative hits keep adding, RESET_REMAINING on a token bucket
+// alternates delete/create, and float64 remaining beyond 2^52 loses integer steps.
+__device__ __forceinline__ bool req_regular(const gub_req& r) {
+  if (r.hits < 0) return false;
+  if (r.algorithm == GUB_TOKEN_BUCKET && (r.behavior & GUB_BEHAVIOR_RESET_REMAINING)) return false;
+  if (r.algorithm == GUB_LEAKY_BUCKET && (r.limit >= (1ll << 52) || r.burst >= (1ll << 52))) return false;
+  return true;
+}
+
+// sum over present blocks b' < b of (fragsize[b'] + 1): the rank of block b's first member of this group
+__device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t pos, uint32_t b) {
+  const uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
+  const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
+  uint32_t base = 0;
+  const uint32_t last = b >> 5;
+#pragma unroll 1
+  for (uint32_t w = 0; w <= last; w++) {
+    uint32_t bits = __ldcg(pres + w);
+    if (w == last) bits &= (1u << (b & 31)) - 1u;
+    if (!bits) continue;
+    if (__popc(bits) <= 2) {  // the common case: a couple of fragments
+      while (bits) { const uint32_t k = __ffs(bits) - 1; bits &= bits - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
+    } else {  // 32 fragment sizes at once: two 128-bit loads, byte-masked by the presence bits
+      const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)), hi = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16));
+      const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const uint32_t m4 = (bits >> (4 * k)) & 0xFu;
+        const uint32_t mask = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit j of m4 -> byte j all ones
+        base = __dp4a(v[k] & mask, 0x01010101u, base);
+      }
+      base += __popc(bits);
+    }
+  }
+  return base;
+}
+
+// One request against its own slot: the path of a key that occurs once in the batch.
+__device__ __forceinline__ void single_eval(const BatchArgs& A, uint32_t i, const gub_req& rq, Tally& t) {
+  Cursor cur;
+  cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+  Delta d = {0, 0, 0};
+  gub_resp r = apply_one(cur.b, rq, A.clk, d);
+  if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
+  t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+  store_resp(A.out + i, r);
+}
+
+__global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
+  __shared__ uint32_t s_base[GROUP_SLOTS];
+  const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
   if (i == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
-    nxt->nlists = 0; nxt->nheavy = 0; nxt->order_bump = 0;
+    nxt->n_mixed = 0; nxt->order_bump = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
-  if (i < A.n) {
-    const uint32_t pos = A.ent[i];
-    const AuxEntry e = A.aux[pos];
-    const uint32_t cnt = aux_count(e.word);
-    if (cnt == 1) {
-      serial_walk(A, 1u, [i](uint32_t) { return i; }, t);
-    } else if (cnt <= (uint32_t)INLINE) {
-      A.lists[(size_t)e.lid * INLINE + A.ticket[i]] = i;
-    } else {
-      atomicOr(&A.bitmaps[(size_t)e.hg * A.bitmap_words + (i >> 5)], 1u << (i & 31));
+  const bool valid = i < A.n;
+  uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
+  gub_req rq;
+  if (valid) {
+    rq = load_req(A.reqs + i);  // independent of the loads below: issued together
+    pos = A.ent[i];
+    const uint32_t m = A.meta[i];
+    sp = m >> 16; local = m & 0xFFFFu;
+    const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
+    cnt = aux_count(e.x);
+    rep = (uint32_t)(e.y & 0xFFFFFFFFull);
+    if (cnt > 1 && local == 0) {
+      const uint32_t base = fragment_base(A, pos, blockIdx.x);
+      s_base[sp] = base;
+      if (base == 0) {  // I am rank 0 of the run: look the key up once for everybody
+        Cursor cur;
+        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+        snap_store(A.snap + (size_t)pos * 6, cur);
+      }
+    }
+  }
+  if (valid && cnt == 1) {
+    single_eval(A, i, rq, t);
+    A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+  }
+  __syncthreads();
+  if (valid && cnt > 1) {
+    A.rank[i] = s_base[sp] + local;
+    bool mixed = !req_regular(rq);
+    if (!mixed && i != rep) mixed = !req_same(rq, load_req(A.reqs + rep));
+    if (mixed) {
+      const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
+      if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
+        BatchCtr* ctr = A.ctr + (A.epoch & 1);
+        A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
+        A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
+      }
     }
   }
   tally_flush_block(t, A.counters);
 }
 
-// ---- kernel 3: repeated keys -----------------------------------------------------------------------------------
-__device__ __forceinline__ void light_group(const BatchArgs& A, uint32_t lid, Tally& t) {
-  const uint32_t pos = A.list_ent[lid];
-  const uint32_t cnt = aux_count(A.aux[pos].word);
-  if (cnt > (uint32_t)INLINE) return;  // promoted to a heavy group
-  uint32_t idx[INLINE];
-  const uint32_t* lst = A.lists + (size_t)lid * INLINE;
-#pragma unroll
-  for (int j = 0; j < INLINE; j++) idx[j] = (j < (int)cnt) ? lst[j] : 0xFFFFFFFFu;
-  // insertion sort by batch index (tickets are arrival order, not index order)
-#pragma unroll 1
-  for (uint32_t a = 1; a < cnt; a++) {
-    const uint32_t v = idx[a];
-    int b = (int)a - 1;
-    while (b >= 0 && idx[b] > v) { idx[b + 1] = idx[b]; b--; }
-    idx[b + 1] = v;
+// ---- kernel 3: every member of a uniform run evaluates its own rank ------------------------------------------------
+__global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
+  const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
+  Tally t = {0, 0, 0, 0, 0};
+  uint32_t dup = 0;
+  if (i < A.n) {
+    const uint32_t pos = A.ent[i];
+    const AuxEntry* e = &A.aux[pos];
+    const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
+    const uint32_t cnt = aux_count(ev.x);
+    if (cnt > 1) {
+      const uint32_t rank = A.rank[i];
+      const bool mixed = ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
+      if (rank == 0) {  // hand the presence bitmap back clean
+        uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
+        for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
+      }
+      if (mixed) {
+        A.order[__ldcg(&e->gbase) + rank] = i;
+      } else {
+        const gub_req rq = load_req(A.reqs + i);
+        Cursor cur;
+        snap_load(A.snap + (size_t)pos * 6, cur);  // not the table: the last rank may already be writing it
+        Delta d = {0, 0, 0};
+        gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
+        if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
+          if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
+          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+          dup = 1;
+        }
+        store_resp(A.out + i, r);
+      }
+    }
   }
-  serial_walk(A, cnt, [&idx](uint32_t j) { return idx[j]; }, t);
+  dup = __reduce_add_sync(0xFFFFFFFFu, dup);
+  if ((threadIdx.x & 31) == 0 && dup) atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)dup);
+  tally_flush_block(t, A.counters);
 }
 
-struct HeavyShared {
-  uint32_t warp_sums[HEAVY_THREADS / 32];
-  uint32_t obase;
+// ---- kernel 4: runs whose requests differ ---------------------------------------------------------------------------
+struct MixedShared {
   uint32_t nseg;
   uint32_t np;
   uint32_t covered;
@@ -360,39 +480,14 @@ struct HeavyShared {
   Piece pieces[MAX_PIECES];
 };
 
-__device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tally& t) {
+__device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Tally& t) {
   const uint32_t tid = threadIdx.x;
-  const uint32_t pos = A.heavy_ent[hg];
-  const uint32_t cnt = aux_count(A.aux[pos].word);
-  uint32_t* bm = A.bitmaps + (size_t)hg * A.bitmap_words;
-  const uint32_t nw = (A.n + 31) >> 5;
-  const uint32_t wpt = (nw + HEAVY_THREADS - 1) / HEAVY_THREADS;  // contiguous words per thread => ranks are ordered by thread
-  const uint32_t w0 = tid * wpt, w1 = min(nw, w0 + wpt);
-  BatchCtr* ctr = A.ctr + (A.epoch & 1);
-
-  if (tid == 0) { S.obase = atomicAdd(&ctr->order_bump, cnt); S.nseg = 0; }
-  // 1. rank = prefix popcount over the group's bitmap
-  uint32_t local = 0;
-  for (uint32_t w = w0; w < w1; w++) local += __popc(bm[w]);
-  uint32_t incl = local;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31) >= (uint32_t)o) incl += v; }
-  if ((tid & 31) == 31) S.warp_sums[tid >> 5] = incl;
+  const uint32_t cnt = aux_count(__ldcg(&A.aux[pos].word));
+  const uint32_t* ord = A.order + __ldcg(&A.aux[pos].gbase);
+  if (tid == 0) S.nseg = 0;
   __syncthreads();
-  uint32_t base = incl - local;
-  for (uint32_t w = 0; w < (tid >> 5); w++) base += S.warp_sums[w];
-  const uint32_t obase = S.obase;
-  // 2. materialise the members in index order and give the bitmap back zeroed
-  uint32_t r = base;
-  for (uint32_t w = w0; w < w1; w++) {
-    uint32_t bits = bm[w];
-    if (bits) bm[w] = 0;
-    while (bits) { const uint32_t bit = __ffs(bits) - 1; bits &= bits - 1; A.order[obase + r++] = (w << 5) + bit; }
-  }
-  __syncthreads();
-  const uint32_t* ord = A.order + obase;
-  // 3. segment boundaries: ranks whose request differs from the previous member's
-  for (uint32_t k = tid; k < cnt; k += HEAVY_THREADS) {
+  // segment boundaries: ranks whose request differs from the previous member's
+  for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
     bool boundary = (k == 0);
     if (!boundary) {
       const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
@@ -419,7 +514,7 @@ __device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tal
     }
   }
   __syncthreads();
-  // 4. per segment: thread 0 plans, everybody evaluates
+  // per segment: thread 0 plans, everybody evaluates
   Cursor cur;
   bool open = false;
   uint64_t ck = 0, ct = 0;
@@ -461,7 +556,7 @@ __device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tal
     }
     __syncthreads();
     const uint32_t np = S.np, covered = S.covered;
-    for (uint32_t k = tid; k < covered; k += HEAVY_THREADS) {
+    for (uint32_t k = tid; k < covered; k += MIXED_THREADS) {
       uint32_t pi = 0;
       while (pi + 1 < np && S.pieces[pi + 1].start <= k) pi++;
       store_resp(A.out + ord[lo + k], eval_piece(S.pieces[pi], k));
@@ -471,29 +566,17 @@ __device__ void heavy_group(const BatchArgs& A, uint32_t hg, HeavyShared& S, Tal
   if (tid == 0 && open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
 }
 
-// Light groups: one thread per repeated key with at most INLINE members.
-constexpr int LIGHT_THREADS = 128;
-__global__ void __launch_bounds__(LIGHT_THREADS) k_light(const BatchArgs A) {
+__global__ void __launch_bounds__(MIXED_THREADS, 2) k_mixed(const BatchArgs A) {
+  __shared__ MixedShared S;
   Tally t = {0, 0, 0, 0, 0};
-  const uint32_t nlists = min(A.ctr[A.epoch & 1].nlists, A.max_lists);
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < nlists; lid += stride) light_group(A, lid, t);
-  tally_flush_block(t, A.counters);
-}
-
-// Heavy groups: one thread block per hot key (grid-stride).
-__global__ void __launch_bounds__(HEAVY_THREADS, 2) k_heavy(const BatchArgs A) {
-  __shared__ HeavyShared S;
-  Tally t = {0, 0, 0, 0, 0};
-  const BatchCtr ctr = A.ctr[A.epoch & 1];
-  const uint32_t nheavy = min(ctr.nheavy, A.max_heavy);
-  for (uint32_t hg = blockIdx.x; hg < nheavy; hg += gridDim.x) {
-    heavy_group(A, hg, S, t);
+  const uint32_t n_mixed = A.ctr[A.epoch & 1].n_mixed;
+  for (uint32_t g = blockIdx.x; g < n_mixed; g += gridDim.x) {
+    mixed_group(A, A.mixed_ent[g], S, t);
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.nlists);
-    atomicAdd(A.counters + C_HEAVY_GROUPS, (unsigned long long)ctr.nheavy);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n_mixed) {
+    atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)n_mixed);
+    atomicAdd(A.counters + C_MIXED_GROUPS, (unsigned long long)n_mixed);
   }
   tally_flush_block(t, A.counters);
 }

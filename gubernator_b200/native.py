@@ -21,7 +21,7 @@ ITEM_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("algorithm", 
                        ("duration", "<i8"), ("remaining", "<i8"), ("remaining_f", "<f8"), ("stamp", "<i8"), ("burst", "<i8"),
                        ("expire_at", "<i8")])
 COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups",
-                  "heavy_groups", "serial_fallbacks")
+                  "mixed_groups", "serial_fallbacks")
 assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 80
 
 EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device",
@@ -226,7 +226,7 @@ class Table:
         ms = np.zeros(4, dtype=np.float64)
         n = C.c_uint64(0)
         _check(lib().gub_get_profile(self._h, ms.ctypes.data, C.byref(n), 1 if reset else 0), "gub_get_profile")
-        return dict(k_group_ms=float(ms[0]), k_single_ms=float(ms[1]), k_light_ms=float(ms[2]), k_heavy_ms=float(ms[3]), launches=int(n.value))
+        return dict(k_group_ms=float(ms[0]), k_rank_ms=float(ms[1]), k_eval_ms=float(ms[2]), k_mixed_ms=float(ms[3]), launches=int(n.value))
 
     # ---- multi-GPU routing
     def route_device(self, ring, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream=0):

@@ -116,8 +116,8 @@ typedef struct {
   uint64_t requests;       /* decisions evaluated */
   uint64_t batches;
   uint64_t dup_groups;     /* keys that occurred more than once within a batch */
-  uint64_t heavy_groups;   /* of those, keys handled by the block-cooperative path */
-  uint64_t serial_fallbacks; /* heavy groups that had to be walked serially */
+  uint64_t mixed_groups;   /* of those, keys whose requests differed within the batch (segment path) */
+  uint64_t serial_fallbacks; /* of those, groups too irregular to plan: walked by one thread */
 } gub_counters;
 
 typedef struct {
@@ -169,7 +169,7 @@ int gub_size(gub_table* t, size_t* n_out);
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
 
-/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_single / k_light / k_heavy), the
+/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_rank / k_eval / k_mixed), the
  * measurement counterpart of the reference's metricFuncTimeDuration summaries (gubernator.go:65-73).  Off by default. */
 int gub_set_profiling(gub_table* t, int on);
 int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int reset);

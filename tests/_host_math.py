@@ -30,6 +30,7 @@ def lib():
         L.hm_table_free.argtypes = [C.c_void_p]
         L.hm_apply_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hm_plan_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.hm_rank_check.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.hm_sizeof_bucket.restype = C.c_size_t
         assert L.hm_sizeof_bucket() == BUCKET_DTYPE.itemsize
         _lib = L
@@ -59,3 +60,7 @@ def plan_check(bucket, req, m, clk, cap=16):
     covered = C.c_uint32(0)
     rc = lib().hm_plan_check(bucket.ctypes.data, req.ctypes.data, m, clk.ctypes.data, cap, C.byref(npieces), C.byref(covered))
     return rc, npieces.value, covered.value
+
+
+def rank_check(bucket, req, m, clk, stride=1):
+    return lib().hm_rank_check(bucket.ctypes.data, req.ctypes.data, m, clk.ctypes.data, stride)

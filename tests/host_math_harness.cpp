@@ -62,5 +62,25 @@ int hm_plan_check(const Bucket* b0, const gub_req* rq, uint32_t m, const gub_clo
   return 0;
 }
 
+// run_to_rank() for every rank (or a sample of ranks) of an m-long run against m sequential apply_one() calls.
+int hm_rank_check(const Bucket* b0, const gub_req* rq, uint32_t m, const gub_clock* clk, uint32_t stride) {
+  Bucket bs = *b0;
+  Delta ds{0, 0, 0};
+  std::vector<gub_resp> want(m);
+  std::vector<Bucket> states(m);
+  std::vector<Delta> deltas(m);
+  for (uint32_t i = 0; i < m; i++) { want[i] = apply_one(bs, *rq, *clk, ds); states[i] = bs; deltas[i] = ds; }
+  for (uint32_t r = 0; r < m; r += (r + 1 == m || r + stride < m) ? stride : (m - 1 - r)) {
+    Bucket b = *b0;
+    Delta d{0, 0, 0};
+    gub_resp got = run_to_rank(b, *rq, r, *clk, d);
+    if (std::memcmp(&want[r], &got, sizeof(gub_resp)) != 0) return 1000 + (int)(r < 1000000 ? r : 999999);
+    if (!bucket_equal(states[r], b)) return 2;
+    if (deltas[r].over != d.over || deltas[r].hit != d.hit || deltas[r].miss != d.miss) return 3;
+    if (r + 1 == m) break;
+  }
+  return 0;
+}
+
 size_t hm_sizeof_bucket() { return sizeof(Bucket); }
 }

@@ -146,7 +146,7 @@ def test_zipf_heavy_duplicates(G, mixed):
     _cmp_counters(tab, pool)
     _check_table_equals_oracle(G, tab, pool)
     c = tab.counters()
-    assert c["heavy_groups"] > 0 and c["dup_groups"] > c["heavy_groups"] and c["serial_fallbacks"] == 0
+    assert c["dup_groups"] > 1000 and c["mixed_groups"] == 0 and c["serial_fallbacks"] == 0
 
 
 def test_many_segments_and_serial_fallback(G):

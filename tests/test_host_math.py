@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_py as O
-from _host_math import BUCKET_DTYPE, F_LEAKY, F_LIVE, F_OVER, HostTable, plan_check
+from _host_math import BUCKET_DTYPE, F_LEAKY, F_LIVE, F_OVER, HostTable, plan_check, rank_check
 from workloads import T0, adversarial_batch, bench_batch, make_clock
 
 
@@ -82,6 +82,8 @@ def test_plan_run_equals_repeated_apply(seed):
         cap = int(rng.choice([2, 4, 16]))
         rc, npieces, covered = plan_check(b, rq, m, clk, cap)
         assert rc == 0, (trial, rc, b, rq, m, cap)
+        rc = rank_check(b, rq, m, clk, stride=1 if m <= 100 else 37)
+        assert rc == 0, ("run_to_rank", trial, rc, b, rq, m)
         if covered == m and npieces < m:
             n_linear += 1
     assert n_linear > 500  # the planner actually compresses runs
@@ -98,3 +100,4 @@ def test_plan_run_compresses_hot_key_run():
         rq["behavior"] = O.REQ_IS_OWNER
         rc, npieces, covered = plan_check(b, rq, 7300, clk, 16)
         assert rc == 0 and covered == 7300 and npieces <= 6, (algo, rc, npieces, covered)
+        assert rank_check(b, rq, 7300, clk, stride=1) == 0
