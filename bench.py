@@ -203,41 +203,19 @@ def run_b200(args):
 
     ring = None
     if N > 1:
+        from gubernator_b200.sharded import shard_addresses
         ring = g.Ring(0, 512)
-        for r in range(N):
-            ring.add(f"gpu:{r}")
+        for a in shard_addresses(N):
+            ring.add(a)
 
     def t2np(t, dtype):
         return t.cpu().numpy().reshape(-1).view(dtype)
 
     # ---- one step of the sharded path (N > 1): route -> all-to-all -> evaluate -> all-to-all back -> unroute
-    class Sharded:
-        def __init__(self, cap):
-            self.cap = cap
-            self.routed = torch.empty((cap, 64), dtype=torch.uint8, device=dev)
-            self.perm = torch.empty(cap, dtype=torch.int32, device=dev)
-            self.counts = torch.zeros(16, dtype=torch.int32, device=dev)
-            self.recv_cap = int(cap * 1.6) + 4096
-            self.recv = torch.empty((self.recv_cap, 64), dtype=torch.uint8, device=dev)
-            self.recv_resp = torch.empty((self.recv_cap, 32), dtype=torch.uint8, device=dev)
-            self.back = torch.empty((cap, 32), dtype=torch.uint8, device=dev)
-
-        def step(self, d_reqs, n, clk, d_out):
-            tab.route_device(ring, d_reqs.data_ptr(), n, self.routed.data_ptr(), self.perm.data_ptr(), self.counts.data_ptr(), stream)
-            send = self.counts[:N].clone()
-            recv = torch.empty_like(send)
-            dist.all_to_all_single(recv, send)
-            send_l, recv_l = send.tolist(), recv.tolist()  # host sync: split sizes for the variable all-to-all
-            m = sum(recv_l)
-            if m > self.recv_cap:
-                raise RuntimeError("receive buffer too small")
-            dist.all_to_all_single(self.recv[:m], self.routed[:n], output_split_sizes=recv_l, input_split_sizes=send_l)
-            tab.submit_device(self.recv.data_ptr(), m, clk, self.recv_resp.data_ptr(), stream)
-            dist.all_to_all_single(self.back[:n], self.recv_resp[:m], output_split_sizes=send_l, input_split_sizes=recv_l)
-            tab.unroute_device(self.back.data_ptr(), self.perm.data_ptr(), n, d_out.data_ptr(), stream)
-            return m
-
-    sharded = Sharded(262144) if N > 1 else None
+    sharded = None
+    if N > 1:
+        from gubernator_b200.sharded import GpuBackend, ShardedStep
+        sharded = ShardedStep(GpuBackend(tab, ring, N, dev, 262144), dist, N)
 
     # ---- warm pass: make every key resident through the real path
     t_fill = time.perf_counter()

@@ -1,0 +1,18 @@
+"""Multi-GPU parity: the CUDA routing kernels + NCCL all-to-all + per-shard evaluation against one oracle per shard.
+Needs >= 2 GPUs on the box (skipped otherwise; the protocol itself is covered on CPU by tests/test_sharded_gloo.py)."""
+import pytest
+
+from test_sharded_gloo import run_workers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_sharded_gpu_matches_per_shard_oracles(nproc):
+    import torch
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    res = run_workers(nproc, "gpu")
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    for r in range(nproc):
+        assert f"rank {r} ok" in res.stdout
