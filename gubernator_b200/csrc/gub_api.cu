@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -74,6 +75,7 @@ struct gub_table {
   uint8_t* d_owner = nullptr; uint32_t* d_tile_counts = nullptr;
   size_t owner_cap = 0, tiles_cap = 0;
   // optional per-kernel timing (bench.py's roofline leg): events bracket every kernel of the batch path
+  bool pdl = true;                    // programmatic dependent launch between the batch kernels (GUB_PDL=0 disables)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;   // 5 events per pending chunk
   size_t prof_pending = 0;            // chunks recorded and not yet accumulated
@@ -94,6 +96,19 @@ int prof_flush(gub_table* t, bool force) {
   }
   t->prof_pending = 0;
   return 0;
+}
+
+// Launches one batch kernel, with programmatic stream serialization when enabled (the kernels call griddepcontrol.wait
+// before touching anything an earlier kernel produced; without the attribute that instruction is a no-op).
+template <typename K>
+cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cudaStream_t st, const gub::BatchArgs& A) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, A);
 }
 
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
@@ -119,14 +134,14 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
     t->prof_pending++;
     CK(cudaEventRecord(pe[0], st));
   }
-  gub::k_group<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
+  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[1], st));
-  gub::k_rank<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
+  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[2], st));
-  gub::k_eval<<<blocks, gub::GROUP_THREADS, 0, st>>>(A);
+  CK(launch_k(t, gub::k_eval, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[3], st));
   // non-uniform groups: one block each, grid-stride (normally there are none and the kernel returns at once)
-  gub::k_mixed<<<std::min<uint32_t>(592u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, 0, st>>>(A);
+  CK(launch_k(t, gub::k_mixed, std::min<uint32_t>(296u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[4], st));
   CK(cudaGetLastError());
   return 0;
@@ -221,6 +236,7 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   if (prop.major < 10) return fail("gub_create: this library is built for sm_100a (B200) only");
   gub_table* t = new gub_table();
   t->device = cfg->device;
+  if (const char* e = getenv("GUB_PDL")) t->pdl = std::atoi(e) != 0;
   t->capacity = cfg->capacity_slots;
   t->max_batch = cfg->max_batch ? cfg->max_batch : 65536u;
   if (t->max_batch < 1024) t->max_batch = 1024;

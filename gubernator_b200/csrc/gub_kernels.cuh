@@ -85,6 +85,14 @@ struct BatchArgs {
 
 __device__ __forceinline__ uint64_t remap_key(uint64_t k) { return k < 2 ? k + 2 : k; }
 
+// Programmatic dependent launch (sm_90+): every batch kernel is launched with programmatic stream serialization, so its
+// blocks may become resident while the previous kernel is still running.  pdl_wait() blocks until every earlier grid of
+// the stream has completed and its writes are visible; only work that depends on nothing earlier may precede it.
+// pdl_release() then lets the NEXT kernel start launching (after our wait, so that kernel may read anything that was
+// complete before this one started, e.g. the request records).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- slot access ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void slot_load(const Slot* s, ulonglong2& a, ulonglong2& b, ulonglong2& c, ulonglong2& d) {
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s);
@@ -255,14 +263,19 @@ __device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, Id
 
 // ---- kernel 1: group the batch by key, rank members inside each block --------------------------------------------
 // Joins `c` members to the batch-wide group of `key`; returns the entry position.  *claimed = this call created the entry.
-__device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, uint32_t c, bool* claimed) {
+__device__ __forceinline__ uint32_t aux_home(const BatchArgs& A, uint64_t key) { return (uint32_t)(key ^ (key >> 29)) & A.aux_mask; }
+
+// `first` = the home entry's word as read earlier (prefetched while the block-local grouping ran).
+__device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, uint32_t c, unsigned long long first, bool* claimed) {
   const uint32_t tag = (uint32_t)(key >> 40);  // 24 bits, disjoint from the position bits below
-  uint32_t pos = (uint32_t)(key ^ (key >> 29)) & A.aux_mask;
+  uint32_t pos = aux_home(A, key);
   const unsigned long long fresh = ((unsigned long long)A.epoch << 48) | ((unsigned long long)tag << 24) | (unsigned long long)c;
   *claimed = false;
+  bool have_first = true;
 #pragma unroll 1
   for (;;) {
-    unsigned long long cur = __ldcg(&A.aux[pos].word);
+    unsigned long long cur = have_first ? first : __ldcg(&A.aux[pos].word);
+    have_first = false;
     if (aux_epoch(cur) != A.epoch) {  // stale entry from an earlier batch == empty
       const unsigned long long old = atomicCAS(&A.aux[pos].word, cur, fresh);
       if (old == cur) { *claimed = true; break; }
@@ -282,14 +295,18 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block (running, in warp order)
   __shared__ uint32_t s_pos[GROUP_SLOTS];  // batch-wide entry position
   for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
+  pdl_wait();
+  pdl_release();
   __syncthreads();
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool valid = i < A.n;
   uint32_t sp = 0xFFFFu;  // shared-memory slot of my key (0xFFFF: no request)
   uint64_t key = 0;
+  unsigned long long first = 0;
   if (valid) {
     key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
+    first = __ldcg(&A.aux[aux_home(A, key)].word);  // consumed much later, by the fragment's first member only
     sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
 #pragma unroll 1
     for (;;) {
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   if (valid && local == 0) {
     const uint32_t c = s_cnt[sp];
     bool claimed;
-    const uint32_t pos = aux_join(A, key, c, &claimed);
+    const uint32_t pos = aux_join(A, key, c, first, &claimed);
     if (claimed) { A.aux[pos].rep = i; A.aux[pos].flags = 0; }
     atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
     A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(c - 1);
@@ -341,30 +358,57 @@ __device__ __forceinline__ bool req_regular(const gub_req& r) {
   return true;
 }
 
-// sum over present blocks b' < b of (fragsize[b'] + 1): the rank of block b's first member of this group
+// sum over present blocks b' < b of (fragsize[b'] + 1): the rank of block b's first member of this group.
+// All loads are issued before any is consumed (a hot key has a fragment in every block: 8 bitmap words + 16 x 16 B of sizes
+// for a 64 k batch), so the cost is two L2 round trips rather than one per word.
+__device__ __forceinline__ uint32_t masked_sum32(const uint4& lo, const uint4& hi, uint32_t bits) {
+  const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t acc = __popc(bits);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t m4 = (bits >> (4 * k)) & 0xFu;
+    const uint32_t mask = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit j of m4 -> byte j all ones
+    acc = __dp4a(v[k] & mask, 0x01010101u, acc);
+  }
+  return acc;
+}
+
 __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t pos, uint32_t b) {
   const uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
   const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
+  const uint32_t last = b >> 5, keep = (1u << (b & 31)) - 1u;
   uint32_t base = 0;
-  const uint32_t last = b >> 5;
+  if (A.pres_words == 8) {  // max_batch = 65536
+    const uint4 p0 = __ldcg(reinterpret_cast<const uint4*>(pres)), p1 = __ldcg(reinterpret_cast<const uint4*>(pres) + 1);
+    uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { bits[w] = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u); any += __popc(bits[w]); }
+    if (any == 0) return 0;
+    if (any <= 2) {  // the common case: a couple of earlier fragments
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        uint32_t x = bits[w];
+        while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
+      }
+      return base;
+    }
+    uint4 lo[8], hi[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      if (bits[w]) { lo[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (bits[w]) base += masked_sum32(lo[w], hi[w], bits[w]);
+    return base;
+  }
 #pragma unroll 1
   for (uint32_t w = 0; w <= last; w++) {
     uint32_t bits = __ldcg(pres + w);
-    if (w == last) bits &= (1u << (b & 31)) - 1u;
+    if (w == last) bits &= keep;
     if (!bits) continue;
-    if (__popc(bits) <= 2) {  // the common case: a couple of fragments
-      while (bits) { const uint32_t k = __ffs(bits) - 1; bits &= bits - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
-    } else {  // 32 fragment sizes at once: two 128-bit loads, byte-masked by the presence bits
-      const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)), hi = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16));
-      const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint32_t m4 = (bits >> (4 * k)) & 0xFu;
-        const uint32_t mask = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit j of m4 -> byte j all ones
-        base = __dp4a(v[k] & mask, 0x01010101u, base);
-      }
-      base += __popc(bits);
-    }
+    const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)), hi = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16));
+    base += masked_sum32(lo, hi, bits);
   }
   return base;
 }
@@ -384,17 +428,19 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
+  const bool valid = i < A.n;
+  gub_req rq;
+  if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
+  pdl_wait();
+  pdl_release();
   if (i == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
     nxt->n_mixed = 0; nxt->order_bump = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
-  const bool valid = i < A.n;
   uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
-  gub_req rq;
   if (valid) {
-    rq = load_req(A.reqs + i);  // independent of the loads below: issued together
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
     sp = m >> 16; local = m & 0xFFFFu;
@@ -437,13 +483,17 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
   uint32_t dup = 0;
+  gub_req rq;
+  if (i < A.n) rq = load_req(A.reqs + i);  // safe ahead of the wait (see k_rank)
+  pdl_wait();
+  pdl_release();
   if (i < A.n) {
     const uint32_t pos = A.ent[i];
+    const uint32_t rank = A.rank[i];             // garbage for singletons; unused then
     const AuxEntry* e = &A.aux[pos];
     const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
     const uint32_t cnt = aux_count(ev.x);
     if (cnt > 1) {
-      const uint32_t rank = A.rank[i];
       const bool mixed = ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
       if (rank == 0) {  // hand the presence bitmap back clean
         uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
@@ -452,7 +502,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
       if (mixed) {
         A.order[__ldcg(&e->gbase) + rank] = i;
       } else {
-        const gub_req rq = load_req(A.reqs + i);
         Cursor cur;
         snap_load(A.snap + (size_t)pos * 6, cur);  // not the table: the last rank may already be writing it
         Delta d = {0, 0, 0};
@@ -569,6 +618,8 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
 __global__ void __launch_bounds__(MIXED_THREADS, 2) k_mixed(const BatchArgs A) {
   __shared__ MixedShared S;
   Tally t = {0, 0, 0, 0, 0};
+  pdl_wait();
+  pdl_release();
   const uint32_t n_mixed = A.ctr[A.epoch & 1].n_mixed;
   for (uint32_t g = blockIdx.x; g < n_mixed; g += gridDim.x) {
     mixed_group(A, A.mixed_ent[g], S, t);
