@@ -363,7 +363,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel
     peak, peak_src = load_peaks()
-    kms = {"k_group": prof["k_group_ms"], "k_rank": prof["k_rank_ms"], "k_eval": prof["k_eval_ms"], "k_mixed": prof["k_mixed_ms"]}
+    kms = {"k_group": prof["k_group_ms"], "k_rank": prof["k_rank_ms"], "k_eval": prof["k_eval_ms"], "k_finish": prof["k_finish_ms"]}
     launches = max(prof["launches"], 1)
     dom = max(kms, key=kms.get)
     st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
@@ -372,9 +372,9 @@ def run_b200(args):
     multi_grp = st["light_groups"] + st["heavy_groups"]
     alg = {  # algorithmic bytes per launch, by kernel (Kernels)
         "k_group": 16.0 * units,                                                        # 8 B key in, ent + meta out
-        "k_rank": ALGO_BYTES_PER_DECISION * st["singles"] + 140.0 * multi_req + 160.0 * multi_grp,  # singles: the whole 224 B; others: request + representative + rank; per key: slot read + snapshot
-        "k_eval": 200.0 * multi_req + 64.0 * multi_grp,                                # request + snapshot + response per member; one slot write-back per key
-        "k_mixed": 0.0,                                                                 # no non-uniform groups in this workload
+        "k_rank": 12.0 * units + 132.0 * multi_req,                                      # ent/meta/entry per request; request + representative + rank per repeated-key member
+        "k_eval": ALGO_BYTES_PER_DECISION * st["singles"] + (64 + 64 + 32 + 12.0) * multi_req + 96.0 * multi_grp,  # singles: the whole 224 B; members: request + slot + response; per key: commit record
+        "k_finish": (96 + 64 + 64.0) * multi_grp,                                        # commit record in, slot compare + write-back
     }
     dom_ms = kms[dom] / launches
     path_ms = sum(kms.values()) / launches

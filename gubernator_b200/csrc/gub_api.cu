@@ -55,7 +55,8 @@ struct gub_table {
   gub::AuxEntry* aux = nullptr; uint32_t aux_entries = 0;
   uint32_t *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *presence = nullptr;
   uint8_t* fragsize = nullptr;
-  ulonglong2* snap = nullptr;
+  ulonglong2* commit = nullptr;
+  uint32_t* commit_ent = nullptr;
   uint32_t pres_words = 0, max_blocks = 0;
   gub::BatchCtr* ctr = nullptr;
   unsigned long long* counters = nullptr;
@@ -120,7 +121,7 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   gub::BatchArgs A;
   A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = t->epoch;
   A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
-  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank; A.snap = t->snap;
+  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank; A.commit = t->commit; A.commit_ent = t->commit_ent;
   A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr; A.counters = t->counters;
   A.clk = *clk;
   const uint32_t blocks = (n + 255) / 256;
@@ -140,8 +141,18 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   if (pe) CK(cudaEventRecord(pe[2], st));
   CK(launch_k(t, gub::k_eval, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[3], st));
-  // non-uniform groups: one block each, grid-stride (normally there are none and the kernel returns at once)
-  CK(launch_k(t, gub::k_mixed, std::min<uint32_t>(296u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, st, A));
+  // commit records (one thread each, at most n/2) + non-uniform groups (one block each, grid-stride; normally none)
+  {
+    const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
+    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (n / 2 + gub::MIXED_THREADS - 1) / gub::MIXED_THREADS));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mixed_blocks + commit_blocks); cfg.blockDim = dim3(gub::MIXED_THREADS); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, gub::k_finish, A, mixed_blocks));
+  }
   if (pe) CK(cudaEventRecord(pe[4], st));
   CK(cudaGetLastError());
   return 0;
@@ -205,7 +216,7 @@ void gub_destroy(gub_table* t) {
   if (!t) return;
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {t->table, t->aux, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->presence, t->fragsize, t->snap, t->ctr, t->counters,
+  void* ptrs[] = {t->table, t->aux, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->presence, t->fragsize, t->commit, t->commit_ent, t->ctr, t->counters,
                   t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& s : t->pipe) {
@@ -260,7 +271,8 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   ALLOC(t->aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
   ALLOC(t->presence, (size_t)t->aux_entries * t->pres_words * 4);
   ALLOC(t->fragsize, (size_t)t->aux_entries * t->max_blocks);
-  ALLOC(t->snap, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
+  ALLOC(t->commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
+  ALLOC(t->commit_ent, ((size_t)B / 2 + 1) * 4);
   ALLOC(t->ent, (size_t)B * 4);
   ALLOC(t->meta, (size_t)B * 4);
   ALLOC(t->rank, (size_t)B * 4);

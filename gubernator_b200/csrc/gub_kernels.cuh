@@ -18,13 +18,17 @@
 //   k_group  (256 consecutive requests per block) shared-memory grouping with index-ordered local ranks; one thread per
 //            distinct (block, key) "fragment" joins the batch-wide group entry (count += members), sets the block's bit
 //            in the group's presence bitmap and stores the fragment size.
-//   k_rank   keys seen once (most keys) are probed + updated + answered right here: one 64 B random HBM read, one
-//            write-back.  Members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank, and
+//            It also prefetches every request's home slot into L2: the table is not needed until two kernels later.
+//   k_rank   (table-free) members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank, and
 //            compare their request with the group's representative; any difference marks the group non-uniform.
-//   k_eval   members of uniform groups: probe, run_to_rank(), answer; the last rank writes the state back.
-//            members of non-uniform groups: order[base + rank] = index.
-//   k_mixed  one block per non-uniform group: split the ordered run into segments of identical requests, plan each with
-//            plan_run() on one thread, evaluate/scatter with all threads (serial walk when there are too many segments).
+//   k_eval   every request of a uniform run (a key seen once is a run of one) probes its slot (64 B, now an L2 hit),
+//            evaluates run_to_rank(bucket, request, rank) and answers.  Singletons write their slot back at once; the
+//            last rank of a longer run parks the final state in a commit record (its siblings may still be reading the
+//            slot).  Members of non-uniform runs only file themselves: order[base + rank] = index.
+//   k_finish commit records are written to the table; one block per non-uniform group splits the ordered run into
+//            segments of identical requests, plans each with plan_run() on one thread and evaluates/scatters with all
+//            threads (serial walk when there are too many segments).
+// k_group and k_rank never read or write bucket state, so they can run for batch b+1 while batch b is still in k_eval.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -56,7 +60,7 @@ __host__ __device__ inline uint32_t aux_count(unsigned long long w) { return (ui
 __host__ __device__ inline uint32_t aux_epoch(unsigned long long w) { return (uint32_t)(w >> 48); }
 __host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint32_t)((w >> 24) & 0xFFFFFFull); }
 
-struct BatchCtr { uint32_t n_mixed, order_bump, _pad0, _pad1; };
+struct BatchCtr { uint32_t n_mixed, order_bump, n_commit, _pad1; };
 
 enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_MIXED_GROUPS, C_SERIAL, C_COUNT };
 
@@ -75,7 +79,8 @@ struct BatchArgs {
   uint32_t* ent;           // [n] group entry of request i
   uint32_t* meta;          // [n] (shared-memory slot of the fragment << 16) | local rank
   uint32_t* rank;          // [n] rank within the group (repeated keys only)
-  ulonglong2* snap;        // [entries * 6] repeated keys: the slot as k_rank found it (k_eval members all start from this)
+  ulonglong2* commit;      // [entries * 6] repeated keys: final state + slot cursor parked by the run's last rank for k_finish
+  uint32_t* commit_ent;    // [max_batch / 2] entries that have a commit record
   uint32_t* order;         // [max_batch] rank-ordered member indices of non-uniform groups
   uint32_t* mixed_ent;     // [max_batch / 2] entries of non-uniform groups
   BatchCtr* ctr;           // [2], indexed by epoch parity
@@ -173,21 +178,22 @@ __device__ __forceinline__ bool cursor_close(Cursor& cur, Slot* table, uint64_t 
   return false;
 }
 
-// A repeated key's slot as found before the batch touched it, parked in scratch by the group's rank-0 member so that
-// every member of the run starts from the same state while the last rank is already writing the table.
-__device__ __forceinline__ void snap_store(ulonglong2* sp, const Cursor& c) {
+// A repeated key's final state, parked in scratch by the run's last rank: its siblings read the slot during k_eval, so the
+// table itself is only written by k_finish.  `who` = request index of the writer (its response reports a full table).
+__device__ __forceinline__ void snap_store(ulonglong2* sp, const Cursor& c, uint32_t who) {
   __stcg(sp + 0, make_ulonglong2(c.b.key, c.b.tag));
   __stcg(sp + 1, make_ulonglong2((uint64_t)c.b.limit, (uint64_t)c.b.duration));
   __stcg(sp + 2, make_ulonglong2(c.b.rem, (uint64_t)c.b.stamp));
   __stcg(sp + 3, make_ulonglong2((uint64_t)c.b.burst, (uint64_t)c.b.expire));
   __stcg(sp + 4, make_ulonglong2((uint64_t)c.b.flags | ((uint64_t)(c.found ? 1u : 0u) << 32), (uint64_t)c.slot));
-  __stcg(sp + 5, make_ulonglong2(c.home, 0ull));
+  __stcg(sp + 5, make_ulonglong2(c.home, (uint64_t)who));
 }
-__device__ __forceinline__ void snap_load(const ulonglong2* sp, Cursor& c) {
+__device__ __forceinline__ uint32_t snap_load(const ulonglong2* sp, Cursor& c) {
   const ulonglong2 a = __ldcg(sp + 0), b = __ldcg(sp + 1), d = __ldcg(sp + 2), e = __ldcg(sp + 3), f = __ldcg(sp + 4), g = __ldcg(sp + 5);
   c.b.key = a.x; c.b.tag = a.y; c.b.limit = (int64_t)b.x; c.b.duration = (int64_t)b.y; c.b.rem = d.x; c.b.stamp = (int64_t)d.y;
   c.b.burst = (int64_t)e.x; c.b.expire = (int64_t)e.y; c.b.flags = (uint32_t)(f.x & 0xFFFFFFFFull); c.found = (f.x >> 32) != 0;
   c.slot = (int64_t)f.y; c.home = g.x; c.old = c.b;
+  return (uint32_t)g.y;
 }
 
 __device__ __forceinline__ gub_req load_req(const gub_req* p) {
@@ -307,6 +313,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   if (valid) {
     key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
     first = __ldcg(&A.aux[aux_home(A, key)].word);  // consumed much later, by the fragment's first member only
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.table + __umul64hi(key, A.capacity)));  // the slot k_eval will probe
     sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
 #pragma unroll 1
     for (;;) {
@@ -413,17 +420,6 @@ __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t p
   return base;
 }
 
-// One request against its own slot: the path of a key that occurs once in the batch.
-__device__ __forceinline__ void single_eval(const BatchArgs& A, uint32_t i, const gub_req& rq, Tally& t) {
-  Cursor cur;
-  cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
-  Delta d = {0, 0, 0};
-  gub_resp r = apply_one(cur.b, rq, A.clk, d);
-  if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
-  t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-  store_resp(A.out + i, r);
-}
-
 __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
@@ -435,7 +431,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   pdl_release();
   if (i == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
-    nxt->n_mixed = 0; nxt->order_bump = 0;
+    nxt->n_mixed = 0; nxt->order_bump = 0; nxt->n_commit = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
@@ -447,19 +443,8 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
     cnt = aux_count(e.x);
     rep = (uint32_t)(e.y & 0xFFFFFFFFull);
-    if (cnt > 1 && local == 0) {
-      const uint32_t base = fragment_base(A, pos, blockIdx.x);
-      s_base[sp] = base;
-      if (base == 0) {  // I am rank 0 of the run: look the key up once for everybody
-        Cursor cur;
-        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
-        snap_store(A.snap + (size_t)pos * 6, cur);
-      }
-    }
-  }
-  if (valid && cnt == 1) {
-    single_eval(A, i, rq, t);
-    A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+    if (cnt > 1 && local == 0) s_base[sp] = fragment_base(A, pos, blockIdx.x);
+    if (cnt == 1) A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
   }
   __syncthreads();
   if (valid && cnt > 1) {
@@ -478,7 +463,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   tally_flush_block(t, A.counters);
 }
 
-// ---- kernel 3: every member of a uniform run evaluates its own rank ------------------------------------------------
+// ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
 __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
@@ -489,30 +474,34 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
   pdl_release();
   if (i < A.n) {
     const uint32_t pos = A.ent[i];
-    const uint32_t rank = A.rank[i];             // garbage for singletons; unused then
+    uint32_t rank = A.rank[i];                   // garbage for singletons; replaced below
     const AuxEntry* e = &A.aux[pos];
     const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
     const uint32_t cnt = aux_count(ev.x);
-    if (cnt > 1) {
-      const bool mixed = ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
-      if (rank == 0) {  // hand the presence bitmap back clean
-        uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
-        for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
-      }
-      if (mixed) {
-        A.order[__ldcg(&e->gbase) + rank] = i;
-      } else {
-        Cursor cur;
-        snap_load(A.snap + (size_t)pos * 6, cur);  // not the table: the last rank may already be writing it
-        Delta d = {0, 0, 0};
-        gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
-        if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
+    const bool mixed = cnt > 1 && ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
+    if (cnt == 1) rank = 0;
+    if (cnt > 1 && rank == 0) {  // hand the presence bitmap back clean
+      uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
+      for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
+    }
+    if (mixed) {
+      A.order[__ldcg(&e->gbase) + rank] = i;
+    } else {
+      Cursor cur;
+      cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+      Delta d = {0, 0, 0};
+      gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
+      if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
+        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+        if (cnt == 1) {
           if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
-          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+        } else {  // siblings may still be reading the slot: k_finish writes it
+          snap_store(A.commit + (size_t)pos * 6, cur, i);
+          A.commit_ent[atomicAdd(&A.ctr[A.epoch & 1].n_commit, 1u)] = pos;
           dup = 1;
         }
-        store_resp(A.out + i, r);
       }
+      store_resp(A.out + i, r);
     }
   }
   dup = __reduce_add_sync(0xFFFFFFFFu, dup);
@@ -615,19 +604,39 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
   if (tid == 0 && open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
 }
 
-__global__ void __launch_bounds__(MIXED_THREADS, 2) k_mixed(const BatchArgs A) {
+// Blocks [0, mixed_blocks): non-uniform groups, one block each (grid-stride).  The rest: commit records, one thread each.
+__global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A, uint32_t mixed_blocks) {
   __shared__ MixedShared S;
   Tally t = {0, 0, 0, 0, 0};
   pdl_wait();
   pdl_release();
-  const uint32_t n_mixed = A.ctr[A.epoch & 1].n_mixed;
-  for (uint32_t g = blockIdx.x; g < n_mixed; g += gridDim.x) {
-    mixed_group(A, A.mixed_ent[g], S, t);
-    __syncthreads();
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && n_mixed) {
-    atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)n_mixed);
-    atomicAdd(A.counters + C_MIXED_GROUPS, (unsigned long long)n_mixed);
+  const BatchCtr ctr = A.ctr[A.epoch & 1];
+  if (blockIdx.x < mixed_blocks) {
+    for (uint32_t g = blockIdx.x; g < ctr.n_mixed; g += mixed_blocks) {
+      mixed_group(A, A.mixed_ent[g], S, t);
+      __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && ctr.n_mixed) {
+      atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.n_mixed);
+      atomicAdd(A.counters + C_MIXED_GROUPS, (unsigned long long)ctr.n_mixed);
+    }
+  } else {
+    const uint32_t stride = (gridDim.x - mixed_blocks) * blockDim.x;
+    for (uint32_t k = (blockIdx.x - mixed_blocks) * blockDim.x + threadIdx.x; k < ctr.n_commit; k += stride) {
+      Cursor cur;
+      const uint32_t who = snap_load(A.commit + (size_t)A.commit_ent[k] * 6, cur);
+      if (cur.found) {  // existing slot: store the whole 64 bytes (cheaper than re-reading it to find what changed)
+        const Bucket& b = cur.b;
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(A.table + cur.slot);
+        __stcg(p, make_ulonglong2(b.key, (b.tag << 8) | (uint64_t)(b.flags & 0xFF)));
+        __stcg(p + 1, make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration));
+        __stcg(p + 2, make_ulonglong2(b.rem, (uint64_t)b.stamp));
+        __stcg(p + 3, make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire));
+      } else if (!cursor_close(cur, A.table, A.capacity, t.inserts)) {
+        store_resp(A.out + who, mk_err(GUB_ERR_TABLE_FULL));
+        t.full++;
+      }
+    }
   }
   tally_flush_block(t, A.counters);
 }

@@ -226,7 +226,7 @@ class Table:
         ms = np.zeros(4, dtype=np.float64)
         n = C.c_uint64(0)
         _check(lib().gub_get_profile(self._h, ms.ctypes.data, C.byref(n), 1 if reset else 0), "gub_get_profile")
-        return dict(k_group_ms=float(ms[0]), k_rank_ms=float(ms[1]), k_eval_ms=float(ms[2]), k_mixed_ms=float(ms[3]), launches=int(n.value))
+        return dict(k_group_ms=float(ms[0]), k_rank_ms=float(ms[1]), k_eval_ms=float(ms[2]), k_finish_ms=float(ms[3]), launches=int(n.value))
 
     # ---- multi-GPU routing
     def route_device(self, ring, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream=0):

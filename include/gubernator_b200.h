@@ -169,7 +169,7 @@ int gub_size(gub_table* t, size_t* n_out);
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
 
-/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_rank / k_eval / k_mixed), the
+/* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_rank / k_eval / k_finish), the
  * measurement counterpart of the reference's metricFuncTimeDuration summaries (gubernator.go:65-73).  Off by default. */
 int gub_set_profiling(gub_table* t, int on);
 int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int reset);
