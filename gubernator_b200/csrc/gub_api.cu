@@ -51,16 +51,25 @@ struct gub_table {
   gub::Slot* table = nullptr;
   uint64_t capacity = 0;
   uint32_t max_batch = 0;
-  // per-batch scratch
-  gub::AuxEntry* aux = nullptr; uint32_t aux_entries = 0;
-  uint32_t *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *presence = nullptr;
-  uint8_t* fragsize = nullptr;
-  ulonglong2* commit = nullptr;
-  uint32_t* commit_ent = nullptr;
-  uint32_t pres_words = 0, max_blocks = 0;
-  gub::BatchCtr* ctr = nullptr;
+  // per-batch scratch, two sets: k_group/k_rank of batch b+1 (prep stream) overlap k_eval/k_finish of batch b
+  struct Scratch {
+    gub::AuxEntry* aux = nullptr;
+    uint32_t *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *presence = nullptr;
+    uint8_t* fragsize = nullptr;
+    ulonglong2* commit = nullptr;
+    uint32_t* commit_ent = nullptr;
+    gub::BatchCtr* ctr = nullptr;
+    uint32_t epoch = 0;
+    cudaEvent_t prep_done = nullptr;   // stage 1 (k_group, k_rank) finished on the prep stream
+    cudaEvent_t eval_done = nullptr;   // stage 2 (k_eval, k_finish) finished: the set may be reused
+    bool used = false;
+  } scr[2];
+  uint32_t next_set = 0;
+  uint32_t aux_entries = 0, pres_words = 0, max_blocks = 0;
   unsigned long long* counters = nullptr;
-  uint32_t epoch = 0;
+  cudaStream_t s_prep = nullptr;
+  cudaEvent_t inputs_ready = nullptr;
+  bool overlap = true;                // GUB_OVERLAP=0: everything on the caller's stream
   // ordering between streams that touch the shared scratch
   cudaEvent_t last_done = nullptr;
   bool have_last = false;
@@ -112,17 +121,43 @@ cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cuda
   return cudaLaunchKernelEx(&cfg, kernel, A);
 }
 
+int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_t st) {
+  // commit records (one thread each, at most n/2) + non-uniform groups (one block each, grid-stride; normally none)
+  const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
+  const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (n / 2 + gub::MIXED_THREADS - 1) / gub::MIXED_THREADS));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(mixed_blocks + commit_blocks); cfg.blockDim = dim3(gub::MIXED_THREADS); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, gub::k_finish, A, mixed_blocks));
+  return 0;
+}
+
+// One batch (<= max_batch requests).  Stage 1 (k_group, k_rank) never touches bucket state, so it runs on the prep
+// stream and overlaps stage 2 (k_eval, k_finish) of the previous batch, which runs on the caller's stream.
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
-  if (t->epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
-    CK(cudaMemsetAsync(t->aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), st));
-    t->epoch = 0;
+  const bool overlap = t->overlap && !t->prof;
+  gub_table::Scratch& sc = t->scr[t->next_set];
+  t->next_set ^= 1u;
+  cudaStream_t sp = overlap ? t->s_prep : st;
+  if (overlap) {
+    CK(cudaEventRecord(t->inputs_ready, st));          // whatever produced d_reqs on the caller's stream
+    CK(cudaStreamWaitEvent(sp, t->inputs_ready, 0));
+    if (sc.used) CK(cudaStreamWaitEvent(sp, sc.eval_done, 0));  // the batch that last used this scratch set is done with it
   }
-  t->epoch++;
+  if (sc.epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
+    CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), sp));
+    sc.epoch = 0;
+  }
+  sc.epoch++;
   gub::BatchArgs A;
-  A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = t->epoch;
-  A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
-  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank; A.commit = t->commit; A.commit_ent = t->commit_ent;
-  A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr; A.counters = t->counters;
+  A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = sc.epoch;
+  A.aux = sc.aux; A.aux_mask = t->aux_entries - 1; A.presence = sc.presence; A.fragsize = sc.fragsize;
+  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = sc.ent; A.meta = sc.meta; A.rank = sc.rank;
+  A.commit = sc.commit; A.commit_ent = sc.commit_ent; A.order = sc.order; A.mixed_ent = sc.mixed_ent; A.ctr = sc.ctr;
+  A.counters = t->counters;
   A.clk = *clk;
   const uint32_t blocks = (n + 255) / 256;
   cudaEvent_t* pe = nullptr;
@@ -135,25 +170,19 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
     t->prof_pending++;
     CK(cudaEventRecord(pe[0], st));
   }
-  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, st, A));
+  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, sp, A));
   if (pe) CK(cudaEventRecord(pe[1], st));
-  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, st, A));
+  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, sp, A));
   if (pe) CK(cudaEventRecord(pe[2], st));
+  if (overlap) {
+    CK(cudaEventRecord(sc.prep_done, sp));
+    CK(cudaStreamWaitEvent(st, sc.prep_done, 0));
+  }
   CK(launch_k(t, gub::k_eval, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[3], st));
-  // commit records (one thread each, at most n/2) + non-uniform groups (one block each, grid-stride; normally none)
-  {
-    const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
-    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (n / 2 + gub::MIXED_THREADS - 1) / gub::MIXED_THREADS));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(mixed_blocks + commit_blocks); cfg.blockDim = dim3(gub::MIXED_THREADS); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
-    CK(cudaLaunchKernelEx(&cfg, gub::k_finish, A, mixed_blocks));
-  }
+  if (launch_finish(t, A, n, st)) return -1;
   if (pe) CK(cudaEventRecord(pe[4], st));
+  if (overlap) { CK(cudaEventRecord(sc.eval_done, st)); sc.used = true; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -216,9 +245,16 @@ void gub_destroy(gub_table* t) {
   if (!t) return;
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
-  void* ptrs[] = {t->table, t->aux, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->presence, t->fragsize, t->commit, t->commit_ent, t->ctr, t->counters,
-                  t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
+  void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& sc : t->scr) {
+    void* sp[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.commit_ent, sc.ctr};
+    for (void* p : sp) if (p) cudaFree(p);
+    if (sc.prep_done) cudaEventDestroy(sc.prep_done);
+    if (sc.eval_done) cudaEventDestroy(sc.eval_done);
+  }
+  if (t->s_prep) cudaStreamDestroy(t->s_prep);
+  if (t->inputs_ready) cudaEventDestroy(t->inputs_ready);
   for (auto& s : t->pipe) {
     if (s.d_req) cudaFree(s.d_req);
     if (s.d_resp) cudaFree(s.d_resp);
@@ -268,20 +304,29 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     cudaMemset((ptr), 0, (bytes));                                           \
   } while (0)
   ALLOC(t->table, t->capacity * sizeof(gub::Slot));
-  ALLOC(t->aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
-  ALLOC(t->presence, (size_t)t->aux_entries * t->pres_words * 4);
-  ALLOC(t->fragsize, (size_t)t->aux_entries * t->max_blocks);
-  ALLOC(t->commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
-  ALLOC(t->commit_ent, ((size_t)B / 2 + 1) * 4);
-  ALLOC(t->ent, (size_t)B * 4);
-  ALLOC(t->meta, (size_t)B * 4);
-  ALLOC(t->rank, (size_t)B * 4);
-  ALLOC(t->order, (size_t)B * 4);
-  ALLOC(t->mixed_ent, ((size_t)B / 2 + 1) * 4);
-  ALLOC(t->ctr, 2 * sizeof(gub::BatchCtr));
+  for (auto& sc : t->scr) {
+    ALLOC(sc.aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
+    ALLOC(sc.presence, (size_t)t->aux_entries * t->pres_words * 4);
+    ALLOC(sc.fragsize, (size_t)t->aux_entries * t->max_blocks);
+    ALLOC(sc.commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
+    ALLOC(sc.commit_ent, ((size_t)B / 2 + 1) * 4);
+    ALLOC(sc.ent, (size_t)B * 4);
+    ALLOC(sc.meta, (size_t)B * 4);
+    ALLOC(sc.rank, (size_t)B * 4);
+    ALLOC(sc.order, (size_t)B * 4);
+    ALLOC(sc.mixed_ent, ((size_t)B / 2 + 1) * 4);
+    ALLOC(sc.ctr, 2 * sizeof(gub::BatchCtr));
+  }
   ALLOC(t->counters, gub::C_COUNT * sizeof(unsigned long long));
   ALLOC(t->d_scalar, 4 * sizeof(unsigned long long));
 #undef ALLOC
+  CK(cudaStreamCreateWithFlags(&t->s_prep, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&t->inputs_ready, cudaEventDisableTiming));
+  for (auto& sc : t->scr) {
+    CK(cudaEventCreateWithFlags(&sc.prep_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sc.eval_done, cudaEventDisableTiming));
+  }
+  if (const char* e = getenv("GUB_OVERLAP")) t->overlap = std::atoi(e) != 0;
   CK(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&t->s_compute, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
