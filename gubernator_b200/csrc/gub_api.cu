@@ -15,6 +15,7 @@
 
 #include "../../include/gubernator_b200.h"
 #include "gub_kernels.cuh"
+#include "gub_global.cuh"
 
 extern "C" uint64_t gub_ring_version_(const gub_ring* r);
 
@@ -559,8 +560,8 @@ static int ensure_ring(gub_table* t, const gub_ring* ring) {
   return 0;
 }
 
-int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs, uint32_t* d_perm,
-                     uint32_t* d_counts, void* stream) {
+static int route_impl(gub_table* t, const gub_ring* ring, int32_t self, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs, uint32_t* d_perm,
+                      uint32_t* d_counts, uint8_t* d_true_owner, void* stream) {
   if (!t || !ring || !d_counts || (n && (!d_reqs || !d_out_reqs || !d_perm))) return fail("gub_route_device: null argument");
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
@@ -574,10 +575,153 @@ int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, 
   const size_t tc = (size_t)ntiles * gub::MAX_SHARDS;
   if (!t->d_tile_counts || t->tiles_cap < tc) { if (t->d_tile_counts) { CK(cudaDeviceSynchronize()); cudaFree(t->d_tile_counts); } CK(cudaMalloc(&t->d_tile_counts, tc * 4)); t->tiles_cap = tc; }
   gub::k_route_count<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, nshards, t->d_owner,
-                                            t->d_tile_counts, ntiles);
+                                            t->d_tile_counts, ntiles, self, d_true_owner);
   gub::k_route_scan<<<1, 1024, 0, st>>>(t->d_tile_counts, nshards * ntiles, nshards, ntiles, d_counts);
   gub::k_route_scatter<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_owner, t->d_tile_counts, ntiles, nshards, d_out_reqs, d_perm);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs, uint32_t* d_perm,
+                     uint32_t* d_counts, void* stream) {
+  return route_impl(t, ring, -1, d_reqs, n, d_out_reqs, d_perm, d_counts, nullptr, stream);
+}
+
+int gub_route_global_device(gub_table* t, const gub_ring* ring, uint32_t self, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs,
+                            uint32_t* d_perm, uint32_t* d_counts, uint8_t* d_owner_out, void* stream) {
+  if (ring && self >= (uint32_t)gub_ring_size(ring)) return fail("gub_route_global_device: self is not a shard of the ring");
+  return route_impl(t, ring, (int32_t)self, d_reqs, n, d_out_reqs, d_perm, d_counts, d_owner_out, stream);
+}
+
+__global__ void k_owner_only(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32_t* peers, uint32_t npts, uint8_t* owner) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) owner[i] = (uint8_t)gub::ring_owner(pts, peers, npts, __ldg(&reqs[i].key_fnv1));
+}
+
+int gub_route_owner_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, uint8_t* d_owner, void* stream) {
+  if (!t || !ring || (n && (!d_reqs || !d_owner))) return fail("gub_route_owner_device: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  if (ensure_ring(t, ring)) return -1;
+  k_owner_only<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, d_owner);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- GLOBAL behaviour: device queues ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct gub_gq {
+  int device = 0;
+  gub::Gq q{};
+  uint32_t* slot_of = nullptr;
+  size_t slot_cap = 0;
+};
+
+extern "C" {
+
+int gub_gq_create(int device, uint32_t capacity, int keep_latest, gub_gq** out) {
+  if (!out || capacity < 64) return fail("gub_gq_create: bad argument");
+  CK(cudaSetDevice(device));
+  gub_gq* g = new gub_gq();
+  g->device = device;
+  const uint32_t cap = next_pow2(capacity);
+  g->q.capacity_mask = cap - 1;
+  g->q.mode = keep_latest ? gub::GQ_KEEP_LAST : gub::GQ_KEEP_FIRST;
+  cudaError_t e = cudaMalloc(&g->q.slots, (size_t)cap * sizeof(gub_req));
+  if (e == cudaSuccess) e = cudaMalloc(&g->q.seq, (size_t)cap * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&g->q.count, 8);
+  if (e == cudaSuccess) e = cudaMemset(g->q.slots, 0, (size_t)cap * sizeof(gub_req));
+  if (e == cudaSuccess) e = cudaMemset(g->q.seq, 0, (size_t)cap * 8);
+  if (e == cudaSuccess) e = cudaMemset(g->q.count, 0, 8);
+  if (e != cudaSuccess) { gub_gq_destroy(g); return fail(std::string("gub_gq_create: ") + cudaGetErrorString(e)); }
+  *out = g;
+  return 0;
+}
+
+void gub_gq_destroy(gub_gq* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  if (g->q.slots) cudaFree(g->q.slots);
+  if (g->q.seq) cudaFree(g->q.seq);
+  if (g->q.count) cudaFree(g->q.count);
+  if (g->slot_of) cudaFree(g->slot_of);
+  delete g;
+}
+
+int gub_gq_accumulate_device(gub_gq* g, const gub_req* d_reqs, size_t n, const uint8_t* d_owner, uint32_t self, uint64_t seq_base, void* stream) {
+  if (!g || (n && !d_reqs)) return fail("gub_gq_accumulate_device: null argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g->slot_cap < n) {
+    CK(cudaStreamSynchronize(st));
+    if (g->slot_of) cudaFree(g->slot_of);
+    g->slot_of = nullptr;
+    CK(cudaMalloc(&g->slot_of, n * 4));
+    g->slot_cap = n;
+  }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  gub::k_gq_claim<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, d_owner, self, d_owner ? 1u : 0u, (unsigned long long)seq_base, g->slot_of);
+  gub::k_gq_fill<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, (unsigned long long)seq_base, g->slot_of);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gub_gq_drain_device(gub_gq* g, gub_req* d_out, size_t cap, uint32_t* d_count, int as_status_query, void* stream) {
+  if (!g || !d_count || (cap && !d_out)) return fail("gub_gq_drain_device: null argument");
+  CK(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_count, 0, 4, st));
+  gub::k_gq_drain<<<148, 256, 0, st>>>(g->q, d_out, (uint32_t)std::min<size_t>(cap, 0xFFFFFFFFu), d_count, as_status_query ? 1u : 0u);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int gub_make_updates_device(gub_table* t, const gub_req* d_queries, const gub_resp* d_resps, size_t n, gub_item* d_items, uint32_t* d_count,
+                            void* stream) {
+  if (!t || !d_count || (n && (!d_queries || !d_resps || !d_items))) return fail("gub_make_updates_device: null argument");
+  CK(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_count, 0, 4, st));
+  if (n == 0) return 0;
+  gub::k_make_updates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_queries, d_resps, (uint32_t)n, d_items, d_count);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void k_add_items_pub(gub::Slot* table, uint64_t cap, const gub_item* items, uint32_t n, int64_t now_ms, unsigned long long* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const gub_item it = items[i];
+  if (it.algorithm != GUB_TOKEN_BUCKET && it.algorithm != GUB_LEAKY_BUCKET) return;
+  gub::Cursor cur;
+  const uint64_t key = gub::remap_key(it.key_xxh64), tag = it.key_fnv1 >> 8;
+  gub::cursor_open(cur, table, cap, key, tag);
+  const bool leaky = it.algorithm == GUB_LEAKY_BUCKET;
+  cur.b.key = key; cur.b.tag = tag;
+  cur.b.flags = gub::F_LIVE | (leaky ? gub::F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? gub::F_OVER : 0u);
+  cur.b.limit = it.limit; cur.b.duration = it.duration;
+  cur.b.rem = leaky ? gub::f2bits(it.remaining_f) : (uint64_t)it.remaining;
+  cur.b.stamp = now_ms; cur.b.burst = leaky ? it.burst : 0; cur.b.expire = it.expire_at;
+  uint32_t ins = 0;
+  if (!gub::cursor_close(cur, table, cap, ins)) atomicAdd(counters + gub::C_FULL, 1ull);
+  if (ins) atomicAdd(counters + gub::C_INSERTS, (unsigned long long)ins);
+}
+
+int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_t now_ms, void* stream) {
+  if (!t || (n && !d_items)) return fail("gub_add_items_device: null argument");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (t->have_last) CK(cudaStreamWaitEvent(st, t->last_done, 0));
+  k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(t->last_done, st));
+  t->have_last = true;
   return 0;
 }
 

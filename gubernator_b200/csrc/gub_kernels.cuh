@@ -719,8 +719,12 @@ __device__ __forceinline__ uint32_t ring_owner(const uint64_t* pts, const int32_
   return (uint32_t)peers[lo];
 }
 
+// `self` >= 0 turns on GLOBAL handling (gubernator.go:257-269): a GLOBAL request this shard does not own is not forwarded
+// but answered from the local replica, so its destination is `self` (bit 7 of dest[] marks it for the scatter to rewrite
+// its behaviour bits).  true_owner (optional) always receives the ring owner.
 __global__ void __launch_bounds__(256) k_route_count(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32_t* peers, uint32_t npts,
-                                                     uint32_t nshards, uint8_t* owner, uint32_t* tile_counts /* [nshards][ntiles] */, uint32_t ntiles) {
+                                                     uint32_t nshards, uint8_t* owner, uint32_t* tile_counts /* [nshards][ntiles] */, uint32_t ntiles,
+                                                     int32_t self, uint8_t* true_owner) {
   __shared__ uint32_t cnt[MAX_SHARDS];
   if (threadIdx.x < MAX_SHARDS) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -728,8 +732,11 @@ __global__ void __launch_bounds__(256) k_route_count(const gub_req* reqs, uint32
   for (uint32_t k = threadIdx.x; k < ROUTE_TILE; k += blockDim.x) {
     const uint32_t i = base + k;
     if (i < n) {
-      const uint32_t o = ring_owner(pts, peers, npts, __ldg(&reqs[i].key_fnv1));
-      owner[i] = (uint8_t)o;
+      uint32_t o = ring_owner(pts, peers, npts, __ldg(&reqs[i].key_fnv1));
+      if (true_owner) true_owner[i] = (uint8_t)o;
+      uint32_t mark = 0;
+      if (self >= 0 && o != (uint32_t)self && (__ldg(&reqs[i].behavior) & GUB_BEHAVIOR_GLOBAL)) { o = (uint32_t)self; mark = 0x80u; }
+      owner[i] = (uint8_t)(o | mark);
       atomicAdd(&cnt[o], 1u);
     }
   }
@@ -780,7 +787,8 @@ __global__ void __launch_bounds__(256) k_route_scatter(const gub_req* reqs, uint
       if (w == warp) {
         const uint32_t i = base + chunk + threadIdx.x;
         const bool valid = i < n;
-        const uint32_t o = valid ? owner[i] : 0xFFu;
+        const uint32_t oraw = valid ? owner[i] : 0xFFu;
+        const uint32_t o = valid ? (oraw & 0x7Fu) : 0xFFu;
         const uint32_t peers_mask = __match_any_sync(0xFFFFFFFFu, o);
         const uint32_t rank = __popc(peers_mask & ((1u << lane) - 1u));
         const uint32_t leader = __ffs(peers_mask) - 1;
@@ -791,7 +799,13 @@ __global__ void __launch_bounds__(256) k_route_scatter(const gub_req* reqs, uint
           const uint32_t dst = start + rank;
           const ulonglong2* src = reinterpret_cast<const ulonglong2*>(reqs + i);
           ulonglong2* d2 = reinterpret_cast<ulonglong2*>(out_reqs + dst);
-          d2[0] = __ldg(src); d2[1] = __ldg(src + 1); d2[2] = __ldg(src + 2); d2[3] = __ldg(src + 3);
+          ulonglong2 last = __ldg(src + 3);
+          if (oraw & 0x80u) {  // GLOBAL on a non-owner: clone with NO_BATCHING set, GLOBAL cleared, IsOwner = false (gubernator.go:408-411)
+            uint32_t beh = (uint32_t)(last.y >> 32);
+            beh = (beh | (uint32_t)GUB_BEHAVIOR_NO_BATCHING) & ~(uint32_t)(GUB_BEHAVIOR_GLOBAL | GUB_REQ_IS_OWNER);
+            last.y = (last.y & 0xFFFFFFFFull) | ((unsigned long long)beh << 32);
+          }
+          d2[0] = __ldg(src); d2[1] = __ldg(src + 1); d2[2] = __ldg(src + 2); d2[3] = last;
           perm[dst] = i;
         }
       }

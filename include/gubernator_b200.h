@@ -202,6 +202,36 @@ int gub_route_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, 
 int gub_unroute_device(gub_table* t, const gub_resp* d_resp_in, const uint32_t* d_perm, size_t n, gub_resp* d_resp_out,
                        void* stream);
 
+/* ---- GLOBAL behaviour (global.go:30-283, gubernator.go:395-459): per-shard queues on the device -------------------
+ * A gub_gq accumulates GLOBAL requests between sync ticks, keyed by the request's XXH64:
+ *   mode 0 (hits queue,    runAsyncHits  global.go:91):  keeps the FIRST request per key, Hits summed, RESET_REMAINING OR-ed;
+ *   mode 1 (update queue,  runBroadcasts global.go:193): keeps the LATEST request per key.
+ * All pointers are device pointers on the queue's GPU; work is enqueued on `stream`. */
+typedef struct gub_gq gub_gq;
+int gub_gq_create(int device, uint32_t capacity, int keep_latest, gub_gq** out);
+void gub_gq_destroy(gub_gq* q);
+/* Feeds the queue from one batch.  d_owner: per-request owning shard (uint8, e.g. from gub_route_device's scratch via
+ * gub_route_owner_device) or NULL.  With d_owner: select GLOBAL requests with Hits != 0 whose owner != self (a non-owner
+ * queues its hits, gubernator.go:402-404).  Without: select every GLOBAL request with Hits != 0 (what an owner has just
+ * evaluated still carries GLOBAL, gubernator.go:604-606).  `seq_base` orders requests across calls (first / latest). */
+int gub_gq_accumulate_device(gub_gq* q, const gub_req* d_reqs, size_t n, const uint8_t* d_owner, uint32_t self,
+                             uint64_t seq_base, void* stream);
+/* Drains the queue into request records and clears it: as_status_query = 0 -> hit requests for the owner (Hits = window
+ * sum, DRAIN_OVER_LIMIT | IS_OWNER set, gubernator.go:510-512); 1 -> Hits = 0 status queries, IsOwner = false
+ * (global.go:238-245).  *d_count (device uint32) receives the number of records (<= cap are written). */
+int gub_gq_drain_device(gub_gq* q, gub_req* d_out, size_t cap, uint32_t* d_count, int as_status_query, void* stream);
+/* Owner side of broadcastPeers (global.go:234-258): status-query requests + their responses -> UpdatePeerGlobal items. */
+int gub_make_updates_device(gub_table* t, const gub_req* d_queries, const gub_resp* d_resps, size_t n, gub_item* d_items,
+                            uint32_t* d_count, void* stream);
+/* Peer side: UpdatePeerGlobals (gubernator.go:425-459) for a device-resident array of items; CreatedAt/UpdatedAt = now_ms. */
+int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_t now_ms, void* stream);
+/* Owning shard of every request of a batch (uint8 per request), by the ring (replicated_hash.go:104-119). */
+int gub_route_owner_device(gub_table* t, const gub_ring* ring, const gub_req* d_reqs, size_t n, uint8_t* d_owner, void* stream);
+/* gub_route_device variant for GLOBAL traffic: GLOBAL requests this shard does not own stay here and are evaluated
+ * against the local replica with GLOBAL cleared, NO_BATCHING set and IsOwner = false (gubernator.go:259-269,408-411). */
+int gub_route_global_device(gub_table* t, const gub_ring* ring, uint32_t self, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs,
+                            uint32_t* d_perm, uint32_t* d_counts, uint8_t* d_owner_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
