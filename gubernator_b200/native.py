@@ -28,7 +28,9 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
            "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys",
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
-           "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device"]
+           "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
+           "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
+           "gub_route_owner_device", "gub_route_global_device"]
 
 
 class Config(C.Structure):
@@ -81,6 +83,14 @@ def lib():
         L.gub_ring_points.argtypes = [vp, vp, vp, sz]; L.gub_ring_points.restype = sz
         L.gub_route_device.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.gub_unroute_device.argtypes = [vp, vp, vp, sz, vp, vp]
+        L.gub_gq_create.argtypes = [i32, C.c_uint32, i32, C.POINTER(vp)]
+        L.gub_gq_destroy.argtypes = [vp]; L.gub_gq_destroy.restype = None
+        L.gub_gq_accumulate_device.argtypes = [vp, vp, sz, vp, C.c_uint32, u64, vp]
+        L.gub_gq_drain_device.argtypes = [vp, vp, sz, vp, i32, vp]
+        L.gub_make_updates_device.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+        L.gub_add_items_device.argtypes = [vp, vp, sz, i64, vp]
+        L.gub_route_owner_device.argtypes = [vp, vp, vp, sz, vp, vp]
+        L.gub_route_global_device.argtypes = [vp, vp, C.c_uint32, vp, sz, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -232,8 +242,47 @@ class Table:
     def route_device(self, ring, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream=0):
         _check(lib().gub_route_device(self._h, ring._r, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, stream), "gub_route_device")
 
+    def route_global_device(self, ring, self_index, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, d_owner_ptr, stream=0):
+        _check(lib().gub_route_global_device(self._h, ring._r, self_index, d_reqs_ptr, n, d_out_reqs_ptr, d_perm_ptr, d_counts_ptr, d_owner_ptr,
+                                             stream), "gub_route_global_device")
+
+    def route_owner_device(self, ring, d_reqs_ptr, n, d_owner_ptr, stream=0):
+        _check(lib().gub_route_owner_device(self._h, ring._r, d_reqs_ptr, n, d_owner_ptr, stream), "gub_route_owner_device")
+
+    def make_updates_device(self, d_queries_ptr, d_resps_ptr, n, d_items_ptr, d_count_ptr, stream=0):
+        _check(lib().gub_make_updates_device(self._h, d_queries_ptr, d_resps_ptr, n, d_items_ptr, d_count_ptr, stream), "gub_make_updates_device")
+
+    def add_items_device(self, d_items_ptr, n, now_ms, stream=0):
+        _check(lib().gub_add_items_device(self._h, d_items_ptr, n, int(now_ms), stream), "gub_add_items_device")
+
     def unroute_device(self, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream=0):
         _check(lib().gub_unroute_device(self._h, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream), "gub_unroute_device")
+
+
+class GlobalQueue:
+    """Device-side hits / updates queue of the GLOBAL manager (global.go:91-231)."""
+
+    def __init__(self, device=0, capacity=1 << 16, keep_latest=False):
+        h = C.c_void_p()
+        _check(lib().gub_gq_create(int(device), int(capacity), 1 if keep_latest else 0, C.byref(h)), "gub_gq_create")
+        self._h = h
+
+    def accumulate_device(self, d_reqs_ptr, n, d_owner_ptr, self_index, seq_base, stream=0):
+        _check(lib().gub_gq_accumulate_device(self._h, d_reqs_ptr, n, d_owner_ptr, self_index, int(seq_base), stream), "gub_gq_accumulate_device")
+
+    def drain_device(self, d_out_ptr, cap, d_count_ptr, as_status_query, stream=0):
+        _check(lib().gub_gq_drain_device(self._h, d_out_ptr, cap, d_count_ptr, 1 if as_status_query else 0, stream), "gub_gq_drain_device")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gub_gq_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Ring:

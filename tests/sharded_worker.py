@@ -44,6 +44,9 @@ class CpuBackend:
     def empty_like(self, t):
         return torch.empty_like(t)
 
+    def two_lists(self, a, b):
+        return [int(x) for x in a.tolist()], [int(x) for x in b.tolist()]
+
     def req_buffer(self, m):
         return torch.empty((m, 64), dtype=torch.uint8)
 
