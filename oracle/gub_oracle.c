@@ -754,6 +754,38 @@ void gubo_submit_hashed(gubo_pool* p, const gubo_hreq* reqs, size_t n, gubo_hres
     apply_hashed(p, gubo_pool_worker_index_for_hash63(p, reqs[i].key_xxh64 >> 1), &reqs[i], &out[i]);
 }
 
+/* Pre-hashed variants: the cache key is the 16 raw bytes (xxh64, fnv1) and the worker comes from the XXH64 itself, exactly
+ * like gubo_submit_hashed, so items added here are the ones later requests see. */
+static int hashed_widx(const gubo_pool* p, uint64_t kx) { return gubo_pool_worker_index_for_hash63(p, kx >> 1); }
+void gubo_pool_add_item_hashed(gubo_pool* p, uint64_t kx, uint64_t kf, const gubo_item* item) {
+  uint64_t key[2] = {kx, kf};
+  lru_add(&p->caches[hashed_widx(p, kx)], (const char*)key, 16, gubo_xxh64(key, 16, 0x9E3779B97F4A7C15ULL), item);
+}
+int gubo_pool_get_item_hashed(gubo_pool* p, uint64_t kx, uint64_t kf, gubo_item* out) {
+  uint64_t key[2] = {kx, kf};
+  node* n = lru_get_item(&p->caches[hashed_widx(p, kx)], (const char*)key, 16, gubo_xxh64(key, 16, 0x9E3779B97F4A7C15ULL));
+  if (!n) return 0;
+  *out = n->item;
+  return 1;
+}
+/* gubernator.go:425-459 for a pre-hashed key */
+void gubo_pool_update_peer_global_hashed(gubo_pool* p, uint64_t kx, uint64_t kf, int32_t algorithm, int64_t duration, int32_t status,
+                                         int64_t limit, int64_t remaining, int64_t reset_time) {
+  int64_t now = p->now_ms;
+  gubo_item it;
+  memset(&it, 0, sizeof it);
+  it.expire_at = reset_time; it.algorithm = algorithm;
+  switch (algorithm) {
+    case GUBO_LEAKY_BUCKET:
+      it.value_kind = 2; it.remaining_f = go_i2f(remaining); it.limit = limit; it.duration = duration; it.burst = limit; it.stamp = now;
+      break;
+    case GUBO_TOKEN_BUCKET:
+      it.value_kind = 1; it.status = status; it.limit = limit; it.duration = duration; it.remaining_i = remaining; it.stamp = now;
+      break;
+  }
+  gubo_pool_add_item_hashed(p, kx, kf, &it);
+}
+
 size_t gubo_pool_each(gubo_pool* p, gubo_item* items, uint64_t* kx, uint64_t* kf, size_t cap) {
   size_t k = 0;
   for (int w = 0; w < p->workers; w++)

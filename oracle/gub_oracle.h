@@ -126,6 +126,11 @@ int gubo_pool_get_item(gubo_pool*, const char* key, size_t klen, gubo_item* out)
 /* UpdatePeerGlobals item construction (gubernator.go:425-459) then AddCacheItem */
 void gubo_pool_update_peer_global(gubo_pool*, const char* key, size_t klen, int32_t algorithm, int64_t duration,
                                   int32_t status, int64_t limit, int64_t remaining, int64_t reset_time);
+/* pre-hashed keys (worker chosen from the XXH64 like gubo_submit_hashed) */
+void gubo_pool_add_item_hashed(gubo_pool*, uint64_t key_xxh64, uint64_t key_fnv1, const gubo_item* item);
+int gubo_pool_get_item_hashed(gubo_pool*, uint64_t key_xxh64, uint64_t key_fnv1, gubo_item* out);
+void gubo_pool_update_peer_global_hashed(gubo_pool*, uint64_t key_xxh64, uint64_t key_fnv1, int32_t algorithm, int64_t duration,
+                                         int32_t status, int64_t limit, int64_t remaining, int64_t reset_time);
 int64_t gubo_pool_size(const gubo_pool*);
 /* counters mirroring metricOverLimitCounter (gubernator.go:74), metricCacheAccess hit/miss (lrucache.go:52),
  * metricCacheUnexpiredEvictions (lrucache.go:56) */

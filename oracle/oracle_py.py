@@ -75,6 +75,9 @@ def lib():
         L.gubo_pool_add_item.argtypes = [vp, C.c_char_p, sz, C.POINTER(Item)]
         L.gubo_pool_get_item.argtypes = [vp, C.c_char_p, sz, C.POINTER(Item)]
         L.gubo_pool_update_peer_global.argtypes = [vp, C.c_char_p, sz, C.c_int32, i64, C.c_int32, i64, i64, i64]
+        L.gubo_pool_add_item_hashed.argtypes = [vp, u64, u64, C.POINTER(Item)]
+        L.gubo_pool_get_item_hashed.argtypes = [vp, u64, u64, C.POINTER(Item)]
+        L.gubo_pool_update_peer_global_hashed.argtypes = [vp, u64, u64, C.c_int32, i64, C.c_int32, i64, i64, i64]
         L.gubo_pool_size.restype = i64; L.gubo_pool_size.argtypes = [vp]
         L.gubo_pool_counters.argtypes = [vp, C.POINTER(i64)]
         L.gubo_pool_each.restype = sz; L.gubo_pool_each.argtypes = [vp, C.POINTER(Item), vp, vp, sz]
@@ -190,6 +193,17 @@ class Pool:
 
     def update_peer_global(self, key: bytes, algorithm, duration, status, limit, remaining, reset_time):
         lib().gubo_pool_update_peer_global(self._p, key, len(key), algorithm, duration, status, limit, remaining, reset_time)
+
+    def add_item_hashed(self, kx, kf, item: Item):
+        lib().gubo_pool_add_item_hashed(self._p, int(kx), int(kf), C.byref(item))
+
+    def get_item_hashed(self, kx, kf):
+        it = Item()
+        ok = lib().gubo_pool_get_item_hashed(self._p, int(kx), int(kf), C.byref(it))
+        return it if ok else None
+
+    def update_peer_global_hashed(self, kx, kf, algorithm, duration, status, limit, remaining, reset_time):
+        lib().gubo_pool_update_peer_global_hashed(self._p, int(kx), int(kf), algorithm, duration, status, limit, remaining, reset_time)
 
     def size(self):
         return lib().gubo_pool_size(self._p)

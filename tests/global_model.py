@@ -92,9 +92,8 @@ class OracleCluster:
                 st = self.pools[g].submit_hashed(q)[0]
                 if int(st["err_code"]) != 0 or int(rec["algorithm"]) > 1:
                     continue
-                key = np.array([kx, kf], dtype=np.uint64).tobytes()
                 for p in range(W):
                     if p != g:
                         self.pools[p].set_now(now_ms)
-                        self.pools[p].update_peer_global(key, int(rec["algorithm"]), int(rec["duration"]), int(st["status"]), int(st["limit"]),
+                        self.pools[p].update_peer_global_hashed(kx, kf, int(rec["algorithm"]), int(rec["duration"]), int(st["status"]), int(st["limit"]),
                                                          int(st["remaining"]), int(st["reset_time"]))

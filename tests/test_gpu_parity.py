@@ -263,8 +263,7 @@ def test_add_get_scan_items(G):
         it.expire_at = int(items["expire_at"][i]); it.status = int(items["status"][i]) if not leaky[i] else 0
         it.limit = 777 if i < 10 else int(items["limit"][i]); it.duration = 60000; it.remaining_i = int(items["remaining"][i])
         it.remaining_f = float(items["remaining_f"][i]); it.stamp = T0; it.burst = int(items["burst"][i]) if leaky[i] else 0
-        key = np.array([xx[i], fv[i]], dtype=np.uint64).tobytes()
-        pool.add_item(key, it)
+        pool.add_item_hashed(xx[i], fv[i], it)
     reqs = np.zeros(n, dtype=G.REQ_DTYPE)
     reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
     reqs["hits"] = 2; reqs["limit"] = items["limit"]; reqs["limit"][:10] = 777; reqs["duration"] = 60000

@@ -254,3 +254,15 @@ def test_go_float_to_int_conversion_edges():
     assert r["status"] == 1 and r["remaining"] == 0
     # ResetTime = createdAt + (0 - 0) * INT64_MIN
     assert r["reset_time"] == K.T0
+
+
+def test_hashed_item_api_routes_like_hashed_requests():
+    # items installed through the pre-hashed API must be visible to pre-hashed requests whatever the worker count
+    for workers in (1, 2, 7):
+        pool = O.Pool(workers=workers, now_ms=K.T0)
+        kx, kf = O.xxh64(b"glob_k1"), O.fnv1_64(b"glob_k1")
+        pool.update_peer_global_hashed(kx, kf, 0, 60000, 0, 80, 24, K.T0 + 60000)
+        assert pool.get_item_hashed(kx, kf).remaining_i == 24
+        r = np.zeros(1, dtype=O.HREQ_DTYPE)
+        r["key_xxh64"], r["key_fnv1"], r["hits"], r["limit"], r["duration"], r["created_at"] = kx, kf, 2, 80, 60000, K.T0
+        assert int(pool.submit_hashed(r)[0]["remaining"]) == 22
