@@ -56,7 +56,8 @@ __global__ void k_gq_claim(Gq q, const gub_req* reqs, uint32_t n, const uint8_t*
     if (old == 0ull) atomicAdd(q.count, 1ull);
     if (old == 0ull || old == key) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&q.slots[pos].hits), (unsigned long long)r.hits);  // global.go:109 (wrapping, like Go)
-      if (r.behavior & GUB_BEHAVIOR_RESET_REMAINING) atomicOr(&q.slots[pos].behavior, (unsigned)GUB_BEHAVIOR_RESET_REMAINING);  // global.go:105-108
+      // only the hits aggregation ORs RESET_REMAINING in (global.go:105-108); the update map just keeps the latest request (global.go:201)
+      if (q.mode == GQ_KEEP_FIRST && (r.behavior & GUB_BEHAVIOR_RESET_REMAINING)) atomicOr(&q.slots[pos].behavior, (unsigned)GUB_BEHAVIOR_RESET_REMAINING);
       const unsigned long long s = seq_base + i + 1;  // 0 = no request yet
       if (q.mode == GQ_KEEP_LAST) atomicMax(&q.seq[pos], s);
       else {
@@ -83,8 +84,8 @@ __global__ void k_gq_fill(Gq q, const gub_req* reqs, uint32_t n, unsigned long l
   gub_req* e = &q.slots[pos];
   e->key_fnv1 = r.key_fnv1; e->limit = r.limit; e->duration = r.duration; e->burst = r.burst; e->created_at = r.created_at;
   e->algorithm = r.algorithm;
-  // behaviour: the winner's bits; RESET_REMAINING accumulated by pass 1 is OR-ed back in
-  atomicOr(&e->behavior, r.behavior & ~(uint32_t)GUB_BEHAVIOR_RESET_REMAINING);
+  if (q.mode == GQ_KEEP_LAST) e->behavior = r.behavior;  // the latest request as it is
+  else atomicOr(&e->behavior, r.behavior);               // the first request's bits; pass 1 may have OR-ed RESET_REMAINING in
 }
 
 // Drain: every live entry becomes one request record in `out` (dense, arbitrary order); the table is cleared.
