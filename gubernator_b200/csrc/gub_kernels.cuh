@@ -46,6 +46,17 @@ constexpr int MIXED_THREADS = 256;
 constexpr int MAX_SEG = 96;          // uniform segments of a non-uniform group planned in parallel; more => serial walk
 constexpr int MAX_PIECES = 16;
 
+// Two placements of the singleton evaluation (compile-time; -DGUB_EARLY_SINGLES=0/1):
+//   1: keys seen once are evaluated in k_rank (their probe overlaps the rank work of repeated keys); the rank-0 member of
+//      a repeated key parks the slot as found in a snapshot, siblings read that in k_eval and the last rank writes the
+//      table directly.  Fewer instructions in the longest kernel; k_rank touches the table, so batches cannot overlap.
+//   0: k_rank stays table-free (stage 1 of batch b+1 may overlap stage 2 of batch b); everything is evaluated in k_eval and
+//      repeated keys are written back by k_finish from commit records.
+#ifndef GUB_EARLY_SINGLES
+#define GUB_EARLY_SINGLES 1
+#endif
+constexpr bool EARLY_SINGLES = GUB_EARLY_SINGLES != 0;
+
 struct __align__(64) Slot { uint64_t w[8]; };
 
 struct __align__(32) AuxEntry {
@@ -443,8 +454,27 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
     cnt = aux_count(e.x);
     rep = (uint32_t)(e.y & 0xFFFFFFFFull);
-    if (cnt > 1 && local == 0) s_base[sp] = fragment_base(A, pos, blockIdx.x);
-    if (cnt == 1) A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+    if (cnt > 1 && local == 0) {
+      const uint32_t base = fragment_base(A, pos, blockIdx.x);
+      s_base[sp] = base;
+      if (EARLY_SINGLES && base == 0) {  // rank 0 of the run: look the key up once for everybody
+        Cursor cur;
+        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+        snap_store(A.commit + (size_t)pos * 6, cur, i);
+      }
+    }
+    if (cnt == 1) {
+      A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+      if (EARLY_SINGLES) {
+        Cursor cur;
+        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+        Delta d = {0, 0, 0};
+        gub_resp r = apply_one(cur.b, rq, A.clk, d);
+        if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
+        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+        store_resp(A.out + i, r);
+      }
+    }
   }
   __syncthreads();
   if (valid && cnt > 1) {
@@ -486,15 +516,17 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
     }
     if (mixed) {
       A.order[__ldcg(&e->gbase) + rank] = i;
-    } else {
+    } else if (!(EARLY_SINGLES && cnt == 1)) {
       Cursor cur;
-      cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+      if (EARLY_SINGLES) snap_load(A.commit + (size_t)pos * 6, cur);  // the slot as k_rank found it (the last rank may already be writing the table)
+      else cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
       Delta d = {0, 0, 0};
       gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
       if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
         t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-        if (cnt == 1) {
+        if (cnt == 1 || EARLY_SINGLES) {
           if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
+          dup = cnt > 1 ? 1u : 0u;
         } else {  // siblings may still be reading the slot: k_finish writes it
           snap_store(A.commit + (size_t)pos * 6, cur, i);
           A.commit_ent[atomicAdd(&A.ctr[A.epoch & 1].n_commit, 1u)] = pos;
