@@ -431,16 +431,42 @@ __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t p
   return base;
 }
 
+// Which request each thread of a 256-thread block evaluates: the block's token-bucket requests first, then its leaky-bucket
+// ones (stable), so that all but one warp run a single algorithm's code path instead of both.  Only reads the 4-byte
+// algorithm field, so it can run in the prologue ahead of pdl_wait().
+__device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, uint32_t n) {
+  __shared__ uint16_t s_perm[GROUP_THREADS];
+  __shared__ uint32_t s_cnt3[GROUP_THREADS / 32][3];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t i = blockIdx.x * GROUP_THREADS + tid;
+  uint32_t cls = 2;
+  if (i < n) { const uint32_t a = __ldg(&reqs[i].algorithm); cls = a < 2u ? a : 2u; }
+  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1), b2 = ~(b0 | b1);
+  if (lane == 0) { s_cnt3[warp][0] = __popc(b0); s_cnt3[warp][1] = __popc(b1); s_cnt3[warp][2] = __popc(b2); }
+  __syncthreads();
+  uint32_t tot0 = 0, tot1 = 0, before = 0;
+#pragma unroll
+  for (int w = 0; w < GROUP_THREADS / 32; w++) {
+    tot0 += s_cnt3[w][0]; tot1 += s_cnt3[w][1];
+    if ((uint32_t)w < warp) before += s_cnt3[w][cls];
+  }
+  const uint32_t mine = cls == 0 ? b0 : (cls == 1 ? b1 : b2);
+  const uint32_t dest = (cls == 0 ? 0u : (cls == 1 ? tot0 : tot0 + tot1)) + before + __popc(mine & ((1u << lane) - 1u));
+  s_perm[dest] = (uint16_t)tid;
+  __syncthreads();
+  return blockIdx.x * GROUP_THREADS + s_perm[tid];
+}
+
 __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
-  const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
+  const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, A.n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
   const bool valid = i < A.n;
   gub_req rq;
   if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
   pdl_wait();
   pdl_release();
-  if (i == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
     nxt->n_mixed = 0; nxt->order_bump = 0; nxt->n_commit = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
@@ -495,7 +521,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
 
 // ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
 __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
-  const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
+  const uint32_t i = partition_by_algorithm(A.reqs, A.n);
   Tally t = {0, 0, 0, 0, 0};
   uint32_t dup = 0;
   gub_req rq;
