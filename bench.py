@@ -39,8 +39,8 @@ ALGO_BYTES_PER_DECISION = 224  # 64 slot read + 64 slot write-ba
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--keys", type=int, default=int(os.environ.get("GUB_BENCH_KEYS", 100_000_000)))
     ap.add_argument("--zipf", type=float, default=1.1)
@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -85,6 +85,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if not self.rows:  # the timed region was shorter than one sampling period: take one reading now
+            try:
+                q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self.rows = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                           capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+            except Exception:
+                pass
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -124,7 +131,7 @@ def batch_stats(ids):
 
 
 # ---- reference arm: the reference's CPU path (oracle port; the Go reference cannot be built in this image) ----------
-def cpu_leg(n_keys, zipf_s, seconds, seed, steps=None, warmup=0):
+def cpu_leg(n_keys, zipf_s, seconds, seed, steps=None, warmup=0, step_size=BATCH):
     import oracle_py as O
     from workloads import bench_requests
     cores = os.cpu_count() or 1
@@ -138,7 +145,7 @@ def cpu_leg(n_keys, zipf_s, seconds, seed, steps=None, warmup=0):
         ids = np.arange(lo, min(n_keys, lo + chunk), dtype=np.int64)
         pool.submit_hashed(bench_requests(ids, T0), threads=cores)
     t_fill = time.perf_counter() - t_fill
-    batches = [gen_batch(rng, BATCH, n_keys, T0 + 1 + b, zipf_s, O.HREQ_DTYPE)[0] for b in range(16)]
+    batches = [gen_batch(rng, step_size, n_keys, T0 + 1 + b, zipf_s, O.HREQ_DTYPE)[0] for b in range(16)]
     for w in range(max(warmup, 1)):
         pool.set_now(T0 + 1 + w)
         pool.submit_hashed(batches[w % len(batches)], threads=cores)
@@ -147,23 +154,25 @@ def cpu_leg(n_keys, zipf_s, seconds, seed, steps=None, warmup=0):
         pool.set_now(T0 + 1 + b)
         pool.submit_hashed(batches[b % len(batches)], threads=cores)
         t_used += pool.last_mt_seconds
-        done += BATCH
+        done += step_size
         b += 1
-    return dict(value=done / t_used, seconds=t_used, steps=b, cores=cores, fill_seconds=t_fill, keys=n_keys)
+    return dict(value=done / t_used, seconds=t_used, steps=b, cores=cores, fill_seconds=t_fill, keys=n_keys, step_size=step_size)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_leg(args.cpu_keys, args.zipf, args.cpu_seconds, 0xB200 + 3, steps=args.steps, warmup=args.warmup)
-    sample = (f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
+    # a step is one batch of the workload; with many steps the batch is shrunk so that the whole run stays within ~a minute
+    step_size = BATCH if args.steps <= 1000 else max(2048, int(BATCH * 1000 / args.steps) // 256 * 256)
+    r = cpu_leg(args.cpu_keys, args.zipf, args.cpu_seconds, 0xB200 + 3, steps=args.steps, warmup=min(args.warmup, 20), step_size=step_size)
+    sample = (f"{r['steps']} x {step_size}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
               f"{args.keys:,} to bound the warm pass), TOKEN/LEAKY 50/50, {r['cores']} worker threads")
     line = {
         "impl": "reference", "metric": "rate-limit decisions/sec", "value": r["value"], "unit": "decisions/s", "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE config 3 shape on CPU: {sample}", "batch": BATCH, "keys": r["keys"], "zipf_s": args.zipf},
+        "config": {"workload": f"BASELINE config 3 shape on CPU: {sample}", "batch": step_size, "keys": r["keys"], "zipf_s": args.zipf},
         "cpu_baseline": {"value": r["value"], "unit": "decisions/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,12 +275,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for b in range(args.warmup):
-        one_step(b)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for b in range(args.warmup):
+        one_step(b)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

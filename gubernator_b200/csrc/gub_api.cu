@@ -140,8 +140,8 @@ int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_
 // stream and overlaps stage 2 (k_eval, k_finish) of the previous batch, which runs on the caller's stream.
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
   const bool overlap = t->overlap && !t->prof && !gub::EARLY_SINGLES;  // k_rank touches the table in the early-singles build
-  gub_table::Scratch& sc = t->scr[t->next_set];
-  t->next_set ^= 1u;
+  gub_table::Scratch& sc = t->scr[overlap ? t->next_set : 0u];  // one set is enough when batches do not overlap
+  if (overlap) t->next_set ^= 1u;
   cudaStream_t sp = overlap ? t->s_prep : st;
   if (overlap) {
     CK(cudaEventRecord(t->inputs_ready, st));          // whatever produced d_reqs on the caller's stream
