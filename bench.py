@@ -388,8 +388,14 @@ def run_b200(args):
     dom_ms = kms[dom] / launches
     path_ms = sum(kms.values()) / launches
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel, from the committed `ncu --set full` capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("bytes_per_launch", {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": {k: v / launches for k, v in kms.items()},
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": {k: v / launches for k, v in kms.items()},
                 "algorithmic_bytes_per_launch": alg,
                 "path": {"achieved": ALGO_BYTES_PER_DECISION * units / (path_ms * 1e-3) / 1e9 if path_ms > 0 else 0.0,
                          "bytes_per_decision": ALGO_BYTES_PER_DECISION, "ms_per_batch_kernels_only": path_ms}}

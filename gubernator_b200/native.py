@@ -30,7 +30,8 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
            "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
-           "gub_route_owner_device", "gub_route_global_device"]
+           "gub_route_owner_device", "gub_route_global_device", "gub_p2p_create", "gub_p2p_destroy", "gub_p2p_export", "gub_p2p_connect",
+           "gub_p2p_connect_local", "gub_p2p_step"]
 
 
 class Config(C.Structure):
@@ -91,6 +92,12 @@ def lib():
         L.gub_add_items_device.argtypes = [vp, vp, sz, i64, vp]
         L.gub_route_owner_device.argtypes = [vp, vp, vp, sz, vp, vp]
         L.gub_route_global_device.argtypes = [vp, vp, C.c_uint32, vp, sz, vp, vp, vp, vp, vp]
+        L.gub_p2p_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.gub_p2p_destroy.argtypes = [vp]; L.gub_p2p_destroy.restype = None
+        L.gub_p2p_export.argtypes = [vp, vp]
+        L.gub_p2p_connect.argtypes = [vp, vp]
+        L.gub_p2p_connect_local.argtypes = [vp, C.POINTER(vp)]
+        L.gub_p2p_step.argtypes = [vp, vp, vp, sz, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -257,6 +264,43 @@ class Table:
 
     def unroute_device(self, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream=0):
         _check(lib().gub_unroute_device(self._h, d_resp_in_ptr, d_perm_ptr, n, d_resp_out_ptr, stream), "gub_unroute_device")
+
+
+class P2P:
+    """Fused routing over NVLink peer memory (gub_p2p_*): one per shard."""
+
+    def __init__(self, table, world, rank, cap):
+        h = C.c_void_p()
+        _check(lib().gub_p2p_create(table._h, world, rank, cap, C.byref(h)), "gub_p2p_create")
+        self._h, self.table, self.world, self.rank = h, table, world, rank
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().gub_p2p_export(self._h, buf), "gub_p2p_export")
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: list of `world` 64-byte handles in rank order (from other processes)."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.world)
+        _check(lib().gub_p2p_connect(self._h, blob), "gub_p2p_connect")
+
+    def connect_local(self, peers):
+        arr = (C.c_void_p * self.world)(*[p._h for p in peers])
+        _check(lib().gub_p2p_connect_local(self._h, arr), "gub_p2p_connect_local")
+
+    def step(self, ring, d_reqs_ptr, n, clk, d_out_ptr, stream=0):
+        _check(lib().gub_p2p_step(self._h, ring._r, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_p2p_step")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().gub_p2p_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class GlobalQueue:

@@ -244,3 +244,29 @@ class GpuBackend:
         items = items.contiguous()
         self.tab.add_items_device(items.data_ptr(), n, now_ms, self._stream())
         self.torch.cuda.current_stream().synchronize()  # `items` may be a temporary
+
+
+class P2PStep:
+    """Same contract as ShardedStep.step, but the records travel by NVLink stores issued from the routing kernels themselves
+    (gub_p2p_step): no NCCL collective and no exchange of split sizes."""
+
+    def __init__(self, table, ring, world, rank, cap=65536):
+        from . import native
+        self.ring, self.world, self.rank = ring, world, rank
+        self.p2p = native.P2P(table, world, rank, cap)
+
+    def connect(self, dist):
+        """One process per GPU: swap cudaIpc handles through torch.distributed."""
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.p2p.export())
+        self.p2p.connect(handles)
+        dist.barrier()
+
+    def connect_local(self, steppers):
+        self.p2p.connect_local([s.p2p for s in steppers])
+
+    def step(self, reqs, n, clk, out, stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self.p2p.step(self.ring, reqs.data_ptr(), n, clk, out.data_ptr(), st)
+        return n

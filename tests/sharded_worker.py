@@ -86,7 +86,13 @@ if USE_GPU:
     backend = GpuBackend(tab, ring, W, dev, 131072)
 else:
     backend = CpuBackend(O.Pool(workers=2, cache_size=10**7, now_ms=T0))
-stepper = ShardedStep(backend, dist, W)
+USE_P2P = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") == "p2p"
+if USE_P2P:  # records travel by NVLink stores from the routing kernels (cudaIpc mailboxes) instead of NCCL all-to-all
+    from gubernator_b200.sharded import P2PStep
+    stepper = P2PStep(tab, ring, W, rank, cap=65536)
+    stepper.connect(dist)
+else:
+    stepper = ShardedStep(backend, dist, W)
 sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(W)]  # local simulation of every shard
 for step in range(12):
     now = T0 + step

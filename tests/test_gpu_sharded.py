@@ -7,12 +7,13 @@ from test_sharded_gloo import run_workers
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("route", ["nccl", "p2p"])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
-def test_sharded_gpu_matches_per_shard_oracles(nproc):
+def test_sharded_gpu_matches_per_shard_oracles(nproc, route):
     import torch
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    res = run_workers(nproc, "gpu")
+    res = run_workers(nproc, "gpu", route=route)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     for r in range(nproc):
         assert f"rank {r} ok" in res.stdout

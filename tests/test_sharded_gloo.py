@@ -9,8 +9,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_workers(nproc, backend, timeout=900):
-    env = dict(os.environ, GUB_ROOT=ROOT, GUB_BACKEND=backend, OMP_NUM_THREADS="1")
+def run_workers(nproc, backend, timeout=900, route="nccl"):
+    env = dict(os.environ, GUB_ROOT=ROOT, GUB_BACKEND=backend, GUB_ROUTE=route, OMP_NUM_THREADS="1")
     port = 29600 + (os.getpid() % 300)
     return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
                            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "sharded_worker.py")], env=env,
