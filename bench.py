@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--route", default=os.environ.get("GUB_ROUTE", "p2p"), choices=["p2p", "nccl"],
+                    help="N > 1: how request records reach their owning GPU (NVLink mailboxes written by the routing kernels, or NCCL all-to-all)")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profile this many extra steps between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)")
     return ap.parse_args()
@@ -223,8 +225,12 @@ def run_b200(args):
     # ---- one step of the sharded path (N > 1): route -> all-to-all -> evaluate -> all-to-all back -> unroute
     sharded = None
     if N > 1:
-        from gubernator_b200.sharded import GpuBackend, ShardedStep
-        sharded = ShardedStep(GpuBackend(tab, ring, N, dev, 262144), dist, N)
+        from gubernator_b200.sharded import GpuBackend, P2PStep, ShardedStep
+        if args.route == "p2p":
+            sharded = P2PStep(tab, ring, N, rank, cap=262144)
+            sharded.connect(dist)
+        else:
+            sharded = ShardedStep(GpuBackend(tab, ring, N, dev, 262144), dist, N)
 
     # ---- warm pass: make every key resident through the real path
     t_fill = time.perf_counter()
@@ -408,13 +414,14 @@ def run_b200(args):
                "sample": f"{r['steps']} x {BATCH}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
                          f"{n_keys:,} to bound the warm pass), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
 
-    per_step_launches = 4 if N == 1 else 4 + 3 + 1  # group/rank/eval/mixed (+ route count/scan/scatter + unroute)
+    per_step_launches = 4 if N == 1 else (4 + 6 if args.route == "p2p" else 4 + 3 + 1)  # group/rank/eval/finish (+ routing kernels)
     line = {
         "metric": "rate-limit decisions/sec", "value": value, "unit": "decisions/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic",
         "config": {"workload": ("BASELINE config 3: 100M keys, Zipf s=1.1, TOKEN/LEAKY 50/50, 1xB200" if N == 1 else
-                                f"BASELINE config 4: 100M keys sharded over {N}xB200 by replicated_hash (fnv1, 512 replicas), NCCL all-to-all routing, Zipf s=1.1"),
+                                f"BASELINE config 4: 100M keys sharded over {N}xB200 by replicated_hash (fnv1, 512 replicas), Zipf s=1.1, routing: " +
+                                ("NVLink peer-memory mailboxes written by the routing kernels" if args.route == "p2p" else "NCCL all-to-all")),
                    "keys": n_keys, "batch_per_gpu": BATCH, "zipf_s": args.zipf, "table_slots_per_gpu": capacity,
                    "cache": f"inputs cycle through {pool_n} resident batches ({pool_n * 6} MiB > L2); table {capacity * 64 / 1e9:.1f} GB >> L2",
                    "batch_profile": st, "fill_seconds": t_fill, "resident_keys_after_fill": c0["inserts"]},
