@@ -742,6 +742,7 @@ int gub_unroute_device(gub_table* t, const gub_resp* d_resp_in, const uint32_t* 
 
 struct gub_p2p {
   gub_table* t = nullptr;
+  const gub_ring* ring = nullptr;
   uint32_t world = 0, rank = 0, cap = 0, epoch = 0;
   void* block = nullptr;           // our peer-visible allocation
   size_t block_bytes = 0;
@@ -750,6 +751,8 @@ struct gub_p2p {
   bool connected = false;
   gub_req* inbox = nullptr; gub_resp* inbox_resp = nullptr; size_t inbox_cap = 0;
   uint32_t *perm = nullptr, *seg_off = nullptr, *m_dev = nullptr, *counts = nullptr, *done_ctr = nullptr, *error = nullptr;
+  uint8_t* owner = nullptr;        // [cap] routing scratch, preallocated: nothing is allocated or freed inside a step
+  uint32_t* tile_off = nullptr;    // [(cap / ROUTE_TILE + 1) * MAX_SHARDS]
   uint32_t* h_m = nullptr;         // pinned
 };
 
@@ -774,17 +777,22 @@ void gub_p2p_destroy(gub_p2p* p) {
   cudaSetDevice(p->t->device);
   cudaDeviceSynchronize();
   for (uint32_t r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
-  void* ptrs[] = {p->block, p->inbox, p->inbox_resp, p->perm, p->seg_off, p->m_dev, p->counts, p->done_ctr, p->error};
+  void* ptrs[] = {p->block, p->inbox, p->inbox_resp, p->perm, p->seg_off, p->m_dev, p->counts, p->done_ctr, p->error, p->owner, p->tile_off};
   for (void* q : ptrs) if (q) cudaFree(q);
   if (p->h_m) cudaFreeHost(p->h_m);
   delete p;
 }
 
-int gub_p2p_create(gub_table* t, uint32_t world, uint32_t rank, uint32_t cap, gub_p2p** out) {
+int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t cap, gub_p2p** out) {
+  const uint32_t world = ring ? (uint32_t)gub_ring_size(ring) : 0;
   if (!t || !out || world == 0 || world > (uint32_t)gub::MAX_SHARDS || rank >= world || cap == 0) return fail("gub_p2p_create: bad argument");
   CK(cudaSetDevice(t->device));
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    if (ensure_ring(t, ring)) return -1;  // upload the ring now: a step never allocates or synchronises the device
+  }
   gub_p2p* p = new gub_p2p();
-  p->t = t; p->world = world; p->rank = rank; p->cap = cap;
+  p->t = t; p->ring = ring; p->world = world; p->rank = rank; p->cap = cap;
   p->block_bytes = p2p_req_bytes(world, cap) + p2p_resp_bytes(world, cap) + (size_t)4 * world * 8;
   cudaError_t e = cudaMalloc(&p->block, p->block_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->block, 0, p->block_bytes);
@@ -797,6 +805,11 @@ int gub_p2p_create(gub_table* t, uint32_t world, uint32_t rank, uint32_t cap, gu
   if (e == cudaSuccess) e = cudaMemset(p->done_ctr, 0, 8);
   if (e == cudaSuccess) e = cudaMemset(p->error, 0, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(&p->h_m, 8, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaMalloc(&p->owner, cap);
+  if (e == cudaSuccess) e = cudaMalloc(&p->tile_off, ((size_t)cap / gub::ROUTE_TILE + 1) * gub::MAX_SHARDS * 4);
+  p->inbox_cap = (size_t)world * cap;  // worst case every shard sends us its whole batch
+  if (e == cudaSuccess) e = cudaMalloc(&p->inbox, p->inbox_cap * sizeof(gub_req));
+  if (e == cudaSuccess) e = cudaMalloc(&p->inbox_resp, p->inbox_cap * sizeof(gub_resp));
   if (e != cudaSuccess) { gub_p2p_destroy(p); return fail(std::string("gub_p2p_create: ") + cudaGetErrorString(e)); }
   for (uint32_t r = 0; r < world; r++) p->views[r] = p2p_view(p->block, world, cap);  // until connected: everything loops back
   CK(cudaDeviceSynchronize());
@@ -840,10 +853,11 @@ int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers) {
   return 0;
 }
 
-int gub_p2p_step(gub_p2p* p, const gub_ring* ring, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
-  if (!p || !ring || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
+int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
+  if (!p || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
   if (n > p->cap) return fail("gub_p2p_step: n exceeds the mailbox capacity");
-  if ((uint32_t)gub_ring_size(ring) != p->world) return fail("gub_p2p_step: ring size != world");
+  const gub_ring* ring = p->ring;
+  if (p->t->ring_cached != ring || p->t->ring_version != gub_ring_version_(ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
   gub_table* t = p->t;
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t ntiles = 0;
@@ -851,32 +865,17 @@ int gub_p2p_step(gub_p2p* p, const gub_ring* ring, const gub_req* d_reqs, size_t
   {
     std::lock_guard<std::mutex> lk(t->mu);
     CK(cudaSetDevice(t->device));
-    if (ensure_ring(t, ring)) return -1;
     p->epoch++;
     for (uint32_t r = 0; r < p->world; r++) A.peers[r] = p->views[r];
     A.world = p->world; A.rank = p->rank; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = p->done_ctr; A.error = p->error;
     if (n) {
       ntiles = (uint32_t)((n + gub::ROUTE_TILE - 1) / gub::ROUTE_TILE);
-      if (!t->d_owner || t->owner_cap < n) { if (t->d_owner) { CK(cudaDeviceSynchronize()); cudaFree(t->d_owner); } CK(cudaMalloc(&t->d_owner, n)); t->owner_cap = n; }
-      const size_t tc = (size_t)ntiles * gub::MAX_SHARDS;
-      if (!t->d_tile_counts || t->tiles_cap < tc) { if (t->d_tile_counts) { CK(cudaDeviceSynchronize()); cudaFree(t->d_tile_counts); } CK(cudaMalloc(&t->d_tile_counts, tc * 4)); t->tiles_cap = tc; }
-      gub::k_route_count<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, p->world, t->d_owner,
-                                                t->d_tile_counts, ntiles, -1, nullptr);
-      gub::k_route_scan<<<1, 1024, 0, st>>>(t->d_tile_counts, p->world * ntiles, p->world, ntiles, p->counts);
-      gub::k_p2p_scatter<<<ntiles, 256, 0, st>>>(A, d_reqs, (uint32_t)n, t->d_owner, t->d_tile_counts, ntiles, p->counts, p->perm);
+      gub::k_route_count<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, p->world, p->owner,
+                                                p->tile_off, ntiles, -1, nullptr);
+      gub::k_route_scan<<<1, 1024, 0, st>>>(p->tile_off, p->world * ntiles, p->world, ntiles, p->counts);
+      gub::k_p2p_scatter<<<ntiles, 256, 0, st>>>(A, d_reqs, (uint32_t)n, p->owner, p->tile_off, ntiles, p->counts, p->perm);
     } else {
       gub::k_p2p_publish_empty<<<1, 32, 0, st>>>(A);
-    }
-    // worst case every shard sends us its whole batch
-    const size_t need = (size_t)p->world * p->cap;
-    if (p->inbox_cap < need) {
-      CK(cudaStreamSynchronize(st));
-      if (p->inbox) cudaFree(p->inbox);
-      if (p->inbox_resp) cudaFree(p->inbox_resp);
-      p->inbox = nullptr; p->inbox_resp = nullptr;
-      CK(cudaMalloc(&p->inbox, need * sizeof(gub_req)));
-      CK(cudaMalloc(&p->inbox_resp, need * sizeof(gub_resp)));
-      p->inbox_cap = need;
     }
     gub::k_p2p_gather<<<148, 256, 0, st>>>(A, p->inbox, p->seg_off, p->m_dev);
     CK(cudaMemcpyAsync(p->h_m, p->m_dev, 4, cudaMemcpyDeviceToHost, st));
@@ -888,7 +887,7 @@ int gub_p2p_step(gub_p2p* p, const gub_ring* ring, const gub_req* d_reqs, size_t
   {
     std::lock_guard<std::mutex> lk(t->mu);
     gub::k_p2p_push_resp<<<148, 256, 0, st>>>(A, p->inbox_resp, p->seg_off);
-    if (n) gub::k_p2p_unroute<<<148, 256, 0, st>>>(A, t->d_tile_counts, ntiles, p->perm, (uint32_t)n, d_out);
+    if (n) gub::k_p2p_unroute<<<148, 256, 0, st>>>(A, p->tile_off, ntiles, p->perm, (uint32_t)n, d_out);
     else gub::k_p2p_wait_resp_only<<<1, 32, 0, st>>>(A);
     CK(cudaGetLastError());
   }

@@ -92,12 +92,12 @@ def lib():
         L.gub_add_items_device.argtypes = [vp, vp, sz, i64, vp]
         L.gub_route_owner_device.argtypes = [vp, vp, vp, sz, vp, vp]
         L.gub_route_global_device.argtypes = [vp, vp, C.c_uint32, vp, sz, vp, vp, vp, vp, vp]
-        L.gub_p2p_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.gub_p2p_create.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         L.gub_p2p_destroy.argtypes = [vp]; L.gub_p2p_destroy.restype = None
         L.gub_p2p_export.argtypes = [vp, vp]
         L.gub_p2p_connect.argtypes = [vp, vp]
         L.gub_p2p_connect_local.argtypes = [vp, C.POINTER(vp)]
-        L.gub_p2p_step.argtypes = [vp, vp, vp, sz, vp, vp, vp]
+        L.gub_p2p_step.argtypes = [vp, vp, sz, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -269,10 +269,10 @@ class Table:
 class P2P:
     """Fused routing over NVLink peer memory (gub_p2p_*): one per shard."""
 
-    def __init__(self, table, world, rank, cap):
+    def __init__(self, table, ring, rank, cap):
         h = C.c_void_p()
-        _check(lib().gub_p2p_create(table._h, world, rank, cap, C.byref(h)), "gub_p2p_create")
-        self._h, self.table, self.world, self.rank = h, table, world, rank
+        _check(lib().gub_p2p_create(table._h, ring._r, rank, cap, C.byref(h)), "gub_p2p_create")
+        self._h, self.table, self.ring, self.world, self.rank = h, table, ring, ring.size(), rank
 
     def export(self) -> bytes:
         buf = C.create_string_buffer(64)
@@ -288,8 +288,8 @@ class P2P:
         arr = (C.c_void_p * self.world)(*[p._h for p in peers])
         _check(lib().gub_p2p_connect_local(self._h, arr), "gub_p2p_connect_local")
 
-    def step(self, ring, d_reqs_ptr, n, clk, d_out_ptr, stream=0):
-        _check(lib().gub_p2p_step(self._h, ring._r, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_p2p_step")
+    def step(self, d_reqs_ptr, n, clk, d_out_ptr, stream=0):
+        _check(lib().gub_p2p_step(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_p2p_step")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -253,7 +253,7 @@ class P2PStep:
     def __init__(self, table, ring, world, rank, cap=65536):
         from . import native
         self.ring, self.world, self.rank = ring, world, rank
-        self.p2p = native.P2P(table, world, rank, cap)
+        self.p2p = native.P2P(table, ring, rank, cap)
 
     def connect(self, dist):
         """One process per GPU: swap cudaIpc handles through torch.distributed."""
@@ -268,5 +268,5 @@ class P2PStep:
     def step(self, reqs, n, clk, out, stream=None):
         import torch
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        self.p2p.step(self.ring, reqs.data_ptr(), n, clk, out.data_ptr(), st)
+        self.p2p.step(reqs.data_ptr(), n, clk, out.data_ptr(), st)
         return n

@@ -238,12 +238,12 @@ int gub_route_global_device(gub_table* t, const gub_ring* ring, uint32_t self, c
  * Collective: every shard of the ring must call gub_p2p_step the same number of times.  n <= cap. */
 typedef struct gub_p2p gub_p2p;
 #define GUB_P2P_HANDLE_BYTES 64
-int gub_p2p_create(gub_table* t, uint32_t world, uint32_t rank, uint32_t cap, gub_p2p** out);
+int gub_p2p_create(gub_table* t, const gub_ring* ring /* one address per shard; must outlive the p2p */, uint32_t rank, uint32_t cap, gub_p2p** out);
 void gub_p2p_destroy(gub_p2p* p);
 int gub_p2p_export(gub_p2p* p, void* handle_out /* GUB_P2P_HANDLE_BYTES: a cudaIpcMemHandle_t */);
 int gub_p2p_connect(gub_p2p* p, const void* handles /* world x GUB_P2P_HANDLE_BYTES, rank order; own entry ignored */);
 int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers /* world pointers, same process */);
-int gub_p2p_step(gub_p2p* p, const gub_ring* ring, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
+int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
 
 #ifdef __cplusplus
 }
