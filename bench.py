@@ -227,7 +227,7 @@ def run_b200(args):
     if N > 1:
         from gubernator_b200.sharded import GpuBackend, P2PStep, ShardedStep
         if args.route == "p2p":
-            sharded = P2PStep(tab, ring, N, rank, cap=262144)
+            sharded = P2PStep(tab, ring, N, rank, cap=BATCH)  # mailbox capacity = the largest batch a shard ingests per step
             sharded.connect(dist)
         else:
             sharded = ShardedStep(GpuBackend(tab, ring, N, dev, 262144), dist, N)
@@ -236,7 +236,7 @@ def run_b200(args):
     t_fill = time.perf_counter()
     clk0 = g.clock_fill(T0)
     from workloads import bench_requests
-    chunk = 262144 if N > 1 else 1 << 20
+    chunk = BATCH if N > 1 else 1 << 20
     d_chunk = torch.empty((chunk, 64), dtype=torch.uint8, device=dev)
     d_chunk_out = torch.empty((chunk, 32), dtype=torch.uint8, device=dev)
     my_lo = (n_keys * rank) // N

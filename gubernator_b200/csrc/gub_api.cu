@@ -139,7 +139,8 @@ int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_
 
 // One batch (<= max_batch requests).  Stage 1 (k_group, k_rank) never touches bucket state, so it runs on the prep
 // stream and overlaps stage 2 (k_eval, k_finish) of the previous batch, which runs on the caller's stream.
-int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
+int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
+                 const uint32_t* n_dev = nullptr, uint32_t n_off = 0) {
   const bool overlap = t->overlap && !t->prof && !gub::EARLY_SINGLES;  // k_rank touches the table in the early-singles build
   gub_table::Scratch& sc = t->scr[overlap ? t->next_set : 0u];  // one set is enough when batches do not overlap
   if (overlap) t->next_set ^= 1u;
@@ -155,7 +156,7 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   }
   sc.epoch++;
   gub::BatchArgs A;
-  A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.epoch = sc.epoch;
+  A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.n_dev = n_dev; A.n_off = n_off; A.epoch = sc.epoch;
   A.aux = sc.aux; A.aux_mask = t->aux_entries - 1; A.presence = sc.presence; A.fragsize = sc.fragsize;
   A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = sc.ent; A.meta = sc.meta; A.rank = sc.rank;
   A.commit = sc.commit; A.commit_ent = sc.commit_ent; A.order = sc.order; A.mixed_ent = sc.mixed_ent; A.ctr = sc.ctr;
@@ -189,11 +190,13 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   return 0;
 }
 
-int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st) {
+// n_dev != nullptr: the real batch size is *n_dev (<= n) on the device; launches are sized for n and trim themselves.
+int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
+                 const uint32_t* n_dev = nullptr) {
   if (t->have_last) CK(cudaStreamWaitEvent(st, t->last_done, 0));
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
-    if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st)) return -1;
+    if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st, n_dev, (uint32_t)off)) return -1;
   }
   CK(cudaEventRecord(t->last_done, st));
   t->have_last = true;
@@ -349,6 +352,14 @@ int gub_submit_device(gub_table* t, const gub_req* d_reqs, size_t n, const gub_c
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
   return launch_batch(t, d_reqs, n, clk, d_out, (cudaStream_t)stream);
+}
+
+int gub_submit_device_n(gub_table* t, const gub_req* d_reqs, size_t n_cap, const uint32_t* d_n, const gub_clock* clk, gub_resp* d_out, void* stream) {
+  if (!t || !clk || !d_n || (n_cap && (!d_reqs || !d_out))) return fail("gub_submit_device_n: null argument");
+  if (n_cap == 0) return 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  return launch_batch(t, d_reqs, n_cap, clk, d_out, (cudaStream_t)stream, d_n);
 }
 
 int gub_pipeline_depth(gub_table*) { return PIPE_DEPTH; }
@@ -878,12 +889,11 @@ int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* c
       gub::k_p2p_publish_empty<<<1, 32, 0, st>>>(A);
     }
     gub::k_p2p_gather<<<148, 256, 0, st>>>(A, p->inbox, p->seg_off, p->m_dev);
-    CK(cudaMemcpyAsync(p->h_m, p->m_dev, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaGetLastError());
   }
-  CK(cudaStreamSynchronize(st));  // the one host round trip of the step: how many records we own (sizes the evaluation launches)
-  const uint32_t m = *p->h_m;
-  if (gub_submit_device(t, p->inbox, m, clk, p->inbox_resp, stream)) return -1;
+  // How many records we own is only known on the device (p->m_dev): the evaluation launches are sized for what a shard may
+  // receive at most and trim themselves, so the step needs no host round trip at all.
+  if (gub_submit_device_n(t, p->inbox, (size_t)p->world * p->cap, p->m_dev, clk, p->inbox_resp, stream)) return -1;
   {
     std::lock_guard<std::mutex> lk(t->mu);
     gub::k_p2p_push_resp<<<148, 256, 0, st>>>(A, p->inbox_resp, p->seg_off);

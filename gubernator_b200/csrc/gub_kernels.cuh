@@ -80,7 +80,9 @@ struct BatchArgs {
   uint64_t capacity;
   const gub_req* reqs;
   gub_resp* out;
-  uint32_t n;
+  uint32_t n;              // requests in this launch (grid size); with n_dev: the most this launch may hold
+  const uint32_t* n_dev;   // optional: the batch size lives on the device (fused routing: known only after the gather kernel);
+  uint32_t n_off;          //           this launch then covers requests [n_off, min(*n_dev, n_off + n)) of the batch
   uint32_t epoch;          // 1..65535
   AuxEntry* aux;
   uint32_t aux_mask;       // entries - 1 (power of two)
@@ -100,6 +102,13 @@ struct BatchArgs {
 };
 
 __device__ __forceinline__ uint64_t remap_key(uint64_t k) { return k < 2 ? k + 2 : k; }
+
+// Number of requests this launch evaluates (see BatchArgs::n_dev).
+__device__ __forceinline__ uint32_t batch_n(const BatchArgs& A) {
+  if (!A.n_dev) return A.n;
+  const uint32_t total = __ldcg(A.n_dev);
+  return total > A.n_off ? min(total - A.n_off, A.n) : 0u;
+}
 
 // Programmatic dependent launch (sm_90+): every batch kernel is launched with programmatic stream serialization, so its
 // blocks may become resident while the previous kernel is still running.  pdl_wait() blocks until every earlier grid of
@@ -317,7 +326,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __syncthreads();
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool valid = i < A.n;
+  const uint32_t n = batch_n(A);  // after the wait: a gather kernel may have just written it
+  if (blockIdx.x * GROUP_THREADS >= n) return;  // whole block beyond the batch (uniform: no barrier is skipped by part of a block)
+  const bool valid = i < n;
   uint32_t sp = 0xFFFFu;  // shared-memory slot of my key (0xFFFF: no request)
   uint64_t key = 0;
   unsigned long long first = 0;
@@ -459,9 +470,10 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
 
 __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
-  const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, A.n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
+  const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
+  const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
-  const bool valid = i < A.n;
+  const bool valid = i < n;
   gub_req rq;
   if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
   pdl_wait();
@@ -469,7 +481,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
     nxt->n_mixed = 0; nxt->order_bump = 0; nxt->n_commit = 0;
-    atomicAdd(A.counters + C_REQUESTS, (unsigned long long)A.n);
+    atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
   uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
@@ -521,14 +533,15 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
 
 // ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
 __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
-  const uint32_t i = partition_by_algorithm(A.reqs, A.n);
+  const uint32_t n = batch_n(A);
+  const uint32_t i = partition_by_algorithm(A.reqs, n);
   Tally t = {0, 0, 0, 0, 0};
   uint32_t dup = 0;
   gub_req rq;
-  if (i < A.n) rq = load_req(A.reqs + i);  // safe ahead of the wait (see k_rank)
+  if (i < n) rq = load_req(A.reqs + i);  // safe ahead of the wait (see k_rank)
   pdl_wait();
   pdl_release();
-  if (i < A.n) {
+  if (i < n) {
     const uint32_t pos = A.ent[i];
     uint32_t rank = A.rank[i];                   // garbage for singletons; replaced below
     const AuxEntry* e = &A.aux[pos];

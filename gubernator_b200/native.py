@@ -24,7 +24,7 @@ COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_ful
                   "mixed_groups", "serial_fallbacks")
 assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 80
 
-EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device",
+EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n",
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
            "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys",
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
@@ -57,6 +57,7 @@ def lib():
         L.gub_last_error.restype = C.c_char_p
         L.gub_submit.argtypes = [vp, vp, sz, vp, vp]
         L.gub_submit_device.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.gub_submit_device_n.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         L.gub_pipeline_depth.argtypes = [vp]
         L.gub_submit_async.argtypes = [vp, vp, sz, vp, vp, C.POINTER(i32)]
         L.gub_wait.argtypes = [vp, i32]

@@ -139,6 +139,8 @@ int gub_abi_version(void);
 int gub_submit(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out);
 /* Device buffers (already resident in this GPU's HBM); enqueued on `stream` (a cudaStream_t), returns immediately. */
 int gub_submit_device(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
+/* Same, when the batch size is only known on the device: *d_n (<= n_cap) requests; launches are sized for n_cap. */
+int gub_submit_device_n(gub_table* t, const gub_req* d_reqs, size_t n_cap, const uint32_t* d_n, const gub_clock* clk, gub_resp* d_out, void* stream);
 /* Pipelined host path: up to gub_pipeline_depth() submissions may be in flight; each uses library-owned pinned
  * staging.  gub_submit_async returns a ticket; gub_wait(ticket) blocks until that batch's responses are in `out`. */
 int gub_pipeline_depth(gub_table* t);

@@ -94,7 +94,7 @@ if USE_P2P:  # records travel by NVLink stores from the routing kernels (cudaIpc
 else:
     stepper = ShardedStep(backend, dist, W)
 sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(W)]  # local simulation of every shard
-for step in range(12):
+for step in range(8):
     now = T0 + step
     reqs = batch_for(rank, step)
     n = len(reqs)
