@@ -302,6 +302,25 @@ def run_b200(args):
         ms = float(tms.item())
     value = N * BATCH * args.steps / (ms * 1e-3)
 
+    # ---- informational: the same path with 4 x larger launches (262 144 requests; one C-ABI call, chunked by max_batch = 65 536
+    # at N = 1): shows how much of the per-batch time is fixed cost rather than per-request work.  Not the headline.
+    big = None
+    if N == 1 and pool_n >= 4:
+        d_big = torch.cat(d_batches[:4], dim=0).contiguous()
+        d_big_out = torch.empty((4 * BATCH, 32), dtype=torch.uint8, device=dev)
+        big_steps = max(10, args.steps // 8)
+        for b in range(3):
+            tab.submit_device(d_big.data_ptr(), 4 * BATCH, clocks[0], d_big_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in range(big_steps):
+            tab.submit_device(d_big.data_ptr(), 4 * BATCH, clocks[min(b, len(clocks) - 1)], d_big_out.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        big = {"requests_per_call": 4 * BATCH, "value": 4 * BATCH * big_steps / (e0.elapsed_time(e1) * 1e-3), "unit": "decisions/s",
+               "note": "same key pool every call: hot keys saturate; informational only"}
+
     # ---- per-kernel timing leg (separate from the number above: events between kernels perturb the pipeline)
     tab.set_profiling(True)
     prof_steps = min(args.steps, 100)
@@ -426,7 +445,7 @@ def run_b200(args):
                    "cache": f"inputs cycle through {pool_n} resident batches ({pool_n * 6} MiB > L2); table {capacity * 64 / 1e9:.1f} GB >> L2",
                    "batch_profile": st, "fill_seconds": t_fill, "resident_keys_after_fill": c0["inserts"]},
         "clocks": clocks_info, "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "larger_calls": big,
         "counters": {k: c1[k] - c0[k] for k in c1},
     }
     print(json.dumps(line))

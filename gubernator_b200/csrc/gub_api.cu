@@ -74,7 +74,9 @@ struct gub_table {
   bool overlap = true;                // GUB_OVERLAP=0: everything on the caller's stream
   // ordering between streams that touch the shared scratch
   cudaEvent_t last_done = nullptr;
-  bool have_last = false;
+  bool have_last = false;            // an event has been recorded for the work on last_stream
+  cudaStream_t last_stream = nullptr; // stream of the most recent table-touching work
+  bool last_pending = false;          // work was enqueued on last_stream after (or without) the last event record
   // host path
   cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
   cudaEvent_t compute_done[PIPE_DEPTH] = {};
@@ -190,16 +192,26 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   return 0;
 }
 
+// Table-touching work from different caller streams must be ordered.  The common case (same stream as last time) costs
+// nothing; only a change of stream records an event on the old stream and makes the new one wait for it.
+int order_after_last(gub_table* t, cudaStream_t st) {
+  if (t->last_pending && t->last_stream != st) {
+    CK(cudaEventRecord(t->last_done, t->last_stream));
+    CK(cudaStreamWaitEvent(st, t->last_done, 0));
+    t->last_pending = false;
+  }
+  return 0;
+}
+
 // n_dev != nullptr: the real batch size is *n_dev (<= n) on the device; launches are sized for n and trim themselves.
 int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
                  const uint32_t* n_dev = nullptr) {
-  if (t->have_last) CK(cudaStreamWaitEvent(st, t->last_done, 0));
+  if (order_after_last(t, st)) return -1;
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
     if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st, n_dev, (uint32_t)off)) return -1;
   }
-  CK(cudaEventRecord(t->last_done, st));
-  t->have_last = true;
+  t->last_stream = st; t->last_pending = true;
   return 0;
 }
 
@@ -729,11 +741,10 @@ int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (t->have_last) CK(cudaStreamWaitEvent(st, t->last_done, 0));
+  if (order_after_last(t, st)) return -1;
   k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(t->last_done, st));
-  t->have_last = true;
+  t->last_stream = st; t->last_pending = true;
   return 0;
 }
 
