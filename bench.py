@@ -406,9 +406,12 @@ def run_b200(args):
     multi_grp = st["light_groups"] + st["heavy_groups"]
     alg = {  # algorithmic bytes per launch, by kernel (Kernels)
         "k_group": 16.0 * units,                                                        # 8 B key in, ent + meta out
-        "k_rank": 12.0 * units + 132.0 * multi_req,                                      # ent/meta/entry per request; request + representative + rank per repeated-key member
-        "k_eval": ALGO_BYTES_PER_DECISION * st["singles"] + (64 + 64 + 32 + 12.0) * multi_req + 96.0 * multi_grp,  # singles: the whole 224 B; members: request + slot + response; per key: commit record
-        "k_finish": (96 + 64 + 64.0) * multi_grp,                                        # commit record in, slot compare + write-back
+        # this build evaluates keys seen once in k_rank (EARLY_SINGLES): the whole 224 B per singleton; every request reads its
+        # ent/meta/entry (12 B); members of repeated keys read their request + the representative's (128 B) and write a rank;
+        # per repeated key one slot probe + one 96 B snapshot
+        "k_rank": ALGO_BYTES_PER_DECISION * st["singles"] + 12.0 * units + 132.0 * multi_req + 160.0 * multi_grp,
+        "k_eval": (64 + 96 + 32 + 12.0) * multi_req + 64.0 * multi_grp,  # request + snapshot + response per member; one slot write-back per key
+        "k_finish": 0.0,                                                   # only non-uniform groups (none in this workload)
     }
     dom_ms = kms[dom] / launches
     path_ms = sum(kms.values()) / launches
