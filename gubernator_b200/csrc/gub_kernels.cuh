@@ -138,13 +138,21 @@ struct Cursor {  // one key's slot while requests are applied to it
 
 // Looks `key` up.  On a hit the slot is loaded into cur.b.  On a miss cur.b is an empty (not live) bucket and cur.slot
 // is the first reusable slot (tombstone or empty) seen, if any.
-__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag) {
+struct HomeSlot { ulonglong2 a, b, c, d; };  // a key's home slot, loaded ahead of time so its latency overlaps other loads
+
+__device__ __forceinline__ void home_load(HomeSlot& h, const Slot* table, uint64_t cap, uint64_t key) {
+  slot_load(table + __umul64hi(key, cap), h.a, h.b, h.c, h.d);
+}
+
+template <bool PRELOADED = false>
+__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag, const HomeSlot* first = nullptr) {
   uint64_t idx = __umul64hi(key, cap);
   cur.home = idx; cur.found = false; cur.slot = -1;
 #pragma unroll 1
   for (int p = 0; p < MAX_PROBE; p++) {
     ulonglong2 a, b, c, d;
-    slot_load(table + idx, a, b, c, d);
+    if (PRELOADED && p == 0) { a = first->a; b = first->b; c = first->c; d = first->d; }
+    else slot_load(table + idx, a, b, c, d);
     if (a.x == key && (a.y >> 8) == tag) {
       bucket_from(cur.b, a, b, c, d);
       cur.old = cur.b; cur.slot = (int64_t)idx; cur.found = true;
@@ -468,7 +476,7 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
   return blockIdx.x * GROUP_THREADS + s_perm[tid];
 }
 
-__global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
+__global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
   const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
@@ -484,28 +492,46 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
-  uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
+  uint32_t pos = 0, cnt = 0, sp = 0, local = 0;
   if (valid) {
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
+    HomeSlot home;
+    const uint64_t key = remap_key(rq.key_xxh64);
+    if (EARLY_SINGLES) home_load(home, A.table, A.capacity, key);  // speculative (an L2 hit after k_group's prefetch): overlaps the entry load
     sp = m >> 16; local = m & 0xFFFFu;
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
     cnt = aux_count(e.x);
-    rep = (uint32_t)(e.y & 0xFFFFFFFFull);
-    if (cnt > 1 && local == 0) {
-      const uint32_t base = fragment_base(A, pos, blockIdx.x);
-      s_base[sp] = base;
-      if (EARLY_SINGLES && base == 0) {  // rank 0 of the run: look the key up once for everybody
-        Cursor cur;
-        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
-        snap_store(A.commit + (size_t)pos * 6, cur, i);
+    const uint32_t rep = (uint32_t)(e.y & 0xFFFFFFFFull);
+    if (cnt > 1) {
+      // uniformity does not need the rank: start the representative's load before anything that waits
+      bool mixed = !req_regular(rq);
+      gub_req rr;
+      const bool cmp = !mixed && i != rep;
+      if (cmp) rr = load_req(A.reqs + rep);
+      if (local == 0) {
+        const uint32_t base = fragment_base(A, pos, blockIdx.x);
+        s_base[sp] = base;
+        if (EARLY_SINGLES && base == 0) {  // rank 0 of the run: look the key up once for everybody
+          Cursor cur;
+          cursor_open<true>(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, &home);
+          snap_store(A.commit + (size_t)pos * 6, cur, i);
+        }
       }
-    }
-    if (cnt == 1) {
+      if (cmp) mixed = !req_same(rq, rr);
+      if (mixed) {
+        const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
+        if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
+          BatchCtr* ctr = A.ctr + (A.epoch & 1);
+          A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
+          A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
+        }
+      }
+    } else if (cnt == 1) {
       A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
       if (EARLY_SINGLES) {
         Cursor cur;
-        cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+        cursor_open<true>(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, &home);
         Delta d = {0, 0, 0};
         gub_resp r = apply_one(cur.b, rq, A.clk, d);
         if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
@@ -515,19 +541,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
     }
   }
   __syncthreads();
-  if (valid && cnt > 1) {
-    A.rank[i] = s_base[sp] + local;
-    bool mixed = !req_regular(rq);
-    if (!mixed && i != rep) mixed = !req_same(rq, load_req(A.reqs + rep));
-    if (mixed) {
-      const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
-      if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
-        BatchCtr* ctr = A.ctr + (A.epoch & 1);
-        A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
-        A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
-      }
-    }
-  }
+  if (valid && cnt > 1) A.rank[i] = s_base[sp] + local;
   tally_flush_block(t, A.counters);
 }
 
