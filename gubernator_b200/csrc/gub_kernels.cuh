@@ -476,7 +476,7 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
   return blockIdx.x * GROUP_THREADS + s_perm[tid];
 }
 
-__global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
+__global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
   const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
@@ -496,9 +496,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
   if (valid) {
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
-    HomeSlot home;
     const uint64_t key = remap_key(rq.key_xxh64);
-    if (EARLY_SINGLES) home_load(home, A.table, A.capacity, key);  // speculative (an L2 hit after k_group's prefetch): overlaps the entry load
     sp = m >> 16; local = m & 0xFFFFu;
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
     cnt = aux_count(e.x);
@@ -514,7 +512,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
         s_base[sp] = base;
         if (EARLY_SINGLES && base == 0) {  // rank 0 of the run: look the key up once for everybody
           Cursor cur;
-          cursor_open<true>(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, &home);
+          cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
           snap_store(A.commit + (size_t)pos * 6, cur, i);
         }
       }
@@ -531,7 +529,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
       A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
       if (EARLY_SINGLES) {
         Cursor cur;
-        cursor_open<true>(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, &home);
+        cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
         Delta d = {0, 0, 0};
         gub_resp r = apply_one(cur.b, rq, A.clk, d);
         if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
