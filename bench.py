@@ -346,22 +346,39 @@ def run_b200(args):
         for k in range(depth):
             pin[k][0].array[:] = host_batches[k % pool_n]
         if N == 1:
-            tickets = [None] * depth
+            def e2e_run(submit):
+                tickets = [None] * depth
+                for b in range(min(args.warmup, 8)):
+                    tab.wait(submit(b % depth, b))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for b in range(e2e_steps):
+                    k = b % depth
+                    if tickets[k] is not None:
+                        tab.wait(tickets[k])  # the response buffer of this slot has been read back
+                    tickets[k] = submit(k, b)
+                for k in range(depth):
+                    if tickets[k] is not None:
+                        tab.wait(tickets[k])
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
             e2e_steps = args.steps
-            for b in range(min(args.warmup, 8)):
-                tab.wait(tab.submit_async(pin[b % depth][0].ptr, BATCH, clocks[b], pin[b % depth][1].ptr))
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for b in range(e2e_steps):
-                k = b % depth
-                if tickets[k] is not None:
-                    tab.wait(tickets[k])  # the response buffer of this slot has been read back
-                tickets[k] = tab.submit_async(pin[k][0].ptr, BATCH, clocks[min(b, len(clocks) - 1)], pin[k][1].ptr)
+            # (a) compact records: 32 B per request + one small parameter table per batch (gub_submit_compact_async)
+            cpin, ppin, bases, nparams = [], [], [], []
             for k in range(depth):
-                if tickets[k] is not None:
-                    tab.wait(tickets[k])
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
+                c, prm, base = g.native.compact_batch(host_batches[k % pool_n])
+                ca, pa = g.native.PinnedArray(BATCH, g.native.CREQ_DTYPE), g.native.PinnedArray(max(len(prm), 1), g.native.PARAMS_DTYPE)
+                ca.array[:] = c; pa.array[:len(prm)] = prm
+                cpin.append(ca); ppin.append(pa); bases.append(base); nparams.append(len(prm))
+            dt = e2e_run(lambda k, b: tab.submit_compact_async(cpin[k].ptr, BATCH, ppin[k].ptr, nparams[k], bases[k],
+                                                               clocks[min(b, len(clocks) - 1)], pin[k][1].ptr))
+            # (b) full 64 B records (gub_submit_async), for comparison
+            dt_full = e2e_run(lambda k, b: tab.submit_async(pin[k][0].ptr, BATCH, clocks[min(b, len(clocks) - 1)], pin[k][1].ptr))
+            e2e_full = {"value": BATCH * e2e_steps / dt_full, "unit": "decisions/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 32,
+                        "api": "gub_submit_async (64-byte records)"}
+            h2d_compact = BATCH * 32 + int(np.mean(nparams)) * 32
+            for a in cpin + ppin:
+                a.free()
         else:
             # sharded e2e: per step copy the batch from pinned host memory, run the routed step, read responses back
             h_in = [torch.from_numpy(host_batches[k % pool_n].view(np.uint8).reshape(BATCH, 64)).pin_memory() for k in range(depth)]
@@ -382,9 +399,12 @@ def run_b200(args):
                 tdt = torch.tensor([dt], device=dev, dtype=torch.float64)
                 dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
                 dt = float(tdt.item())
-        e2e = {"value": N * BATCH * e2e_steps / dt, "unit": "decisions/s", "h2d_bytes_per_step": N * BATCH * 64,
-               "d2h_bytes_per_step": N * BATCH * 32, "api": "gub_submit_async (pinned host buffers, depth 4)" if N == 1 else
-               "pinned H2D + route/all-to-all/evaluate/all-to-all/unroute + D2H per step"}
+        e2e = {"value": N * BATCH * e2e_steps / dt, "unit": "decisions/s", "h2d_bytes_per_step": h2d_compact if N == 1 else N * BATCH * 64,
+               "d2h_bytes_per_step": N * BATCH * 32,
+               "api": "gub_submit_compact_async (pinned host buffers, 32-byte records + parameter table, depth 4)" if N == 1 else
+               "pinned H2D + route/exchange/evaluate/return/unroute + D2H per step"}
+        if N == 1:
+            e2e["full_records"] = e2e_full
         for a, b_ in pin:
             a.free(); b_.free()
 

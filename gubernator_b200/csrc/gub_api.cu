@@ -38,7 +38,9 @@ constexpr int PIPE_DEPTH = 4;
 struct PipeSlot {
   gub_req* d_req = nullptr;
   gub_resp* d_resp = nullptr;
-  size_t cap = 0;
+  gub_creq* d_creq = nullptr;       // compact submissions: what arrives over PCIe
+  gub_params* d_params = nullptr;
+  size_t cap = 0, params_cap = 0;
   cudaEvent_t in_done = nullptr, out_done = nullptr;
   bool busy = false;
 };
@@ -219,7 +221,8 @@ int ensure_slot(PipeSlot& s, size_t n) {
   if (s.cap >= n) return 0;
   if (s.d_req) cudaFree(s.d_req);
   if (s.d_resp) cudaFree(s.d_resp);
-  s.d_req = nullptr; s.d_resp = nullptr; s.cap = 0;
+  if (s.d_creq) cudaFree(s.d_creq);
+  s.d_req = nullptr; s.d_resp = nullptr; s.d_creq = nullptr; s.cap = 0;
   CK(cudaMalloc(&s.d_req, n * sizeof(gub_req)));
   CK(cudaMalloc(&s.d_resp, n * sizeof(gub_resp)));
   s.cap = n;
@@ -275,6 +278,8 @@ void gub_destroy(gub_table* t) {
   for (auto& s : t->pipe) {
     if (s.d_req) cudaFree(s.d_req);
     if (s.d_resp) cudaFree(s.d_resp);
+    if (s.d_creq) cudaFree(s.d_creq);
+    if (s.d_params) cudaFree(s.d_params);
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.out_done) cudaEventDestroy(s.out_done);
   }
@@ -399,6 +404,40 @@ int gub_submit_async(gub_table* t, const gub_req* reqs, size_t n, const gub_cloc
   return 0;
 }
 
+int gub_submit_compact_async(gub_table* t, const gub_creq* reqs, size_t n, const gub_params* params, size_t n_params, int64_t created_base,
+                             const gub_clock* clk, gub_resp* out, int* ticket) {
+  if (!t || !clk || !ticket || (n && (!reqs || !out || !params))) return fail("gub_submit_compact_async: null argument");
+  if (n > 0xFFFFFFFFull || n_params > 0xFFFFFFFFull) return fail("gub_submit_compact_async: too large");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  const int si = t->next_slot;
+  t->next_slot = (t->next_slot + 1) % PIPE_DEPTH;
+  PipeSlot& s = t->pipe[si];
+  if (s.busy) { CK(cudaEventSynchronize(s.out_done)); s.busy = false; }
+  *ticket = si;
+  if (n == 0) { CK(cudaEventRecord(s.out_done, t->s_d2h)); s.busy = true; return 0; }
+  if (ensure_slot(s, n)) return -1;
+  if (!s.d_creq) CK(cudaMalloc(&s.d_creq, s.cap * sizeof(gub_creq)));
+  if (s.params_cap < n_params || !s.d_params) {
+    if (s.d_params) cudaFree(s.d_params);
+    s.d_params = nullptr;
+    s.params_cap = std::max<size_t>(n_params, 1024);
+    CK(cudaMalloc(&s.d_params, s.params_cap * sizeof(gub_params)));
+  }
+  CK(cudaMemcpyAsync(s.d_creq, reqs, n * sizeof(gub_creq), cudaMemcpyHostToDevice, t->s_h2d));
+  if (n_params) CK(cudaMemcpyAsync(s.d_params, params, n_params * sizeof(gub_params), cudaMemcpyHostToDevice, t->s_h2d));
+  CK(cudaEventRecord(s.in_done, t->s_h2d));
+  CK(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
+  gub::k_expand<<<(unsigned)((n + 255) / 256), 256, 0, t->s_compute>>>(s.d_creq, (uint32_t)n, s.d_params, (uint32_t)n_params, created_base, s.d_req);
+  if (launch_batch(t, s.d_req, n, clk, s.d_resp, t->s_compute)) return -1;
+  CK(cudaEventRecord(t->compute_done[si], t->s_compute));
+  CK(cudaStreamWaitEvent(t->s_d2h, t->compute_done[si], 0));
+  CK(cudaMemcpyAsync(out, s.d_resp, n * sizeof(gub_resp), cudaMemcpyDeviceToHost, t->s_d2h));
+  CK(cudaEventRecord(s.out_done, t->s_d2h));
+  s.busy = true;
+  return 0;
+}
+
 int gub_wait(gub_table* t, int ticket) {
   if (!t || ticket < 0 || ticket >= PIPE_DEPTH) return fail("gub_wait: bad ticket");
   cudaEvent_t ev;
@@ -412,6 +451,13 @@ int gub_wait(gub_table* t, int ticket) {
   std::lock_guard<std::mutex> lk(t->mu);
   t->pipe[ticket].busy = false;
   return 0;
+}
+
+int gub_submit_compact(gub_table* t, const gub_creq* reqs, size_t n, const gub_params* params, size_t n_params, int64_t created_base,
+                       const gub_clock* clk, gub_resp* out) {
+  int ticket = -1;
+  if (gub_submit_compact_async(t, reqs, n, params, n_params, created_base, clk, out, &ticket)) return -1;
+  return gub_wait(t, ticket);
 }
 
 int gub_submit(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out) {

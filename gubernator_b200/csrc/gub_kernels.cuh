@@ -724,6 +724,27 @@ __global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A, 
   tally_flush_block(t, A.counters);
 }
 
+// ---- compact requests -> gub_req records (see gub_creq in the header) --------------------------------------------------
+__global__ void __launch_bounds__(256) k_expand(const gub_creq* creqs, uint32_t n, const gub_params* params, uint32_t n_params, int64_t created_base,
+                                                gub_req* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(creqs + i);
+  const ulonglong2 a = __ldcs(p), b = __ldcs(p + 1);  // streamed once
+  const uint32_t pi = (uint32_t)(b.y & 0xFFFFFFFFull);
+  const int32_t delta = (int32_t)(uint32_t)(b.y >> 32);
+  ulonglong2 q0 = make_ulonglong2(0, 0), q1 = make_ulonglong2(0, 0xFFFFFFFFull);  // unknown parameter set -> invalid algorithm (in-band error)
+  if (pi < n_params) {
+    const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(params + pi);
+    q0 = __ldg(pp); q1 = __ldg(pp + 1);
+  }
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(out + i);
+  o[0] = a;                                                                   // key_xxh64, key_fnv1
+  o[1] = make_ulonglong2(b.x, q0.x);                                          // hits, limit
+  o[2] = make_ulonglong2(q0.y, q1.x);                                         // duration, burst
+  o[3] = make_ulonglong2((uint64_t)wadd(created_base, (int64_t)delta), q1.y); // created_at, algorithm | behavior << 32
+}
+
 // ---- maintenance kernels -------------------------------------------------------------------------------------
 // Upsert whole items: WorkerPool.AddCacheItem / Load / UpdatePeerGlobals.  Keys are unique within one launch.
 struct DevItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags; uint32_t _pad; };

@@ -22,9 +22,12 @@ ITEM_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("algorithm", 
                        ("expire_at", "<i8")])
 COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups",
                   "mixed_groups", "serial_fallbacks")
+CREQ_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("hits", "<i8"), ("params", "<u4"), ("created_delta", "<i4")])
+PARAMS_DTYPE = np.dtype([("limit", "<i8"), ("duration", "<i8"), ("burst", "<i8"), ("algorithm", "<u4"), ("behavior", "<u4")])
+assert CREQ_DTYPE.itemsize == 32 and PARAMS_DTYPE.itemsize == 32
 assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 80
 
-EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n",
+EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n", "gub_submit_compact", "gub_submit_compact_async",
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
            "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys",
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
@@ -58,6 +61,8 @@ def lib():
         L.gub_submit.argtypes = [vp, vp, sz, vp, vp]
         L.gub_submit_device.argtypes = [vp, vp, sz, vp, vp, vp]
         L.gub_submit_device_n.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.gub_submit_compact.argtypes = [vp, vp, sz, vp, sz, i64, vp, vp]
+        L.gub_submit_compact_async.argtypes = [vp, vp, sz, vp, sz, i64, vp, vp, C.POINTER(i32)]
         L.gub_pipeline_depth.argtypes = [vp]
         L.gub_submit_async.argtypes = [vp, vp, sz, vp, vp, C.POINTER(i32)]
         L.gub_wait.argtypes = [vp, i32]
@@ -134,6 +139,24 @@ def hash_keys(keys):
     return xx, fv
 
 
+def compact_batch(reqs: np.ndarray):
+    """gub_req records -> (gub_creq records, gub_params table, created_base): what a shim that knows its limit
+    configurations fills directly.  created_base is the smallest created_at (deltas must fit int32)."""
+    cfg = np.zeros(len(reqs), dtype=PARAMS_DTYPE)
+    for f in ("limit", "duration", "burst", "algorithm", "behavior"):
+        cfg[f] = reqs[f]
+    params, inv = np.unique(cfg, return_inverse=True)
+    base = int(reqs["created_at"].min()) if len(reqs) else 0
+    delta = reqs["created_at"] - base
+    if len(reqs) and (delta.max() > 0x7FFFFFFF):
+        raise ValueError("created_at spread does not fit the compact record")
+    c = np.zeros(len(reqs), dtype=CREQ_DTYPE)
+    c["key_xxh64"], c["key_fnv1"], c["hits"] = reqs["key_xxh64"], reqs["key_fnv1"], reqs["hits"]
+    c["params"] = inv.astype(np.uint32).reshape(-1)
+    c["created_delta"] = delta.astype(np.int32)
+    return c, np.ascontiguousarray(params), base
+
+
 def clock_fill(now_ms):
     clk = np.zeros(1, dtype=CLOCK_DTYPE)
     _check(lib().gub_clock_fill(int(now_ms), clk.ctypes.data), "gub_clock_fill")
@@ -198,6 +221,20 @@ class Table:
 
     def wait(self, ticket):
         _check(lib().gub_wait(self._h, ticket), "gub_wait")
+
+    def submit_compact(self, creqs: np.ndarray, params: np.ndarray, created_base, clk: np.ndarray, out: np.ndarray = None):
+        assert creqs.dtype == CREQ_DTYPE and params.dtype == PARAMS_DTYPE and creqs.flags.c_contiguous and params.flags.c_contiguous
+        if out is None:
+            out = np.zeros(len(creqs), dtype=RESP_DTYPE)
+        _check(lib().gub_submit_compact(self._h, creqs.ctypes.data, len(creqs), params.ctypes.data, len(params), int(created_base),
+                                        clk.ctypes.data, out.ctypes.data), "gub_submit_compact")
+        return out
+
+    def submit_compact_async(self, creqs_ptr, n, params_ptr, n_params, created_base, clk: np.ndarray, out_ptr):
+        ticket = C.c_int(-1)
+        _check(lib().gub_submit_compact_async(self._h, creqs_ptr, n, params_ptr, n_params, int(created_base), clk.ctypes.data, out_ptr,
+                                              C.byref(ticket)), "gub_submit_compact_async")
+        return ticket.value
 
     def submit_device(self, d_reqs_ptr, n, clk: np.ndarray, d_out_ptr, stream=0):
         _check(lib().gub_submit_device(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_submit_device")

@@ -147,6 +147,27 @@ int gub_pipeline_depth(gub_table* t);
 int gub_submit_async(gub_table* t, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out, int* ticket);
 int gub_wait(gub_table* t, int ticket);
 
+/* ---- compact requests: the host link is the bottleneck of the host-to-host path (64 B per request over PCIe), and most
+ * of a RateLimitReq is per-limit configuration that repeats across a batch.  A compact batch carries 32-byte records
+ * plus one small table of the distinct (limit, duration, burst, algorithm, behavior) tuples; a kernel expands it to
+ * gub_req records on the device and the normal path runs.  Results are identical to submitting the expanded batch. */
+typedef struct {
+  uint64_t key_xxh64;
+  uint64_t key_fnv1;
+  int64_t hits;
+  uint32_t params;        /* index into the batch's gub_params table */
+  int32_t created_delta;  /* created_at = created_base + created_delta (ms) */
+} gub_creq;               /* 32 bytes */
+typedef struct {
+  int64_t limit, duration, burst;
+  uint32_t algorithm;
+  uint32_t behavior;      /* Behavior bits | GUB_REQ_IS_OWNER */
+} gub_params;             /* 32 bytes */
+int gub_submit_compact_async(gub_table* t, const gub_creq* reqs, size_t n, const gub_params* params, size_t n_params,
+                             int64_t created_base, const gub_clock* clk, gub_resp* out, int* ticket);
+int gub_submit_compact(gub_table* t, const gub_creq* reqs, size_t n, const gub_params* params, size_t n_params,
+                       int64_t created_base, const gub_clock* clk, gub_resp* out);
+
 /* Page-locked host memory for request/response buffers: with these the H2D/D2H copies of gub_submit_async are truly
  * asynchronous (a Go shim allocates its batch arenas here once).  Any other host memory works too, just slower. */
 void* gub_host_alloc(size_t bytes);

@@ -296,6 +296,27 @@ def test_async_pipeline_matches_sync(G):
         rq.free(); rs.free()
 
 
+def test_compact_requests_equal_full_records(G):
+    """gub_submit_compact (32-byte records + a parameter table, expanded on the device) == gub_submit of the same batch."""
+    rng = np.random.default_rng(61)
+    a, b = G.Table(1 << 16), G.Table(1 << 16)
+    pool = O.Pool(now_ms=T0)
+    for step in range(4):
+        now = T0 + 500 * step
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, [5000, 1, 65536, 3000][step], 200, now)
+        creqs, params, base = G.native.compact_batch(reqs)
+        clk = G.clock_fill(now)
+        want = pool.submit_hashed(reqs)
+        _cmp(a.submit(reqs, clk), want, f"full step {step}")
+        _cmp(b.submit_compact(creqs, params, base, clk), want, f"compact step {step}")
+    # an out-of-range parameter index is an in-band error, nothing is stored
+    creqs, params, base = G.native.compact_batch(adversarial_batch(rng, 10, 3, T0))
+    creqs["params"][3] = 10_000
+    out = b.submit_compact(creqs, params, base, G.clock_fill(T0))
+    assert out["err_code"][3] == G.native.ERR_INVALID_ALGORITHM
+
+
 def test_submit_device_and_route(G):
     """Device-resident buffers (torch is only the allocator) + the ring routing kernels vs the oracle ring."""
     import torch
