@@ -17,18 +17,19 @@
 //
 //   k_group  (256 consecutive requests per block) shared-memory grouping with index-ordered local ranks; one thread per
 //            distinct (block, key) "fragment" joins the batch-wide group entry (count += members), sets the block's bit
-//            in the group's presence bitmap and stores the fragment size.
-//            It also prefetches every request's home slot into L2: the table is not needed until two kernels later.
-//   k_rank   (table-free) members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank, and
-//            compare their request with the group's representative; any difference marks the group non-uniform.
-//   k_eval   every request of a uniform run (a key seen once is a run of one) probes its slot (64 B, now an L2 hit),
-//            evaluates run_to_rank(bucket, request, rank) and answers.  Singletons write their slot back at once; the
-//            last rank of a longer run parks the final state in a commit record (its siblings may still be reading the
-//            slot).  Members of non-uniform runs only file themselves: order[base + rank] = index.
-//   k_finish commit records are written to the table; one block per non-uniform group splits the ordered run into
-//            segments of identical requests, plans each with plan_run() on one thread and evaluates/scatters with all
-//            threads (serial walk when there are too many segments).
-// k_group and k_rank never read or write bucket state, so they can run for batch b+1 while batch b is still in k_eval.
+//            in the group's presence bitmap and stores the fragment size.  Prefetches every request's home slot into L2.
+//   k_rank   members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank and compare their
+//            request with the group's representative; any difference marks the group non-uniform.  In the default build
+//            (GUB_EARLY_SINGLES=1) keys seen once — most keys — are also evaluated right here (probe, apply_one, write-back,
+//            response) and the rank-0 member of a repeated key parks the slot as found in a snapshot.
+//   k_eval   every member of a uniform run evaluates run_to_rank(snapshot, request, rank) and answers; the last rank writes
+//            the slot back.  Members of non-uniform runs only file themselves: order[base + rank] = index.
+//   k_finish one block per non-uniform group: split the ordered run into segments of identical requests, plan each with
+//            plan_run() on one thread, evaluate/scatter with all threads (serial walk when there are too many segments).
+// With GUB_EARLY_SINGLES=0, k_group and k_rank never touch bucket state (everything is evaluated in k_eval, repeated keys
+// are written back by k_finish from commit records), so stage 1 of batch b+1 may overlap stage 2 of batch b.
+// The four kernels are chained with programmatic dependent launch; block requests are partitioned by algorithm so that a
+// warp runs one bucket algorithm's code path.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -138,21 +139,13 @@ struct Cursor {  // one key's slot while requests are applied to it
 
 // Looks `key` up.  On a hit the slot is loaded into cur.b.  On a miss cur.b is an empty (not live) bucket and cur.slot
 // is the first reusable slot (tombstone or empty) seen, if any.
-struct HomeSlot { ulonglong2 a, b, c, d; };  // a key's home slot, loaded ahead of time so its latency overlaps other loads
-
-__device__ __forceinline__ void home_load(HomeSlot& h, const Slot* table, uint64_t cap, uint64_t key) {
-  slot_load(table + __umul64hi(key, cap), h.a, h.b, h.c, h.d);
-}
-
-template <bool PRELOADED = false>
-__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag, const HomeSlot* first = nullptr) {
+__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag) {
   uint64_t idx = __umul64hi(key, cap);
   cur.home = idx; cur.found = false; cur.slot = -1;
 #pragma unroll 1
   for (int p = 0; p < MAX_PROBE; p++) {
     ulonglong2 a, b, c, d;
-    if (PRELOADED && p == 0) { a = first->a; b = first->b; c = first->c; d = first->d; }
-    else slot_load(table + idx, a, b, c, d);
+    slot_load(table + idx, a, b, c, d);
     if (a.x == key && (a.y >> 8) == tag) {
       bucket_from(cur.b, a, b, c, d);
       cur.old = cur.b; cur.slot = (int64_t)idx; cur.found = true;
