@@ -165,8 +165,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # a step is one batch of the workload; with many steps the batch is shrunk so that the whole run stays within ~a minute
-    step_size = BATCH if args.steps <= 1000 else max(2048, int(BATCH * 1000 / args.steps) // 256 * 256)
+    # a step is one 65 536-request batch of the workload (~2.5 ms on 128 threads); only beyond 20 000 steps is the batch shrunk so
+    # that the whole run stays within about a minute
+    step_size = BATCH if args.steps <= 20000 else max(2048, int(BATCH * 20000 / args.steps) // 256 * 256)
     r = cpu_leg(args.cpu_keys, args.zipf, args.cpu_seconds, 0xB200 + 3, steps=args.steps, warmup=min(args.warmup, 20), step_size=step_size)
     sample = (f"{r['steps']} x {step_size}-request Zipf({args.zipf}) batches over {r['keys']:,} resident keys (scaled down from "
               f"{args.keys:,} to bound the warm pass), TOKEN/LEAKY 50/50, {r['cores']} worker threads")
