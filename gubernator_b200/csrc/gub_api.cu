@@ -589,6 +589,17 @@ int gub_get_counters(gub_table* t, gub_counters* out) {
   return 0;
 }
 
+int gub_hash_keys_device(gub_table* t, const char* d_bytes, const uint64_t* d_offsets, size_t n, uint64_t* d_xxh64_out, uint64_t* d_fnv1_out,
+                         gub_req* d_reqs_out, void* stream) {
+  if (!t || (n && (!d_bytes || !d_offsets))) return fail("gub_hash_keys_device: null argument");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(t->device));
+  gub::k_hash_keys<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(d_bytes), d_offsets, (uint32_t)n,
+                                                                                 d_xxh64_out, d_fnv1_out, d_reqs_out);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int gub_set_profiling(gub_table* t, int on) {
   if (!t) return fail("gub_set_profiling: null argument");
   std::lock_guard<std::mutex> lk(t->mu);

@@ -717,6 +717,61 @@ __global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A, 
   tally_flush_block(t, A.counters);
 }
 
+// ---- key hashing on the device: client.go:39-41 HashKey + workers.go:153 XXH64 + replicated_hash.go:108 FNV-1 ----------
+// One thread per key; keys are packed back to back (key i = bytes[offsets[i] .. offsets[i+1])).  The step right before the
+// path: a shim can ship raw key bytes instead of hashing on the CPU.
+__device__ __forceinline__ uint64_t rotl64(uint64_t v, int s) { return (v << s) | (v >> (64 - s)); }
+__device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
+  uint64_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) v |= (uint64_t)p[k] << (8 * k);
+  return v;
+}
+__device__ __forceinline__ uint64_t xxh_lane(uint64_t acc, uint64_t w) { return rotl64(acc + w * 0xC2B2AE3D27D4EB4Full, 31) * 0x9E3779B185EBCA87ull; }
+
+__global__ void __launch_bounds__(256) k_hash_keys(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint64_t* xxh_out, uint64_t* fnv_out,
+                                                   gub_req* reqs_out /* optional: fill key_xxh64 / key_fnv1 of request i */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull,
+                     P5 = 0x27D4EB2F165667C5ull;
+  const uint8_t* p = bytes + offsets[i];
+  const uint64_t len = offsets[i + 1] - offsets[i];
+  // FNV-1 64 over the whole key
+  uint64_t f = 0xCBF29CE484222325ull;
+  for (uint64_t k = 0; k < len; k++) f = (f * 0x100000001B3ull) ^ p[k];
+  // XXH64, seed 0
+  const uint8_t* q = p;
+  const uint8_t* const end = p + len;
+  uint64_t h;
+  if (len >= 32) {
+    uint64_t v1 = P1 + P2, v2 = P2, v3 = 0, v4 = 0 - P1;
+    for (; end - q >= 32; q += 32) {
+      v1 = xxh_lane(v1, load_u64_le(q)); v2 = xxh_lane(v2, load_u64_le(q + 8));
+      v3 = xxh_lane(v3, load_u64_le(q + 16)); v4 = xxh_lane(v4, load_u64_le(q + 24));
+    }
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = (h ^ xxh_lane(0, v1)) * P1 + P4; h = (h ^ xxh_lane(0, v2)) * P1 + P4;
+    h = (h ^ xxh_lane(0, v3)) * P1 + P4; h = (h ^ xxh_lane(0, v4)) * P1 + P4;
+  } else {
+    h = P5;
+  }
+  h += len;
+  for (; end - q >= 8; q += 8) h = rotl64(h ^ xxh_lane(0, load_u64_le(q)), 27) * P1 + P4;
+  if (end - q >= 4) {
+    const uint64_t w = (uint64_t)q[0] | ((uint64_t)q[1] << 8) | ((uint64_t)q[2] << 16) | ((uint64_t)q[3] << 24);
+    h = rotl64(h ^ (w * P1), 23) * P2 + P3;
+    q += 4;
+  }
+  for (; q < end; q++) h = rotl64(h ^ (*q * P5), 11) * P1;
+  h = (h ^ (h >> 33)) * P2;
+  h = (h ^ (h >> 29)) * P3;
+  h ^= h >> 32;
+  if (xxh_out) xxh_out[i] = h;
+  if (fnv_out) fnv_out[i] = f;
+  if (reqs_out) { reqs_out[i].key_xxh64 = h; reqs_out[i].key_fnv1 = f; }
+}
+
 // ---- compact requests -> gub_req records (see gub_creq in the header) --------------------------------------------------
 __global__ void __launch_bounds__(256) k_expand(const gub_creq* creqs, uint32_t n, const gub_params* params, uint32_t n_params, int64_t created_base,
                                                 gub_req* out) {

@@ -29,7 +29,7 @@ assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.it
 
 EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n", "gub_submit_compact", "gub_submit_compact_async",
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
-           "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys",
+           "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys", "gub_hash_keys_device",
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
            "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
@@ -78,6 +78,7 @@ def lib():
         L.gub_set_profiling.argtypes = [vp, i32]
         L.gub_get_profile.argtypes = [vp, vp, vp, i32]
         L.gub_hash_keys.argtypes = [vp, vp, sz, vp, vp]
+        L.gub_hash_keys_device.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.gub_xxh64.argtypes = [C.c_char_p, sz, u64]; L.gub_xxh64.restype = u64
         L.gub_fnv1_64.argtypes = [C.c_char_p, sz]; L.gub_fnv1_64.restype = u64
         L.gub_fnv1a_64.argtypes = [C.c_char_p, sz]; L.gub_fnv1a_64.restype = u64
@@ -273,6 +274,9 @@ class Table:
         c = np.zeros(len(COUNTER_FIELDS), dtype=np.uint64)
         _check(lib().gub_get_counters(self._h, c.ctypes.data), "gub_get_counters")
         return {k: int(v) for k, v in zip(COUNTER_FIELDS, c)}
+
+    def hash_keys_device(self, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr=None, stream=0):
+        _check(lib().gub_hash_keys_device(self._h, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr, stream), "gub_hash_keys_device")
 
     def set_profiling(self, on):
         _check(lib().gub_set_profiling(self._h, 1 if on else 0), "gub_set_profiling")

@@ -200,6 +200,10 @@ int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int r
 /* ---- key hashing: client.go:39-41 HashKey + workers.go:153 + replicated_hash.go:108 -------------------------
  * keys are packed back to back in `bytes`; key i is bytes[offsets[i] .. offsets[i+1]).  Host implementation. */
 int gub_hash_keys(const char* bytes, const uint64_t* offsets, size_t n, uint64_t* xxh64_out, uint64_t* fnv1_out);
+/* The same on the device (all pointers device pointers on the table's GPU, enqueued on `stream`): outputs may be NULL;
+ * d_reqs_out, when given, receives the two hashes in request i's key_xxh64 / key_fnv1 fields. */
+int gub_hash_keys_device(gub_table* t, const char* d_bytes, const uint64_t* d_offsets, size_t n, uint64_t* d_xxh64_out,
+                         uint64_t* d_fnv1_out, gub_req* d_reqs_out, void* stream);
 uint64_t gub_xxh64(const void* data, size_t len, uint64_t seed);
 uint64_t gub_fnv1_64(const void* data, size_t len);
 uint64_t gub_fnv1a_64(const void* data, size_t len);

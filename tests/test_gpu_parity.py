@@ -8,7 +8,7 @@ import pytest
 import oracle_py as O
 from golden import reference_kat as K
 from kat_player import play_missing_fields, play_scenario
-from workloads import T0, adversarial_batch, bench_batch, key_hashes
+from workloads import T0, adversarial_batch, bench_batch, extreme_batch, key_hashes
 
 pytestmark = pytest.mark.gpu
 
@@ -108,6 +108,23 @@ def test_adversarial_differential(G, seed, n_keys, n):
     _check_table_equals_oracle(G, tab, pool)
     c = tab.counters()
     assert c["requests"] == 8 * n and c["table_full"] == 0
+
+
+@pytest.mark.parametrize("seed,n_keys", [(0, 5), (1, 300), (2, 4000)])
+def test_numeric_extremes_differential(G, seed, n_keys):
+    """int64 wrap-around, float64 beyond 2^52 / 2^63, Go's int64(float64) on overflow and NaN (cvt.rzi saturates on the GPU and
+    is patched in f2i), negative limits and durations, created_at +-2^62."""
+    rng = np.random.default_rng(7000 + seed)
+    tab = G.Table(1 << 16)
+    pool = O.Pool(workers=4, cache_size=10_000_000, now_ms=T0)
+    now = T0
+    for b in range(8):
+        now += int(rng.choice([0, 1, 1000, 61000]))
+        pool.set_now(now)
+        reqs = extreme_batch(rng, 12000, n_keys, now)
+        _cmp(tab.submit(reqs, G.clock_fill(now)), pool.submit_hashed(reqs), f"batch {b}")
+        _cmp_counters(tab, pool)
+    _check_table_equals_oracle(G, tab, pool)
 
 
 def test_config2_uniform_token_1m_keys(G):
@@ -373,3 +390,27 @@ def test_epoch_wrap(G):
         if b in checkpoints:
             torch.cuda.synchronize()
             _cmp(d_out.cpu().numpy().reshape(-1).view(G.RESP_DTYPE), want, f"batch {b}")
+
+
+def test_device_key_hashing_matches_host(G):
+    """XXH64 + FNV-1 of packed key strings on the device == the host implementation (itself pinned to python-xxhash and the
+    reference's ring golden vector): every length 0..200 incl. the >= 32-byte XXH64 path, and the BASELINE key format."""
+    import torch
+    rng = np.random.default_rng(5)
+    keys = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in range(0, 201)] + [f"bench_k{i:09d}".encode() for i in range(5000)]
+    keys += [b"test_over_limit_account:1234", b"a" * 1000]
+    offs = np.zeros(len(keys) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(k) for k in keys])
+    blob = np.frombuffer(b"".join(keys), dtype=np.uint8)
+    tab = G.Table(1024)
+    d_blob, d_offs = torch.from_numpy(blob.copy()).cuda(), torch.from_numpy(offs.view(np.int64).copy()).cuda()
+    d_xx = torch.zeros(len(keys), dtype=torch.int64, device="cuda"); d_fv = torch.zeros_like(d_xx)
+    d_reqs = torch.zeros((len(keys), 64), dtype=torch.uint8, device="cuda")
+    tab.hash_keys_device(d_blob.data_ptr(), d_offs.data_ptr(), len(keys), d_xx.data_ptr(), d_fv.data_ptr(), d_reqs.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    xx, fv = G.hash_keys(keys)
+    assert np.array_equal(d_xx.cpu().numpy().view(np.uint64), xx) and np.array_equal(d_fv.cpu().numpy().view(np.uint64), fv)
+    r = d_reqs.cpu().numpy().reshape(-1).view(G.REQ_DTYPE)
+    assert np.array_equal(r["key_xxh64"], xx) and np.array_equal(r["key_fnv1"], fv)
+    assert int(xx[keys.index(b"bench_k000000042")]) == O.xxh64(b"bench_k000000042")

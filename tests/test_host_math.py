@@ -5,7 +5,7 @@ import pytest
 
 import oracle_py as O
 from _host_math import BUCKET_DTYPE, F_LEAKY, F_LIVE, F_OVER, HostTable, plan_check, rank_check
-from workloads import T0, adversarial_batch, bench_batch, make_clock
+from workloads import T0, adversarial_batch, bench_batch, extreme_batch, make_clock
 
 
 def _cmp(a, b):
@@ -101,3 +101,21 @@ def test_plan_run_compresses_hot_key_run():
         rc, npieces, covered = plan_check(b, rq, 7300, clk, 16)
         assert rc == 0 and covered == 7300 and npieces <= 6, (algo, rc, npieces, covered)
         assert rank_check(b, rq, 7300, clk, stride=1) == 0
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_apply_one_matches_oracle_on_numeric_extremes(seed):
+    """int64 wrap-around, float64 beyond 2^52 / 2^63, Go's int64(float64) on overflow and NaN, negative limits/durations."""
+    rng = np.random.default_rng(4000 + seed)
+    pool = O.Pool(workers=3, cache_size=10_000_000, now_ms=T0)
+    host = HostTable()
+    now = T0
+    for batch in range(10):
+        now += int(rng.choice([0, 1, 1000, 61000]))
+        pool.set_now(now)
+        reqs = extreme_batch(rng, 4000, int(rng.choice([5, 60, 900])), now)
+        want = pool.submit_hashed(reqs)
+        got, ctr = host.apply_seq(reqs, make_clock(now))
+        _cmp(got, want)
+        oc = pool.counters()
+        assert (ctr["over_limit"], ctr["cache_hit"], ctr["cache_miss"]) == (oc["over_limit"], oc["cache_hit"], oc["cache_miss"])

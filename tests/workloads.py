@@ -190,3 +190,30 @@ def bench_requests(ids, created_at, mixed=True, prefix=b"bench_k", dtype=None):
     reqs["algorithm"] = (ids & 1) if mixed else 0
     reqs["behavior"] = O.REQ_IS_OWNER
     return reqs
+
+
+def extreme_batch(rng, n, n_keys, now_ms):
+    """Requests whose numeric fields sit on the edges of int64 / float64: wrapping sums, 2^52..2^63 leaky values, zero and
+    negative limits and durations, created_at far in the past and future.  Same-key repeats included."""
+    E = np.array([0, 1, -1, 2, 7, 100, (1 << 31), (1 << 52) - 1, (1 << 52), (1 << 53) + 1, (1 << 62), (1 << 63) - 1, -(1 << 63),
+                  -(1 << 62), -(1 << 53), -3, 60000, 1000], dtype=np.int64)
+    reqs = np.zeros(n, dtype=O.HREQ_DTYPE)
+    ids = rng.integers(0, n_keys, n)
+    reqs["key_xxh64"], reqs["key_fnv1"] = key_hashes(ids, name="ext")
+    reqs["hits"] = rng.choice(E, n); reqs["limit"] = rng.choice(E, n); reqs["duration"] = rng.choice(E, n)
+    reqs["burst"] = rng.choice(E, n)
+    reqs["created_at"] = now_ms + rng.choice(np.array([0, 0, 1, -1, 60000, -60000, 1 << 40, -(1 << 40), (1 << 62)], dtype=np.int64), n)
+    reqs["algorithm"] = rng.integers(0, 2, n)
+    reqs["behavior"] = rng.choice(np.array([0, 0, O.RESET_REMAINING, O.DRAIN_OVER_LIMIT, O.DURATION_IS_GREGORIAN], dtype=np.uint32), n) | np.uint32(O.REQ_IS_OWNER)
+    greg = (reqs["behavior"] & O.DURATION_IS_GREGORIAN) != 0
+    reqs["duration"][greg] = rng.integers(-1, 7, int(greg.sum()))
+    # make a third of the traffic repeat the previous request of the same key exactly (uniform runs of extreme values)
+    last = {}
+    for i in range(n):
+        k = int(ids[i])
+        if k in last and rng.random() < 0.35:
+            j = last[k]
+            for f in ("hits", "limit", "duration", "burst", "created_at", "algorithm", "behavior"):
+                reqs[f][i] = reqs[f][j]
+        last[k] = i
+    return reqs
