@@ -1,7 +1,11 @@
 // host_v1.cpp — C++ stand-in for the Go side of the boundary (include/gubernator_b200_host.h): the request loop of
 // V1Instance.GetRateLimits (gubernator.go:183-295) re-expressed as "validate, hash, one device batch, map errors".
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,13 +58,19 @@ void gub_instance_destroy(gub_instance* s) { delete s; }
 void gub_instance_set_clock(gub_instance* s, int64_t frozen_now_ms) { s->frozen_now = frozen_now_ms; }
 int64_t gub_instance_now(gub_instance* s) { return s->frozen_now >= 0 ? s->frozen_now : wall_ms(); }
 
-int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out) {
-  if (!s || (n && (!reqs || !out))) return -1;
-  const int64_t now = gub_instance_now(s);  // gubernator.go:195: one timestamp per call
+}  // extern "C"
+
+namespace {
+// One GetRateLimits call, validated and hashed (gubernator.go:195-220): the requests that reach the device and where their
+// answers go.
+struct PreparedCall {
   std::vector<gub_req> batch;
-  std::vector<size_t> where;      // batch position -> request index
+  std::vector<size_t> where;      // batch position -> request index of the call
   std::vector<std::string> keys;  // for error text
-  batch.reserve(n); where.reserve(n); keys.reserve(n);
+};
+
+void prepare_call(const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out, int64_t now, PreparedCall& pc) {
+  pc.batch.reserve(n); pc.where.reserve(n); pc.keys.reserve(n);
   for (size_t i = 0; i < n; i++) {
     gub_rate_limit_resp& o = out[i];
     std::memset(&o, 0, sizeof o);
@@ -84,22 +94,36 @@ int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit
     r.created_at = reqs[i].created_at != 0 ? reqs[i].created_at : now;  // :218-220
     r.algorithm = (uint32_t)reqs[i].algorithm;
     r.behavior = ((uint32_t)reqs[i].behavior & 0xFFu) | GUB_REQ_IS_OWNER;  // one-node cluster: every key is ours (:247-250)
-    batch.push_back(r); where.push_back(i); keys.push_back(std::move(key));
+    pc.batch.push_back(r); pc.where.push_back(i); pc.keys.push_back(std::move(key));
   }
-  if (batch.empty()) return 0;
-  gub_clock clk;
-  gub_clock_fill(now, &clk);
-  std::vector<gub_resp> resp(batch.size());
-  if (gub_submit(s->table, batch.data(), batch.size(), &clk, resp.data()) != 0) return -1;
-  for (size_t j = 0; j < batch.size(); j++) {
-    gub_rate_limit_resp& o = out[where[j]];
+}
+
+void finish_call(const PreparedCall& pc, const gub_rate_limit_req* reqs, const gub_resp* resp, gub_rate_limit_resp* out) {
+  for (size_t j = 0; j < pc.batch.size(); j++) {
+    gub_rate_limit_resp& o = out[pc.where[j]];
     o.err_code = (int32_t)resp[j].err_code;
     if (resp[j].err_code) {
-      gub_format_error((int)resp[j].err_code, keys[j].c_str(), reqs[where[j]].algorithm, o.error, sizeof o.error);
+      gub_format_error((int)resp[j].err_code, pc.keys[j].c_str(), reqs[pc.where[j]].algorithm, o.error, sizeof o.error);
     } else {
       o.status = (int32_t)resp[j].status; o.limit = resp[j].limit; o.remaining = resp[j].remaining; o.reset_time = resp[j].reset_time;
     }
   }
+}
+}  // namespace
+
+extern "C" {
+
+int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out) {
+  if (!s || (n && (!reqs || !out))) return -1;
+  const int64_t now = gub_instance_now(s);  // gubernator.go:195: one timestamp per call
+  PreparedCall pc;
+  prepare_call(reqs, n, out, now, pc);
+  if (pc.batch.empty()) return 0;
+  gub_clock clk;
+  gub_clock_fill(now, &clk);
+  std::vector<gub_resp> resp(pc.batch.size());
+  if (gub_submit(s->table, pc.batch.data(), pc.batch.size(), &clk, resp.data()) != 0) return -1;
+  finish_call(pc, reqs, resp.data(), out);
   return 0;
 }
 
@@ -122,6 +146,114 @@ int gub_instance_update_peer_global(gub_instance* s, const char* key, int32_t al
   if (algorithm == GUB_LEAKY_BUCKET) { it.remaining_f = (double)remaining; it.burst = limit; }  // :435-442
   else { it.status = status; it.remaining = remaining; }                                       // :443-450
   return gub_add_items(s->table, &it, 1);
+}
+
+}  // extern "C"
+
+// ---- RPC aggregator ---------------------------------------------------------------------------------------------
+struct gub_aggregator {
+  gub_instance* inst = nullptr;
+  uint32_t max_batch = 65536, window_us = 500;
+  struct Call {
+    const gub_rate_limit_req* reqs; size_t n; gub_rate_limit_resp* out;
+    PreparedCall pc;
+    bool done = false; int rc = 0;
+  };
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<Call*> queue;
+  size_t queued = 0;
+  bool stop = false;
+  uint64_t batches = 0, requests = 0;
+  std::thread flusher;
+
+  void run() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv_work.wait(lk, [&] { return stop || !queue.empty(); });
+      if (stop && queue.empty()) return;
+      // BatchWait: give other callers `window_us` to join, unless the batch is already full (peer_client.go:296-330)
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(window_us);
+      cv_work.wait_until(lk, deadline, [&] { return stop || queued >= max_batch; });
+      std::vector<Call*> calls(queue.begin(), queue.end());
+      queue.clear();
+      queued = 0;
+      lk.unlock();
+      flush(calls);
+      lk.lock();
+      for (Call* c : calls) c->done = true;
+      cv_done.notify_all();
+    }
+  }
+
+  void flush(std::vector<Call*>& calls) {
+    // arrival order, each call's requests in index order: sequential semantics across the coalesced calls
+    std::vector<gub_req> batch;
+    size_t total = 0;
+    for (Call* c : calls) total += c->pc.batch.size();
+    batch.reserve(total);
+    for (Call* c : calls) batch.insert(batch.end(), c->pc.batch.begin(), c->pc.batch.end());
+    int rc = 0;
+    std::vector<gub_resp> resp(total);
+    if (total) {
+      gub_clock clk;
+      gub_clock_fill(gub_instance_now(inst), &clk);
+      rc = gub_submit(inst->table, batch.data(), total, &clk, resp.data());
+    }
+    size_t off = 0;
+    for (Call* c : calls) {
+      c->rc = rc;
+      if (rc == 0) finish_call(c->pc, c->reqs, resp.data() + off, c->out);
+      off += c->pc.batch.size();
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    batches += total ? 1 : 0;
+    requests += total;
+  }
+};
+
+extern "C" {
+
+int gub_aggregator_create(gub_instance* s, uint32_t max_batch, uint32_t window_us, gub_aggregator** out) {
+  if (!s || !out) return -1;
+  gub_aggregator* a = new gub_aggregator();
+  a->inst = s;
+  a->max_batch = max_batch ? max_batch : 65536;
+  a->window_us = window_us;
+  a->flusher = std::thread([a] { a->run(); });
+  *out = a;
+  return 0;
+}
+
+void gub_aggregator_destroy(gub_aggregator* a) {
+  if (!a) return;
+  {
+    std::lock_guard<std::mutex> lk(a->mu);
+    a->stop = true;
+  }
+  a->cv_work.notify_all();
+  a->flusher.join();
+  delete a;
+}
+
+int gub_aggregator_get_rate_limits(gub_aggregator* a, const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out) {
+  if (!a || (n && (!reqs || !out))) return -1;
+  if (n > GUB_MAX_BATCH_SIZE) return GUB_E_TOO_LARGE;  // gubernator.go:189-193
+  gub_aggregator::Call call;
+  call.reqs = reqs; call.n = n; call.out = out;
+  prepare_call(reqs, n, out, gub_instance_now(a->inst), call.pc);  // gubernator.go:195: the call's own timestamp
+  std::unique_lock<std::mutex> lk(a->mu);
+  a->queue.push_back(&call);
+  a->queued += call.pc.batch.size();
+  a->cv_work.notify_all();
+  a->cv_done.wait(lk, [&] { return call.done; });
+  return call.rc;
+}
+
+void gub_aggregator_stats(gub_aggregator* a, uint64_t* batches, uint64_t* requests) {
+  std::lock_guard<std::mutex> lk(a->mu);
+  if (batches) *batches = a->batches;
+  if (requests) *requests = a->requests;
 }
 
 }  // extern "C"

@@ -56,6 +56,10 @@ def _bind():
         L.gub_instance_get_rate_limits.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
         L.gub_instance_get_rate_limits_unbounded.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
         L.gub_instance_update_peer_global.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]
+        L.gub_aggregator_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+        L.gub_aggregator_destroy.argtypes = [vp]; L.gub_aggregator_destroy.restype = None
+        L.gub_aggregator_get_rate_limits.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
+        L.gub_aggregator_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]; L.gub_aggregator_stats.restype = None
         _bound = True
     return L
 
@@ -83,7 +87,11 @@ class V1Instance:
     def advance(self, ms):
         self.set_now(self.now() + int(ms))
 
-    def get_rate_limits(self, reqs, unbounded=False):
+    def aggregator(self, max_batch=65536, window_us=500):
+        """RPC aggregator over this instance: concurrent get_rate_limits calls share device batches."""
+        return Aggregator(self, max_batch, window_us)
+
+    def get_rate_limits(self, reqs, unbounded=False, _via=None):
         """reqs: list of RateLimitReq or dicts.  Returns list of dicts like the oracle binding (status, limit, remaining,
         reset_time, error).  Raises ValueError for more than 1000 requests (gubernator.go:189-193)."""
         L = _bind()
@@ -98,8 +106,11 @@ class V1Instance:
             arr[i].burst = r.get("burst", 0); arr[i].algorithm = r.get("algorithm", 0); arr[i].behavior = r.get("behavior", 0)
             arr[i].created_at = r.get("created_at", 0) or 0
         out = (_Resp * max(n, 1))()
-        fn = L.gub_instance_get_rate_limits_unbounded if unbounded else L.gub_instance_get_rate_limits
-        rc = fn(self._h, arr, n, out)
+        if _via is not None:
+            rc = L.gub_aggregator_get_rate_limits(_via, arr, n, out)  # releases the GIL: other threads' calls join the batch
+        else:
+            fn = L.gub_instance_get_rate_limits_unbounded if unbounded else L.gub_instance_get_rate_limits
+            rc = fn(self._h, arr, n, out)
         if rc == -2:
             raise ValueError("Requests.RateLimits list too large; max size is '1000'")
         if rc != 0:
@@ -118,6 +129,38 @@ class V1Instance:
     def close(self):
         if getattr(self, "_h", None):
             _bind().gub_instance_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Aggregator:
+    """Coalesces concurrent GetRateLimits calls into device batches (gub_aggregator_*): the stand-in for the batching the Go
+    shim does in front of the C ABI, shaped after PeerClient.runBatch (peer_client.go:284-337)."""
+
+    def __init__(self, instance, max_batch=65536, window_us=500):
+        L = _bind()
+        self.instance = instance
+        h = C.c_void_p()
+        if L.gub_aggregator_create(instance._h, max_batch, window_us, C.byref(h)) != 0:
+            raise native.GubError("gub_aggregator_create failed")
+        self._h = h
+
+    def get_rate_limits(self, reqs):
+        return self.instance.get_rate_limits(reqs, _via=self._h)
+
+    def stats(self):
+        b, r = C.c_uint64(0), C.c_uint64(0)
+        _bind().gub_aggregator_stats(self._h, C.byref(b), C.byref(r))
+        return dict(batches=b.value, requests=r.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _bind().gub_aggregator_destroy(self._h)
             self._h = None
 
     def __del__(self):

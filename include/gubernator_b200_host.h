@@ -51,6 +51,19 @@ int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit
 /* V1Instance.UpdatePeerGlobals (gubernator.go:425-459) for one entry: builds the replica item and upserts it. */
 int gub_instance_update_peer_global(gub_instance* s, const char* key, int32_t algorithm, int64_t duration, int32_t status,
                                     int64_t limit, int64_t remaining, int64_t reset_time);
+/* ---- RPC aggregator: concurrent GetRateLimits calls (<= 1000 requests each, gubernator.go:40) are
+ * coalesced into one device batch, the way PeerClient.runBatch coalesces peer requests (peer_client.go:284-337): a flush
+ * happens when `max_batch` requests are queued or `window_us` after the first queued call (BatchWait = 500 us,
+ * config.go:128).  Calls are applied in arrival order, each call's requests in index order, so every caller sees exactly
+ * what it would see if the calls had been served one after another.  Thread-safe; blocks the caller until its responses
+ * are filled.  Returns GUB_E_TOO_LARGE for more than 1000 requests. */
+typedef struct gub_aggregator gub_aggregator;
+int gub_aggregator_create(gub_instance* s, uint32_t max_batch, uint32_t window_us, gub_aggregator** out);
+void gub_aggregator_destroy(gub_aggregator* a);
+int gub_aggregator_get_rate_limits(gub_aggregator* a, const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out);
+/* device batches flushed / requests carried so far */
+void gub_aggregator_stats(gub_aggregator* a, uint64_t* batches, uint64_t* requests);
+
 /* RateLimitResp.Error text for an in-band error code on `key` (workers.go:304-318, gubernator.go:252,600). */
 void gub_format_error(int err_code, const char* key, int32_t algorithm, char* out, size_t cap);
 

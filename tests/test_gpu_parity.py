@@ -414,3 +414,36 @@ def test_device_key_hashing_matches_host(G):
     r = d_reqs.cpu().numpy().reshape(-1).view(G.REQ_DTYPE)
     assert np.array_equal(r["key_xxh64"], xx) and np.array_equal(r["key_fnv1"], fv)
     assert int(xx[keys.index(b"bench_k000000042")]) == O.xxh64(b"bench_k000000042")
+
+
+def test_rpc_aggregator_coalesces_concurrent_calls(G):
+    """Many threads call GetRateLimits (<= 1000 requests each) at once; the aggregator serves them from shared device batches.
+    Per-thread key spaces are disjoint, so every thread must see exactly what the oracle gives for its own call sequence,
+    whatever the interleaving; a shared key checks conservation across threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    inst = G.V1Instance(capacity_slots=1 << 16, now_ms=K.T0)
+    agg = inst.aggregator(max_batch=8192, window_us=2000)
+    n_threads, calls, per_call = 16, 6, 300
+
+    def worker(t):
+        pool = O.Pool(now_ms=K.T0)
+        rng = np.random.default_rng(t)
+        shared_under = 0
+        for c in range(calls):
+            reqs = [dict(name=f"agg{t}", unique_key=f"k{int(rng.integers(0, 40))}", algorithm=int(rng.integers(0, 2)), limit=25, duration=60000,
+                         hits=int(rng.integers(0, 3))) for _ in range(per_call)]
+            got = agg.get_rate_limits(reqs)
+            want = pool.get_rate_limits(reqs)
+            assert got == want, (t, c)
+            sh = agg.get_rate_limits([dict(name="shared", unique_key="one", limit=100, duration=60000, hits=1)])[0]
+            shared_under += sh["status"] == 0
+        return shared_under
+    with ThreadPoolExecutor(n_threads) as ex:
+        under = sum(ex.map(worker, range(n_threads)))
+    assert under == min(100, n_threads * calls)  # 96 single hits against a limit of 100: all under the limit, none lost
+    st = agg.stats()
+    assert st["requests"] == n_threads * calls * (per_call + 1)
+    assert st["batches"] < n_threads * calls * 2  # calls really were coalesced
+    with pytest.raises(ValueError):
+        agg.get_rate_limits([dict(name="n", unique_key=str(i), limit=1, duration=1, hits=1) for i in range(1001)])
+    agg.close()
