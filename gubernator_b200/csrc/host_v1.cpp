@@ -6,6 +6,7 @@
 #include <deque>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -15,6 +16,8 @@
 struct gub_instance {
   gub_table* table = nullptr;
   int64_t frozen_now = -1;
+  bool has_store = false;
+  gub_store store{};
 };
 
 namespace {
@@ -111,7 +114,80 @@ void finish_call(const PreparedCall& pc, const gub_rate_limit_req* reqs, const g
 }
 }  // namespace
 
+namespace {
+// Store plugin around one batch (see gub_store in the header).  Distinct keys in first-occurrence order.
+struct StoreKeys {
+  std::vector<size_t> first, last;  // batch positions of each distinct key's first / last request
+  std::vector<uint64_t> kx, kf;
+  std::vector<char> reset_token;    // some TOKEN_BUCKET request of the key carries RESET_REMAINING
+};
+
+void collect_keys(const PreparedCall& pc, StoreKeys& sk) {
+  std::unordered_map<uint64_t, size_t> seen;
+  for (size_t j = 0; j < pc.batch.size(); j++) {
+    const gub_req& r = pc.batch[j];
+    const uint64_t h = r.key_xxh64 ^ (r.key_fnv1 * 0x9E3779B97F4A7C15ULL);
+    auto it = seen.find(h);
+    size_t k;
+    if (it == seen.end()) {
+      k = sk.first.size();
+      seen.emplace(h, k);
+      sk.first.push_back(j); sk.last.push_back(j); sk.kx.push_back(r.key_xxh64); sk.kf.push_back(r.key_fnv1); sk.reset_token.push_back(0);
+    } else {
+      k = it->second;
+      sk.last[k] = j;
+    }
+    if (r.algorithm == GUB_TOKEN_BUCKET && (r.behavior & GUB_BEHAVIOR_RESET_REMAINING)) sk.reset_token[k] = 1;
+  }
+}
+
+int submit_with_store(gub_instance* s, const PreparedCall& pc, const gub_rate_limit_req* reqs, const gub_clock& clk, gub_resp* resp) {
+  StoreKeys sk;
+  collect_keys(pc, sk);
+  const size_t nk = sk.first.size();
+  std::vector<gub_item> before(nk), after(nk);
+  std::vector<uint8_t> had(nk), has(nk);
+  if (gub_get_items(s->table, sk.kx.data(), sk.kf.data(), nk, clk.now_ms, before.data(), had.data()) != 0) return -1;
+  // cache miss -> Store.Get (algorithms.go:45-51); what it returns is added to the cache before the request runs
+  std::vector<gub_item> loaded;
+  for (size_t k = 0; k < nk; k++) {
+    if (had[k] || !s->store.get) continue;
+    const size_t j = sk.first[k];
+    gub_item it;
+    std::memset(&it, 0, sizeof it);
+    if (s->store.get(s->store.user, &reqs[pc.where[j]], pc.keys[j].c_str(), &it)) {
+      it.key_xxh64 = sk.kx[k]; it.key_fnv1 = sk.kf[k];
+      loaded.push_back(it);
+      before[k] = it; had[k] = 2;  // present, from the store
+    }
+  }
+  if (!loaded.empty() && gub_add_items(s->table, loaded.data(), loaded.size()) != 0) return -1;
+  if (gub_submit(s->table, pc.batch.data(), pc.batch.size(), &clk, resp) != 0) return -1;
+  if (gub_get_items(s->table, sk.kx.data(), sk.kf.data(), nk, clk.now_ms, after.data(), has.data()) != 0) return -1;
+  for (size_t k = 0; k < nk; k++) {
+    const size_t jf = sk.first[k], jl = sk.last[k];
+    // Store.Remove: the item that existed was deleted — RESET_REMAINING on a token bucket (algorithms.go:78-83) or the
+    // client switched algorithms (algorithms.go:91-100, 308-315)
+    const bool existed = had[k] != 0 && (had[k] == 2 ? before[k].expire_at >= clk.now_ms : true);
+    if (existed && s->store.remove) {
+      const bool switched = before[k].algorithm != (int32_t)pc.batch[jf].algorithm && pc.batch[jf].algorithm <= 1u;
+      if (switched || sk.reset_token[k]) s->store.remove(s->store.user, pc.keys[jf].c_str());
+    }
+    // Store.OnChange: once per key, with the item as the batch left it (owner requests only: algorithms.go:149,252)
+    if (has[k] && s->store.on_change && resp[jl].err_code == 0 && (pc.batch[jl].behavior & GUB_REQ_IS_OWNER))
+      s->store.on_change(s->store.user, &reqs[pc.where[jl]], pc.keys[jl].c_str(), &after[k]);
+  }
+  return 0;
+}
+}  // namespace
+
 extern "C" {
+
+void gub_instance_set_store(gub_instance* s, const gub_store* store) {
+  if (!s) return;
+  s->has_store = store != nullptr;
+  if (store) s->store = *store;
+}
 
 int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit_req* reqs, size_t n, gub_rate_limit_resp* out) {
   if (!s || (n && (!reqs || !out))) return -1;
@@ -122,7 +198,11 @@ int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit
   gub_clock clk;
   gub_clock_fill(now, &clk);
   std::vector<gub_resp> resp(pc.batch.size());
-  if (gub_submit(s->table, pc.batch.data(), pc.batch.size(), &clk, resp.data()) != 0) return -1;
+  if (s->has_store) {
+    if (submit_with_store(s, pc, reqs, clk, resp.data()) != 0) return -1;
+  } else if (gub_submit(s->table, pc.batch.data(), pc.batch.size(), &clk, resp.data()) != 0) {
+    return -1;
+  }
   finish_call(pc, reqs, resp.data(), out);
   return 0;
 }

@@ -19,6 +19,29 @@ class _Resp(C.Structure):
                 ("reset_time", C.c_int64), ("error", C.c_char * 256)]
 
 
+class _Item(C.Structure):  # gub_item
+    _fields_ = [("key_xxh64", C.c_uint64), ("key_fnv1", C.c_uint64), ("algorithm", C.c_int32), ("status", C.c_int32), ("limit", C.c_int64),
+                ("duration", C.c_int64), ("remaining", C.c_int64), ("remaining_f", C.c_double), ("stamp", C.c_int64), ("burst", C.c_int64),
+                ("expire_at", C.c_int64)]
+
+
+_GET_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_Req), C.c_char_p, C.POINTER(_Item))
+_CHANGE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(_Req), C.c_char_p, C.POINTER(_Item))
+_REMOVE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p)
+
+
+class _Store(C.Structure):  # gub_store
+    _fields_ = [("user", C.c_void_p), ("get", _GET_FN), ("on_change", _CHANGE_FN), ("remove", _REMOVE_FN)]
+
+
+_ITEM_FIELDS = ("algorithm", "status", "limit", "duration", "remaining", "remaining_f", "stamp", "burst", "expire_at")
+
+
+def _req_dict(r):
+    return dict(name=(r.name or b"").decode(), unique_key=(r.unique_key or b"").decode(), hits=r.hits, limit=r.limit, duration=r.duration,
+                burst=r.burst, algorithm=r.algorithm, behavior=r.behavior, created_at=r.created_at)
+
+
 @dataclass
 class RateLimitReq:  # gubernator.proto:137-183
     name: str = ""
@@ -56,6 +79,7 @@ def _bind():
         L.gub_instance_get_rate_limits.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
         L.gub_instance_get_rate_limits_unbounded.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
         L.gub_instance_update_peer_global.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64]
+        L.gub_instance_set_store.argtypes = [vp, C.POINTER(_Store)]; L.gub_instance_set_store.restype = None
         L.gub_aggregator_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]
         L.gub_aggregator_destroy.argtypes = [vp]; L.gub_aggregator_destroy.restype = None
         L.gub_aggregator_get_rate_limits.argtypes = [vp, C.POINTER(_Req), C.c_size_t, C.POINTER(_Resp)]
@@ -86,6 +110,31 @@ class V1Instance:
 
     def advance(self, ms):
         self.set_now(self.now() + int(ms))
+
+    def set_store(self, store):
+        """Config.Store (config.go:95).  `store` has get(req: dict, key: str) -> dict | None (item fields: algorithm, status,
+        limit, duration, remaining, remaining_f, stamp, burst, expire_at), on_change(req, key, item: dict), remove(key)."""
+        if store is None:
+            _bind().gub_instance_set_store(self._h, None)
+            self._store_refs = None
+            return
+
+        def _get(_u, req, key, out):
+            it = store.get(_req_dict(req.contents), key.decode())
+            if it is None:
+                return 0
+            for f in _ITEM_FIELDS:
+                setattr(out.contents, f, it.get(f, 0))
+            return 1
+
+        def _change(_u, req, key, item):
+            store.on_change(_req_dict(req.contents), key.decode(), {f: getattr(item.contents, f) for f in _ITEM_FIELDS})
+
+        def _remove(_u, key):
+            store.remove(key.decode())
+        st = _Store(None, _GET_FN(_get), _CHANGE_FN(_change), _REMOVE_FN(_remove))
+        self._store_refs = st  # keep the callbacks alive
+        _bind().gub_instance_set_store(self._h, C.byref(st))
 
     def aggregator(self, max_batch=65536, window_us=500):
         """RPC aggregator over this instance: concurrent get_rate_limits calls share device batches."""

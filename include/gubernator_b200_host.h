@@ -51,6 +51,23 @@ int gub_instance_get_rate_limits_unbounded(gub_instance* s, const gub_rate_limit
 /* V1Instance.UpdatePeerGlobals (gubernator.go:425-459) for one entry: builds the replica item and upserts it. */
 int gub_instance_update_peer_global(gub_instance* s, const char* key, int32_t algorithm, int64_t duration, int32_t status,
                                     int64_t limit, int64_t remaining, int64_t reset_time);
+/* ---- Store plugin (store.go:49-65) honoured at batch granularity -----------------------------------
+ * The reference calls Store.Get on every cache miss, Store.OnChange after every owner-side mutation and Store.Remove when an
+ * item is deleted — synchronously, per request (algorithms.go:45-51,149-153,250-254,81-83,98-100).  Behind a device batch
+ * that becomes, per GetRateLimits call: one lookup of the call's distinct keys; Store.Get for each key the table does not hold
+ * (the item it returns is installed before the batch runs, like c.Add at algorithms.go:49); the batch; then Store.Remove for
+ * keys whose item was deleted (token RESET_REMAINING, or an algorithm switch) and ONE Store.OnChange per key with the item as
+ * the batch left it (the reference would have called it once per request, with the intermediate states).
+ * Keys are the reference's HashKey strings (Name + "_" + UniqueKey).  Callbacks run on the calling thread. */
+typedef struct {
+  void* user;
+  int (*get)(void* user, const gub_rate_limit_req* req, const char* key, gub_item* item_out); /* 1 = found (item_out filled; key hashes are set by the caller) */
+  void (*on_change)(void* user, const gub_rate_limit_req* req, const char* key, const gub_item* item);
+  void (*remove)(void* user, const char* key);
+} gub_store;
+/* Config.Store (config.go:95).  NULL detaches.  The struct is copied. */
+void gub_instance_set_store(gub_instance* s, const gub_store* store);
+
 /* ---- RPC aggregator: concurrent GetRateLimits calls (<= 1000 requests each, gubernator.go:40) are
  * coalesced into one device batch, the way PeerClient.runBatch coalesces peer requests (peer_client.go:284-337): a flush
  * happens when `max_batch` requests are queued or `window_us` after the first queued call (BatchWait = 500 us,

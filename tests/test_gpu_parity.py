@@ -447,3 +447,79 @@ def test_rpc_aggregator_coalesces_concurrent_calls(G):
     with pytest.raises(ValueError):
         agg.get_rate_limits([dict(name="n", unique_key=str(i), limit=1, duration=1, hits=1) for i in range(1001)])
     agg.close()
+
+
+class _MockStore:
+    """MockStore2 of the reference (mock_store_test.go:28): records the calls, returns programmed items."""
+
+    def __init__(self):
+        self.calls, self.items = [], {}
+
+    def get(self, req, key):
+        self.calls.append(("Get", key))
+        return self.items.get(key)
+
+    def on_change(self, req, key, item):
+        self.calls.append(("OnChange", key, item))
+
+    def remove(self, key):
+        self.calls.append(("Remove", key))
+
+
+@pytest.mark.parametrize("algo", [0, 1])
+def test_store_plugin_call_sequences(G, algo):
+    """store_test.go:127-533 TestStore: which Store methods run, in which order, with which item, for a cache miss, a cache
+    hit, an item found in the store, an algorithm switch, a duration change and a duration change that expires the item."""
+    key = "test_over_limit_account:1234"
+    req = dict(name="test_over_limit", unique_key="account:1234", algorithm=algo, duration=1000, limit=10, hits=1)
+
+    def setup():
+        inst = G.V1Instance(capacity_slots=4096, now_ms=K.T0)
+        st = _MockStore()
+        inst.set_store(st)
+        return inst, st
+
+    def item(duration=1000, stamp=K.T0, expire=None, algorithm=algo):
+        return dict(algorithm=algorithm, limit=10, duration=duration, remaining=10, remaining_f=10.0, stamp=stamp, burst=10,
+                    expire_at=expire if expire is not None else stamp + duration)
+
+    # First rate check pulls from store (miss) -> Get, OnChange; second comes from the cache -> OnChange only (:228-271)
+    inst, st = setup()
+    r = inst.get_rate_limits([req])[0]
+    assert (r["limit"], r["status"]) == (10, 0)
+    assert [c[0] for c in st.calls] == ["Get", "OnChange"] and st.calls[1][2]["limit"] == 10 and st.calls[1][2]["duration"] == 1000
+    st.calls.clear()
+    inst.get_rate_limits([req])
+    assert [c[0] for c in st.calls] == ["OnChange"]
+
+    # Found in store after cache miss (:273-308)
+    inst, st = setup()
+    st.items[key] = item()
+    r = inst.get_rate_limits([req])[0]
+    assert (r["limit"], r["status"], r["remaining"]) == (10, 0, 9)
+    assert [c[0] for c in st.calls] == ["Get", "OnChange"]
+
+    # Algorithm changed: the stored item is of another type -> Remove, then OnChange with the new item (:310-348)
+    inst, st = setup()
+    st.items[key] = item(algorithm=1 - algo)
+    r = inst.get_rate_limits([req])[0]
+    assert (r["limit"], r["status"]) == (10, 0)
+    assert [c[0] for c in st.calls] == ["Get", "Remove", "OnChange"] and st.calls[2][2]["algorithm"] == algo
+
+    if algo == 0:
+        # Duration changed (:353-439): ExpireAt == CreatedAt + newDuration
+        inst, st = setup()
+        st.items[key] = item(duration=5000)
+        req2 = dict(req, duration=8000)
+        r = inst.get_rate_limits([req2])[0]
+        assert (r["limit"], r["status"]) == (10, 0)
+        it = st.calls[-1][2]
+        assert st.calls[-1][0] == "OnChange" and it["expire_at"] == it["stamp"] + 8000 and it["duration"] == 8000 and it["limit"] == 10
+        # Duration changed and immediately expired (:441-531): renewed expiration, remaining reset
+        inst, st = setup()
+        long_ago = K.T0 - 100000
+        st.items[key] = item(duration=500000, stamp=long_ago, expire=long_ago + 500000)
+        r = inst.get_rate_limits([req2])[0]
+        assert (r["limit"], r["status"]) == (10, 0)
+        it = st.calls[-1][2]
+        assert it["expire_at"] == it["stamp"] + 8000 and it["stamp"] == K.T0 and it["duration"] == 8000
