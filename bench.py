@@ -352,18 +352,27 @@ def run_b200(args):
                 for b in range(min(args.warmup, 8)):
                     tab.wait(submit(b % depth, b))
                 torch.cuda.synchronize()
+                t_sub = t_wait = 0.0
                 t0 = time.perf_counter()
                 for b in range(e2e_steps):
                     k = b % depth
+                    a = time.perf_counter()
                     if tickets[k] is not None:
                         tab.wait(tickets[k])  # the response buffer of this slot has been read back
+                    c = time.perf_counter()
                     tickets[k] = submit(k, b)
+                    t_wait += c - a
+                    t_sub += time.perf_counter() - c
                 for k in range(depth):
                     if tickets[k] is not None:
                         tab.wait(tickets[k])
                 torch.cuda.synchronize()
-                return time.perf_counter() - t0
+                dt_ = time.perf_counter() - t0
+                e2e_split.append({"cpu_us_in_submit": 1e6 * t_sub / e2e_steps, "cpu_us_in_wait": 1e6 * t_wait / e2e_steps,
+                                  "us_per_step": 1e6 * dt_ / e2e_steps})
+                return dt_
             e2e_steps = args.steps
+            e2e_split = []
             # (a) compact records: 32 B per request + one small parameter table per batch (gub_submit_compact_async)
             cpin, ppin, bases, nparams = [], [], [], []
             for k in range(depth):
@@ -378,6 +387,8 @@ def run_b200(args):
             e2e_full = {"value": BATCH * e2e_steps / dt_full, "unit": "decisions/s", "h2d_bytes_per_step": BATCH * 64, "d2h_bytes_per_step": BATCH * 32,
                         "api": "gub_submit_async (64-byte records)"}
             h2d_compact = BATCH * 32 + int(np.mean(nparams)) * 32
+            e2e_full["host_time"] = e2e_split[1]
+
             for a in cpin + ppin:
                 a.free()
         else:
@@ -405,6 +416,7 @@ def run_b200(args):
                "api": "gub_submit_compact_async (pinned host buffers, 32-byte records + parameter table, depth 4)" if N == 1 else
                "pinned H2D + route/exchange/evaluate/return/unroute + D2H per step"}
         if N == 1:
+            e2e["host_time"] = e2e_split[0]
             e2e["full_records"] = e2e_full
         for a, b_ in pin:
             a.free(); b_.free()

@@ -92,6 +92,10 @@ struct gub_table {
   size_t owner_cap = 0, tiles_cap = 0;
   // optional per-kernel timing (bench.py's roofline leg): events bracket every kernel of the batch path
   bool pdl = true;                    // programmatic dependent launch between the batch kernels (GUB_PDL=0 disables)
+  // GUB_PIPE_TRACE=<file>: stage timestamps of the first host-to-host submissions (diagnostic; see profiles/README.md)
+  std::string trace_path;
+  cudaEvent_t trace_base = nullptr;
+  std::vector<cudaEvent_t> trace_ev;  // 6 per traced submission
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;   // 5 events per pending chunk
   size_t prof_pending = 0;            // chunks recorded and not yet accumulated
@@ -112,6 +116,31 @@ int prof_flush(gub_table* t, bool force) {
   }
   t->prof_pending = 0;
   return 0;
+}
+
+constexpr size_t TRACE_MAX = 400;  // submissions
+inline bool tracing(gub_table* t) { return t->trace_base && t->trace_ev.size() < TRACE_MAX * 6; }
+int trace_mark(gub_table* t, cudaStream_t st) {
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(e, st));
+  t->trace_ev.push_back(e);
+  return 0;
+}
+void trace_dump(gub_table* t) {
+  if (!t->trace_base || t->trace_ev.empty()) return;
+  cudaDeviceSynchronize();
+  if (FILE* f = std::fopen(t->trace_path.c_str(), "w")) {
+    std::fprintf(f, "# us since table creation: h2d_start h2d_done compute_start compute_done d2h_start d2h_done\n");
+    for (size_t i = 0; i + 6 <= t->trace_ev.size(); i += 6) {
+      for (int k = 0; k < 6; k++) { float ms = 0; cudaEventElapsedTime(&ms, t->trace_base, t->trace_ev[i + k]); std::fprintf(f, "%.1f%c", ms * 1e3, k == 5 ? '\n' : ' '); }
+    }
+    std::fclose(f);
+  }
+  for (auto e : t->trace_ev) cudaEventDestroy(e);
+  t->trace_ev.clear();
+  cudaEventDestroy(t->trace_base);
+  t->trace_base = nullptr;  // one dump per table
 }
 
 // Launches one batch kernel, with programmatic stream serialization when enabled (the kernels call griddepcontrol.wait
@@ -265,6 +294,7 @@ void gub_destroy(gub_table* t) {
   if (!t) return;
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
+  trace_dump(t);
   void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& sc : t->scr) {
@@ -358,6 +388,11 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     CK(cudaEventCreateWithFlags(&t->pipe[i].out_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&t->compute_done[i], cudaEventDisableTiming));
   }
+  if (const char* e = getenv("GUB_PIPE_TRACE")) {
+    t->trace_path = e;
+    CK(cudaEventCreate(&t->trace_base));
+    CK(cudaEventRecord(t->trace_base, t->s_h2d));
+  }
   CK(cudaDeviceSynchronize());
   *out = t;
   return 0;
@@ -418,22 +453,41 @@ int gub_submit_compact_async(gub_table* t, const gub_creq* reqs, size_t n, const
   if (n == 0) { CK(cudaEventRecord(s.out_done, t->s_d2h)); s.busy = true; return 0; }
   if (ensure_slot(s, n)) return -1;
   if (!s.d_creq) CK(cudaMalloc(&s.d_creq, s.cap * sizeof(gub_creq)));
-  if (s.params_cap < n_params || !s.d_params) {
+  const bool inl = n_params <= gub::INLINE_PARAMS;  // the table travels in the kernel arguments: no second copy
+  if (!inl && (s.params_cap < n_params || !s.d_params)) {
     if (s.d_params) cudaFree(s.d_params);
     s.d_params = nullptr;
     s.params_cap = std::max<size_t>(n_params, 1024);
     CK(cudaMalloc(&s.d_params, s.params_cap * sizeof(gub_params)));
   }
+  const bool tr = tracing(t);
+  if (tr && trace_mark(t, t->s_h2d)) return -1;
   CK(cudaMemcpyAsync(s.d_creq, reqs, n * sizeof(gub_creq), cudaMemcpyHostToDevice, t->s_h2d));
-  if (n_params) CK(cudaMemcpyAsync(s.d_params, params, n_params * sizeof(gub_params), cudaMemcpyHostToDevice, t->s_h2d));
+  if (!inl) CK(cudaMemcpyAsync(s.d_params, params, n_params * sizeof(gub_params), cudaMemcpyHostToDevice, t->s_h2d));
   CK(cudaEventRecord(s.in_done, t->s_h2d));
+  if (tr && trace_mark(t, t->s_h2d)) return -1;
   CK(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
-  gub::k_expand<<<(unsigned)((n + 255) / 256), 256, 0, t->s_compute>>>(s.d_creq, (uint32_t)n, s.d_params, (uint32_t)n_params, created_base, s.d_req);
+  if (tr && trace_mark(t, t->s_compute)) return -1;
+  // The expansion runs on the compute stream: a kernel behind a copy on the copy stream costs an engine switch per batch that
+  // stalls the ingest stage by ~45 us under PCIe load (measured, profiles/r01_e2e_pipeline.md).
+  if (inl) {
+    gub::InlineParams P;
+    static_assert(sizeof(gub_params) == 32, "gub_params is two 16-byte words");
+    std::memset(&P, 0, sizeof P);
+    std::memcpy(&P, params, n_params * sizeof(gub_params));
+    gub::k_expand_inline<<<(unsigned)((n + 255) / 256), 256, 0, t->s_compute>>>(s.d_creq, (uint32_t)n, P, (uint32_t)n_params, created_base, s.d_req);
+  } else {
+    gub::k_expand<<<(unsigned)((n + 255) / 256), 256, 0, t->s_compute>>>(s.d_creq, (uint32_t)n, s.d_params, (uint32_t)n_params, created_base, s.d_req);
+  }
   if (launch_batch(t, s.d_req, n, clk, s.d_resp, t->s_compute)) return -1;
   CK(cudaEventRecord(t->compute_done[si], t->s_compute));
+  if (tr && trace_mark(t, t->s_compute)) return -1;
   CK(cudaStreamWaitEvent(t->s_d2h, t->compute_done[si], 0));
+  if (tr && trace_mark(t, t->s_d2h)) return -1;
   CK(cudaMemcpyAsync(out, s.d_resp, n * sizeof(gub_resp), cudaMemcpyDeviceToHost, t->s_d2h));
   CK(cudaEventRecord(s.out_done, t->s_d2h));
+  if (tr && trace_mark(t, t->s_d2h)) return -1;
+  if (tr && t->trace_ev.size() >= TRACE_MAX * 6) trace_dump(t);
   s.busy = true;
   return 0;
 }

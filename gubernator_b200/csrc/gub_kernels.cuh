@@ -773,6 +773,17 @@ __global__ void __launch_bounds__(256) k_hash_keys(const uint8_t* bytes, const u
 }
 
 // ---- compact requests -> gub_req records (see gub_creq in the header) --------------------------------------------------
+__device__ __forceinline__ void expand_one(const gub_creq* creqs, uint32_t i, ulonglong2 q0, ulonglong2 q1, bool known, ulonglong2 a, ulonglong2 b,
+                                           int64_t created_base, gub_req* out) {
+  if (!known) { q0 = make_ulonglong2(0, 0); q1 = make_ulonglong2(0, 0xFFFFFFFFull); }  // unknown parameter set -> invalid algorithm (in-band error)
+  const int32_t delta = (int32_t)(uint32_t)(b.y >> 32);
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(out + i);
+  o[0] = a;                                                                   // key_xxh64, key_fnv1
+  o[1] = make_ulonglong2(b.x, q0.x);                                          // hits, limit
+  o[2] = make_ulonglong2(q0.y, q1.x);                                         // duration, burst
+  o[3] = make_ulonglong2((uint64_t)wadd(created_base, (int64_t)delta), q1.y); // created_at, algorithm | behavior << 32
+}
+
 __global__ void __launch_bounds__(256) k_expand(const gub_creq* creqs, uint32_t n, const gub_params* params, uint32_t n_params, int64_t created_base,
                                                 gub_req* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -780,17 +791,30 @@ __global__ void __launch_bounds__(256) k_expand(const gub_creq* creqs, uint32_t 
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(creqs + i);
   const ulonglong2 a = __ldcs(p), b = __ldcs(p + 1);  // streamed once
   const uint32_t pi = (uint32_t)(b.y & 0xFFFFFFFFull);
-  const int32_t delta = (int32_t)(uint32_t)(b.y >> 32);
-  ulonglong2 q0 = make_ulonglong2(0, 0), q1 = make_ulonglong2(0, 0xFFFFFFFFull);  // unknown parameter set -> invalid algorithm (in-band error)
+  ulonglong2 q0 = make_ulonglong2(0, 0), q1 = q0;
   if (pi < n_params) {
     const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(params + pi);
     q0 = __ldg(pp); q1 = __ldg(pp + 1);
   }
-  ulonglong2* o = reinterpret_cast<ulonglong2*>(out + i);
-  o[0] = a;                                                                   // key_xxh64, key_fnv1
-  o[1] = make_ulonglong2(b.x, q0.x);                                          // hits, limit
-  o[2] = make_ulonglong2(q0.y, q1.x);                                         // duration, burst
-  o[3] = make_ulonglong2((uint64_t)wadd(created_base, (int64_t)delta), q1.y); // created_at, algorithm | behavior << 32
+  expand_one(creqs, i, q0, q1, pi < n_params, a, b, created_base, out);
+}
+
+// Same, with the parameter table passed by value in the kernel arguments.  A deployment has a handful of limit
+// configurations, and a separate small host-to-device copy per batch stalls the copy stream far longer than its size
+// suggests (measured: +25 us per step next to 2 MiB copies, profiles/r01_pipe_probe.txt), so tables of up to
+// INLINE_PARAMS sets travel with the launch instead.
+constexpr uint32_t INLINE_PARAMS = 32;
+struct InlineParams { ulonglong2 q[INLINE_PARAMS][2]; };
+__global__ void __launch_bounds__(256) k_expand_inline(const gub_creq* creqs, uint32_t n, const InlineParams P, uint32_t n_params, int64_t created_base,
+                                                       gub_req* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(creqs + i);
+  const ulonglong2 a = __ldcs(p), b = __ldcs(p + 1);
+  const uint32_t pi = (uint32_t)(b.y & 0xFFFFFFFFull);
+  const bool known = pi < n_params;
+  const uint32_t k = known ? pi : 0u;
+  expand_one(creqs, i, P.q[k][0], P.q[k][1], known, a, b, created_base, out);
 }
 
 // ---- maintenance kernels -------------------------------------------------------------------------------------
