@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--route", default=os.environ.get("GUB_ROUTE", "p2p"), choices=["p2p", "nccl"],
                     help="N > 1: how request records reach their owning GPU (NVLink mailboxes written by the routing kernels, or NCCL all-to-all)")
+    ap.add_argument("--no-route-overlap", action="store_true", help="p2p route: run routing and evaluation on one stream (no overlap of step e+1's routing with step e's evaluation)")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profile this many extra steps between cudaProfilerStart/Stop (run under `ncu --profile-from-start off`)")
     return ap.parse_args()
@@ -270,12 +271,19 @@ def run_b200(args):
     d_outs = [torch.empty((BATCH, 32), dtype=torch.uint8, device=dev) for _ in range(pool_n)]
     clocks = [g.clock_fill(T0 + 1 + b) for b in range(args.steps + args.warmup + 8)]
 
+    # p2p route: the routing kernels run on their own (ingest) stream, so step e+1 is routed while step e is evaluated
+    step_kw = {}
+    ingest = None
+    if N > 1 and args.route == "p2p" and not args.no_route_overlap:
+        ingest = torch.cuda.Stream(device=dev)
+        step_kw = {"ingest_stream": ingest.cuda_stream}
+
     def one_step(b):
         k = b % pool_n
         if N == 1:
             tab.submit_device(d_batches[k].data_ptr(), BATCH, clocks[min(b, len(clocks) - 1)], d_outs[k].data_ptr(), stream)
         else:
-            sharded.step(d_batches[k], BATCH, clocks[min(b, len(clocks) - 1)], d_outs[k])
+            sharded.step(d_batches[k], BATCH, clocks[min(b, len(clocks) - 1)], d_outs[k], **step_kw)
 
     def barrier():
         if dist is not None:
@@ -400,10 +408,16 @@ def run_b200(args):
             e2e_steps = args.steps
             barrier()
             t0 = time.perf_counter()
+            d_ins = [torch.empty((BATCH, 64), dtype=torch.uint8, device=dev) for _ in range(2)]
             for b in range(e2e_steps):
                 k = b % depth
-                d_in.copy_(h_in[k], non_blocking=True)
-                sharded.step(d_in, BATCH, clocks[min(b, len(clocks) - 1)], d_o)
+                if ingest is not None:  # ingest copy + routing on the ingest stream, evaluation + read-back on the current one
+                    with torch.cuda.stream(ingest):
+                        d_ins[b & 1].copy_(h_in[k], non_blocking=True)
+                    sharded.step(d_ins[b & 1], BATCH, clocks[min(b, len(clocks) - 1)], d_o, **step_kw)
+                else:
+                    d_in.copy_(h_in[k], non_blocking=True)
+                    sharded.step(d_in, BATCH, clocks[min(b, len(clocks) - 1)], d_o)
                 h_out[k].copy_(d_o, non_blocking=True)
             barrier()
             dt = time.perf_counter() - t0
@@ -476,7 +490,7 @@ def run_b200(args):
         "dtype": "int64+f64", "data": "synthetic",
         "config": {"workload": ("BASELINE config 3: 100M keys, Zipf s=1.1, TOKEN/LEAKY 50/50, 1xB200" if N == 1 else
                                 f"BASELINE config 4: 100M keys sharded over {N}xB200 by replicated_hash (fnv1, 512 replicas), Zipf s=1.1, routing: " +
-                                ("NVLink peer-memory mailboxes written by the routing kernels" if args.route == "p2p" else "NCCL all-to-all")),
+                                ("NVLink peer-memory mailboxes written by the routing kernels" + ("" if args.no_route_overlap else ", routing of step e+1 overlapped with evaluation of step e (two streams)") if args.route == "p2p" else "NCCL all-to-all")),
                    "keys": n_keys, "batch_per_gpu": BATCH, "zipf_s": args.zipf, "table_slots_per_gpu": capacity,
                    "cache": f"inputs cycle through {pool_n} resident batches ({pool_n * 6} MiB > L2); table {capacity * 64 / 1e9:.1f} GB >> L2",
                    "batch_profile": st, "fill_seconds": t_fill, "resident_keys_after_fill": c0["inserts"]},

@@ -883,9 +883,18 @@ struct gub_p2p {
   void* opened[gub::MAX_SHARDS] = {};
   bool connected = false;
   gub_req* inbox = nullptr; gub_resp* inbox_resp = nullptr; size_t inbox_cap = 0;
-  uint32_t *perm = nullptr, *seg_off = nullptr, *m_dev = nullptr, *counts = nullptr, *done_ctr = nullptr, *error = nullptr;
-  uint8_t* owner = nullptr;        // [cap] routing scratch, preallocated: nothing is allocated or freed inside a step
-  uint32_t* tile_off = nullptr;    // [(cap / ROUTE_TILE + 1) * MAX_SHARDS]
+  uint32_t *seg_off = nullptr, *m_dev = nullptr, *done_ctr = nullptr, *error = nullptr;
+  // Routing scratch, preallocated (nothing is allocated or freed inside a step) and double-buffered by step parity: with a
+  // separate ingest stream the routing of step e+1 runs while step e is still being evaluated and un-routed.
+  struct Route {
+    uint8_t* owner = nullptr;      // [cap]
+    uint32_t* tile_off = nullptr;  // [(cap / ROUTE_TILE + 1) * MAX_SHARDS]
+    uint32_t* counts = nullptr;    // [MAX_SHARDS]
+    uint32_t* perm = nullptr;      // [cap]
+    cudaEvent_t routed = nullptr;     // this parity's scatter has been issued and completed (ingest stream)
+    cudaEvent_t step_done = nullptr;  // this parity's un-route has completed (evaluation stream)
+    bool step_done_valid = false;
+  } rt[2];
   uint32_t* h_m = nullptr;         // pinned
 };
 
@@ -910,8 +919,14 @@ void gub_p2p_destroy(gub_p2p* p) {
   cudaSetDevice(p->t->device);
   cudaDeviceSynchronize();
   for (uint32_t r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
-  void* ptrs[] = {p->block, p->inbox, p->inbox_resp, p->perm, p->seg_off, p->m_dev, p->counts, p->done_ctr, p->error, p->owner, p->tile_off};
+  void* ptrs[] = {p->block, p->inbox, p->inbox_resp, p->seg_off, p->m_dev, p->done_ctr, p->error};
   for (void* q : ptrs) if (q) cudaFree(q);
+  for (auto& r : p->rt) {
+    void* rp[] = {r.owner, r.tile_off, r.counts, r.perm};
+    for (void* q : rp) if (q) cudaFree(q);
+    if (r.routed) cudaEventDestroy(r.routed);
+    if (r.step_done) cudaEventDestroy(r.step_done);
+  }
   if (p->h_m) cudaFreeHost(p->h_m);
   delete p;
 }
@@ -929,17 +944,21 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t c
   p->block_bytes = p2p_req_bytes(world, cap) + p2p_resp_bytes(world, cap) + (size_t)4 * world * 8;
   cudaError_t e = cudaMalloc(&p->block, p->block_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->block, 0, p->block_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&p->perm, (size_t)cap * 4);
   if (e == cudaSuccess) e = cudaMalloc(&p->seg_off, (gub::MAX_SHARDS + 1) * 4);
   if (e == cudaSuccess) e = cudaMalloc(&p->m_dev, 4);
-  if (e == cudaSuccess) e = cudaMalloc(&p->counts, gub::MAX_SHARDS * 4);
   if (e == cudaSuccess) e = cudaMalloc(&p->done_ctr, 8);
   if (e == cudaSuccess) e = cudaMalloc(&p->error, 4);
   if (e == cudaSuccess) e = cudaMemset(p->done_ctr, 0, 8);
   if (e == cudaSuccess) e = cudaMemset(p->error, 0, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(&p->h_m, 8, cudaHostAllocDefault);
-  if (e == cudaSuccess) e = cudaMalloc(&p->owner, cap);
-  if (e == cudaSuccess) e = cudaMalloc(&p->tile_off, ((size_t)cap / gub::ROUTE_TILE + 1) * gub::MAX_SHARDS * 4);
+  for (auto& r : p->rt) {
+    if (e == cudaSuccess) e = cudaMalloc(&r.owner, cap);
+    if (e == cudaSuccess) e = cudaMalloc(&r.tile_off, ((size_t)cap / gub::ROUTE_TILE + 1) * gub::MAX_SHARDS * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&r.counts, gub::MAX_SHARDS * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&r.perm, (size_t)cap * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.routed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.step_done, cudaEventDisableTiming);
+  }
   p->inbox_cap = (size_t)world * cap;  // worst case every shard sends us its whole batch
   if (e == cudaSuccess) e = cudaMalloc(&p->inbox, p->inbox_cap * sizeof(gub_req));
   if (e == cudaSuccess) e = cudaMalloc(&p->inbox_resp, p->inbox_cap * sizeof(gub_resp));
@@ -986,30 +1005,39 @@ int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers) {
   return 0;
 }
 
-int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
+int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream, void* stream) {
   if (!p || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
   if (n > p->cap) return fail("gub_p2p_step: n exceeds the mailbox capacity");
   const gub_ring* ring = p->ring;
   if (p->t->ring_cached != ring || p->t->ring_version != gub_ring_version_(ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
   gub_table* t = p->t;
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)ingest_stream;
+  const bool two = si != st;
   uint32_t ntiles = 0;
   gub::P2PArgs A;
+  gub_p2p::Route* rt = nullptr;
   {
     std::lock_guard<std::mutex> lk(t->mu);
     CK(cudaSetDevice(t->device));
     p->epoch++;
+    rt = &p->rt[p->epoch & 1u];
     for (uint32_t r = 0; r < p->world; r++) A.peers[r] = p->views[r];
     A.world = p->world; A.rank = p->rank; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = p->done_ctr; A.error = p->error;
+    // ---- ingest stream: partition by owner and store the records into the owners' mailboxes.  This parity's scratch and
+    // mailbox halves were last used two steps ago; that step's un-route (on the evaluation stream) must have finished, which
+    // also means every peer has drained what we sent it then.
+    if (two && rt->step_done_valid) CK(cudaStreamWaitEvent(si, rt->step_done, 0));
     if (n) {
       ntiles = (uint32_t)((n + gub::ROUTE_TILE - 1) / gub::ROUTE_TILE);
-      gub::k_route_count<<<ntiles, 256, 0, st>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, p->world, p->owner,
-                                                p->tile_off, ntiles, -1, nullptr);
-      gub::k_route_scan<<<1, 1024, 0, st>>>(p->tile_off, p->world * ntiles, p->world, ntiles, p->counts);
-      gub::k_p2p_scatter<<<ntiles, 256, 0, st>>>(A, d_reqs, (uint32_t)n, p->owner, p->tile_off, ntiles, p->counts, p->perm);
+      gub::k_route_count<<<ntiles, 256, 0, si>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, p->world, rt->owner,
+                                                rt->tile_off, ntiles, -1, nullptr);
+      gub::k_route_scan<<<1, 1024, 0, si>>>(rt->tile_off, p->world * ntiles, p->world, ntiles, rt->counts);
+      gub::k_p2p_scatter<<<ntiles, 256, 0, si>>>(A, d_reqs, (uint32_t)n, rt->owner, rt->tile_off, ntiles, rt->counts, rt->perm);
     } else {
-      gub::k_p2p_publish_empty<<<1, 32, 0, st>>>(A);
+      gub::k_p2p_publish_empty<<<1, 32, 0, si>>>(A);
     }
+    if (two) CK(cudaEventRecord(rt->routed, si));
+    // ---- evaluation stream: the gather synchronises with every source (ourselves included) through the mailbox flags
     gub::k_p2p_gather<<<148, 256, 0, st>>>(A, p->inbox, p->seg_off, p->m_dev);
     CK(cudaGetLastError());
   }
@@ -1019,11 +1047,17 @@ int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* c
   {
     std::lock_guard<std::mutex> lk(t->mu);
     gub::k_p2p_push_resp<<<148, 256, 0, st>>>(A, p->inbox_resp, p->seg_off);
-    if (n) gub::k_p2p_unroute<<<148, 256, 0, st>>>(A, p->tile_off, ntiles, p->perm, (uint32_t)n, d_out);
+    if (two) CK(cudaStreamWaitEvent(st, rt->routed, 0));  // the un-route reads this parity's offsets and permutation
+    if (n) gub::k_p2p_unroute<<<148, 256, 0, st>>>(A, rt->tile_off, ntiles, rt->perm, (uint32_t)n, d_out);
     else gub::k_p2p_wait_resp_only<<<1, 32, 0, st>>>(A);
+    if (two) { CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true; }
     CK(cudaGetLastError());
   }
   return 0;
+}
+
+int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
+  return gub_p2p_step_streams(p, d_reqs, n, clk, d_out, stream, stream);
 }
 
 }  // extern "C"

@@ -34,7 +34,7 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
            "gub_route_owner_device", "gub_route_global_device", "gub_p2p_create", "gub_p2p_destroy", "gub_p2p_export", "gub_p2p_connect",
-           "gub_p2p_connect_local", "gub_p2p_step"]
+           "gub_p2p_connect_local", "gub_p2p_step", "gub_p2p_step_streams"]
 
 
 class Config(C.Structure):
@@ -105,6 +105,7 @@ def lib():
         L.gub_p2p_connect.argtypes = [vp, vp]
         L.gub_p2p_connect_local.argtypes = [vp, C.POINTER(vp)]
         L.gub_p2p_step.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.gub_p2p_step_streams.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -330,8 +331,11 @@ class P2P:
         arr = (C.c_void_p * self.world)(*[p._h for p in peers])
         _check(lib().gub_p2p_connect_local(self._h, arr), "gub_p2p_connect_local")
 
-    def step(self, d_reqs_ptr, n, clk, d_out_ptr, stream=0):
-        _check(lib().gub_p2p_step(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_p2p_step")
+    def step(self, d_reqs_ptr, n, clk, d_out_ptr, stream=0, ingest_stream=None):
+        if ingest_stream is None:
+            _check(lib().gub_p2p_step(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_p2p_step")
+        else:
+            _check(lib().gub_p2p_step_streams(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, ingest_stream, stream), "gub_p2p_step_streams")
 
     def close(self):
         if getattr(self, "_h", None):

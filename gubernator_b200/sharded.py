@@ -265,8 +265,10 @@ class P2PStep:
     def connect_local(self, steppers):
         self.p2p.connect_local([s.p2p for s in steppers])
 
-    def step(self, reqs, n, clk, out, stream=None):
+    def step(self, reqs, n, clk, out, stream=None, ingest_stream=None):
+        """ingest_stream: the stream `reqs` was produced on; when given, routing runs there and overlaps the evaluation of
+        the previous step, which runs on `stream` (where `out` becomes valid)."""
         import torch
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        self.p2p.step(reqs.data_ptr(), n, clk, out.data_ptr(), st)
+        self.p2p.step(reqs.data_ptr(), n, clk, out.data_ptr(), st, ingest_stream)
         return n

@@ -271,6 +271,12 @@ int gub_p2p_export(gub_p2p* p, void* handle_out /* GUB_P2P_HANDLE_BYTES: a cudaI
 int gub_p2p_connect(gub_p2p* p, const void* handles /* world x GUB_P2P_HANDLE_BYTES, rank order; own entry ignored */);
 int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers /* world pointers, same process */);
 int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
+/* Same step on two streams: the routing kernels (partition + NVLink stores into the owners' mailboxes) run on
+ * `ingest_stream`, the stream d_reqs was produced on; gather, evaluation, response return and un-route run on `stream`,
+ * where d_out becomes valid.  Routing touches no bucket state, so the routing of step e+1 overlaps the evaluation of step
+ * e (the reference overlaps forwarding and evaluation the same way: peer_client.go:284 runs in its own goroutine). */
+int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream,
+                         void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,8 @@ if USE_GPU:
     backend = GpuBackend(tab, ring, W, dev, 131072)
 else:
     backend = CpuBackend(O.Pool(workers=2, cache_size=10**7, now_ms=T0))
-USE_P2P = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") == "p2p"
+USE_P2P = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") in ("p2p", "p2p2")
+PIPELINED = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") == "p2p2"  # two streams, all steps in flight before any is checked
 if USE_P2P:  # records travel by NVLink stores from the routing kernels (cudaIpc mailboxes) instead of NCCL all-to-all
     from gubernator_b200.sharded import P2PStep
     stepper = P2PStep(tab, ring, W, rank, cap=65536)
@@ -94,12 +95,28 @@ if USE_P2P:  # records travel by NVLink stores from the routing kernels (cudaIpc
 else:
     stepper = ShardedStep(backend, dist, W)
 sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(W)]  # local simulation of every shard
+got_all = None
+if PIPELINED:
+    s_in, s_ev = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    bufs, outs = [], []
+    for step in range(8):
+        reqs = batch_for(rank, step)
+        n = len(reqs)
+        bufs.append(torch.from_numpy(reqs.view(np.uint8).reshape(n, 64).copy()).to(dev) if n else torch.empty((1, 64), dtype=torch.uint8, device=dev))
+        outs.append(torch.zeros((max(n, 1), 32), dtype=torch.uint8, device=dev))
+    torch.cuda.synchronize()
+    for step in range(8):
+        stepper.step(bufs[step], len(batch_for(rank, step)), g.clock_fill(T0 + step), outs[step], stream=s_ev.cuda_stream, ingest_stream=s_in.cuda_stream)
+    torch.cuda.synchronize()
+    got_all = [outs[step][:len(batch_for(rank, step))].cpu().numpy().reshape(-1).view(O.HRESP_DTYPE) for step in range(8)]
 for step in range(8):
     now = T0 + step
     reqs = batch_for(rank, step)
     n = len(reqs)
     host = torch.from_numpy(reqs.view(np.uint8).reshape(n, 64).copy())
-    if USE_GPU:
+    if got_all is not None:
+        got = got_all[step]
+    elif USE_GPU:
         buf = host.to(dev) if n else torch.empty((1, 64), dtype=torch.uint8, device=dev)
         out = torch.zeros((max(n, 1), 32), dtype=torch.uint8, device=dev)
         stepper.step(buf, n, g.clock_fill(now), out)

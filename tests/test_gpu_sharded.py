@@ -7,7 +7,7 @@ from test_sharded_gloo import run_workers
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("route", ["nccl", "p2p"])
+@pytest.mark.parametrize("route", ["nccl", "p2p", "p2p2"])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_sharded_gpu_matches_per_shard_oracles(nproc, route):
     import torch
