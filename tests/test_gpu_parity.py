@@ -8,7 +8,7 @@ import pytest
 import oracle_py as O
 from golden import reference_kat as K
 from kat_player import play_missing_fields, play_scenario
-from workloads import T0, adversarial_batch, bench_batch, extreme_batch, key_hashes
+from workloads import T0, adversarial_batch, bench_batch, bench_requests, extreme_batch, key_hashes, zipf_ids
 
 pytestmark = pytest.mark.gpu
 
@@ -327,6 +327,21 @@ def test_compact_requests_equal_full_records(G):
         want = pool.submit_hashed(reqs)
         _cmp(a.submit(reqs, clk), want, f"full step {step}")
         _cmp(b.submit_compact(creqs, params, base, clk), want, f"compact step {step}")
+    # tables of up to 32 parameter sets travel in the kernel arguments (k_expand_inline), larger ones by a device copy: both
+    # sides of the boundary, and the two-set table of the bench workload
+    for n_sets in (2, 32, 33):
+        now = T0 + 5000 + n_sets
+        pool.set_now(now)
+        ids = zipf_ids(rng, 20000, 3000, 1.1)
+        reqs = bench_requests(ids, now)
+        reqs["limit"] = 50 + (ids % n_sets)
+        reqs["algorithm"] = (ids % n_sets) & 1
+        creqs, params, base = G.native.compact_batch(reqs)
+        assert len(params) == n_sets
+        clk = G.clock_fill(now)
+        want = pool.submit_hashed(reqs)
+        _cmp(a.submit(reqs, clk), want, f"full, {n_sets} sets")
+        _cmp(b.submit_compact(creqs, params, base, clk), want, f"compact, {n_sets} sets")
     # an out-of-range parameter index is an in-band error, nothing is stored
     creqs, params, base = G.native.compact_batch(adversarial_batch(rng, 10, 3, T0))
     creqs["params"][3] = 10_000
