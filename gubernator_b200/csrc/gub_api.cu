@@ -76,7 +76,6 @@ struct gub_table {
   bool overlap = true;                // GUB_OVERLAP=0: everything on the caller's stream
   // ordering between streams that touch the shared scratch
   cudaEvent_t last_done = nullptr;
-  bool have_last = false;            // an event has been recorded for the work on last_stream
   cudaStream_t last_stream = nullptr; // stream of the most recent table-touching work
   bool last_pending = false;          // work was enqueued on last_stream after (or without) the last event record
   // host path
@@ -895,7 +894,6 @@ struct gub_p2p {
     cudaEvent_t step_done = nullptr;  // this parity's un-route has completed (evaluation stream)
     bool step_done_valid = false;
   } rt[2];
-  uint32_t* h_m = nullptr;         // pinned
 };
 
 namespace {
@@ -927,7 +925,6 @@ void gub_p2p_destroy(gub_p2p* p) {
     if (r.routed) cudaEventDestroy(r.routed);
     if (r.step_done) cudaEventDestroy(r.step_done);
   }
-  if (p->h_m) cudaFreeHost(p->h_m);
   delete p;
 }
 
@@ -950,7 +947,6 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t c
   if (e == cudaSuccess) e = cudaMalloc(&p->error, 4);
   if (e == cudaSuccess) e = cudaMemset(p->done_ctr, 0, 8);
   if (e == cudaSuccess) e = cudaMemset(p->error, 0, 4);
-  if (e == cudaSuccess) e = cudaHostAlloc(&p->h_m, 8, cudaHostAllocDefault);
   for (auto& r : p->rt) {
     if (e == cudaSuccess) e = cudaMalloc(&r.owner, cap);
     if (e == cudaSuccess) e = cudaMalloc(&r.tile_off, ((size_t)cap / gub::ROUTE_TILE + 1) * gub::MAX_SHARDS * 4);
