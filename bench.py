@@ -475,6 +475,16 @@ def run_b200(args):
                 "path": {"achieved": ALGO_BYTES_PER_DECISION * units / (path_ms * 1e-3) / 1e9 if path_ms > 0 else 0.0,
                          "bytes_per_decision": ALGO_BYTES_PER_DECISION, "ms_per_batch_kernels_only": path_ms}}
     roofline["path"]["frac"] = roofline["path"]["achieved"] / peak
+    # secondary ceiling (north_star's "HBM-random-access roofline"): the measured random 64-byte read-modify-write rate of this
+    # device over this very table, with the loads / stores the batch kernels use; the path's slot traffic (64 B read + 64 B
+    # write-back per decision, algorithmic) as a fraction of it.  Runs last: nothing measured above can be disturbed by it.
+    try:
+        ra_gbs = tab.probe_random_access(1 << 26)
+        slot_gbs = (value / N) * 128.0 / 1e9
+        roofline["random_access"] = {"measured_gbs": ra_gbs, "accesses": 1 << 26, "bytes_per_access": 128,
+                                     "path_slot_gbs": slot_gbs, "frac": slot_gbs / ra_gbs if ra_gbs > 0 else None}
+    except Exception as ex:  # diagnostic only
+        roofline["random_access"] = {"error": str(ex)}
 
     cpu = None
     if not args.no_cpu_baseline and N == 1:

@@ -673,6 +673,30 @@ int gub_get_profile(gub_table* t, double kernel_ms[4], uint64_t* launches, int r
   return 0;
 }
 
+// Measures the random 64-byte read-modify-write rate of this device over the table itself (contents unchanged): the
+// "HBM random access" ceiling the batch path is compared with.  accesses are spread over all slots; returns GB/s moved
+// (64 B read + 64 B written per access) in *gbs.
+int gub_probe_random_access(gub_table* t, uint64_t accesses, double* gbs) {
+  if (!t || !gbs || accesses == 0) return fail("gub_probe_random_access: bad argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const uint64_t zero = (uint64_t)(getenv("GUB_PROBE_NONZERO") != nullptr);  // always 0 in practice; opaque to the compiler
+  gub::k_random_rmw<<<148 * 16, 256>>>(t->table, t->capacity, accesses / 8 + 1, 1, zero);  // warm-up
+  CK(cudaEventRecord(e0, 0));
+  gub::k_random_rmw<<<148 * 16, 256>>>(t->table, t->capacity, accesses, 12345, zero);
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *gbs = ms > 0 ? (double)accesses * 128.0 / (ms * 1e-3) * 1e-9 : 0.0;
+  return 0;
+}
+
 // ---- multi-GPU routing ----------------------------------------------------------------------------------------
 static int ensure_ring(gub_table* t, const gub_ring* ring) {
   const uint64_t ver = gub_ring_version_(ring);

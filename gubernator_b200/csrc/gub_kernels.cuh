@@ -882,6 +882,22 @@ __global__ void k_sweep(Slot* table, uint64_t cap, int64_t now_ms, unsigned long
   if (mine) atomicAdd(removed, mine);
 }
 
+// Roofline denominator for this path ("HBM random access"): every thread reads one pseudo-random 64-byte slot with
+// the four 128-bit loads the batch kernels use and writes the same 64 bytes back (`zero` is 0 at run time, unknown at compile
+// time, so the stores stay).  The table's contents are unchanged.  Must not run concurrently with a batch.
+__global__ void __launch_bounds__(256) k_random_rmw(Slot* table, uint64_t cap, uint64_t n, uint64_t seed, uint64_t zero) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t h = (i + seed) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+    Slot* s = table + __umul64hi(h, cap);
+    ulonglong2 a, b, c, d;
+    slot_load(s, a, b, c, d);
+    ulonglong2* q = reinterpret_cast<ulonglong2*>(s);
+    a.x ^= zero; b.x ^= zero; c.x ^= zero; d.x ^= zero;
+    q[0] = a; q[1] = b; q[2] = c; q[3] = d;
+  }
+}
+
 // ---- multi-GPU routing ----------------------------------------------------------------------------------------
 // Owner of a key = first ring point >= FNV-1(key), wrapping (replicated_hash.go:104-119).  Stable partition of the
 // batch by owner: per-tile counts -> exclusive scan over (owner, tile) -> ordered scatter.

@@ -29,7 +29,7 @@ assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.it
 
 EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n", "gub_submit_compact", "gub_submit_compact_async",
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",
-           "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_set_profiling", "gub_get_profile", "gub_hash_keys", "gub_hash_keys_device",
+           "gub_add_items", "gub_get_items", "gub_scan", "gub_size", "gub_sweep", "gub_get_counters", "gub_probe_random_access", "gub_set_profiling", "gub_get_profile", "gub_hash_keys", "gub_hash_keys_device",
            "gub_xxh64", "gub_fnv1_64", "gub_fnv1a_64", "gub_ring_create", "gub_ring_destroy", "gub_ring_add", "gub_ring_size",
            "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
@@ -105,6 +105,7 @@ def lib():
         L.gub_p2p_connect.argtypes = [vp, vp]
         L.gub_p2p_connect_local.argtypes = [vp, C.POINTER(vp)]
         L.gub_p2p_step.argtypes = [vp, vp, sz, vp, vp, vp]
+        L.gub_probe_random_access.argtypes = [vp, C.c_uint64, C.POINTER(C.c_double)]
         L.gub_p2p_step_streams.argtypes = [vp, vp, sz, vp, vp, vp, vp]
         _lib = L
     return _lib
@@ -237,6 +238,12 @@ class Table:
         _check(lib().gub_submit_compact_async(self._h, creqs_ptr, n, params_ptr, n_params, int(created_base), clk.ctypes.data, out_ptr,
                                               C.byref(ticket)), "gub_submit_compact_async")
         return ticket.value
+
+    def probe_random_access(self, accesses=1 << 26):
+        """GB/s of random 64-byte read-modify-write over this table's slots (contents unchanged); synchronises the device."""
+        gbs = C.c_double(0.0)
+        _check(lib().gub_probe_random_access(self._h, int(accesses), C.byref(gbs)), "gub_probe_random_access")
+        return gbs.value
 
     def submit_device(self, d_reqs_ptr, n, clk: np.ndarray, d_out_ptr, stream=0):
         _check(lib().gub_submit_device(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, stream), "gub_submit_device")

@@ -192,6 +192,9 @@ int gub_size(gub_table* t, size_t* n_out);
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
 
+/* Diagnostic: random 64-byte read-modify-write rate of the device over the table's own slots (contents unchanged), in GB/s
+ * moved (64 B read + 64 B written per access): the "HBM random access" ceiling bench.py reports the path against. */
+int gub_probe_random_access(gub_table* t, uint64_t accesses, double* gbs);
 /* Optional per-kernel device timing of the batch path (CUDA events around k_group / k_rank / k_eval / k_finish), the
  * measurement counterpart of the reference's metricFuncTimeDuration summaries (gubernator.go:65-73).  Off by default. */
 int gub_set_profiling(gub_table* t, int on);

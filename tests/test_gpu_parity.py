@@ -92,6 +92,23 @@ def test_update_peer_globals_items(G):
         assert inst.get_rate_limits([r]) == pool.get_rate_limits([r])
 
 
+def test_random_access_probe_leaves_table_unchanged(G):
+    """gub_probe_random_access (bench.py's random-access ceiling) rewrites slots with their own contents: the table a scan
+    returns is bit-identical before and after, and requests still evaluate like the oracle's."""
+    rng = np.random.default_rng(12)
+    tab = G.Table(1 << 12)
+    pool = O.Pool(now_ms=T0)
+    reqs = adversarial_batch(rng, 3000, 400, T0)
+    _cmp(tab.submit(reqs, G.clock_fill(T0)), pool.submit_hashed(reqs), "before the probe")
+    before = np.sort(tab.scan(), order=["key_xxh64", "key_fnv1"])
+    assert tab.probe_random_access(1 << 18) > 0.0
+    after = np.sort(tab.scan(), order=["key_xxh64", "key_fnv1"])
+    assert before.tobytes() == after.tobytes()
+    reqs = adversarial_batch(rng, 3000, 400, T0 + 7)
+    pool.set_now(T0 + 7)
+    _cmp(tab.submit(reqs, G.clock_fill(T0 + 7)), pool.submit_hashed(reqs), "after the probe")
+
+
 # ---- randomized differential tests --------------------------------------------------------------------------
 @pytest.mark.parametrize("seed,n_keys,n", [(0, 3, 2000), (1, 40, 6000), (2, 400, 6000), (3, 5000, 20000), (4, 1, 3000), (5, 40, 65536)])
 def test_adversarial_differential(G, seed, n_keys, n):
