@@ -114,3 +114,20 @@ def test_error_strings_match_oracle(G):
         buf = C.create_string_buffer(256)
         L.gub_format_error(want["err_code"], b"n_k", r.get("algorithm", 0), buf, 256)
         assert buf.value.decode() == want["error"]
+
+
+def test_compact_batch_round_trip(G):
+    """native.compact_batch (what a shim fills for gub_submit_compact*): expanding the 32-byte records with the parameter
+    table, as k_expand does on the device, gives back the 64-byte records field for field."""
+    from workloads import T0, adversarial_batch, bench_requests, zipf_ids
+    rng = np.random.default_rng(5)
+    for reqs in (adversarial_batch(rng, 5000, 300, T0), bench_requests(zipf_ids(rng, 4000, 1000, 1.1), T0 + 3), adversarial_batch(rng, 1, 1, T0)):
+        reqs = reqs.astype(G.REQ_DTYPE) if reqs.dtype != G.REQ_DTYPE else reqs
+        c, params, base = G.native.compact_batch(reqs)
+        assert c.dtype.itemsize == 32 and params.dtype.itemsize == 32 and len(c) == len(reqs)
+        back = np.zeros(len(reqs), dtype=G.REQ_DTYPE)
+        back["key_xxh64"], back["key_fnv1"], back["hits"] = c["key_xxh64"], c["key_fnv1"], c["hits"]
+        for f in ("limit", "duration", "burst", "algorithm", "behavior"):
+            back[f] = params[f][c["params"]]
+        back["created_at"] = base + c["created_delta"].astype(np.int64)
+        assert back.tobytes() == reqs.tobytes()
