@@ -150,7 +150,10 @@ int gub_wait(gub_table* t, int ticket);
 /* ---- compact requests: the host link is the bottleneck of the host-to-host path (64 B per request over PCIe), and most
  * of a RateLimitReq is per-limit configuration that repeats across a batch.  A compact batch carries 32-byte records
  * plus one small table of the distinct (limit, duration, burst, algorithm, behavior) tuples; a kernel expands it to
- * gub_req records on the device and the normal path runs.  Results are identical to submitting the expanded batch. */
+ * gub_req records on the device and the normal path runs.  Results are identical to submitting the expanded batch.
+ * Tables of up to 32 sets travel inside the kernel launch (read during the call: `params` may be reused right after it
+ * returns; `reqs` and `out` must stay valid until gub_wait); larger tables are copied to the device separately, which
+ * costs the pipeline far more than their size suggests (profiles/r01_e2e_pipeline.md): keep tables small. */
 typedef struct {
   uint64_t key_xxh64;
   uint64_t key_fnv1;
