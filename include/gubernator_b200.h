@@ -152,8 +152,8 @@ int gub_wait(gub_table* t, int ticket);
  * plus one small table of the distinct (limit, duration, burst, algorithm, behavior) tuples; a kernel expands it to
  * gub_req records on the device and the normal path runs.  Results are identical to submitting the expanded batch.
  * Tables of up to 32 sets travel inside the kernel launch (read during the call: `params` may be reused right after it
- * returns; `reqs` and `out` must stay valid until gub_wait); larger tables are copied to the device separately, which
- * costs the pipeline far more than their size suggests (profiles/r01_e2e_pipeline.md): keep tables small. */
+ * returns; `reqs` and `out` must stay valid until gub_wait); larger tables are copied to the device separately (then `params` must
+ * stay valid until gub_wait as well), which costs the pipeline far more than their size suggests (profiles/r01_e2e_pipeline.md): keep tables small. */
 typedef struct {
   uint64_t key_xxh64;
   uint64_t key_fnv1;
