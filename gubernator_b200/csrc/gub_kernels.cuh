@@ -31,7 +31,9 @@
 // The four kernels are chained with programmatic dependent launch; block requests are partitioned by algorithm so that a
 // warp runs one bucket algorithm's code path.
 #pragma once
+#if !defined(GUB_EMULATE)  // tests/kernel_emu_harness.cpp compiles this header for the CPU on top of tests/cuda_emu.h
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "bucket_math.cuh"
@@ -116,8 +118,15 @@ __device__ __forceinline__ uint32_t batch_n(const BatchArgs& A) {
 // the stream has completed and its writes are visible; only work that depends on nothing earlier may precede it.
 // pdl_release() then lets the NEXT kernel start launching (after our wait, so that kernel may read anything that was
 // complete before this one started, e.g. the request records).
+#if defined(GUB_EMULATE)
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_release() {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 // ---- slot access ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void slot_load(const Slot* s, ulonglong2& a, ulonglong2& b, ulonglong2& c, ulonglong2& d) {
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   if (valid) {
     key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
     first = __ldcg(&A.aux[aux_home(A, key)].word);  // consumed much later, by the fragment's first member only
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.table + __umul64hi(key, A.capacity)));  // the slot k_eval will probe
+    prefetch_l2(A.table + __umul64hi(key, A.capacity));  // the slot k_eval will probe
     sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
 #pragma unroll 1
     for (;;) {

@@ -1,0 +1,116 @@
+"""Builds/loads the TEST-ONLY CPU emulation of the CUDA kernels (tests/kernel_emu_harness.cpp on tests/cuda_emu.h): the
+kernel source of gubernator_b200/csrc/gub_kernels.cuh, compiled with g++ and run with fibers standing in for threads."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "libkernel_emu_test.so")
+SRC = [os.path.join(HERE, "kernel_emu_harness.cpp"), os.path.join(HERE, "cuda_emu.h"),
+       os.path.join(ROOT, "gubernator_b200", "csrc", "gub_kernels.cuh"), os.path.join(ROOT, "gubernator_b200", "csrc", "bucket_math.cuh"),
+       os.path.join(ROOT, "include", "gubernator_b200.h")]
+COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups", "mixed_groups",
+                 "serial_fallbacks"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRC):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                                   "-I", os.path.join(ROOT, "include"), "-x", "c++", SRC[0], "-o", SO])
+        L = C.CDLL(SO)
+        vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
+        L.emu_create.argtypes = [u64, u32]; L.emu_create.restype = vp
+        L.emu_destroy.argtypes = [vp]; L.emu_destroy.restype = None
+        L.emu_set_epoch.argtypes = [vp, u32]; L.emu_set_epoch.restype = None
+        L.emu_submit.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.emu_submit_compact.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, vp, vp]
+        L.emu_counters.argtypes = [vp, vp]; L.emu_counters.restype = None
+        L.emu_scan.argtypes = [vp, vp, u64]; L.emu_scan.restype = u64
+        L.emu_sweep.argtypes = [vp, i64]; L.emu_sweep.restype = u64
+        L.emu_hash_keys.argtypes = [vp, vp, u32, vp, vp]; L.emu_hash_keys.restype = None
+        L.emu_route.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, vp, vp]; L.emu_route.restype = None
+        L.emu_unroute.argtypes = [vp, vp, u32, vp]; L.emu_unroute.restype = None
+        assert L.emu_counter_count() == len(COUNTER_NAMES)
+        _lib = L
+    return _lib
+
+
+class EmuTable:
+    """Same surface as gubernator_b200.native.Table for what the CPU tests need."""
+
+    def __init__(self, capacity_slots, max_batch=65536):
+        self._h = lib().emu_create(int(capacity_slots), int(max_batch))
+        self.capacity = int(capacity_slots)
+
+    def submit(self, reqs, clk, resp_dtype):
+        out = np.zeros(len(reqs), dtype=resp_dtype)
+        reqs = np.ascontiguousarray(reqs)
+        assert reqs.dtype.itemsize == 64 and out.dtype.itemsize == 32
+        lib().emu_submit(self._h, reqs.ctypes.data, len(reqs), clk.ctypes.data, out.ctypes.data)
+        return out
+
+    def submit_compact(self, creqs, params, created_base, clk, resp_dtype):
+        out = np.zeros(len(creqs), dtype=resp_dtype)
+        lib().emu_submit_compact(self._h, creqs.ctypes.data, len(creqs), params.ctypes.data, len(params), int(created_base), clk.ctypes.data,
+                                 out.ctypes.data)
+        return out
+
+    def set_epoch(self, e):
+        lib().emu_set_epoch(self._h, int(e))
+
+    def counters(self):
+        c = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+        lib().emu_counters(self._h, c.ctypes.data)
+        return dict(zip(COUNTER_NAMES, (int(v) for v in c)))
+
+    def scan(self, item_dtype):
+        out = np.zeros(self.capacity, dtype=item_dtype)
+        n = lib().emu_scan(self._h, out.ctypes.data, len(out))
+        return out[:n]
+
+    def sweep(self, now_ms):
+        return int(lib().emu_sweep(self._h, int(now_ms)))
+
+    def __del__(self):
+        try:
+            lib().emu_destroy(self._h)
+        except Exception:
+            pass
+
+
+def hash_keys(keys):
+    """XXH64 and FNV-1 of every key (bytes) through k_hash_keys."""
+    blob = b"".join(keys)
+    offs = np.zeros(len(keys) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(k) for k in keys])
+    buf = np.frombuffer(blob + b"\0", dtype=np.uint8)
+    xx, fv = np.zeros(len(keys), dtype=np.uint64), np.zeros(len(keys), dtype=np.uint64)
+    lib().emu_hash_keys(buf.ctypes.data, offs.ctypes.data, len(keys), xx.ctypes.data, fv.ctypes.data)
+    return xx, fv
+
+
+def route(reqs, pts, peers, nshards):
+    """(partitioned requests, perm, counts, owner) as gub_route_device produces them."""
+    n = len(reqs)
+    out = np.zeros(max(n, 1), dtype=reqs.dtype)
+    perm, counts, owner = np.zeros(max(n, 1), dtype=np.uint32), np.zeros(nshards, dtype=np.uint32), np.zeros(max(n, 1), dtype=np.uint8)
+    pts, peers = np.ascontiguousarray(pts, dtype=np.uint64), np.ascontiguousarray(peers, dtype=np.int32)
+    reqs = np.ascontiguousarray(reqs)
+    lib().emu_route(reqs.ctypes.data, n, pts.ctypes.data, peers.ctypes.data, len(pts), nshards, out.ctypes.data, perm.ctypes.data, counts.ctypes.data,
+                    owner.ctypes.data)
+    return out[:n], perm[:n], counts, owner[:n]
+
+
+def unroute(resps, perm):
+    out = np.zeros(len(resps), dtype=resps.dtype)
+    resps = np.ascontiguousarray(resps)
+    if len(resps):
+        lib().emu_unroute(resps.ctypes.data, perm.ctypes.data, len(resps), out.ctypes.data)
+    return out

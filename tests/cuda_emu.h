@@ -1,0 +1,228 @@
+// cuda_emu.h — TEST-ONLY: just enough of the CUDA execution model to run gubernator_b200/csrc/gub_kernels.cuh on a CPU.
+//
+// Why: the parity tests proper need a B200 (`-m gpu`); this lets the very same kernel source — grouping, ranks, snapshots,
+// segment planning, routing, hashing — be checked against the oracle in the CPU suite, and lets a kernel change be tried
+// without spending GPU minutes.  It is an emulation of the *programming model*, not of the hardware: no timing, one
+// interleaving.
+//
+// Model: a launch runs its blocks one after another; the threads of a block are ucontext fibers on one OS thread, run
+// round-robin and switched only at synchronisation points (__syncthreads and the warp collectives).  Atomics are therefore
+// plain read-modify-writes, `__shared__` is a function-local static (one block is alive at a time), and a thread that
+// returns early leaves the barriers it would have joined, as on the device.  What this cannot show: data races, memory
+// ordering, anything that needs two blocks to run concurrently (the peer-memory mailbox kernels spin on flags written by
+// other launches and are not emulated).
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define __shared__ static
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { ulonglong2 v; v.x = x; v.y = y; return v; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+using std::max;
+using std::min;
+
+namespace emu {
+
+struct Sync { unsigned live = 0, arrived = 0, gen = 0; };
+struct Warp {
+  Sync sync;
+  unsigned long long val[32];
+  bool present[32];
+};
+struct Fiber {
+  ucontext_t ctx;
+  uint3 tid;
+  bool done = false;
+};
+
+struct State {
+  ucontext_t sched;
+  Fiber* cur = nullptr;
+  std::vector<Fiber> fibers;
+  std::vector<void*> stacks;
+  Sync block;
+  std::vector<Warp> warps;
+  uint3 block_idx{0, 0, 0};
+  dim3 block_dim, grid_dim;
+  std::function<void()> body;
+  unsigned long progress = 0;  // bumped on every barrier arrival / opening and when a fiber finishes: a whole pass without any is a deadlock
+};
+inline State& st() { static State s; return s; }
+
+inline void yield() { State& s = st(); swapcontext(&s.cur->ctx, &s.sched); }
+inline void open_if_complete(Sync& y) {
+  if (y.live > 0 && y.arrived == y.live) { y.arrived = 0; y.gen++; st().progress++; }
+}
+inline void arrive_and_wait(Sync& y) {
+  const unsigned my = y.gen;
+  y.arrived++;
+  st().progress++;
+  open_if_complete(y);
+  while (y.gen == my) yield();
+}
+inline Warp& my_warp() { State& s = st(); return s.warps[s.cur->tid.x >> 5]; }
+
+// deposit -> everybody has deposited -> compute -> everybody has read
+template <class F>
+inline auto warp_collective(unsigned long long mine, F compute) {
+  Warp& w = my_warp();
+  const unsigned lane = st().cur->tid.x & 31u;
+  w.val[lane] = mine;
+  arrive_and_wait(w.sync);
+  auto r = compute(w, lane);
+  arrive_and_wait(w.sync);
+  return r;
+}
+
+inline void trampoline() {
+  State& s = st();
+  s.body();
+  Fiber* f = s.cur;
+  f->done = true;
+  s.progress++;
+  Warp& w = s.warps[f->tid.x >> 5];
+  w.present[f->tid.x & 31u] = false;
+  s.block.live--; open_if_complete(s.block);
+  w.sync.live--; open_if_complete(w.sync);
+  swapcontext(&f->ctx, &s.sched);  // never resumed
+}
+
+constexpr size_t STACK_BYTES = 256 * 1024;
+
+// Runs kernel(args...) for grid x block threads.
+template <class K, class... Args>
+void launch(K kernel, unsigned grid, unsigned block, Args... args) {
+  State& s = st();
+  if (block == 0 || grid == 0) return;
+  if (block % 32 != 0) { std::fprintf(stderr, "cuda_emu: block size %u is not a multiple of 32\n", block); std::abort(); }
+  while (s.stacks.size() < block) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, STACK_BYTES)) std::abort();
+    s.stacks.push_back(p);
+  }
+  s.block_dim = dim3(block);
+  s.grid_dim = dim3(grid);
+  s.body = [&]() { kernel(args...); };
+  for (unsigned b = 0; b < grid; b++) {
+    s.block_idx = uint3{b, 0, 0};
+    s.fibers.assign(block, Fiber());
+    s.warps.assign(block / 32, Warp());
+    s.block = Sync();
+    s.block.live = block;
+    for (unsigned t = 0; t < block; t++) {
+      Fiber& f = s.fibers[t];
+      f.tid = uint3{t, 0, 0};
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = s.stacks[t];
+      f.ctx.uc_stack.ss_size = STACK_BYTES;
+      f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+      Warp& w = s.warps[t >> 5];
+      w.sync.live++;
+      w.present[t & 31u] = true;
+    }
+    unsigned alive = block;
+    while (alive) {
+      const unsigned long before = s.progress;
+      alive = 0;
+      for (unsigned t = 0; t < block; t++) {
+        Fiber& f = s.fibers[t];
+        if (f.done) continue;
+        s.cur = &f;
+        swapcontext(&s.sched, &f.ctx);
+        if (!f.done) alive++;
+      }
+      if (alive && s.progress == before) {
+        std::fprintf(stderr, "cuda_emu: deadlock in block %u (%u threads wait at a barrier the others never reach)\n", b, alive);
+        std::abort();
+      }
+    }
+  }
+  s.cur = nullptr;
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::st().cur->tid)
+#define blockIdx (emu::st().block_idx)
+#define blockDim (emu::st().block_dim)
+#define gridDim (emu::st().grid_dim)
+
+inline void __syncthreads() { emu::arrive_and_wait(emu::st().block); }
+inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::arrive_and_wait(emu::my_warp().sync); }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+
+inline unsigned __match_any_sync(unsigned, unsigned long long v) {
+  return emu::warp_collective(v, [v](emu::Warp& w, unsigned) {
+    unsigned m = 0;
+    for (unsigned l = 0; l < 32; l++) if (w.present[l] && w.val[l] == v) m |= 1u << l;
+    return m;
+  });
+}
+inline unsigned __shfl_sync(unsigned, unsigned v, unsigned src) {
+  return emu::warp_collective(v, [src](emu::Warp& w, unsigned) { return (unsigned)w.val[src & 31u]; });
+}
+inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned delta) {
+  return emu::warp_collective(v, [delta, v](emu::Warp& w, unsigned lane) { return lane >= delta ? (unsigned)w.val[lane - delta] : v; });
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  return emu::warp_collective(pred ? 1ull : 0ull, [](emu::Warp& w, unsigned) {
+    unsigned m = 0;
+    for (unsigned l = 0; l < 32; l++) if (w.present[l] && w.val[l]) m |= 1u << l;
+    return m;
+  });
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  return emu::warp_collective(v, [](emu::Warp& w, unsigned) {
+    unsigned sum = 0;
+    for (unsigned l = 0; l < 32; l++) if (w.present[l]) sum += (unsigned)w.val[l];
+    return sum;
+  });
+}
+
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline void __stcg(T* p, const T& v) { *p = v; }
+template <class T> inline void __stcs(T* p, const T& v) { *p = v; }
+
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
+inline unsigned atomicExch(unsigned* p, unsigned v) { const unsigned o = *p; *p = v; return o; }
+inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { const unsigned o = *p; if (o == cmp) *p = v; return o; }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) {
+  const unsigned long long o = *p;
+  if (o == cmp) *p = v;
+  return o;
+}
+
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xFFu) * ((b >> (8 * k)) & 0xFFu);
+  return c;
+}

@@ -1,0 +1,170 @@
+// TEST-ONLY: the batch kernels of gubernator_b200/csrc/gub_kernels.cuh compiled for the CPU on top of tests/cuda_emu.h,
+// driven the way gub_api.cu drives them (same scratch sizing, same launch sequence and grid sizes), so that the kernel source
+// itself can be checked against the oracle where there is no GPU.  Built by tests/_kernel_emu.py with g++; never part of the
+// product library, which has no CPU path.
+#define GUB_EMULATE 1
+#include "cuda_emu.h"
+
+#include "../gubernator_b200/csrc/gub_kernels.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace gub;
+
+namespace {
+
+uint32_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t)p; }
+
+template <class T> T* zalloc(size_t n) {
+  void* p = nullptr;
+  if (posix_memalign(&p, 64, std::max<size_t>(n * sizeof(T), 64))) std::abort();
+  std::memset(p, 0, std::max<size_t>(n * sizeof(T), 64));
+  return static_cast<T*>(p);
+}
+
+struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
+  Slot* table = nullptr;
+  uint64_t capacity = 0;
+  uint32_t max_batch = 0, aux_entries = 0, max_blocks = 0, pres_words = 0, epoch = 0;
+  AuxEntry* aux = nullptr;
+  uint32_t *presence = nullptr, *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *commit_ent = nullptr;
+  uint8_t* fragsize = nullptr;
+  ulonglong2* commit = nullptr;
+  BatchCtr* ctr = nullptr;
+  unsigned long long* counters = nullptr;
+};
+
+}  // namespace
+
+extern "C" {
+
+void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
+  EmuTable* t = new EmuTable();
+  t->capacity = capacity_slots;
+  uint32_t B = max_batch ? max_batch : 65536u;
+  if (B < 1024) B = 1024;
+  B = (B + 255u) & ~255u;
+  t->max_batch = B;
+  t->aux_entries = next_pow2((uint64_t)B * 4);
+  t->max_blocks = (B / GROUP_THREADS + 31u) & ~31u;
+  t->pres_words = t->max_blocks / 32;
+  t->table = zalloc<Slot>(capacity_slots);
+  t->aux = zalloc<AuxEntry>(t->aux_entries);
+  t->presence = zalloc<uint32_t>((size_t)t->aux_entries * t->pres_words);
+  t->fragsize = zalloc<uint8_t>((size_t)t->aux_entries * t->max_blocks);
+  t->commit = zalloc<ulonglong2>((size_t)t->aux_entries * 6);
+  t->commit_ent = zalloc<uint32_t>((size_t)B / 2 + 1);
+  t->ent = zalloc<uint32_t>(B); t->meta = zalloc<uint32_t>(B); t->rank = zalloc<uint32_t>(B); t->order = zalloc<uint32_t>(B);
+  t->mixed_ent = zalloc<uint32_t>((size_t)B / 2 + 1);
+  t->ctr = zalloc<BatchCtr>(2);
+  t->counters = zalloc<unsigned long long>(C_COUNT);
+  return t;
+}
+
+void emu_destroy(void* tv) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  void* ptrs[] = {t->table, t->aux, t->presence, t->fragsize, t->commit, t->commit_ent, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->ctr, t->counters};
+  for (void* p : ptrs) std::free(p);
+  delete t;
+}
+
+void emu_set_epoch(void* tv, uint32_t epoch) { static_cast<EmuTable*>(tv)->epoch = epoch; }
+
+// launch_batch / launch_chunk / launch_finish of gub_api.cu, minus streams.
+int emu_submit(void* tv, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  for (size_t off = 0; off < n; off += t->max_batch) {
+    const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
+    if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); t->epoch = 0; }
+    t->epoch++;
+    BatchArgs A;
+    std::memset(&A, 0, sizeof A);
+    A.table = t->table; A.capacity = t->capacity; A.reqs = reqs + off; A.out = out + off; A.n = m; A.n_dev = nullptr; A.n_off = 0; A.epoch = t->epoch;
+    A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
+    A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank;
+    A.commit = t->commit; A.commit_ent = t->commit_ent; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
+    A.counters = t->counters;
+    A.clk = *clk;
+    const uint32_t blocks = (m + 255) / 256;
+    emu::launch(k_group, blocks, GROUP_THREADS, A);
+    emu::launch(k_rank, blocks, GROUP_THREADS, A);
+    emu::launch(k_eval, blocks, GROUP_THREADS, A);
+    const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, m / 2));
+    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (m / 2 + MIXED_THREADS - 1) / MIXED_THREADS));
+    emu::launch(k_finish, mixed_blocks + commit_blocks, MIXED_THREADS, A, mixed_blocks);
+  }
+  return 0;
+}
+
+int emu_submit_compact(void* tv, const gub_creq* creqs, size_t n, const gub_params* params, size_t n_params, int64_t created_base, const gub_clock* clk,
+                       gub_resp* out) {
+  std::vector<gub_req> reqs(std::max<size_t>(n, 1));
+  if (n) {
+    if (n_params <= INLINE_PARAMS) {
+      InlineParams P;
+      std::memset(&P, 0, sizeof P);
+      std::memcpy(&P, params, n_params * sizeof(gub_params));
+      emu::launch(k_expand_inline, (unsigned)((n + 255) / 256), 256u, creqs, (uint32_t)n, P, (uint32_t)n_params, created_base, reqs.data());
+    } else {
+      emu::launch(k_expand, (unsigned)((n + 255) / 256), 256u, creqs, (uint32_t)n, params, (uint32_t)n_params, created_base, reqs.data());
+    }
+  }
+  return emu_submit(tv, reqs.data(), n, clk, out);
+}
+
+void emu_counters(void* tv, unsigned long long* out /* C_COUNT */) { std::memcpy(out, static_cast<EmuTable*>(tv)->counters, C_COUNT * sizeof(unsigned long long)); }
+int emu_counter_count(void) { return C_COUNT; }
+
+// Live items, as gub_scan reports them (k_scan + the DevItem -> gub_item mapping of gub_api.cu).
+uint64_t emu_scan(void* tv, gub_item* out, uint64_t cap) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  std::vector<DevItem> dev(std::max<uint64_t>(cap, 1));
+  unsigned long long n = 0;
+  emu::launch(k_scan, 4u, 256u, (const Slot*)t->table, t->capacity, dev.data(), (unsigned long long)cap, &n);
+  const uint64_t m = std::min<uint64_t>(n, cap);
+  for (uint64_t i = 0; i < m; i++) {
+    const DevItem& d = dev[i];
+    gub_item it;
+    std::memset(&it, 0, sizeof it);
+    it.key_xxh64 = d.key; it.key_fnv1 = d.tag << 8;
+    const bool leaky = (d.flags & F_LEAKY) != 0;
+    it.algorithm = leaky ? GUB_LEAKY_BUCKET : GUB_TOKEN_BUCKET;
+    it.status = (d.flags & F_OVER) ? GUB_OVER_LIMIT : GUB_UNDER_LIMIT;
+    it.limit = (int64_t)d.w[0]; it.duration = (int64_t)d.w[1];
+    if (leaky) std::memcpy(&it.remaining_f, &d.w[2], 8); else it.remaining = (int64_t)d.w[2];
+    it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5];
+    out[i] = it;
+  }
+  return n;
+}
+
+uint64_t emu_sweep(void* tv, int64_t now_ms) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  unsigned long long removed = 0;
+  emu::launch(k_sweep, 4u, 256u, t->table, t->capacity, now_ms, &removed);
+  return removed;
+}
+
+// k_hash_keys: XXH64 + FNV-1 over packed keys.
+void emu_hash_keys(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint64_t* xxh_out, uint64_t* fnv_out) {
+  if (n) emu::launch(k_hash_keys, (n + 255) / 256, 256u, bytes, offsets, n, xxh_out, fnv_out, (gub_req*)nullptr);
+}
+
+// gub_route_device: owner of every request by the ring + stable partition by owner (k_route_count / k_route_scan / k_route_scatter),
+// and k_unroute for the way back.
+void emu_route(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32_t* peers, uint32_t npts, uint32_t nshards, gub_req* out_reqs, uint32_t* perm,
+               uint32_t* counts, uint8_t* owner) {
+  if (!n) { std::memset(counts, 0, nshards * 4); return; }
+  const uint32_t ntiles = (n + ROUTE_TILE - 1) / ROUTE_TILE;
+  std::vector<uint32_t> tile_counts((size_t)nshards * ntiles + 1);
+  emu::launch(k_route_count, ntiles, 256u, reqs, n, pts, peers, npts, nshards, owner, tile_counts.data(), ntiles, -1, (uint8_t*)nullptr);
+  emu::launch(k_route_scan, 1u, 1024u, tile_counts.data(), nshards * ntiles, nshards, ntiles, counts);
+  emu::launch(k_route_scatter, ntiles, 256u, reqs, n, (const uint8_t*)owner, (const uint32_t*)tile_counts.data(), ntiles, nshards, out_reqs, perm);
+}
+void emu_unroute(const gub_resp* in, const uint32_t* perm, uint32_t n, gub_resp* out) {
+  if (n) emu::launch(k_unroute, (n + 255) / 256, 256u, in, perm, n, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,209 @@
+"""The CUDA kernel source itself, on the CPU: gubernator_b200/csrc/gub_kernels.cuh compiled with g++ on top of tests/cuda_emu.h
+(fibers standing in for the threads of a block; tests/kernel_emu_harness.cpp drives the launches exactly like gub_api.cu) and
+checked against the oracle — responses, counters and final table, bit for bit.  This is NOT a product path (the library has no
+CPU fallback) and not a replacement for the `-m gpu` parity tests: it explores one interleaving and no memory-model effects.
+It keeps the grouping / rank / snapshot / segment logic, the routing kernels and the hashing kernel under test where there is
+no GPU, and lets a kernel change be tried before GPU minutes are spent on it."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+import _kernel_emu as E
+from _host_math import CLOCK_DTYPE
+from workloads import T0, adversarial_batch, bench_requests, extreme_batch, key_hashes, make_clock, zipf_ids
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gubernator_b200 as g  # dtypes and the host-side helpers only; nothing here touches CUDA
+    return g
+
+
+def _cmp(got, want, what=""):
+    if not np.array_equal(got, want):
+        bad = np.nonzero(got != want)[0]
+        i = int(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} of {len(got)} responses differ; first at {i}: got {got[i]} want {want[i]}")
+
+
+def _check_state(G, tab, pool):
+    c, oc = tab.counters(), pool.counters()
+    for k in ("over_limit", "cache_hit", "cache_miss"):
+        assert c[k] == oc[k], (k, c, oc)
+    items = pool.each()
+    scan = tab.scan(G.ITEM_DTYPE)
+    dev = {(int(s["key_xxh64"]), int(s["key_fnv1"]) >> 8): s for s in scan}
+    assert len(dev) == len(scan) == len(items)
+    for (kx, kf), it in items.items():
+        s = dev[(kx if kx >= 2 else kx + 2, kf >> 8)]
+        assert (int(s["limit"]), int(s["duration"]), int(s["stamp"]), int(s["expire_at"])) == (it.limit, it.duration, it.stamp, it.expire_at)
+        if it.value_kind == 2:
+            assert int(s["algorithm"]) == 1 and int(s["burst"]) == it.burst
+            assert np.float64(s["remaining_f"]).view(np.uint64) == np.float64(it.remaining_f).view(np.uint64)
+        else:
+            assert int(s["algorithm"]) == 0 and int(s["remaining"]) == it.remaining_i and int(s["status"]) == it.status
+
+
+@pytest.mark.parametrize("seed,n_keys,n", [(0, 3, 1500), (1, 40, 3000), (2, 2500, 3000), (3, 1, 700)])
+def test_adversarial_batches_match_oracle(G, seed, n_keys, n):
+    """Every behaviour bit, both algorithms, parameter changes mid-run, time steps that expire items: few keys exercise the
+    non-uniform (segment) path of k_finish, many keys the singleton path of k_rank."""
+    rng = np.random.default_rng(100 + seed)
+    tab, pool = E.EmuTable(1 << 13, max_batch=2048), O.Pool(now_ms=T0)
+    now = T0
+    for step in range(3):
+        now += int(rng.choice([0, 1, 900, 70000]))
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, n, n_keys, now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    _check_state(G, tab, pool)
+
+
+def test_zipf_uniform_runs_use_the_rank_path(G):
+    """The bench workload's shape: identical requests per key, heavy repeats — run_to_rank per member, no non-uniform groups."""
+    rng = np.random.default_rng(7)
+    tab, pool = E.EmuTable(1 << 13), O.Pool(now_ms=T0)
+    for step in range(3):
+        now = T0 + 400 * step
+        pool.set_now(now)
+        reqs = bench_requests(zipf_ids(rng, 4096, 1500, 1.1), now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    c = tab.counters()
+    assert c["mixed_groups"] == 0 and c["dup_groups"] > 0
+    _check_state(G, tab, pool)
+
+
+def test_numeric_extremes(G):
+    rng = np.random.default_rng(31)
+    tab, pool = E.EmuTable(1 << 12), O.Pool(now_ms=T0)
+    for step in range(2):
+        now = T0 + 1000 * step
+        pool.set_now(now)
+        reqs = extreme_batch(rng, 2000, 30, now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    _check_state(G, tab, pool)
+
+
+def test_many_segments_force_the_serial_walk(G):
+    rng = np.random.default_rng(77)
+    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+    n = 1200
+    reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+    xx, fv = key_hashes([1] * n, name="hot")
+    reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
+    reqs["hits"] = rng.integers(0, 3, n); reqs["limit"] = rng.choice([50, 100], n); reqs["duration"] = 60000
+    reqs["created_at"] = T0 + rng.integers(0, 5, n); reqs["algorithm"] = 1; reqs["behavior"] = G.native.REQ_IS_OWNER
+    _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs))
+    assert tab.counters()["serial_fallbacks"] == 1
+    reqs2 = reqs.copy()
+    reqs2["hits"] = 1; reqs2["limit"] = 100; reqs2["created_at"] = T0 + 10 + (np.arange(n) // 200)  # six long uniform segments
+    pool.set_now(T0 + 10)
+    _cmp(tab.submit(reqs2, make_clock(T0 + 10), O.HRESP_DTYPE), pool.submit_hashed(reqs2))
+    assert tab.counters()["serial_fallbacks"] == 1
+    _check_state(G, tab, pool)
+
+
+def test_token_reset_flipflop(G):
+    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+    n = 300
+    reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+    xx, fv = key_hashes([7] * n, name="flip")
+    reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
+    reqs["hits"] = 1; reqs["limit"] = 10; reqs["duration"] = 60000; reqs["created_at"] = T0
+    reqs["behavior"] = G.native.REQ_IS_OWNER | G.native.RESET_REMAINING
+    _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs))
+    _check_state(G, tab, pool)
+
+
+def test_ragged_sizes_and_chunking(G):
+    rng = np.random.default_rng(5)
+    tab, pool = E.EmuTable(1 << 12, max_batch=1024), O.Pool(now_ms=T0)
+    assert len(tab.submit(np.zeros(0, dtype=G.REQ_DTYPE), make_clock(T0), O.HRESP_DTYPE)) == 0
+    for n in (1, 2, 31, 32, 33, 255, 257, 1023, 1024, 1025, 2500):  # the last two cross the max_batch chunking
+        reqs = adversarial_batch(rng, n, 50, T0)
+        _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"n={n}")
+    _check_state(G, tab, pool)
+
+
+def test_sentinel_hashes_table_full_and_sweep(G):
+    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+    reqs = np.zeros(8, dtype=G.REQ_DTYPE)
+    reqs["key_xxh64"] = [0, 1, 2, 3, 0, 1, 2, 3]
+    reqs["key_fnv1"] = [10 << 8, 11 << 8, 12 << 8, 13 << 8, 10 << 8, 11 << 8, 12 << 8, 13 << 8]
+    reqs["hits"] = 1; reqs["limit"] = 5; reqs["duration"] = 1000; reqs["created_at"] = T0
+    _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs))
+    small = E.EmuTable(64)
+    n = 1500
+    reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+    xx, fv = key_hashes(np.arange(n), name="full")
+    reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
+    reqs["hits"] = 1; reqs["limit"] = 5; reqs["duration"] = 100000; reqs["created_at"] = T0
+    out = small.submit(reqs, make_clock(T0), O.HRESP_DTYPE)
+    ok = out["err_code"] == 0
+    assert ok.sum() == 64 and np.all(out["err_code"][~ok] == G.native.ERR_TABLE_FULL)
+    assert len(small.scan(G.ITEM_DTYPE)) == 64 and small.counters()["table_full"] == n - 64
+    assert small.sweep(T0 + 100001) == 64 and len(small.scan(G.ITEM_DTYPE)) == 0
+    assert np.all(small.submit(reqs[:64], make_clock(T0 + 100001), O.HRESP_DTYPE)["err_code"] == 0)
+
+
+def test_epoch_wrap(G):
+    """16-bit epoch tags of the grouping table: batches on both sides of the wrap (the launcher clears the table at 65535)."""
+    rng = np.random.default_rng(41)
+    tab, pool = E.EmuTable(1 << 12, max_batch=1024), O.Pool(now_ms=T0)
+    reqs = adversarial_batch(rng, 64, 5, T0)
+    clk = make_clock(T0)
+    _cmp(tab.submit(reqs, clk, O.HRESP_DTYPE), pool.submit_hashed(reqs), "first")
+    tab.set_epoch(65530)
+    for b in range(12):
+        _cmp(tab.submit(reqs, clk, O.HRESP_DTYPE), pool.submit_hashed(reqs), f"batch {b} after epoch 65530")
+
+
+def test_compact_records_expand_like_the_full_ones(G):
+    rng = np.random.default_rng(61)
+    a, b, pool = E.EmuTable(1 << 13), E.EmuTable(1 << 13), O.Pool(now_ms=T0)
+    for n_sets in (2, 32, 33):  # <= 32 sets travel in the kernel arguments (k_expand_inline), more by pointer (k_expand)
+        now = T0 + n_sets
+        pool.set_now(now)
+        ids = zipf_ids(rng, 3000, 800, 1.1)
+        reqs = bench_requests(ids, now)
+        reqs["limit"] = 50 + (ids % n_sets)
+        reqs["algorithm"] = (ids % n_sets) & 1
+        creqs, params, base = G.native.compact_batch(reqs.astype(G.REQ_DTYPE))
+        assert len(params) == n_sets
+        want = pool.submit_hashed(reqs)
+        _cmp(a.submit(reqs, make_clock(now), O.HRESP_DTYPE), want, f"full, {n_sets} sets")
+        _cmp(b.submit_compact(creqs, params, base, make_clock(now), O.HRESP_DTYPE), want, f"compact, {n_sets} sets")
+    creqs, params, base = G.native.compact_batch(adversarial_batch(rng, 10, 3, T0).astype(G.REQ_DTYPE))
+    creqs["params"][3] = 10_000  # unknown parameter set: in-band error
+    assert b.submit_compact(creqs, params, base, make_clock(T0), O.HRESP_DTYPE)["err_code"][3] == G.native.ERR_INVALID_ALGORITHM
+
+
+def test_hash_kernel_matches_oracle_hashes():
+    rng = np.random.default_rng(9)
+    keys = [b"", b"a", b"bench_k000000042", b"x" * 31, b"y" * 32, b"z" * 33, b"w" * 100] + [bytes(rng.integers(0, 256, int(l), dtype=np.uint8))
+                                                                                           for l in rng.integers(0, 90, 200)]
+    xx, fv = E.hash_keys(keys)
+    for k, x, f in zip(keys, xx, fv):
+        assert int(x) == O.xxh64(k) and int(f) == O.fnv1_64(k), k
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_route_kernels_partition_stably_by_ring_owner(G, world):
+    from gubernator_b200.sharded import shard_addresses
+    oring = O.Ring(0, 512)
+    for a in shard_addresses(world):
+        oring.add(a)
+    pts, peers = oring.points()
+    rng = np.random.default_rng(world)
+    for n in (1, 1000, 1024, 3333):
+        reqs = bench_requests(zipf_ids(rng, n, 5000, 1.1), T0).astype(G.REQ_DTYPE)
+        out, perm, counts, owner = E.route(reqs, pts, peers, world)
+        want_owner = np.array([oring.get_by_hash(int(h)) for h in reqs["key_fnv1"]], dtype=np.int64)
+        assert np.array_equal(owner.astype(np.int64), want_owner)
+        order = np.argsort(want_owner, kind="stable")  # the stable partition, by definition
+        assert np.array_equal(perm.astype(np.int64), order) and out.tobytes() == reqs[order].tobytes()
+        assert np.array_equal(counts.astype(np.int64), np.bincount(want_owner, minlength=world))
+        resps = np.zeros(n, dtype=O.HRESP_DTYPE)
+        resps["remaining"] = np.arange(n)
+        back = E.unroute(resps, perm)
+        assert np.array_equal(back["remaining"][order], np.arange(n))
