@@ -15,16 +15,17 @@ SRC = [os.path.join(HERE, "kernel_emu_harness.cpp"), os.path.join(HERE, "cuda_em
 COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups", "mixed_groups",
                  "serial_fallbacks"]
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRC):
+def lib(early_singles=1):
+    """early_singles: the GUB_EARLY_SINGLES build variant of the kernels (1 = default build, 0 = table-free k_rank + commit records)."""
+    if early_singles not in _libs:
+        so = SO if early_singles == 1 else SO.replace(".so", "_es0.so")
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in SRC):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                                   "-I", os.path.join(ROOT, "include"), "-x", "c++", SRC[0], "-o", SO])
-        L = C.CDLL(SO)
+                                   f"-DGUB_EARLY_SINGLES={early_singles}", "-I", os.path.join(ROOT, "include"), "-x", "c++", SRC[0], "-o", so])
+        L = C.CDLL(so)
         vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
         L.emu_create.argtypes = [u64, u32]; L.emu_create.restype = vp
         L.emu_destroy.argtypes = [vp]; L.emu_destroy.restype = None
@@ -38,49 +39,50 @@ def lib():
         L.emu_route.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, vp, vp]; L.emu_route.restype = None
         L.emu_unroute.argtypes = [vp, vp, u32, vp]; L.emu_unroute.restype = None
         assert L.emu_counter_count() == len(COUNTER_NAMES)
-        _lib = L
-    return _lib
+        _libs[early_singles] = L
+    return _libs[early_singles]
 
 
 class EmuTable:
     """Same surface as gubernator_b200.native.Table for what the CPU tests need."""
 
-    def __init__(self, capacity_slots, max_batch=65536):
-        self._h = lib().emu_create(int(capacity_slots), int(max_batch))
+    def __init__(self, capacity_slots, max_batch=65536, early_singles=1):
+        self._L = lib(early_singles)
+        self._h = self._L.emu_create(int(capacity_slots), int(max_batch))
         self.capacity = int(capacity_slots)
 
     def submit(self, reqs, clk, resp_dtype):
         out = np.zeros(len(reqs), dtype=resp_dtype)
         reqs = np.ascontiguousarray(reqs)
         assert reqs.dtype.itemsize == 64 and out.dtype.itemsize == 32
-        lib().emu_submit(self._h, reqs.ctypes.data, len(reqs), clk.ctypes.data, out.ctypes.data)
+        self._L.emu_submit(self._h, reqs.ctypes.data, len(reqs), clk.ctypes.data, out.ctypes.data)
         return out
 
     def submit_compact(self, creqs, params, created_base, clk, resp_dtype):
         out = np.zeros(len(creqs), dtype=resp_dtype)
-        lib().emu_submit_compact(self._h, creqs.ctypes.data, len(creqs), params.ctypes.data, len(params), int(created_base), clk.ctypes.data,
+        self._L.emu_submit_compact(self._h, creqs.ctypes.data, len(creqs), params.ctypes.data, len(params), int(created_base), clk.ctypes.data,
                                  out.ctypes.data)
         return out
 
     def set_epoch(self, e):
-        lib().emu_set_epoch(self._h, int(e))
+        self._L.emu_set_epoch(self._h, int(e))
 
     def counters(self):
         c = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
-        lib().emu_counters(self._h, c.ctypes.data)
+        self._L.emu_counters(self._h, c.ctypes.data)
         return dict(zip(COUNTER_NAMES, (int(v) for v in c)))
 
     def scan(self, item_dtype):
         out = np.zeros(self.capacity, dtype=item_dtype)
-        n = lib().emu_scan(self._h, out.ctypes.data, len(out))
+        n = self._L.emu_scan(self._h, out.ctypes.data, len(out))
         return out[:n]
 
     def sweep(self, now_ms):
-        return int(lib().emu_sweep(self._h, int(now_ms)))
+        return int(self._L.emu_sweep(self._h, int(now_ms)))
 
     def __del__(self):
         try:
-            lib().emu_destroy(self._h)
+            self._L.emu_destroy(self._h)
         except Exception:
             pass
 

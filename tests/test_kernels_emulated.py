@@ -9,7 +9,6 @@ import pytest
 
 import oracle_py as O
 import _kernel_emu as E
-from _host_math import CLOCK_DTYPE
 from workloads import T0, adversarial_batch, bench_requests, extreme_batch, key_hashes, make_clock, zipf_ids
 
 
@@ -55,6 +54,19 @@ def test_adversarial_batches_match_oracle(G, seed, n_keys, n):
         now += int(rng.choice([0, 1, 900, 70000]))
         pool.set_now(now)
         reqs = adversarial_batch(rng, n, n_keys, now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    _check_state(G, tab, pool)
+
+
+def test_table_free_build_variant(G):
+    """GUB_EARLY_SINGLES=0: k_rank never touches the table, everything is evaluated in k_eval and repeated keys are written back by
+    k_finish from commit records (the variant that lets two batches overlap).  Not the default build; kept working here."""
+    rng = np.random.default_rng(11)
+    tab, pool = E.EmuTable(1 << 13, max_batch=2048, early_singles=0), O.Pool(now_ms=T0)
+    for step, n_keys in enumerate([3, 0, 2500, 0, 40]):
+        now = T0 + 800 * step
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
         _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
     _check_state(G, tab, pool)
 
