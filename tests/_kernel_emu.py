@@ -30,6 +30,7 @@ def lib(early_singles=1):
         L.emu_create.argtypes = [u64, u32]; L.emu_create.restype = vp
         L.emu_destroy.argtypes = [vp]; L.emu_destroy.restype = None
         L.emu_set_epoch.argtypes = [vp, u32]; L.emu_set_epoch.restype = None
+        L.emu_set_finish_cap.argtypes = [u32]; L.emu_set_finish_cap.restype = None
         L.emu_submit.argtypes = [vp, vp, C.c_size_t, vp, vp]
         L.emu_submit_compact.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, vp, vp]
         L.emu_counters.argtypes = [vp, vp]; L.emu_counters.restype = None
@@ -38,6 +39,9 @@ def lib(early_singles=1):
         L.emu_hash_keys.argtypes = [vp, vp, u32, vp, vp]; L.emu_hash_keys.restype = None
         L.emu_route.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, vp, vp]; L.emu_route.restype = None
         L.emu_unroute.argtypes = [vp, vp, u32, vp]; L.emu_unroute.restype = None
+        L.emu_p2p_create.argtypes = [u32, u32, u64, u32, vp, vp, u32]; L.emu_p2p_create.restype = vp
+        L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
+        L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp]
         assert L.emu_counter_count() == len(COUNTER_NAMES)
         _libs[early_singles] = L
     return _libs[early_singles]
@@ -116,3 +120,29 @@ def unroute(resps, perm):
     if len(resps):
         lib().emu_unroute(resps.ctypes.data, perm.ctypes.data, len(resps), out.ctypes.data)
     return out
+
+
+class EmuP2PCluster:
+    """W shards in one process stepping through gub_p2p_step's kernels phase by phase (see kernel_emu_harness.cpp)."""
+
+    def __init__(self, world, cap, capacity_slots, pts, peers, max_batch=4096, finish_cap=148):
+        self.world = world
+        self._L = lib()
+        self._finish_cap = finish_cap
+        pts, peers = np.ascontiguousarray(pts, dtype=np.uint64), np.ascontiguousarray(peers, dtype=np.int32)
+        self._h = self._L.emu_p2p_create(world, cap, int(capacity_slots), int(max_batch), pts.ctypes.data, peers.ctypes.data, len(pts))
+
+    def step(self, batches, clk, resp_dtype):
+        """batches: one request array per shard (what that shard ingests); returns one response array per shard."""
+        batches = [np.ascontiguousarray(b) for b in batches]
+        outs = [np.zeros(max(len(b), 1), dtype=resp_dtype) for b in batches]
+        rp = (C.c_void_p * self.world)(*[b.ctypes.data if len(b) else None for b in batches])
+        op = (C.c_void_p * self.world)(*[o.ctypes.data for o in outs])
+        n = np.array([len(b) for b in batches], dtype=np.uint32)
+        self._L.emu_set_finish_cap(self._finish_cap)
+        try:
+            rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op)
+        finally:
+            self._L.emu_set_finish_cap(148)
+        assert rc == 0, "a mailbox flag wait timed out"
+        return [o[:len(b)] for o, b in zip(outs, batches)]

@@ -9,8 +9,8 @@
 // round-robin and switched only at synchronisation points (__syncthreads and the warp collectives).  Atomics are therefore
 // plain read-modify-writes, `__shared__` is a function-local static (one block is alive at a time), and a thread that
 // returns early leaves the barriers it would have joined, as on the device.  What this cannot show: data races, memory
-// ordering, anything that needs two blocks to run concurrently (the peer-memory mailbox kernels spin on flags written by
-// other launches and are not emulated).
+// ordering, anything that needs two blocks or two launches to run concurrently (the peer-memory mailbox kernels spin on flags
+// written by other launches: the harness runs them phase by phase, so the flags are already there).
 #pragma once
 #include <ucontext.h>
 

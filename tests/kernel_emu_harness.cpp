@@ -6,6 +6,7 @@
 #include "cuda_emu.h"
 
 #include "../gubernator_b200/csrc/gub_kernels.cuh"
+#include "../gubernator_b200/csrc/gub_p2p.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +24,8 @@ template <class T> T* zalloc(size_t n) {
   std::memset(p, 0, std::max<size_t>(n * sizeof(T), 64));
   return static_cast<T*>(p);
 }
+
+uint32_t g_finish_cap = 148;
 
 struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   Slot* table = nullptr;
@@ -70,18 +73,19 @@ void emu_destroy(void* tv) {
   delete t;
 }
 
+void emu_set_finish_cap(uint32_t blocks) { g_finish_cap = blocks ? blocks : 148u; }
 void emu_set_epoch(void* tv, uint32_t epoch) { static_cast<EmuTable*>(tv)->epoch = epoch; }
 
-// launch_batch / launch_chunk / launch_finish of gub_api.cu, minus streams.
-int emu_submit(void* tv, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out) {
-  EmuTable* t = static_cast<EmuTable*>(tv);
+// launch_batch / launch_chunk / launch_finish of gub_api.cu, minus streams.  n_dev != nullptr: the batch size is *n_dev (<= n), as in
+// gub_submit_device_n.
+static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_t* n_dev, const gub_clock* clk, gub_resp* out) {
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
     if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); t->epoch = 0; }
     t->epoch++;
     BatchArgs A;
     std::memset(&A, 0, sizeof A);
-    A.table = t->table; A.capacity = t->capacity; A.reqs = reqs + off; A.out = out + off; A.n = m; A.n_dev = nullptr; A.n_off = 0; A.epoch = t->epoch;
+    A.table = t->table; A.capacity = t->capacity; A.reqs = reqs + off; A.out = out + off; A.n = m; A.n_dev = n_dev; A.n_off = (uint32_t)off; A.epoch = t->epoch;
     A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
     A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank;
     A.commit = t->commit; A.commit_ent = t->commit_ent; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
@@ -91,11 +95,17 @@ int emu_submit(void* tv, const gub_req* reqs, size_t n, const gub_clock* clk, gu
     emu::launch(k_group, blocks, GROUP_THREADS, A);
     emu::launch(k_rank, blocks, GROUP_THREADS, A);
     emu::launch(k_eval, blocks, GROUP_THREADS, A);
-    const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, m / 2));
-    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (m / 2 + MIXED_THREADS - 1) / MIXED_THREADS));
+    // gub_api.cu caps both at 148 (one per SM); the cap only changes how the grid-stride loops of k_finish are split, and every
+    // emulated block costs 256 fibers, so tests may lower it (emu_set_finish_cap)
+    const uint32_t mixed_blocks = std::min<uint32_t>(g_finish_cap, std::max<uint32_t>(1u, m / 2));
+    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(g_finish_cap, (m / 2 + MIXED_THREADS - 1) / MIXED_THREADS));
     emu::launch(k_finish, mixed_blocks + commit_blocks, MIXED_THREADS, A, mixed_blocks);
   }
   return 0;
+}
+
+int emu_submit(void* tv, const gub_req* reqs, size_t n, const gub_clock* clk, gub_resp* out) {
+  return submit_impl(static_cast<EmuTable*>(tv), reqs, n, nullptr, clk, out);
 }
 
 int emu_submit_compact(void* tv, const gub_creq* creqs, size_t n, const gub_params* params, size_t n_params, int64_t created_base, const gub_clock* clk,
@@ -165,6 +175,84 @@ void emu_route(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32
 }
 void emu_unroute(const gub_resp* in, const uint32_t* perm, uint32_t n, gub_resp* out) {
   if (n) emu::launch(k_unroute, (n + 255) / 256, 256u, in, perm, n, out);
+}
+
+// ---- gub_p2p_step for W shards living in one process, phase by phase: every shard scatters, then every shard gathers,
+// evaluates and returns responses, then every shard un-routes.  The flag waits of the real kernels find their flags already
+// published, so the spin loops fall through; what is exercised is the mailbox indexing, the (source rank, source index) order at
+// the owner, the device-side batch size and the way back.
+struct EmuP2P {
+  uint32_t world = 0, cap = 0, epoch = 0;
+  std::vector<EmuTable*> tabs;
+  std::vector<uint64_t> pts; std::vector<int32_t> peers;
+  struct Rank {
+    P2PView view;
+    gub_req* inbox; gub_resp* inbox_resp;
+    uint32_t *seg_off, *m_dev, *done_ctr, *error, *tile_off, *counts, *perm;
+    uint8_t* owner;
+  };
+  std::vector<Rank> ranks;
+};
+
+void* emu_p2p_create(uint32_t world, uint32_t cap, uint64_t capacity_slots, uint32_t max_batch, const uint64_t* pts, const int32_t* peers, uint32_t npts) {
+  EmuP2P* p = new EmuP2P();
+  p->world = world; p->cap = cap;
+  p->pts.assign(pts, pts + npts); p->peers.assign(peers, peers + npts);
+  for (uint32_t r = 0; r < world; r++) {
+    p->tabs.push_back(static_cast<EmuTable*>(emu_create(capacity_slots, max_batch)));
+    EmuP2P::Rank k;
+    k.view.req_mb = zalloc<gub_req>((size_t)2 * world * cap);
+    k.view.resp_mb = zalloc<gub_resp>((size_t)2 * world * cap);
+    k.view.req_flag = zalloc<unsigned long long>((size_t)2 * world);
+    k.view.resp_flag = zalloc<unsigned long long>((size_t)2 * world);
+    k.inbox = zalloc<gub_req>((size_t)world * cap); k.inbox_resp = zalloc<gub_resp>((size_t)world * cap);
+    k.seg_off = zalloc<uint32_t>(MAX_SHARDS + 1); k.m_dev = zalloc<uint32_t>(1); k.done_ctr = zalloc<uint32_t>(2); k.error = zalloc<uint32_t>(1);
+    k.tile_off = zalloc<uint32_t>(((size_t)cap / ROUTE_TILE + 1) * MAX_SHARDS); k.counts = zalloc<uint32_t>(MAX_SHARDS); k.perm = zalloc<uint32_t>(cap);
+    k.owner = zalloc<uint8_t>(cap);
+    p->ranks.push_back(k);
+  }
+  return p;
+}
+
+void* emu_p2p_table(void* pv, uint32_t rank) { return static_cast<EmuP2P*>(pv)->tabs[rank]; }
+
+int emu_p2p_step(void* pv, const gub_req* const* reqs, const uint32_t* n, const gub_clock* clk, gub_resp* const* outs) {
+  EmuP2P* p = static_cast<EmuP2P*>(pv);
+  p->epoch++;
+  std::vector<P2PArgs> args(p->world);
+  std::vector<uint32_t> ntiles(p->world, 0);
+  for (uint32_t r = 0; r < p->world; r++) {
+    P2PArgs& A = args[r];
+    for (uint32_t q = 0; q < p->world; q++) A.peers[q] = p->ranks[q].view;
+    A.world = p->world; A.rank = r; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = p->ranks[r].done_ctr; A.error = p->ranks[r].error;
+  }
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 1: partition by owner, store into the owners' mailboxes, publish counts
+    EmuP2P::Rank& k = p->ranks[r];
+    if (n[r]) {
+      ntiles[r] = (n[r] + ROUTE_TILE - 1) / ROUTE_TILE;
+      emu::launch(k_route_count, ntiles[r], 256u, reqs[r], n[r], (const uint64_t*)p->pts.data(), (const int32_t*)p->peers.data(), (uint32_t)p->pts.size(), p->world,
+                  k.owner, k.tile_off, ntiles[r], -1, (uint8_t*)nullptr);
+      emu::launch(k_route_scan, 1u, 1024u, k.tile_off, p->world * ntiles[r], p->world, ntiles[r], k.counts);
+      emu::launch(k_p2p_scatter, ntiles[r], 256u, args[r], reqs[r], n[r], (const uint8_t*)k.owner, (const uint32_t*)k.tile_off, ntiles[r], (const uint32_t*)k.counts,
+                  k.perm);
+    } else {
+      emu::launch(k_p2p_publish_empty, 1u, 32u, args[r]);
+    }
+  }
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 2: gather, evaluate what we own (batch size on the "device"), return responses
+    EmuP2P::Rank& k = p->ranks[r];
+    emu::launch(k_p2p_gather, 4u, 256u, args[r], k.inbox, k.seg_off, k.m_dev);
+    submit_impl(p->tabs[r], k.inbox, (size_t)p->world * p->cap, k.m_dev, clk, k.inbox_resp);
+    emu::launch(k_p2p_push_resp, 4u, 256u, args[r], (const gub_resp*)k.inbox_resp, (const uint32_t*)k.seg_off);
+  }
+  int err = 0;
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 3: responses back in request order
+    EmuP2P::Rank& k = p->ranks[r];
+    if (n[r]) emu::launch(k_p2p_unroute, 4u, 256u, args[r], (const uint32_t*)k.tile_off, ntiles[r], (const uint32_t*)k.perm, n[r], outs[r]);
+    else emu::launch(k_p2p_wait_resp_only, 1u, 32u, args[r]);
+    err |= (int)*k.error;
+  }
+  return err;
 }
 
 }  // extern "C"

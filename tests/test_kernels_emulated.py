@@ -219,3 +219,41 @@ def test_route_kernels_partition_stably_by_ring_owner(G, world):
         resps["remaining"] = np.arange(n)
         back = E.unroute(resps, perm)
         assert np.array_equal(back["remaining"][order], np.arange(n))
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_mailbox_routing_kernels_match_per_shard_oracles(G, world):
+    """gub_p2p.cuh (partition + stores into the owners' mailboxes, gather, device-side batch size, responses back, un-route)
+    for W shards in one process: every response equals what one oracle per shard gives when it applies the records of source 0
+    (in index order), then source 1, ... — the order tests/test_gpu_p2p.py checks on the GPU."""
+    from gubernator_b200.sharded import shard_addresses
+    oring = O.Ring(0, 512)
+    for a in shard_addresses(world):
+        oring.add(a)
+    pts, peers = oring.points()
+    cl = E.EmuP2PCluster(world, cap=2048, capacity_slots=1 << 13, pts=pts, peers=peers, max_batch=2048, finish_cap=3)  # inbox > max_batch: chunked
+    sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(world)]
+    sizes = [[900, 1, 0, 2048, 5], [600, 0, 0, 2048, 300], [1, 1500, 0, 100, 2048], [2048, 0, 0, 7, 300]]
+    for step in range(5):
+        now = T0 + step
+        batches = []
+        for r in range(world):
+            rng = np.random.default_rng(77 * step + r)
+            n = sizes[r % 4][step]
+            if n == 0:
+                batches.append(np.zeros(0, dtype=G.REQ_DTYPE))
+            elif step % 2:
+                batches.append(adversarial_batch(rng, n, 41, now).astype(G.REQ_DTYPE))
+            else:
+                batches.append(bench_requests(zipf_ids(rng, n, 3000, 1.1), now).astype(G.REQ_DTYPE))
+        got = cl.step(batches, make_clock(now), O.HRESP_DTYPE)
+        owners = [np.array([oring.get_by_hash(int(h)) for h in b["key_fnv1"]], dtype=np.int64) for b in batches]
+        want = [np.zeros(len(b), dtype=O.HRESP_DTYPE) for b in batches]
+        for gi in range(world):
+            sim[gi].set_now(now)
+            for s_ in range(world):
+                idx = np.nonzero(owners[s_] == gi)[0]
+                if len(idx):
+                    want[s_][idx] = sim[gi].submit_hashed(np.ascontiguousarray(batches[s_][idx]))
+        for r in range(world):
+            _cmp(got[r], want[r], f"step {step} shard {r}")
