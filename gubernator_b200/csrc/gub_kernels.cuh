@@ -326,11 +326,43 @@ __device__ __forceinline__ uint32_t aux_join(const BatchArgs& A, uint64_t key, u
   return pos;
 }
 
+// Group entries are matched on 24 bits of the key plus the entry position, so two different keys can share one (about 2^-42 per
+// pair of keys in a batch).  That is harmless across blocks: the merged group is found non-uniform in k_rank and k_finish walks it
+// key by key.  Inside ONE block, though, a group entry has room for one fragment only (one presence bit, one size byte, local
+// ranks starting at 0), so fragments of a block that landed in the same entry are folded into one here: their members are
+// re-ranked together in index order, pointed at the first fragment's shared-memory slot (k_rank keeps the fragment's base rank
+// there) and the combined size is stored.  One thread does it; it runs once in ~10^7 blocks.
+__device__ void merge_colliding_fragments(const BatchArgs& A, const uint32_t* s_pos, bool valid, uint32_t& sp, uint32_t& local) {
+  __shared__ uint16_t s_tsp[GROUP_THREADS], s_tlocal[GROUP_THREADS];
+  s_tsp[threadIdx.x] = valid ? (uint16_t)sp : (uint16_t)0xFFFFu;
+  s_tlocal[threadIdx.x] = (uint16_t)0xFFFFu;  // 0xFFFF: keep the rank computed above
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t t = 0; t < (uint32_t)GROUP_THREADS; t++) {
+      const uint32_t spt = s_tsp[t];
+      if (spt == 0xFFFFu || s_tlocal[t] != 0xFFFFu) continue;  // no request, or already folded into an earlier fragment
+      const uint32_t pos = s_pos[spt];
+      bool shared = false;
+      for (uint32_t u = t + 1; u < (uint32_t)GROUP_THREADS && !shared; u++) shared = s_tsp[u] != 0xFFFFu && s_tsp[u] != spt && s_pos[s_tsp[u]] == pos;
+      if (!shared) continue;
+      uint32_t cnt = 0;
+      for (uint32_t u = t; u < (uint32_t)GROUP_THREADS; u++) {
+        if (s_tsp[u] != 0xFFFFu && s_pos[s_tsp[u]] == pos) { s_tlocal[u] = (uint16_t)cnt++; s_tsp[u] = (uint16_t)spt; }
+      }
+      A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(cnt - 1);
+    }
+  }
+  __syncthreads();
+  if (valid && s_tlocal[threadIdx.x] != 0xFFFFu) { local = s_tlocal[threadIdx.x]; sp = s_tsp[threadIdx.x]; }
+}
+
 __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ unsigned long long s_key[GROUP_SLOTS];
   __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block (running, in warp order)
   __shared__ uint32_t s_pos[GROUP_SLOTS];  // batch-wide entry position
+  __shared__ uint32_t s_conflict;          // two fragments of this block joined the same group entry (see merge_colliding_fragments)
   for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
+  if (threadIdx.x == 0) s_conflict = 0u;
   pdl_wait();
   pdl_release();
   __syncthreads();
@@ -375,11 +407,14 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     bool claimed;
     const uint32_t pos = aux_join(A, key, c, first, &claimed);
     if (claimed) { A.aux[pos].rep = i; A.aux[pos].flags = 0; }
-    atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
+    const uint32_t bit = 1u << (blockIdx.x & 31);
+    const uint32_t was = atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], bit);
     A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(c - 1);
     s_pos[sp] = pos;
+    if (was & bit) s_conflict = 1u;  // the bitmap is clean between batches: another fragment of this block is in this entry already
   }
   __syncthreads();
+  if (s_conflict) merge_colliding_fragments(A, s_pos, valid, sp, local);  // block-uniform, next to never taken
   if (valid) {
     A.ent[i] = s_pos[sp];
     A.meta[i] = (sp << 16) | local;

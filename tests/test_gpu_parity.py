@@ -243,6 +243,38 @@ def test_sentinel_key_hashes(G):
     _cmp(got, pool.submit_hashed(reqs))
 
 
+def test_keys_colliding_in_the_grouping_table(G):
+    """Two different keys sharing one batch-wide grouping entry (same position, same 24-bit tag), with requests in the same block:
+    k_group folds their fragments (merge_colliding_fragments), k_rank finds the run non-uniform, k_finish walks it key by key.
+    Same scenario as tests/test_kernels_emulated.py, where the CPU emulation of the kernels first exposed it."""
+    max_batch = 1024
+    mask = 4 * max_batch - 1
+    rng = np.random.default_rng(2024)
+    top = np.uint64(0xABCDEF) << np.uint64(40)
+    keys = top | rng.integers(2, 1 << 40, 4000).astype(np.uint64)
+    home = ((keys ^ (keys >> np.uint64(29))) & np.uint64(mask)).astype(np.int64)
+    order = np.argsort(home, kind="stable")
+    same = np.nonzero(np.diff(home[order]) == 0)[0]
+    ka, kb = keys[order[same[0]]], keys[order[same[0] + 1]]
+    assert ka != kb
+    tab = G.Table(4096, max_batch=max_batch)
+    pool = O.Pool(now_ms=T0)
+    for step in range(3):
+        now = T0 + step
+        pool.set_now(now)
+        n = 600
+        reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+        pick = rng.integers(0, 3, n)
+        reqs["key_xxh64"] = np.where(pick == 0, ka, np.where(pick == 1, kb, keys[rng.integers(0, 50, n)]))
+        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        reqs["hits"] = 1 if step < 2 else rng.integers(0, 3, n)
+        reqs["limit"] = 500; reqs["duration"] = 60000; reqs["created_at"] = now
+        reqs["algorithm"] = (reqs["key_xxh64"] & np.uint64(1)).astype(np.uint32); reqs["behavior"] = G.native.REQ_IS_OWNER
+        _cmp(tab.submit(reqs, G.clock_fill(now)), pool.submit_hashed(reqs), f"step {step}")
+    assert tab.counters()["mixed_groups"] > 0
+    _check_table_equals_oracle(G, tab, pool)
+
+
 def test_table_full_is_reported(G):
     tab = G.Table(64)
     n = 4000

@@ -257,3 +257,38 @@ def test_mailbox_routing_kernels_match_per_shard_oracles(G, world):
                     want[s_][idx] = sim[gi].submit_hashed(np.ascontiguousarray(batches[s_][idx]))
         for r in range(world):
             _cmp(got[r], want[r], f"step {step} shard {r}")
+
+
+@pytest.mark.parametrize("early_singles", [1, 0])
+def test_keys_colliding_in_the_grouping_table(G, early_singles):
+    """Two different keys that share the batch-wide grouping entry (same home position and the same 24-bit tag = top bits of the
+    XXH64): they are grouped as one run, found different from the representative, and walked key by key in k_finish.  When both
+    have requests in the same block, k_group has to fold their fragments into one (merge_colliding_fragments) — this test found
+    that case broken (duplicate ranks) before the fold existed."""
+    max_batch = 1024
+    mask = 4 * max_batch - 1                          # aux entries - 1 (gub_create: next_pow2(4 * max_batch))
+    rng = np.random.default_rng(2024)
+    top = np.uint64(0xABCDEF) << np.uint64(40)
+    lows = rng.integers(2, 1 << 40, 4000).astype(np.uint64)
+    keys = top | lows
+    home = ((keys ^ (keys >> np.uint64(29))) & np.uint64(mask)).astype(np.int64)
+    order = np.argsort(home, kind="stable")
+    same = np.nonzero(np.diff(home[order]) == 0)[0]
+    assert len(same) > 0
+    ka, kb = keys[order[same[0]]], keys[order[same[0] + 1]]
+    assert ka != kb
+    tab, pool = E.EmuTable(4096, max_batch=max_batch, early_singles=early_singles), O.Pool(now_ms=T0)
+    for step in range(3):
+        now = T0 + step
+        pool.set_now(now)
+        n = 600
+        reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+        pick = rng.integers(0, 3, n)
+        reqs["key_xxh64"] = np.where(pick == 0, ka, np.where(pick == 1, kb, keys[rng.integers(0, 50, n)]))
+        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        reqs["hits"] = 1 if step < 2 else rng.integers(0, 3, n)
+        reqs["limit"] = 500; reqs["duration"] = 60000; reqs["created_at"] = now
+        reqs["algorithm"] = (reqs["key_xxh64"] & np.uint64(1)).astype(np.uint32); reqs["behavior"] = G.native.REQ_IS_OWNER
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    assert tab.counters()["mixed_groups"] > 0
+    _check_state(G, tab, pool)
