@@ -292,3 +292,75 @@ def test_keys_colliding_in_the_grouping_table(G, early_singles):
         _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
     assert tab.counters()["mixed_groups"] > 0
     _check_state(G, tab, pool)
+
+
+def test_colliding_keys_in_few_long_segments(G):
+    """The same collision, but each key's requests are contiguous: two segments, planned by plan_run with a cursor switch between them
+    (the test above, with its random interleaving, ends in the serial walk)."""
+    max_batch = 1024
+    rng = np.random.default_rng(2024)
+    keys = (np.uint64(0xABCDEF) << np.uint64(40)) | rng.integers(2, 1 << 40, 4000).astype(np.uint64)
+    home = ((keys ^ (keys >> np.uint64(29))) & np.uint64(4 * max_batch - 1)).astype(np.int64)
+    order = np.argsort(home, kind="stable")
+    same = np.nonzero(np.diff(home[order]) == 0)[0]
+    ka, kb = keys[order[same[0]]], keys[order[same[0] + 1]]
+    tab, pool = E.EmuTable(4096, max_batch=max_batch), O.Pool(now_ms=T0)
+    for step in range(2):
+        now = T0 + step
+        pool.set_now(now)
+        n = 500
+        reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+        reqs["key_xxh64"] = np.where(np.arange(n) < 230, ka, kb)  # both keys inside block 0, kb alone in block 1
+        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        reqs["hits"] = 1; reqs["limit"] = 300; reqs["duration"] = 60000; reqs["created_at"] = now
+        reqs["algorithm"] = step; reqs["behavior"] = G.native.REQ_IS_OWNER
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    c = tab.counters()
+    assert c["mixed_groups"] == 2 and c["serial_fallbacks"] == 0
+    _check_state(G, tab, pool)
+
+
+def test_probe_window_wraps_and_skips_tombstones(G):
+    """Keys whose home slot is at the very end of a small table (the linear probe wraps to slot 0), expiring at different times:
+    after a sweep the survivors are found behind tombstones and new keys reuse the freed slots."""
+    cap = 256
+    rng = np.random.default_rng(8)
+    cand = rng.integers(2, 1 << 62, 200000).astype(np.uint64) | (np.uint64(0xFF) << np.uint64(56))  # home = (key * cap) >> 64 = 255
+    keys = np.unique(cand)[:60]
+    assert np.all((keys >> np.uint64(56)) == 255)
+    tab, pool = E.EmuTable(cap), O.Pool(now_ms=T0)
+
+    def batch(ks, now, duration):
+        r = np.zeros(len(ks), dtype=G.REQ_DTYPE)
+        r["key_xxh64"] = ks; r["key_fnv1"] = (ks * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        r["hits"] = 1; r["limit"] = 10; r["duration"] = duration; r["created_at"] = now
+        r["algorithm"] = (ks & np.uint64(1)).astype(np.uint32); r["behavior"] = G.native.REQ_IS_OWNER
+        return r
+    first = batch(keys[:40], T0, np.where(np.arange(40) % 2 == 0, 1000, 100000))  # every other item is short-lived
+    _cmp(tab.submit(first, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(first), "fill")
+    now = T0 + 5000
+    pool.set_now(now)
+    assert tab.sweep(now) == 20
+    again = batch(np.concatenate([keys[:40], keys[40:60]]), now, 100000)  # survivors, re-created short-lived ones, brand-new keys
+    rng.shuffle(again)
+    _cmp(tab.submit(again, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(again), "after the sweep")
+    _check_state(G, tab, pool)
+
+
+@pytest.mark.parametrize("seed,n_keys,early_singles", [(0, 2500, 1), (4, 2500, 0), (5, 1200, 1)])
+def test_fuzz_with_frequent_grouping_collisions(G, seed, n_keys, early_singles):
+    """Adversarial traffic over a key space with only 48 distinct 24-bit tags and a 4096-entry grouping table: several pairs (and
+    triples) of different keys share a group entry in every batch, inside and across blocks."""
+    rng, krng = np.random.default_rng(900 + seed), np.random.default_rng(seed)
+    tags = krng.integers(0, 1 << 24, 48).astype(np.uint64)
+    newk = (tags[krng.integers(0, len(tags), 8000)] << np.uint64(40)) | krng.integers(2, 1 << 40, 8000).astype(np.uint64)
+    tab, pool = E.EmuTable(1 << 13, max_batch=1024, early_singles=early_singles), O.Pool(now_ms=T0)
+    now = T0
+    for step in range(3):
+        now += int(rng.choice([0, 1, 900]))
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, 3000, n_keys, now).astype(G.REQ_DTYPE)
+        reqs["key_xxh64"] = newk[(reqs["key_xxh64"] % np.uint64(len(newk))).astype(np.int64)]
+        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    _check_state(G, tab, pool)
