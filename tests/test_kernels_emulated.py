@@ -364,3 +364,61 @@ def test_fuzz_with_frequent_grouping_collisions(G, seed, n_keys, early_singles):
         reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
         _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
     _check_state(G, tab, pool)
+
+
+# ---- the reference's own known-answer tables through the emulated kernels -----------------------------------------------------
+class _EmuInstance:
+    """The frozen-clock backend tests/kat_player.py expects, over the emulated kernels: the host-side steps of
+    V1Instance.GetRateLimits (gubernator.go:203-220: field checks, CreatedAt default, HashKey) are restated here in Python; hashes
+    come from the oracle's XXH64 / FNV-1, error strings from the product's gub_format_error."""
+
+    def __init__(self, G, now_ms):
+        import ctypes as C
+        self.G, self.C, self._now = G, C, now_ms
+        self.tab = E.EmuTable(1 << 12)
+        self.L = G.native.lib()
+        self.L.gub_format_error.argtypes = [C.c_int, C.c_char_p, C.c_int32, C.c_char_p, C.c_size_t]
+
+    def now(self):
+        return self._now
+
+    def advance(self, ms):
+        self._now += ms
+
+    def _err(self, code, key, algorithm):
+        buf = self.C.create_string_buffer(512)
+        self.L.gub_format_error(code, key, algorithm, buf, 512)
+        return buf.value.decode()
+
+    def get_rate_limits(self, reqs):
+        G = self.G
+        out = [None] * len(reqs)
+        rec, where = np.zeros(len(reqs), dtype=G.REQ_DTYPE), []
+        for i, r in enumerate(reqs):
+            name, uk = r.get("name", ""), r.get("unique_key", "")
+            if uk == "" or name == "":  # unique_key is checked first (gubernator.go:208-217)
+                code = G.native.ERR_UNIQUE_KEY_EMPTY if uk == "" else G.native.ERR_NAMESPACE_EMPTY
+                out[i] = dict(status=0, limit=0, remaining=0, reset_time=0, error=self._err(code, b"", 0))
+                continue
+            key = (name + "_" + uk).encode()
+            k = len(where)
+            rec[k]["key_xxh64"], rec[k]["key_fnv1"] = O.xxh64(key), O.fnv1_64(key)
+            for f in ("hits", "limit", "duration", "burst", "algorithm"):
+                rec[k][f] = r.get(f, 0)
+            rec[k]["behavior"] = r.get("behavior", 0) | G.native.REQ_IS_OWNER
+            rec[k]["created_at"] = r.get("created_at", 0) or self._now
+            where.append((i, key, r.get("algorithm", 0)))
+        resp = self.tab.submit(rec[:len(where)], make_clock(self._now), O.HRESP_DTYPE)
+        for (i, key, algo), o in zip(where, resp):
+            err = self._err(int(o["err_code"]), key, algo) if o["err_code"] else ""
+            out[i] = dict(status=int(o["status"]), limit=int(o["limit"]), remaining=int(o["remaining"]), reset_time=int(o["reset_time"]), error=err)
+        return out
+
+
+def test_reference_scenarios_through_the_emulated_kernels(G):
+    """functional_test.go's tables (tests/golden/reference_kat.py) played against the CUDA kernel source on the CPU."""
+    from golden import reference_kat as K
+    from kat_player import play_missing_fields, play_scenario
+    for sc in K.SCENARIOS:
+        play_scenario(_EmuInstance(G, K.T0), sc)
+    play_missing_fields(_EmuInstance(G, K.T0))
