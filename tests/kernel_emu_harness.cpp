@@ -150,6 +150,12 @@ uint64_t emu_scan(void* tv, gub_item* out, uint64_t cap) {
   return n;
 }
 
+// gub_probe_random_access's kernel (the timing around it is host code): the table must come out unchanged.
+void emu_random_rmw(void* tv, uint64_t accesses) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  emu::launch(k_random_rmw, 4u, 256u, t->table, t->capacity, accesses, (uint64_t)12345, (uint64_t)0);
+}
+
 uint64_t emu_sweep(void* tv, int64_t now_ms) {
   EmuTable* t = static_cast<EmuTable*>(tv);
   unsigned long long removed = 0;
