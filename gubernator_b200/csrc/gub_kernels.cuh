@@ -60,6 +60,15 @@ constexpr int MAX_PIECES = 16;
 #endif
 constexpr bool EARLY_SINGLES = GUB_EARLY_SINGLES != 0;
 
+// Experimental (-DGUB_GROUP_ONEPASS=1, default 0 until measured on a B200): k_group ranks a block's requests with one barrier
+// instead of eight warp turns, and the blocks of k_finish that have nothing to do return before the counter flush.  ncu (profiles/r01_ncu_full_v7_raw.csv) attributes most of k_group's issue stalls to those
+// barriers (17.5 stalled warps per issued instruction on `barrier`, against 9.9 on memory).  Each warp counts its members per
+// key (match.any) into s_wcnt[slot][warp]; after one barrier a member's local rank is the sum over earlier warps + its rank
+// inside the warp.  Same results (checked on the CPU emulation, tests/test_kernels_emulated.py).
+#ifndef GUB_GROUP_ONEPASS
+#define GUB_GROUP_ONEPASS 0
+#endif
+
 struct __align__(64) Slot { uint64_t w[8]; };
 
 struct __align__(32) AuxEntry {
@@ -363,6 +372,11 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ uint32_t s_conflict;          // two fragments of this block joined the same group entry (see merge_colliding_fragments)
   for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
   if (threadIdx.x == 0) s_conflict = 0u;
+#if GUB_GROUP_ONEPASS
+  __shared__ __align__(16) uint8_t s_wcnt[GROUP_SLOTS][GROUP_THREADS / 32];  // [key slot][warp]: members of the key among the warp's lanes (<= 32)
+  static_assert(sizeof(s_wcnt) == GROUP_THREADS * sizeof(uint4), "one 16-byte store per thread clears it");
+  reinterpret_cast<uint4*>(&s_wcnt[0][0])[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+#endif
   pdl_wait();
   pdl_release();
   __syncthreads();
@@ -387,8 +401,26 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     }
   }
   __syncthreads();
-  // local rank in index order: warps take turns in order; inside a warp the lanes sharing a key are ranked by lane id
   uint32_t local = 0;
+#if GUB_GROUP_ONEPASS
+  // every warp records how many of its lanes hold each key; a member's local rank = members in earlier warps + earlier lanes
+  {
+    constexpr int NW = GROUP_THREADS / 32;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sp);
+    const uint32_t leader = __ffs(peers) - 1;
+    if (valid && lane == leader) s_wcnt[sp][warp] = (uint8_t)__popc(peers);
+    __syncthreads();
+    if (valid) {
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) { const uint32_t c = s_wcnt[sp][w]; total += c; before += ((uint32_t)w < warp) ? c : 0u; }
+      local = before + __popc(peers & ((1u << lane) - 1u));
+      if (local == 0) s_cnt[sp] = total;
+    }
+    __syncthreads();
+  }
+#else
+  // local rank in index order: warps take turns in order; inside a warp the lanes sharing a key are ranked by lane id
 #pragma unroll 1
   for (uint32_t w = 0; w < GROUP_THREADS / 32; w++) {
     if (warp == w) {
@@ -401,6 +433,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     }
     __syncthreads();
   }
+#endif
   // the first member of each fragment joins the batch-wide group
   if (valid && local == 0) {
     const uint32_t c = s_cnt[sp];
@@ -731,6 +764,9 @@ __global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A, 
   pdl_wait();
   pdl_release();
   const BatchCtr ctr = A.ctr[A.epoch & 1];
+#if GUB_GROUP_ONEPASS  // same experimental switch: a launch with nothing to finish (the usual case) skips the counter flush's barriers
+  if (blockIdx.x < mixed_blocks ? ctr.n_mixed == 0 : ctr.n_commit == 0) return;
+#endif
   if (blockIdx.x < mixed_blocks) {
     for (uint32_t g = blockIdx.x; g < ctr.n_mixed; g += mixed_blocks) {
       mixed_group(A, A.mixed_ent[g], S, t);

@@ -18,13 +18,16 @@ COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full
 _libs = {}
 
 
-def lib(early_singles=1):
-    """early_singles: the GUB_EARLY_SINGLES build variant of the kernels (1 = default build, 0 = table-free k_rank + commit records)."""
-    if early_singles not in _libs:
-        so = SO if early_singles == 1 else SO.replace(".so", "_es0.so")
+def lib(early_singles=1, onepass=0):
+    """Build variants of the kernels: early_singles = GUB_EARLY_SINGLES (1 = default build, 0 = table-free k_rank + commit records),
+    onepass = GUB_GROUP_ONEPASS (0 = default, 1 = k_group ranks a block with one barrier)."""
+    variant = (early_singles, onepass)
+    if variant not in _libs:
+        so = SO if variant == (1, 0) else SO.replace(".so", f"_es{early_singles}_op{onepass}.so")
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in SRC):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                                   f"-DGUB_EARLY_SINGLES={early_singles}", "-I", os.path.join(ROOT, "include"), "-x", "c++", SRC[0], "-o", so])
+                                   f"-DGUB_EARLY_SINGLES={early_singles}", f"-DGUB_GROUP_ONEPASS={onepass}", "-I", os.path.join(ROOT, "include"),
+                                   "-x", "c++", SRC[0], "-o", so])
         L = C.CDLL(so)
         vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
         L.emu_create.argtypes = [u64, u32]; L.emu_create.restype = vp
@@ -44,15 +47,15 @@ def lib(early_singles=1):
         L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
         L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp]
         assert L.emu_counter_count() == len(COUNTER_NAMES)
-        _libs[early_singles] = L
-    return _libs[early_singles]
+        _libs[variant] = L
+    return _libs[variant]
 
 
 class EmuTable:
     """Same surface as gubernator_b200.native.Table for what the CPU tests need."""
 
-    def __init__(self, capacity_slots, max_batch=65536, early_singles=1):
-        self._L = lib(early_singles)
+    def __init__(self, capacity_slots, max_batch=65536, early_singles=1, onepass=0):
+        self._L = lib(early_singles, onepass)
         self._h = self._L.emu_create(int(capacity_slots), int(max_batch))
         self.capacity = int(capacity_slots)
 

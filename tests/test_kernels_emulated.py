@@ -71,6 +71,32 @@ def test_table_free_build_variant(G):
     _check_state(G, tab, pool)
 
 
+@pytest.mark.parametrize("early_singles", [1, 0])
+def test_group_onepass_build_variant(G, early_singles):
+    """GUB_GROUP_ONEPASS=1 (experimental, off by default until measured): one barrier instead of eight warp turns in k_group;
+    local ranks must come out the same, including for the colliding-key fold."""
+    rng = np.random.default_rng(5)
+    tab, pool = E.EmuTable(1 << 13, max_batch=2048, early_singles=early_singles, onepass=1), O.Pool(now_ms=T0)
+    for step, n_keys in enumerate([3, 0, 2500, 40, 0, 1]):
+        now = T0 + 700 * step
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    _check_state(G, tab, pool)
+    # keys colliding in the grouping table (see test_fuzz_with_frequent_grouping_collisions)
+    krng = np.random.default_rng(4)
+    tags = krng.integers(0, 1 << 24, 48).astype(np.uint64)
+    newk = (tags[krng.integers(0, len(tags), 8000)] << np.uint64(40)) | krng.integers(2, 1 << 40, 8000).astype(np.uint64)
+    tab, pool = E.EmuTable(1 << 13, max_batch=1024, early_singles=early_singles, onepass=1), O.Pool(now_ms=T0)
+    rng = np.random.default_rng(904)
+    for step in range(2):
+        reqs = adversarial_batch(rng, 3000, 2500, T0).astype(G.REQ_DTYPE)
+        reqs["key_xxh64"] = newk[(reqs["key_xxh64"] % np.uint64(len(newk))).astype(np.int64)]
+        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"collisions, step {step}")
+    _check_state(G, tab, pool)
+
+
 def test_zipf_uniform_runs_use_the_rank_path(G):
     """The bench workload's shape: identical requests per key, heavy repeats — run_to_rank per member, no non-uniform groups."""
     rng = np.random.default_rng(7)
