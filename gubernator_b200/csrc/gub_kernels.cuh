@@ -69,6 +69,17 @@ constexpr bool EARLY_SINGLES = GUB_EARLY_SINGLES != 0;
 #define GUB_GROUP_ONEPASS 0
 #endif
 
+// Experimental (-DGUB_RANK_CLASS_SORT=1, default 0 until measured; needs GUB_EARLY_SINGLES=1): k_rank deals a block's requests to its
+// threads by class — keys seen once (token, then leaky), then members of repeated keys — instead of by algorithm only.  A warp of
+// the default build holds both kinds and walks both dependent chains one after the other (slot probe + update for the singletons;
+// bitmap -> size row -> rank, representative compare for the members): ncu shows 11.6 of 32 lanes active per instruction in k_rank.
+// The class is only known after the group entry has been read, so the deal happens after the wait, with the group data staged
+// through shared memory.
+#ifndef GUB_RANK_CLASS_SORT
+#define GUB_RANK_CLASS_SORT 0
+#endif
+static_assert(!(GUB_RANK_CLASS_SORT && !GUB_EARLY_SINGLES), "GUB_RANK_CLASS_SORT needs the default GUB_EARLY_SINGLES=1 build");
+
 struct __align__(64) Slot { uint64_t w[8]; };
 
 struct __align__(32) AuxEntry {
@@ -546,9 +557,58 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
   return blockIdx.x * GROUP_THREADS + s_perm[tid];
 }
 
+#if GUB_RANK_CLASS_SORT
+// Stable partition of the block's threads by class (0..3); returns the thread whose request this thread takes over.
+__device__ __forceinline__ uint32_t partition_by_class(uint32_t cls) {
+  __shared__ uint16_t s_src[GROUP_THREADS];
+  __shared__ uint32_t s_cnt4[GROUP_THREADS / 32][4];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1), b2 = __ballot_sync(0xFFFFFFFFu, cls == 2),
+                 b3 = ~(b0 | b1 | b2);
+  if (lane < 4) s_cnt4[warp][lane] = __popc(lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3)));
+  __syncthreads();
+  uint32_t start = 0, before = 0;
+#pragma unroll
+  for (int w = 0; w < GROUP_THREADS / 32; w++) {
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+      const uint32_t k = s_cnt4[w][c];
+      if (c < cls) start += k;
+      if (c == cls && (uint32_t)w < warp) before += k;
+    }
+  }
+  const uint32_t mine = cls == 0 ? b0 : (cls == 1 ? b1 : (cls == 2 ? b2 : b3));
+  s_src[start + before + __popc(mine & ((1u << lane) - 1u))] = (uint16_t)tid;
+  __syncthreads();
+  return s_src[tid];
+}
+#endif
+
 __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
+#if GUB_RANK_CLASS_SORT
+  __shared__ uint32_t s_pre_pos[GROUP_THREADS], s_pre_meta[GROUP_THREADS];
+  __shared__ ulonglong2 s_pre_ent[GROUP_THREADS];
+  const uint32_t j = blockIdx.x * GROUP_THREADS + threadIdx.x;  // the request whose group data this thread fetches
+  uint32_t algo_j = 2;
+  if (j < n) algo_j = __ldg(&A.reqs[j].algorithm);  // safe ahead of the wait, like the records
+  Tally t = {0, 0, 0, 0, 0};
+  pdl_wait();
+  pdl_release();
+  uint32_t cls = 3;  // no request
+  if (j < n) {
+    const uint32_t pj = A.ent[j];
+    const ulonglong2 ej = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pj]));
+    s_pre_pos[threadIdx.x] = pj; s_pre_meta[threadIdx.x] = A.meta[j]; s_pre_ent[threadIdx.x] = ej;
+    cls = aux_count(ej.x) > 1 ? 2u : (algo_j == 1u ? 1u : 0u);
+  }
+  const uint32_t src = partition_by_class(cls);  // two barriers: the staged group data is visible afterwards
+  const uint32_t i = blockIdx.x * GROUP_THREADS + src;
+  const bool valid = i < n;
+  gub_req rq;
+  if (valid) rq = load_req(A.reqs + i);
+#else
   const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
   Tally t = {0, 0, 0, 0, 0};
   const bool valid = i < n;
@@ -556,6 +616,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
   pdl_wait();
   pdl_release();
+#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
     nxt->n_mixed = 0; nxt->order_bump = 0; nxt->n_commit = 0;
@@ -564,11 +625,17 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
   }
   uint32_t pos = 0, cnt = 0, sp = 0, local = 0;
   if (valid) {
+#if GUB_RANK_CLASS_SORT
+    pos = s_pre_pos[src];
+    const uint32_t m = s_pre_meta[src];
+    const ulonglong2 e = s_pre_ent[src];
+#else
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
+    const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
+#endif
     const uint64_t key = remap_key(rq.key_xxh64);
     sp = m >> 16; local = m & 0xFFFFu;
-    const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
     cnt = aux_count(e.x);
     const uint32_t rep = (uint32_t)(e.y & 0xFFFFFFFFull);
     if (cnt > 1) {

@@ -18,15 +18,16 @@ COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full
 _libs = {}
 
 
-def lib(early_singles=1, onepass=0):
+def lib(early_singles=1, onepass=0, class_sort=0):
     """Build variants of the kernels: early_singles = GUB_EARLY_SINGLES (1 = default build, 0 = table-free k_rank + commit records),
-    onepass = GUB_GROUP_ONEPASS (0 = default, 1 = k_group ranks a block with one barrier)."""
-    variant = (early_singles, onepass)
+    onepass = GUB_GROUP_ONEPASS (0 = default, 1 = k_group ranks a block with one barrier), class_sort = GUB_RANK_CLASS_SORT (0 = default,
+    1 = k_rank deals requests to threads by class)."""
+    variant = (early_singles, onepass, class_sort)
     if variant not in _libs:
-        so = SO if variant == (1, 0) else SO.replace(".so", f"_es{early_singles}_op{onepass}.so")
+        so = SO if variant == (1, 0, 0) else SO.replace(".so", f"_es{early_singles}_op{onepass}_cs{class_sort}.so")
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in SRC):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                                   f"-DGUB_EARLY_SINGLES={early_singles}", f"-DGUB_GROUP_ONEPASS={onepass}", "-I", os.path.join(ROOT, "include"),
+                                   f"-DGUB_EARLY_SINGLES={early_singles}", f"-DGUB_GROUP_ONEPASS={onepass}", f"-DGUB_RANK_CLASS_SORT={class_sort}", "-I", os.path.join(ROOT, "include"),
                                    "-x", "c++", SRC[0], "-o", so])
         L = C.CDLL(so)
         vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
@@ -54,8 +55,8 @@ def lib(early_singles=1, onepass=0):
 class EmuTable:
     """Same surface as gubernator_b200.native.Table for what the CPU tests need."""
 
-    def __init__(self, capacity_slots, max_batch=65536, early_singles=1, onepass=0):
-        self._L = lib(early_singles, onepass)
+    def __init__(self, capacity_slots, max_batch=65536, early_singles=1, onepass=0, class_sort=0):
+        self._L = lib(early_singles, onepass, class_sort)
         self._h = self._L.emu_create(int(capacity_slots), int(max_batch))
         self.capacity = int(capacity_slots)
 

@@ -97,6 +97,23 @@ def test_group_onepass_build_variant(G, early_singles):
     _check_state(G, tab, pool)
 
 
+@pytest.mark.parametrize("onepass", [0, 1])
+def test_rank_class_sort_build_variant(G, onepass):
+    """GUB_RANK_CLASS_SORT=1 (experimental, off by default until measured): k_rank deals a block's requests to its threads by class
+    (single token / single leaky / member of a repeated key); alone and together with GUB_GROUP_ONEPASS."""
+    rng = np.random.default_rng(5)
+    tab, pool = E.EmuTable(1 << 13, max_batch=2048, onepass=onepass, class_sort=1), O.Pool(now_ms=T0)
+    for step, n_keys in enumerate([3, 0, 2500, 40, 0, 1]):
+        now = T0 + 700 * step
+        pool.set_now(now)
+        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
+    for n in (1, 33, 255, 257, 2049):  # ragged tails and the max_batch chunking
+        reqs = adversarial_batch(rng, n, 50, now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"n={n}")
+    _check_state(G, tab, pool)
+
+
 def test_zipf_uniform_runs_use_the_rank_path(G):
     """The bench workload's shape: identical requests per key, heavy repeats — run_to_rank per member, no non-uniform groups."""
     rng = np.random.default_rng(7)
