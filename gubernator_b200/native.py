@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgubernator_b200.so")
+# GUB_LIB=<path>: load an experimental build variant instead (gubernator_b200.build.build(out=..., defines=...)); unset = the product library
+LIB_PATH = os.environ.get("GUB_LIB") or os.path.join(_HERE, "libgubernator_b200.so")
 
 TOKEN_BUCKET, LEAKY_BUCKET = 0, 1
 UNDER_LIMIT, OVER_LIMIT = 0, 1
