@@ -9,7 +9,9 @@
 // request's XXH64, filled by two small kernels per batch (claim: insert / sum hits / order by sequence; fill: the winning
 // request writes its parameters) and drained into a dense array of request records at each sync tick.
 #pragma once
+#if !defined(GUB_EMULATE)  // tests/kernel_emu_harness.cpp compiles this header for the CPU (see gub_kernels.cuh)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/gubernator_b200.h"

@@ -44,6 +44,10 @@ def lib(early_singles=1, onepass=0, class_sort=0):
         L.emu_hash_keys.argtypes = [vp, vp, u32, vp, vp]; L.emu_hash_keys.restype = None
         L.emu_route.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, vp, vp]; L.emu_route.restype = None
         L.emu_unroute.argtypes = [vp, vp, u32, vp]; L.emu_unroute.restype = None
+        L.emu_gq_create.argtypes = [u32, u32]; L.emu_gq_create.restype = vp
+        L.emu_gq_accumulate.argtypes = [vp, vp, u32, vp, u32, u64]; L.emu_gq_accumulate.restype = None
+        L.emu_gq_drain.argtypes = [vp, vp, u32, u32]; L.emu_gq_drain.restype = u32
+        L.emu_make_updates.argtypes = [vp, vp, u32, vp]; L.emu_make_updates.restype = u32
         L.emu_p2p_create.argtypes = [u32, u32, u64, u32, vp, vp, u32]; L.emu_p2p_create.restype = vp
         L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
         L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp]
@@ -154,3 +158,31 @@ class EmuP2PCluster:
             self._L.emu_set_finish_cap(148)
         assert rc == 0, "a mailbox flag wait timed out"
         return [o[:len(b)] for o, b in zip(outs, batches)]
+
+
+class EmuGq:
+    """gub_gq_* (the GLOBAL manager's hits / updates queues) over the emulated kernels."""
+
+    def __init__(self, capacity=1 << 12, keep_latest=False):
+        self._L = lib()
+        self._h = self._L.emu_gq_create(int(capacity), 1 if keep_latest else 0)
+
+    def accumulate(self, reqs, owner, self_index, seq_base):
+        reqs = np.ascontiguousarray(reqs)
+        op = None
+        if owner is not None:
+            owner = np.ascontiguousarray(owner, dtype=np.uint8)
+            op = owner.ctypes.data
+        self._L.emu_gq_accumulate(self._h, reqs.ctypes.data, len(reqs), op, int(self_index), int(seq_base))
+
+    def drain(self, req_dtype, as_status_query, cap=1 << 12):
+        out = np.zeros(cap, dtype=req_dtype)
+        n = self._L.emu_gq_drain(self._h, out.ctypes.data, cap, 1 if as_status_query else 0)
+        return out[:n]
+
+
+def make_updates(queries, resps, item_dtype):
+    out = np.zeros(max(len(queries), 1), dtype=item_dtype)
+    queries, resps = np.ascontiguousarray(queries), np.ascontiguousarray(resps)
+    n = lib().emu_make_updates(queries.ctypes.data, resps.ctypes.data, len(queries), out.ctypes.data)
+    return out[:n]

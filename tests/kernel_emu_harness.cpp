@@ -7,6 +7,7 @@
 
 #include "../gubernator_b200/csrc/gub_kernels.cuh"
 #include "../gubernator_b200/csrc/gub_p2p.cuh"
+#include "../gubernator_b200/csrc/gub_global.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -181,6 +182,39 @@ void emu_route(const gub_req* reqs, uint32_t n, const uint64_t* pts, const int32
 }
 void emu_unroute(const gub_resp* in, const uint32_t* perm, uint32_t n, gub_resp* out) {
   if (n) emu::launch(k_unroute, (n + 255) / 256, 256u, in, perm, n, out);
+}
+
+// ---- GLOBAL queues (gub_gq_*): claim + fill per batch, drain at a tick -----------------------------------------------------------
+struct EmuGq { Gq q; uint32_t capacity; };
+
+void* emu_gq_create(uint32_t capacity, uint32_t keep_latest) {
+  EmuGq* g = new EmuGq();
+  g->capacity = next_pow2(capacity);
+  g->q.slots = zalloc<gub_req>(g->capacity);
+  g->q.seq = zalloc<unsigned long long>(g->capacity);
+  g->q.count = zalloc<unsigned long long>(1);
+  g->q.capacity_mask = g->capacity - 1;
+  g->q.mode = keep_latest ? GQ_KEEP_LAST : GQ_KEEP_FIRST;
+  return g;
+}
+// owner == nullptr: the updates queue of an owner (every GLOBAL request with hits counts); else the hits queue of shard `self`
+void emu_gq_accumulate(void* gv, const gub_req* reqs, uint32_t n, const uint8_t* owner, uint32_t self, unsigned long long seq_base) {
+  EmuGq* g = static_cast<EmuGq*>(gv);
+  if (!n) return;
+  std::vector<uint32_t> slot_of(n);
+  emu::launch(k_gq_claim, (n + 255) / 256, 256u, g->q, reqs, n, owner, self, owner ? 1u : 0u, seq_base, slot_of.data());
+  emu::launch(k_gq_fill, (n + 255) / 256, 256u, g->q, reqs, n, seq_base, (const uint32_t*)slot_of.data());
+}
+uint32_t emu_gq_drain(void* gv, gub_req* out, uint32_t cap, uint32_t as_status_query) {
+  EmuGq* g = static_cast<EmuGq*>(gv);
+  uint32_t count = 0;
+  emu::launch(k_gq_drain, 4u, 256u, g->q, out, cap, &count, as_status_query);
+  return count;
+}
+uint32_t emu_make_updates(const gub_req* queries, const gub_resp* resps, uint32_t n, gub_item* out) {
+  uint32_t count = 0;
+  if (n) emu::launch(k_make_updates, (n + 255) / 256, 256u, queries, resps, n, out, &count);
+  return count;
 }
 
 // ---- gub_p2p_step for W shards living in one process, phase by phase: every shard scatters, then every shard gathers,

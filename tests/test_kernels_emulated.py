@@ -511,3 +511,65 @@ def test_gpu_test_bodies_on_the_emulator(G, name):
     surface above can be run the same way)."""
     import test_gpu_parity as gpu_tests
     getattr(gpu_tests, name)(_fake_g(G))
+
+
+@pytest.mark.parametrize("keep_latest", [False, True])
+def test_global_queues_match_the_reference_maps(G, keep_latest):
+    """gub_global.cuh against a dict model of global.go: the hits queue (runAsyncHits, global.go:91-141) keeps the FIRST request of a
+    key with Hits summed over the window and RESET_REMAINING OR-ed in, for keys this shard does not own; the updates queue
+    (runBroadcasts, global.go:193-231) keeps the LATEST request seen.  Draining empties the queue."""
+    N = G.native
+    rng = np.random.default_rng(17 + keep_latest)
+    q = E.EmuGq(capacity=256, keep_latest=keep_latest)
+    self_index, seq = 1, 0
+    for window in range(3):
+        model = {}
+        for batch in range(3):
+            n = int(rng.choice([1, 40, 300]))
+            reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+            ids = rng.integers(0, 25, n)
+            reqs["key_xxh64"], reqs["key_fnv1"] = key_hashes(ids, name="gq")
+            reqs["hits"] = rng.integers(-2, 4, n); reqs["limit"] = rng.integers(1, 50, n); reqs["duration"] = rng.choice([1000, 60000], n)
+            reqs["created_at"] = T0 + rng.integers(0, 9, n); reqs["algorithm"] = ids & 1
+            reqs["behavior"] = (rng.choice([0, N.GLOBAL, N.GLOBAL, N.GLOBAL | N.RESET_REMAINING], n) | N.REQ_IS_OWNER).astype(np.uint32)
+            owner = rng.integers(0, 3, n).astype(np.uint8)
+            q.accumulate(reqs, None if keep_latest else owner, self_index, seq)
+            for i in range(n):
+                r = reqs[i]
+                if not (int(r["behavior"]) & N.GLOBAL) or int(r["hits"]) == 0:
+                    continue
+                if not keep_latest and int(owner[i]) == self_index:
+                    continue
+                k = int(r["key_xxh64"])
+                if k not in model:
+                    model[k] = dict(first=r.copy(), last=r.copy(), hits=0, reset=0)
+                m = model[k]
+                m["hits"] += int(r["hits"]); m["last"] = r.copy(); m["reset"] |= int(r["behavior"]) & N.RESET_REMAINING
+            seq += n
+        got = q.drain(G.REQ_DTYPE, as_status_query=keep_latest)
+        assert len(got) == len(model) == len(set(got["key_xxh64"].tolist()))
+        for e in got:
+            m = model[int(e["key_xxh64"])]
+            src = m["last"] if keep_latest else m["first"]
+            for f in ("key_fnv1", "limit", "duration", "burst", "created_at", "algorithm"):
+                assert e[f] == src[f], (f, e, src)
+            if keep_latest:   # status query for the broadcast: Hits = 0, evaluated with IsOwner = false (global.go:238-245)
+                assert int(e["hits"]) == 0 and int(e["behavior"]) == int(src["behavior"]) & ~N.REQ_IS_OWNER
+            else:             # forwarded to the owner: summed hits, DRAIN_OVER_LIMIT added there (gubernator.go:510-512)
+                assert int(e["hits"]) == m["hits"]
+                assert int(e["behavior"]) == int(src["behavior"]) | m["reset"] | N.DRAIN_OVER_LIMIT | N.REQ_IS_OWNER
+        assert len(q.drain(G.REQ_DTYPE, as_status_query=keep_latest)) == 0  # drained
+
+
+def test_update_items_built_from_status_queries(G):
+    """k_make_updates: the CacheItem a peer installs for an UpdatePeerGlobal (gubernator.go:427-451)."""
+    q = np.zeros(3, dtype=G.REQ_DTYPE)
+    q["key_xxh64"] = [11, 12, 13]; q["key_fnv1"] = [21 << 8, 22 << 8, 23 << 8]; q["duration"] = [1000, 2000, 3000]; q["algorithm"] = [0, 1, 7]
+    r = np.zeros(3, dtype=O.HRESP_DTYPE)
+    r["status"] = [1, 0, 0]; r["limit"] = [10, 20, 30]; r["remaining"] = [0, 7, 1]; r["reset_time"] = [T0 + 5, T0 + 6, T0 + 7]
+    items = E.make_updates(q, r, G.ITEM_DTYPE)
+    assert len(items) == 2  # the invalid algorithm is skipped (logged in the reference, global.go:246-249)
+    by = {int(i["key_xxh64"]): i for i in items}
+    t, l = by[11], by[12]
+    assert (int(t["algorithm"]), int(t["status"]), int(t["limit"]), int(t["duration"]), int(t["remaining"]), int(t["expire_at"])) == (0, 1, 10, 1000, 0, T0 + 5)
+    assert (int(l["algorithm"]), int(l["limit"]), int(l["duration"]), float(l["remaining_f"]), int(l["burst"]), int(l["expire_at"])) == (1, 20, 2000, 7.0, 20, T0 + 6)
