@@ -573,3 +573,19 @@ def test_update_items_built_from_status_queries(G):
     t, l = by[11], by[12]
     assert (int(t["algorithm"]), int(t["status"]), int(t["limit"]), int(t["duration"]), int(t["remaining"]), int(t["expire_at"])) == (0, 1, 10, 1000, 0, T0 + 5)
     assert (int(l["algorithm"]), int(l["limit"]), int(l["duration"]), float(l["remaining_f"]), int(l["burst"]), int(l["expire_at"])) == (1, 20, 2000, 7.0, 20, T0 + 6)
+
+
+def test_global_queue_overflow_drops_whole_keys(G):
+    """More GLOBAL keys in one window than the queue has slots: the surplus keys are not queued (their hits are not synchronised in
+    this window — the reference's map is unbounded, so size the queue for the hot set), the ones that are queued stay exact."""
+    N = G.native
+    q = E.EmuGq(capacity=64, keep_latest=False)
+    n = 200
+    reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+    reqs["key_xxh64"], reqs["key_fnv1"] = key_hashes(np.arange(100).repeat(2), name="gqo")
+    reqs["hits"] = 3; reqs["limit"] = 9; reqs["duration"] = 1000; reqs["created_at"] = T0
+    reqs["behavior"] = N.GLOBAL | N.REQ_IS_OWNER
+    q.accumulate(reqs, np.zeros(n, dtype=np.uint8), 1, 0)
+    got = q.drain(G.REQ_DTYPE, as_status_query=False)
+    assert len(got) == 64 and len(set(got["key_xxh64"].tolist())) == 64
+    assert np.all(got["hits"] == 6) and np.all(got["limit"] == 9)
