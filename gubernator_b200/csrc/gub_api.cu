@@ -184,6 +184,9 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   }
   if (sc.epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
     CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), sp));
+    // 65535 -> 1 keeps the parity: the batch after the wrap reuses ctr[1], which k_rank (it only resets the OTHER parity) left
+    // holding batch 65535's allocators.  Clear both.
+    CK(cudaMemsetAsync(sc.ctr, 0, 2 * sizeof(gub::BatchCtr), sp));
     sc.epoch = 0;
   }
   sc.epoch++;

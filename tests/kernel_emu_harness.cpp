@@ -82,7 +82,7 @@ void emu_set_epoch(void* tv, uint32_t epoch) { static_cast<EmuTable*>(tv)->epoch
 static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_t* n_dev, const gub_clock* clk, gub_resp* out) {
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
-    if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); t->epoch = 0; }
+    if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); std::memset(t->ctr, 0, 2 * sizeof(BatchCtr)); t->epoch = 0; }
     t->epoch++;
     BatchArgs A;
     std::memset(&A, 0, sizeof A);

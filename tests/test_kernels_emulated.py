@@ -213,6 +213,20 @@ def test_epoch_wrap(G):
         _cmp(tab.submit(reqs, clk, O.HRESP_DTYPE), pool.submit_hashed(reqs), f"batch {b} after epoch 65530")
 
 
+def test_epoch_wrap_with_mixed_groups(G):
+    """The wrap 65535 -> 1 keeps the epoch parity, so the batch after it reuses the allocator pair the batch before it filled
+    (ADVICE r1): several hundred requests on a few keys (non-uniform groups on both sides of the wrap), state and counters checked."""
+    rng = np.random.default_rng(43)
+    tab, pool = E.EmuTable(1 << 12, max_batch=1024), O.Pool(now_ms=T0)
+    clk = make_clock(T0)
+    tab.set_epoch(65530)
+    for b in range(10):
+        reqs = adversarial_batch(rng, 600, 5, T0)
+        _cmp(tab.submit(reqs, clk, O.HRESP_DTYPE), pool.submit_hashed(reqs), f"batch {b} after epoch 65530")
+    c = tab.counters()
+    assert c["requests"] == 6000 and c["mixed_groups"] <= 50
+
+
 def test_compact_records_expand_like_the_full_ones(G):
     rng = np.random.default_rng(61)
     a, b, pool = E.EmuTable(1 << 13), E.EmuTable(1 << 13), O.Pool(now_ms=T0)
