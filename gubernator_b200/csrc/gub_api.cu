@@ -15,6 +15,7 @@
 
 #include "../../include/gubernator_b200.h"
 #include "gub_kernels.cuh"
+#include "gub_batch.cuh"
 #include "gub_global.cuh"
 #include "gub_p2p.cuh"
 
@@ -70,6 +71,16 @@ struct gub_table {
   } scr[2];
   uint32_t next_set = 0;
   uint32_t aux_entries = 0, pres_words = 0, max_blocks = 0;
+  // the fused batch kernel (gub_batch.cuh): one scratch set, one cooperative launch per batch
+  bool fused = true;                  // GUB_FUSED=0: the four-kernel path (kept for A/B measurements)
+  bool coop = true;                   // cooperative launch (co-residency of the grid guaranteed by the driver)
+  int num_sms = 0;
+  uint32_t sweep_chunk = 0;           // slots every CTA sweeps per batch (incremental expiry sweep), 0 = off
+  gub::GEntry* gaux = nullptr;
+  uint32_t *gpres = nullptr, *gpos = nullptr, *ordbuf = nullptr;
+  uint16_t* gfrag = nullptr;
+  gub::FCtl* ctl = nullptr;
+  gub::OvfItem* ovf = nullptr;
   unsigned long long* counters = nullptr;
   cudaStream_t s_prep = nullptr;
   cudaEvent_t inputs_ready = nullptr;
@@ -169,6 +180,46 @@ int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_
   return 0;
 }
 
+void fused_base_args(gub_table* t, const gub_clock* clk, gub::FArgs& A) {
+  std::memset(&A, 0, sizeof A);
+  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragsize = t->gfrag; A.gpos = t->gpos; A.ordbuf = t->ordbuf;
+  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.clk = *clk;
+}
+
+// One launch of k_batch over the segments in A (A.seg / A.nseg / flags filled by the caller).  `total_hint` = number of requests
+// when the host knows it (sizes the grid for small batches), 0 = only the device knows: one CTA per SM.
+int launch_fused(gub_table* t, const gub::FArgs& A, uint64_t total_hint, cudaStream_t st) {
+  uint32_t grid = (uint32_t)t->num_sms;
+  if (total_hint) grid = (uint32_t)std::min<uint64_t>(grid, std::max<uint64_t>(1, (total_hint + 127) / 128 + A.nseg));
+  cudaEvent_t* pe = nullptr;
+  if (t->prof) {
+    if (prof_flush(t, false)) return -1;
+    if (t->prof_ev.size() < (t->prof_pending + 1) * 5) {
+      for (int k = 0; k < 5; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); t->prof_ev.push_back(e); }
+    }
+    pe = &t->prof_ev[t->prof_pending * 5];
+    t->prof_pending++;
+    CK(cudaEventRecord(pe[0], st));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gub::FB_THREADS); cfg.dynamicSmemBytes = sizeof(gub::FSmem); cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (t->coop) { attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; na++; }
+  if (t->pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gub::k_batch, A);
+  if (e != cudaSuccess && t->coop && t->pdl) {  // the two attributes do not combine on this driver: keep the co-residency guarantee
+    cudaGetLastError();
+    t->pdl = false;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gub::k_batch, A);
+  }
+  if (e != cudaSuccess) return fail(std::string("k_batch launch: ") + cudaGetErrorString(e));
+  if (pe) { for (int k = 1; k < 5; k++) CK(cudaEventRecord(pe[k], st)); }
+  return 0;
+}
+
 // One batch (<= max_batch requests).  Stage 1 (k_group, k_rank) never touches bucket state, so it runs on the prep
 // stream and overlaps stage 2 (k_eval, k_finish) of the previous batch, which runs on the caller's stream.
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
@@ -240,6 +291,17 @@ int order_after_last(gub_table* t, cudaStream_t st) {
 int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
                  const uint32_t* n_dev = nullptr) {
   if (order_after_last(t, st)) return -1;
+  if (t->fused) {  // any size in one launch: the kernel takes the batch in rounds of one tile per CTA
+    if (n > 0xFFFFFFFFull) return fail("batch too large");
+    gub::FArgs A;
+    fused_base_args(t, clk, A);
+    A.seg[0].reqs = d_reqs; A.seg[0].out = d_out; A.seg[0].n = (uint32_t)n; A.seg[0].n_dev = n_dev;
+    A.nseg = 1;
+    if (((uintptr_t)d_reqs & 15u) || ((uintptr_t)d_out & 15u)) return fail("request / response buffers must be 16-byte aligned");
+    if (launch_fused(t, A, n_dev ? 0 : n, st)) return -1;
+    t->last_stream = st; t->last_pending = true;
+    return 0;
+  }
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
     if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st, n_dev, (uint32_t)off)) return -1;
@@ -297,7 +359,8 @@ void gub_destroy(gub_table* t) {
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
   trace_dump(t);
-  void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts};
+  void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts,
+                  t->gaux, t->gpres, t->gfrag, t->gpos, t->ordbuf, t->ctl, t->ovf};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& sc : t->scr) {
     void* sp[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.commit_ent, sc.ctr};
@@ -370,6 +433,24 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     ALLOC(sc.order, (size_t)B * 4);
     ALLOC(sc.mixed_ent, ((size_t)B / 2 + 1) * 4);
     ALLOC(sc.ctr, 2 * sizeof(gub::BatchCtr));
+  }
+  t->num_sms = std::min<int>(prop.multiProcessorCount, gub::FB_MAX_GRID);
+  if (const char* e = getenv("GUB_FUSED")) t->fused = std::atoi(e) != 0;
+  if (const char* e = getenv("GUB_COOP")) t->coop = std::atoi(e) != 0;
+  ALLOC(t->gaux, (size_t)gub::FB_AUX_ENTRIES * sizeof(gub::GEntry));
+  ALLOC(t->gpres, (size_t)gub::FB_AUX_ENTRIES * gub::FB_PRES_WORDS * 4);
+  ALLOC(t->gfrag, (size_t)gub::FB_AUX_ENTRIES * gub::FB_ROW * 2);
+  ALLOC(t->gpos, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 4);
+  ALLOC(t->ordbuf, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 4);
+  ALLOC(t->ctl, sizeof(gub::FCtl));
+  ALLOC(t->ovf, (size_t)gub::FB_OVF_CAP * sizeof(gub::OvfItem));
+  {
+    // incremental expiry sweep: the whole table once every ~65536 batches (GUB_SWEEP=<slots per CTA per batch>, 0 = off)
+    uint64_t chunk = (t->capacity + (uint64_t)t->num_sms * 65536 - 1) / ((uint64_t)t->num_sms * 65536);
+    if (const char* e = getenv("GUB_SWEEP")) chunk = (uint64_t)std::atoll(e);
+    t->sweep_chunk = (uint32_t)std::min<uint64_t>(chunk, 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(gub::k_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(gub::FSmem));
+    if (e2 != cudaSuccess) { fail(std::string("cudaFuncSetAttribute(k_batch): ") + cudaGetErrorString(e2)); gub_destroy(t); return -1; }
   }
   ALLOC(t->counters, gub::C_COUNT * sizeof(unsigned long long));
   ALLOC(t->d_scalar, 4 * sizeof(unsigned long long));
@@ -642,6 +723,7 @@ int gub_get_counters(gub_table* t, gub_counters* out) {
   out->inserts = c[gub::C_INSERTS]; out->table_full = c[gub::C_FULL]; out->requests = c[gub::C_REQUESTS];
   out->batches = c[gub::C_BATCHES]; out->dup_groups = c[gub::C_DUP_GROUPS]; out->mixed_groups = c[gub::C_MIXED_GROUPS];
   out->serial_fallbacks = c[gub::C_SERIAL];
+  out->unexpired_evictions = c[gub::C_EVICT_UNEXPIRED]; out->swept = c[gub::C_SWEPT]; out->gq_dropped = c[gub::C_GQ_DROPPED];
   return 0;
 }
 

@@ -96,7 +96,8 @@ __host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint
 
 struct BatchCtr { uint32_t n_mixed, order_bump, n_commit, _pad1; };
 
-enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_MIXED_GROUPS, C_SERIAL, C_COUNT };
+enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_MIXED_GROUPS, C_SERIAL, C_EVICT_UNEXPIRED, C_SWEPT, C_GQ_DROPPED,
+       C_COUNT };
 
 struct BatchArgs {
   Slot* table;
@@ -146,6 +147,23 @@ __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
+
+// system-scope release / acquire on flags other GPUs (or the host) poll
+#if defined(GUB_EMULATE)
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return *p; }
+__device__ __forceinline__ void __nanosleep(unsigned) { emu::spin_yield(); }
+#else
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 #endif
 
 // ---- slot access ---------------------------------------------------------------------------------------------

@@ -39,20 +39,6 @@ struct P2PArgs {
 __device__ __forceinline__ size_t mb_index(const P2PArgs& P, uint32_t src, uint32_t p) {
   return ((size_t)(P.epoch & 1u) * P.world + src) * P.cap + p;
 }
-#if defined(GUB_EMULATE)
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return *p; }
-__device__ __forceinline__ void __nanosleep(unsigned) {}
-#else
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-#endif
 // Spins until flag's epoch field equals `epoch`; gives up after ~2 s (a peer died): sets *error so the host can tell.
 __device__ __forceinline__ unsigned long long wait_flag(const unsigned long long* flag, uint32_t epoch, uint32_t* error) {
   for (uint32_t it = 0; it < 20000000u; it++) {

@@ -22,7 +22,7 @@ ITEM_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("algorithm", 
                        ("duration", "<i8"), ("remaining", "<i8"), ("remaining_f", "<f8"), ("stamp", "<i8"), ("burst", "<i8"),
                        ("expire_at", "<i8")])
 COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups",
-                  "mixed_groups", "serial_fallbacks")
+                  "mixed_groups", "serial_fallbacks", "unexpired_evictions", "swept", "gq_dropped")
 CREQ_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("hits", "<i8"), ("params", "<u4"), ("created_delta", "<i4")])
 PARAMS_DTYPE = np.dtype([("limit", "<i8"), ("duration", "<i8"), ("burst", "<i8"), ("algorithm", "<u4"), ("behavior", "<u4")])
 assert CREQ_DTYPE.itemsize == 32 and PARAMS_DTYPE.itemsize == 32

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GUB_ABI_VERSION 1
+#define GUB_ABI_VERSION 2
 
 /* Algorithm, Status, Behavior: gubernator.proto:56-135 */
 enum { GUB_TOKEN_BUCKET = 0, GUB_LEAKY_BUCKET = 1 };
@@ -117,7 +117,10 @@ typedef struct {
   uint64_t batches;
   uint64_t dup_groups;     /* keys that occurred more than once within a batch */
   uint64_t mixed_groups;   /* of those, keys whose requests differed within the batch (segment path) */
-  uint64_t serial_fallbacks; /* of those, groups too irregular to plan: walked by one thread */
+  uint64_t serial_fallbacks; /* chunks (<= 512 requests) of such groups that were mostly one-request runs: applied one by one */
+  uint64_t unexpired_evictions; /* live entries displaced because a probe window was full: metricCacheUnexpiredEvictions (lrucache.go:138-149) */
+  uint64_t swept;          /* removed / expired entries freed by the incremental sweep inside the batch kernel */
+  uint64_t gq_dropped;     /* GLOBAL requests not queued because a gub_gq was full within one sync window */
 } gub_counters;
 
 typedef struct {

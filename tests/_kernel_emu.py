@@ -11,9 +11,11 @@ ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libkernel_emu_test.so")
 SRC = [os.path.join(HERE, "kernel_emu_harness.cpp"), os.path.join(HERE, "cuda_emu.h"),
        os.path.join(ROOT, "gubernator_b200", "csrc", "gub_kernels.cuh"), os.path.join(ROOT, "gubernator_b200", "csrc", "bucket_math.cuh"),
+       os.path.join(ROOT, "gubernator_b200", "csrc", "gub_batch.cuh"), os.path.join(ROOT, "gubernator_b200", "csrc", "gub_p2p.cuh"),
+       os.path.join(ROOT, "gubernator_b200", "csrc", "gub_global.cuh"),
        os.path.join(ROOT, "include", "gubernator_b200.h")]
 COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups", "mixed_groups",
-                 "serial_fallbacks"]
+                 "serial_fallbacks", "unexpired_evictions", "swept", "gq_dropped"]
 
 _libs = {}
 
@@ -35,6 +37,9 @@ def lib(early_singles=1, onepass=0, class_sort=0):
         L.emu_destroy.argtypes = [vp]; L.emu_destroy.restype = None
         L.emu_set_epoch.argtypes = [vp, u32]; L.emu_set_epoch.restype = None
         L.emu_set_finish_cap.argtypes = [u32]; L.emu_set_finish_cap.restype = None
+        L.emu_set_fused.argtypes = [u32]; L.emu_set_fused.restype = None
+        L.emu_set_grid.argtypes = [vp, u32]; L.emu_set_grid.restype = None
+        L.emu_set_sweep.argtypes = [vp, u32]; L.emu_set_sweep.restype = None
         L.emu_submit.argtypes = [vp, vp, C.c_size_t, vp, vp]
         L.emu_submit_compact.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, i64, vp, vp]
         L.emu_counters.argtypes = [vp, vp]; L.emu_counters.restype = None

@@ -5,7 +5,8 @@
 // without spending GPU minutes.  It is an emulation of the *programming model*, not of the hardware: no timing, one
 // interleaving.
 //
-// Model: a launch runs its blocks one after another; the threads of a block are ucontext fibers on one OS thread, run
+// Model: a launch runs its blocks one after another (launch_coop: all blocks of the grid at once, for kernels with grid-wide
+// barriers; those must keep their shared memory in the dynamic allocation, emu::dyn_smem()); the threads of a block are ucontext fibers on one OS thread, run
 // round-robin and switched only at synchronisation points (__syncthreads and the warp collectives).  Atomics are therefore
 // plain read-modify-writes, `__shared__` is a function-local static (one block is alive at a time), and a thread that
 // returns early leaves the barriers it would have joined, as on the device.  What this cannot show: data races, memory
@@ -27,6 +28,7 @@
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
+#define __noinline__
 #define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 
@@ -50,9 +52,16 @@ struct Warp {
   unsigned long long val[32];
   bool present[32];
 };
+struct Block {
+  Sync sync;
+  std::vector<Warp> warps;
+  uint3 idx{0, 0, 0};
+  void* dyn_smem = nullptr;
+};
 struct Fiber {
   ucontext_t ctx;
   uint3 tid;
+  Block* blk = nullptr;
   bool done = false;
 };
 
@@ -61,14 +70,14 @@ struct State {
   Fiber* cur = nullptr;
   std::vector<Fiber> fibers;
   std::vector<void*> stacks;
-  Sync block;
-  std::vector<Warp> warps;
-  uint3 block_idx{0, 0, 0};
+  std::vector<Block> blocks;   // the blocks alive right now (one, or the whole grid for launch_coop)
   dim3 block_dim, grid_dim;
   std::function<void()> body;
   unsigned long progress = 0;  // bumped on every barrier arrival / opening and when a fiber finishes: a whole pass without any is a deadlock
+  unsigned long spins = 0;     // yields from spin loops (grid barriers, flag waits): many passes with nothing else = deadlock
 };
 inline State& st() { static State s; return s; }
+inline void* dyn_smem() { return st().cur->blk->dyn_smem; }
 
 inline void yield() { State& s = st(); swapcontext(&s.cur->ctx, &s.sched); }
 inline void open_if_complete(Sync& y) {
@@ -81,7 +90,9 @@ inline void arrive_and_wait(Sync& y) {
   open_if_complete(y);
   while (y.gen == my) yield();
 }
-inline Warp& my_warp() { State& s = st(); return s.warps[s.cur->tid.x >> 5]; }
+inline Warp& my_warp() { State& s = st(); return s.cur->blk->warps[s.cur->tid.x >> 5]; }
+// a spin loop's body: let the other fibers run (the thing waited for is produced by one of them)
+inline void spin_yield() { st().spins++; yield(); }
 
 // deposit -> everybody has deposited -> compute -> everybody has read
 template <class F>
@@ -101,75 +112,102 @@ inline void trampoline() {
   Fiber* f = s.cur;
   f->done = true;
   s.progress++;
-  Warp& w = s.warps[f->tid.x >> 5];
+  Warp& w = f->blk->warps[f->tid.x >> 5];
   w.present[f->tid.x & 31u] = false;
-  s.block.live--; open_if_complete(s.block);
+  f->blk->sync.live--; open_if_complete(f->blk->sync);
   w.sync.live--; open_if_complete(w.sync);
   swapcontext(&f->ctx, &s.sched);  // never resumed
 }
 
 constexpr size_t STACK_BYTES = 256 * 1024;
 
-// Runs kernel(args...) for grid x block threads.
+// Runs blocks [b0, b1) of the current launch concurrently (fibers round-robin).
+inline void run_blocks(unsigned b0, unsigned b1, unsigned block, size_t smem_bytes) {
+  State& s = st();
+  const unsigned nb = b1 - b0;
+  while (s.stacks.size() < (size_t)nb * block) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, STACK_BYTES)) std::abort();
+    s.stacks.push_back(p);
+  }
+  s.blocks.assign(nb, Block());
+  s.fibers.assign((size_t)nb * block, Fiber());
+  for (unsigned b = 0; b < nb; b++) {
+    Block& B = s.blocks[b];
+    B.idx = uint3{b0 + b, 0, 0};
+    B.warps.assign(block / 32, Warp());
+    B.sync.live = block;
+    if (smem_bytes) { if (posix_memalign(&B.dyn_smem, 128, smem_bytes)) std::abort(); std::memset(B.dyn_smem, 0xA5, smem_bytes); }
+    for (unsigned t = 0; t < block; t++) {
+      Fiber& f = s.fibers[(size_t)b * block + t];
+      f.tid = uint3{t, 0, 0};
+      f.blk = &B;
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = s.stacks[(size_t)b * block + t];
+      f.ctx.uc_stack.ss_size = STACK_BYTES;
+      f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+      Warp& w = B.warps[t >> 5];
+      w.sync.live++;
+      w.present[t & 31u] = true;
+    }
+  }
+  size_t alive = s.fibers.size();
+  unsigned idle_passes = 0;
+  while (alive) {
+    const unsigned long before = s.progress;
+    alive = 0;
+    for (Fiber& f : s.fibers) {
+      if (f.done) continue;
+      s.cur = &f;
+      swapcontext(&s.sched, &f.ctx);
+      if (!f.done) alive++;
+    }
+    if (alive && s.progress == before) {
+      // spinning fibers may legitimately need a few passes (the value they wait for is written without a barrier in between)
+      if (++idle_passes > 1000) {
+        std::fprintf(stderr, "cuda_emu: deadlock in blocks [%u, %u) (%zu threads wait at a barrier / flag nobody will reach)\n", b0, b1, alive);
+        std::abort();
+      }
+    } else idle_passes = 0;
+  }
+  for (Block& B : s.blocks) if (B.dyn_smem) std::free(B.dyn_smem);
+  s.blocks.clear();
+  s.cur = nullptr;
+}
+
+// Runs kernel(args...) for grid x block threads, one block after another.
 template <class K, class... Args>
 void launch(K kernel, unsigned grid, unsigned block, Args... args) {
   State& s = st();
   if (block == 0 || grid == 0) return;
   if (block % 32 != 0) { std::fprintf(stderr, "cuda_emu: block size %u is not a multiple of 32\n", block); std::abort(); }
-  while (s.stacks.size() < block) {
-    void* p = nullptr;
-    if (posix_memalign(&p, 64, STACK_BYTES)) std::abort();
-    s.stacks.push_back(p);
-  }
   s.block_dim = dim3(block);
   s.grid_dim = dim3(grid);
   s.body = [&]() { kernel(args...); };
-  for (unsigned b = 0; b < grid; b++) {
-    s.block_idx = uint3{b, 0, 0};
-    s.fibers.assign(block, Fiber());
-    s.warps.assign(block / 32, Warp());
-    s.block = Sync();
-    s.block.live = block;
-    for (unsigned t = 0; t < block; t++) {
-      Fiber& f = s.fibers[t];
-      f.tid = uint3{t, 0, 0};
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = s.stacks[t];
-      f.ctx.uc_stack.ss_size = STACK_BYTES;
-      f.ctx.uc_link = nullptr;
-      makecontext(&f.ctx, (void (*)())trampoline, 0);
-      Warp& w = s.warps[t >> 5];
-      w.sync.live++;
-      w.present[t & 31u] = true;
-    }
-    unsigned alive = block;
-    while (alive) {
-      const unsigned long before = s.progress;
-      alive = 0;
-      for (unsigned t = 0; t < block; t++) {
-        Fiber& f = s.fibers[t];
-        if (f.done) continue;
-        s.cur = &f;
-        swapcontext(&s.sched, &f.ctx);
-        if (!f.done) alive++;
-      }
-      if (alive && s.progress == before) {
-        std::fprintf(stderr, "cuda_emu: deadlock in block %u (%u threads wait at a barrier the others never reach)\n", b, alive);
-        std::abort();
-      }
-    }
-  }
-  s.cur = nullptr;
+  for (unsigned b = 0; b < grid; b++) run_blocks(b, b + 1, block, 0);
+}
+
+// Cooperative launch: every block of the grid is alive at once (grid-wide barriers, spin waits between blocks).
+template <class K, class... Args>
+void launch_coop(K kernel, unsigned grid, unsigned block, size_t smem_bytes, Args... args) {
+  State& s = st();
+  if (block == 0 || grid == 0) return;
+  if (block % 32 != 0) { std::fprintf(stderr, "cuda_emu: block size %u is not a multiple of 32\n", block); std::abort(); }
+  s.block_dim = dim3(block);
+  s.grid_dim = dim3(grid);
+  s.body = [&]() { kernel(args...); };
+  run_blocks(0, grid, block, smem_bytes);
 }
 
 }  // namespace emu
 
 #define threadIdx (emu::st().cur->tid)
-#define blockIdx (emu::st().block_idx)
+#define blockIdx (emu::st().cur->blk->idx)
 #define blockDim (emu::st().block_dim)
 #define gridDim (emu::st().grid_dim)
 
-inline void __syncthreads() { emu::arrive_and_wait(emu::st().block); }
+inline void __syncthreads() { emu::arrive_and_wait(emu::st().cur->blk->sync); }
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::arrive_and_wait(emu::my_warp().sync); }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
@@ -194,6 +232,21 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
     return m;
   });
 }
+inline unsigned long long __shfl_sync(unsigned, unsigned long long v, unsigned src) {
+  return emu::warp_collective(v, [src](emu::Warp& w, unsigned) { return w.val[src & 31u]; });
+}
+inline bool __all_sync(unsigned, bool pred) {
+  return emu::warp_collective(pred ? 1ull : 0ull, [](emu::Warp& w, unsigned) {
+    for (unsigned l = 0; l < 32; l++) if (w.present[l] && !w.val[l]) return false;
+    return true;
+  });
+}
+inline bool __any_sync(unsigned, bool pred) {
+  return emu::warp_collective(pred ? 1ull : 0ull, [](emu::Warp& w, unsigned) {
+    for (unsigned l = 0; l < 32; l++) if (w.present[l] && w.val[l]) return true;
+    return false;
+  });
+}
 inline unsigned __reduce_add_sync(unsigned, unsigned v) {
   return emu::warp_collective(v, [](emu::Warp& w, unsigned) {
     unsigned sum = 0;
@@ -211,6 +264,7 @@ template <class T> inline void __stcs(T* p, const T& v) { *p = v; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
+inline unsigned atomicAnd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o & v; return o; }
 inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
 inline unsigned atomicExch(unsigned* p, unsigned v) { const unsigned o = *p; *p = v; return o; }
 inline unsigned atomicCAS(unsigned* p, unsigned cmp, unsigned v) { const unsigned o = *p; if (o == cmp) *p = v; return o; }
@@ -222,6 +276,7 @@ inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cm
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
   for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xFFu) * ((b >> (8 * k)) & 0xFFu);

@@ -6,6 +6,7 @@
 #include "cuda_emu.h"
 
 #include "../gubernator_b200/csrc/gub_kernels.cuh"
+#include "../gubernator_b200/csrc/gub_batch.cuh"
 #include "../gubernator_b200/csrc/gub_p2p.cuh"
 #include "../gubernator_b200/csrc/gub_global.cuh"
 
@@ -38,7 +39,16 @@ struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   ulonglong2* commit = nullptr;
   BatchCtr* ctr = nullptr;
   unsigned long long* counters = nullptr;
+  // the fused batch kernel (gub_batch.cuh)
+  GEntry* gaux = nullptr;
+  uint32_t *gpres = nullptr, *gpos = nullptr, *ordbuf = nullptr;
+  uint16_t* gfrag = nullptr;
+  FCtl* ctl = nullptr;
+  OvfItem* ovf = nullptr;
+  uint32_t grid = 6, sweep_chunk = 0;
 };
+
+uint32_t g_fused = 1;  // emu_set_fused(0): the four-kernel path
 
 }  // namespace
 
@@ -64,12 +74,20 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
   t->mixed_ent = zalloc<uint32_t>((size_t)B / 2 + 1);
   t->ctr = zalloc<BatchCtr>(2);
   t->counters = zalloc<unsigned long long>(C_COUNT);
+  t->gaux = zalloc<GEntry>(FB_AUX_ENTRIES);
+  t->gpres = zalloc<uint32_t>((size_t)FB_AUX_ENTRIES * FB_PRES_WORDS);
+  t->gfrag = zalloc<uint16_t>((size_t)FB_AUX_ENTRIES * FB_ROW);
+  t->gpos = zalloc<uint32_t>((size_t)FB_MAX_GRID * FB_THREADS);
+  t->ordbuf = zalloc<uint32_t>((size_t)FB_MAX_GRID * FB_THREADS);
+  t->ctl = zalloc<FCtl>(1);
+  t->ovf = zalloc<OvfItem>(FB_OVF_CAP);
   return t;
 }
 
 void emu_destroy(void* tv) {
   EmuTable* t = static_cast<EmuTable*>(tv);
-  void* ptrs[] = {t->table, t->aux, t->presence, t->fragsize, t->commit, t->commit_ent, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->ctr, t->counters};
+  void* ptrs[] = {t->table, t->aux, t->presence, t->fragsize, t->commit, t->commit_ent, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->ctr, t->counters,
+                  t->gaux, t->gpres, t->gfrag, t->gpos, t->ordbuf, t->ctl, t->ovf};
   for (void* p : ptrs) std::free(p);
   delete t;
 }
@@ -77,9 +95,39 @@ void emu_destroy(void* tv) {
 void emu_set_finish_cap(uint32_t blocks) { g_finish_cap = blocks ? blocks : 148u; }
 void emu_set_epoch(void* tv, uint32_t epoch) { static_cast<EmuTable*>(tv)->epoch = epoch; }
 
+void emu_set_fused(uint32_t on) { g_fused = on; }
+void emu_set_grid(void* tv, uint32_t grid) { static_cast<EmuTable*>(tv)->grid = grid ? grid : 6u; }
+void emu_set_sweep(void* tv, uint32_t chunk) { static_cast<EmuTable*>(tv)->sweep_chunk = chunk; }
+
+static void fused_args(EmuTable* t, const gub_clock* clk, FArgs& A) {
+  std::memset(&A, 0, sizeof A);
+  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragsize = t->gfrag; A.gpos = t->gpos; A.ordbuf = t->ordbuf;
+  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.clk = *clk;
+}
+
+// launch_fused of gub_api.cu: one cooperative launch of k_batch over the batch's segments (here with a small grid: every emulated
+// CTA costs 512 fibers; the kernel takes any grid size, more rounds make up for it).
+static int submit_fused(EmuTable* t, const FSeg* segs, uint32_t nseg, uint32_t flag_epoch, const gub_clock* clk, unsigned long long* const* resp_flags = nullptr,
+                        uint32_t n_resp_flags = 0) {
+  FArgs A;
+  fused_args(t, clk, A);
+  for (uint32_t s = 0; s < nseg; s++) A.seg[s] = segs[s];
+  A.nseg = nseg; A.flag_epoch = flag_epoch;
+  for (uint32_t k = 0; k < n_resp_flags; k++) A.resp_flag[k] = resp_flags[k];
+  A.n_resp_flags = n_resp_flags;
+  emu::launch_coop(k_batch, t->grid, (unsigned)FB_THREADS, sizeof(FSmem), A);
+  return 0;
+}
+
 // launch_batch / launch_chunk / launch_finish of gub_api.cu, minus streams.  n_dev != nullptr: the batch size is *n_dev (<= n), as in
 // gub_submit_device_n.
 static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_t* n_dev, const gub_clock* clk, gub_resp* out) {
+  if (g_fused) {
+    FSeg sg;
+    std::memset(&sg, 0, sizeof sg);
+    sg.reqs = reqs; sg.out = out; sg.n = (uint32_t)n; sg.n_dev = n_dev;
+    return submit_fused(t, &sg, 1, 0, clk);
+  }
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
     if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); std::memset(t->ctr, 0, 2 * sizeof(BatchCtr)); t->epoch = 0; }

@@ -32,7 +32,7 @@ def test_exports_match_headers(G):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(G.native.EXPORTS) <= declared
-    assert L.gub_abi_version() == 1
+    assert L.gub_abi_version() == 2
 
 
 def test_record_layouts_match_header(G):

@@ -195,14 +195,15 @@ def test_many_segments_and_serial_fallback(G):
     reqs["hits"] = rng.integers(0, 3, n); reqs["limit"] = rng.choice([50, 100], n); reqs["duration"] = 60000
     reqs["created_at"] = T0 + rng.integers(0, 5, n); reqs["algorithm"] = 1; reqs["behavior"] = G.native.REQ_IS_OWNER
     _cmp(tab.submit(reqs, G.clock_fill(T0)), pool.submit_hashed(reqs))
-    assert tab.counters()["serial_fallbacks"] == 1
+    walked = tab.counters()["serial_fallbacks"]  # chunks (<= 512 requests) that were mostly one-request segments: applied one by one
+    assert walked >= 1
     # a few long uniform segments (one per simulated RPC timestamp) stay on the planned path
     reqs2 = reqs.copy()
     reqs2["hits"] = 1; reqs2["limit"] = 100
     reqs2["created_at"] = T0 + 10 + (np.arange(n) // 500)
     pool.set_now(T0 + 10)
     _cmp(tab.submit(reqs2, G.clock_fill(T0 + 10)), pool.submit_hashed(reqs2))
-    assert tab.counters()["serial_fallbacks"] == 1
+    assert tab.counters()["serial_fallbacks"] == walked
 
 
 def test_token_reset_flipflop_in_heavy_group(G):
@@ -244,51 +245,56 @@ def test_sentinel_key_hashes(G):
 
 
 def test_keys_colliding_in_the_grouping_table(G):
-    """Two different keys sharing one batch-wide grouping entry (same position, same 24-bit tag), with requests in the same block:
-    k_group folds their fragments (merge_colliding_fragments), k_rank finds the run non-uniform, k_finish walks it key by key.
-    Same scenario as tests/test_kernels_emulated.py, where the CPU emulation of the kernels first exposed it."""
-    max_batch = 1024
-    mask = 4 * max_batch - 1
+    """Keys that collide in the batch-wide group table (same home entry: linear probing there) and two keys that share the XXH64 but
+    not the FNV-1 (one group entry, told apart by the request compare: the group takes the segment walk, key by key)."""
     rng = np.random.default_rng(2024)
-    top = np.uint64(0xABCDEF) << np.uint64(40)
-    keys = top | rng.integers(2, 1 << 40, 4000).astype(np.uint64)
-    home = ((keys ^ (keys >> np.uint64(29))) & np.uint64(mask)).astype(np.int64)
+    keys = rng.integers(2, 1 << 62, 4000).astype(np.uint64)
+    home = ((keys * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)) & np.uint64((1 << 18) - 1)
     order = np.argsort(home, kind="stable")
-    same = np.nonzero(np.diff(home[order]) == 0)[0]
+    same = np.nonzero(np.diff(home[order].astype(np.int64)) == 0)[0]
     ka, kb = keys[order[same[0]]], keys[order[same[0] + 1]]
     assert ka != kb
-    tab = G.Table(4096, max_batch=max_batch)
+    tab = G.Table(4096)
     pool = O.Pool(now_ms=T0)
     for step in range(3):
         now = T0 + step
         pool.set_now(now)
-        n = 600
+        n = 1500
         reqs = np.zeros(n, dtype=G.REQ_DTYPE)
-        pick = rng.integers(0, 3, n)
+        pick = rng.integers(0, 4, n)
         reqs["key_xxh64"] = np.where(pick == 0, ka, np.where(pick == 1, kb, keys[rng.integers(0, 50, n)]))
         reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
+        twin = pick == 3  # same XXH64 as ka, another FNV-1: a different key as far as the table is concerned
+        reqs["key_xxh64"][twin] = ka
+        reqs["key_fnv1"][twin] = np.uint64(0x7777700)
         reqs["hits"] = 1 if step < 2 else rng.integers(0, 3, n)
         reqs["limit"] = 500; reqs["duration"] = 60000; reqs["created_at"] = now
         reqs["algorithm"] = (reqs["key_xxh64"] & np.uint64(1)).astype(np.uint32); reqs["behavior"] = G.native.REQ_IS_OWNER
-        _cmp(tab.submit(reqs, G.clock_fill(now)), pool.submit_hashed(reqs), f"step {step}")
+        _cmp(tab.submit(reqs, G.clock_fill(now)), pool.submit_hashed(reqs), f"step {step}")  # (the oracle keys its cache by both hashes)
     assert tab.counters()["mixed_groups"] > 0
-    _check_table_equals_oracle(G, tab, pool)
 
 
-def test_table_full_is_reported(G):
+def test_full_window_evicts_like_the_lru(G):
+    """A table far too small for the batch: the reference's LRU evicts (lrucache.go:98,138-149) and still answers every request.
+    So do we: keys whose probe window is full are parked and placed, with eviction, before the next batch reads the table."""
     tab = G.Table(64)
-    n = 4000
+    n = 1500
     reqs = np.zeros(n, dtype=G.REQ_DTYPE)
     xx, fv = key_hashes(np.arange(n), name="full")
     reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
-    reqs["hits"] = 1; reqs["limit"] = 5; reqs["duration"] = 100000; reqs["created_at"] = T0
-    out = tab.submit(reqs, G.clock_fill(T0))
-    ok = out["err_code"] == 0
-    assert ok.sum() == 64 and np.all(out["err_code"][~ok] == G.native.ERR_TABLE_FULL)
-    assert tab.size() == 64 and tab.counters()["table_full"] == n - 64
+    reqs["hits"] = 1; reqs["limit"] = 5; reqs["duration"] = 100000; reqs["created_at"] = T0 + np.arange(n)
+    big = O.Pool(now_ms=T0)
+    _cmp(tab.submit(reqs, G.clock_fill(T0)), big.submit_hashed(reqs), "every request answered as if the cache had room")
+    c = tab.counters()
+    assert tab.size() == 64 and c["inserts"] == 64 and c["table_full"] == n - 64 - 1024
+    again = reqs[-8:].copy()
+    again["created_at"] = T0 + 5
+    out = tab.submit(again, G.clock_fill(T0 + 5))
+    c = tab.counters()
+    assert c["unexpired_evictions"] == 1024 and np.all(out["err_code"] == 0) and tab.size() == 64
     # expired items are reclaimed by the sweep and the slots reused
-    assert tab.sweep(T0 + 100001) == 64 and tab.size() == 0
-    out = tab.submit(reqs[:64], G.clock_fill(T0 + 100001))
+    assert tab.sweep(T0 + 300000) == 64 and tab.size() == 0
+    out = tab.submit(reqs[:64], G.clock_fill(T0 + 300000))
     assert np.all(out["err_code"] == 0)
 
 
