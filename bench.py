@@ -347,6 +347,25 @@ def run_b200(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
 
+    # ---- phase trace of the batch kernel (diagnostic): per-CTA %globaltimer stamps of one launch
+    phase_trace = None
+    try:
+        tab.set_trace(True)
+        for b in range(3):
+            one_step(args.warmup + args.steps + prof_steps + 64 + b)
+        torch.cuda.synchronize()
+        phase_trace = tab.get_trace()
+        raw = tab.get_trace_raw()
+        live = raw[:, 0] > 0
+        t0 = raw[live, 0].min()
+        rel = (raw[live].astype(np.int64) - np.int64(t0)) / 1e3
+        slow = int(np.argmax(rel[:, 10]))
+        phase_trace["slowest_cta"] = {"cta": int(np.nonzero(live)[0][slow]), "us": [round(float(v), 2) for v in rel[slow]]}
+        phase_trace["median_cta_us"] = [round(float(v), 2) for v in np.median(rel, axis=0)]
+        tab.set_trace(False)
+    except Exception as ex:
+        phase_trace = {"error": str(ex)}
+
     # ---- end-to-end leg through the host API with pinned buffers (N == 1 path; at N > 1 each rank ingests from its host)
     e2e = None
     if not args.no_e2e:
@@ -505,7 +524,7 @@ def run_b200(args):
                    "cache": f"inputs cycle through {pool_n} resident batches ({pool_n * 6} MiB > L2); table {capacity * 64 / 1e9:.1f} GB >> L2",
                    "batch_profile": st, "fill_seconds": t_fill, "resident_keys_after_fill": c0["inserts"]},
         "clocks": clocks_info, "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu, "larger_calls": big,
+        "roofline": roofline, "cpu_baseline": cpu, "larger_calls": big, "phase_trace": phase_trace,
         "counters": {k: c1[k] - c0[k] for k in c1},
     }
     print(json.dumps(line))

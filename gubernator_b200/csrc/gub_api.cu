@@ -5,6 +5,8 @@
 // There is no CPU fallback: every entry point that evaluates requests launches CUDA kernels or fails.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,10 +79,11 @@ struct gub_table {
   int num_sms = 0;
   uint32_t sweep_chunk = 0;           // slots every CTA sweeps per batch (incremental expiry sweep), 0 = off
   gub::GEntry* gaux = nullptr;
-  uint32_t *gpres = nullptr, *gpos = nullptr, *ordbuf = nullptr;
-  uint16_t* gfrag = nullptr;
+  uint32_t *gpres = nullptr, *gfrag = nullptr;
+  uint16_t* gmembers = nullptr;
   gub::FCtl* ctl = nullptr;
   gub::OvfItem* ovf = nullptr;
+  unsigned long long* trace = nullptr; // per-CTA phase timestamps of the last k_batch launch (gub_set_trace)
   unsigned long long* counters = nullptr;
   cudaStream_t s_prep = nullptr;
   cudaEvent_t inputs_ready = nullptr;
@@ -97,7 +100,7 @@ struct gub_table {
   // maintenance scratch
   unsigned long long* d_scalar = nullptr;
   // route
-  uint64_t* d_ring_pts = nullptr; int32_t* d_ring_peers = nullptr; uint32_t ring_npts = 0; const gub_ring* ring_cached = nullptr; uint64_t ring_version = 0;
+  uint64_t* d_ring_pts = nullptr; int32_t* d_ring_peers = nullptr; uint16_t* d_ring_lut = nullptr; uint32_t ring_npts = 0; const gub_ring* ring_cached = nullptr; uint64_t ring_version = 0;
   uint8_t* d_owner = nullptr; uint32_t* d_tile_counts = nullptr;
   size_t owner_cap = 0, tiles_cap = 0;
   // optional per-kernel timing (bench.py's roofline leg): events bracket every kernel of the batch path
@@ -182,8 +185,8 @@ int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_
 
 void fused_base_args(gub_table* t, const gub_clock* clk, gub::FArgs& A) {
   std::memset(&A, 0, sizeof A);
-  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragsize = t->gfrag; A.gpos = t->gpos; A.ordbuf = t->ordbuf;
-  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.clk = *clk;
+  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragrow = t->gfrag; A.members = t->gmembers;
+  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.trace = t->trace; A.clk = *clk;
 }
 
 // One launch of k_batch over the segments in A (A.seg / A.nseg / flags filled by the caller).  `total_hint` = number of requests
@@ -359,8 +362,8 @@ void gub_destroy(gub_table* t) {
   cudaSetDevice(t->device);
   cudaDeviceSynchronize();
   trace_dump(t);
-  void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_owner, t->d_tile_counts,
-                  t->gaux, t->gpres, t->gfrag, t->gpos, t->ordbuf, t->ctl, t->ovf};
+  void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_ring_lut, t->d_owner, t->d_tile_counts,
+                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf, t->trace};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& sc : t->scr) {
     void* sp[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.commit_ent, sc.ctr};
@@ -439,9 +442,8 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   if (const char* e = getenv("GUB_COOP")) t->coop = std::atoi(e) != 0;
   ALLOC(t->gaux, (size_t)gub::FB_AUX_ENTRIES * sizeof(gub::GEntry));
   ALLOC(t->gpres, (size_t)gub::FB_AUX_ENTRIES * gub::FB_PRES_WORDS * 4);
-  ALLOC(t->gfrag, (size_t)gub::FB_AUX_ENTRIES * gub::FB_ROW * 2);
-  ALLOC(t->gpos, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 4);
-  ALLOC(t->ordbuf, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 4);
+  ALLOC(t->gfrag, (size_t)gub::FB_AUX_ENTRIES * gub::FB_ROW * 4);
+  ALLOC(t->gmembers, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 2);
   ALLOC(t->ctl, sizeof(gub::FCtl));
   ALLOC(t->ovf, (size_t)gub::FB_OVF_CAP * sizeof(gub::OvfItem));
   {
@@ -738,6 +740,66 @@ int gub_hash_keys_device(gub_table* t, const char* d_bytes, const uint64_t* d_of
   return 0;
 }
 
+/* Incremental expiry sweep inside the batch kernel: every CTA frees the removed / expired entries of `slots_per_cta` slots per batch
+ * (0 = off).  The default visits the whole table once every ~65536 batches. */
+int gub_set_sweep(gub_table* t, uint32_t slots_per_cta) {
+  if (!t) return fail("gub_set_sweep: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  t->sweep_chunk = std::min<uint32_t>(slots_per_cta, 1024u);
+  return 0;
+}
+
+/* Diagnostic: per-CTA %globaltimer stamps at the phase boundaries of k_batch.  gub_get_trace reports, for the LAST launch, the
+ * time (us since the earliest CTA entered the kernel) at which the last CTA passed each of the 12 marks, and the mean over CTAs. */
+int gub_set_trace(gub_table* t, int on) {
+  if (!t) return fail("gub_set_trace: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  if (on && !t->trace) {
+    CK(cudaMalloc(&t->trace, (size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS * 8));
+    CK(cudaMemset(t->trace, 0, (size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS * 8));
+  } else if (!on && t->trace) {
+    cudaFree(t->trace);
+    t->trace = nullptr;
+  }
+  return 0;
+}
+int gub_get_trace(gub_table* t, double* max_us /* 12 */, double* mean_us /* 12 */) {
+  if (!t || !max_us || !mean_us) return fail("gub_get_trace: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  if (!t->trace) return fail("gub_get_trace: tracing is off");
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h((size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS);
+  CK(cudaMemcpy(h.data(), t->trace, h.size() * 8, cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  int ctas = 0;
+  for (int b = 0; b < gub::FB_MAX_GRID; b++) if (h[(size_t)b * gub::FB_TRACE_MARKS]) { t0 = std::min(t0, h[(size_t)b * gub::FB_TRACE_MARKS]); ctas++; }
+  for (int k = 0; k < gub::FB_TRACE_MARKS; k++) {
+    double mx = 0, sum = 0;
+    for (int b = 0; b < gub::FB_MAX_GRID; b++) {
+      const unsigned long long v = h[(size_t)b * gub::FB_TRACE_MARKS + k];
+      if (!h[(size_t)b * gub::FB_TRACE_MARKS] || v < t0) continue;
+      const double us = (double)(v - t0) * 1e-3;
+      mx = std::max(mx, us); sum += us;
+    }
+    max_us[k] = mx; mean_us[k] = ctas ? sum / ctas : 0;
+  }
+  return 0;
+}
+
+/* Raw stamps of the last launch: out[cta * 12 + mark] in ns (0 = CTA not launched). */
+int gub_get_trace_raw(gub_table* t, uint64_t* out /* 256 x 12 */) {
+  if (!t || !out) return fail("gub_get_trace_raw: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  if (!t->trace) return fail("gub_get_trace_raw: tracing is off");
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, t->trace, (size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int gub_set_profiling(gub_table* t, int on) {
   if (!t) return fail("gub_set_profiling: null argument");
   std::lock_guard<std::mutex> lk(t->mu);
@@ -799,6 +861,20 @@ static int ensure_ring(gub_table* t, const gub_ring* ring) {
   CK(cudaMalloc(&t->d_ring_peers, npts * 4));
   CK(cudaMemcpy(t->d_ring_pts, hs.data(), npts * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(t->d_ring_peers, ps.data(), npts * 4, cudaMemcpyHostToDevice));
+  {  // direct-mapped entry into the sorted points by the hash's top 16 bits: first point >= (bucket << 48)
+    if (npts > 0xFFFFu) return fail("gub_route_device: ring has too many points");
+    std::vector<uint16_t> lut(65536);
+    size_t k = 0;
+    for (uint32_t b = 0; b < 65536; b++) {
+      const uint64_t lo = (uint64_t)b << 48;
+      while (k < npts && hs[k] < lo) k++;
+      lut[b] = (uint16_t)k;
+    }
+    if (t->d_ring_lut) cudaFree(t->d_ring_lut);
+    t->d_ring_lut = nullptr;
+    CK(cudaMalloc(&t->d_ring_lut, 65536 * 2));
+    CK(cudaMemcpy(t->d_ring_lut, lut.data(), 65536 * 2, cudaMemcpyHostToDevice));
+  }
   t->ring_npts = (uint32_t)npts; t->ring_cached = ring; t->ring_version = ver;
   return 0;
 }
@@ -862,6 +938,28 @@ struct gub_gq {
   size_t slot_cap = 0;
 };
 
+namespace {
+int gq_reserve(gub_gq* g, size_t n, cudaStream_t st) {
+  if (g->slot_cap >= n) return 0;
+  CK(cudaStreamSynchronize(st));
+  if (g->slot_of) cudaFree(g->slot_of);
+  g->slot_of = nullptr;
+  CK(cudaMalloc(&g->slot_of, n * 4));
+  g->slot_cap = n;
+  return 0;
+}
+// n_dev (optional): the batch size lives on the device (<= n)
+int gq_accumulate(gub_gq* g, const gub_req* d_reqs, size_t n, const uint32_t* n_dev, const uint8_t* d_owner, uint32_t self, uint64_t seq_base, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (gq_reserve(g, n, st)) return -1;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  gub::k_gq_claim<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, n_dev, d_owner, self, d_owner ? 1u : 0u, (unsigned long long)seq_base, g->slot_of);
+  gub::k_gq_fill<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, n_dev, (unsigned long long)seq_base, g->slot_of);
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 int gub_gq_create(int device, uint32_t capacity, int keep_latest, gub_gq** out) {
@@ -874,7 +972,9 @@ int gub_gq_create(int device, uint32_t capacity, int keep_latest, gub_gq** out) 
   g->q.mode = keep_latest ? gub::GQ_KEEP_LAST : gub::GQ_KEEP_FIRST;
   cudaError_t e = cudaMalloc(&g->q.slots, (size_t)cap * sizeof(gub_req));
   if (e == cudaSuccess) e = cudaMalloc(&g->q.seq, (size_t)cap * 8);
-  if (e == cudaSuccess) e = cudaMalloc(&g->q.count, 8);
+  if (e == cudaSuccess) e = cudaMalloc(&g->q.count, 16);
+  if (e == cudaSuccess) e = cudaMemset(g->q.count, 0, 16);
+  if (e == cudaSuccess) g->q.dropped = g->q.count + 1;
   if (e == cudaSuccess) e = cudaMemset(g->q.slots, 0, (size_t)cap * sizeof(gub_req));
   if (e == cudaSuccess) e = cudaMemset(g->q.seq, 0, (size_t)cap * 8);
   if (e == cudaSuccess) e = cudaMemset(g->q.count, 0, 8);
@@ -898,18 +998,15 @@ int gub_gq_accumulate_device(gub_gq* g, const gub_req* d_reqs, size_t n, const u
   if (!g || (n && !d_reqs)) return fail("gub_gq_accumulate_device: null argument");
   if (n == 0) return 0;
   CK(cudaSetDevice(g->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (g->slot_cap < n) {
-    CK(cudaStreamSynchronize(st));
-    if (g->slot_of) cudaFree(g->slot_of);
-    g->slot_of = nullptr;
-    CK(cudaMalloc(&g->slot_of, n * 4));
-    g->slot_cap = n;
-  }
-  const unsigned blocks = (unsigned)((n + 255) / 256);
-  gub::k_gq_claim<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, d_owner, self, d_owner ? 1u : 0u, (unsigned long long)seq_base, g->slot_of);
-  gub::k_gq_fill<<<blocks, 256, 0, st>>>(g->q, d_reqs, (uint32_t)n, (unsigned long long)seq_base, g->slot_of);
-  CK(cudaGetLastError());
+  return gq_accumulate(g, d_reqs, n, nullptr, d_owner, self, seq_base, (cudaStream_t)stream);
+}
+
+int gub_gq_dropped(gub_gq* g, uint64_t* dropped) {
+  if (!g || !dropped) return fail("gub_gq_dropped: null argument");
+  CK(cudaSetDevice(g->device));
+  unsigned long long v = 0;
+  CK(cudaMemcpy(&v, g->q.dropped, 8, cudaMemcpyDeviceToHost));
+  *dropped = v;
   return 0;
 }
 
@@ -930,7 +1027,7 @@ int gub_make_updates_device(gub_table* t, const gub_req* d_queries, const gub_re
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(d_count, 0, 4, st));
   if (n == 0) return 0;
-  gub::k_make_updates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_queries, d_resps, (uint32_t)n, d_items, d_count);
+  gub::k_make_updates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_queries, d_resps, (uint32_t)n, nullptr, d_items, d_count);
   CK(cudaGetLastError());
   return 0;
 }
@@ -981,6 +1078,12 @@ int gub_unroute_device(gub_table* t, const gub_resp* d_resp_in, const uint32_t* 
 // ---- fused routing over peer memory -----------------------------------------------------------------------------
 }  // extern "C"
 
+extern "C" void gub_nccl_comm_destroy_(void* comm);
+struct gub_p2p;
+namespace {
+int gq_accumulate_segments(gub_p2p* p, const gub::P2PArgs& A, cudaStream_t st);
+}
+
 struct gub_p2p {
   gub_table* t = nullptr;
   const gub_ring* ring = nullptr;
@@ -990,19 +1093,28 @@ struct gub_p2p {
   gub::P2PView views[gub::MAX_SHARDS];
   void* opened[gub::MAX_SHARDS] = {};
   bool connected = false;
-  gub_req* inbox = nullptr; gub_resp* inbox_resp = nullptr; size_t inbox_cap = 0;
-  uint32_t *seg_off = nullptr, *m_dev = nullptr, *done_ctr = nullptr, *error = nullptr;
+  uint32_t* error = nullptr;       // device flag: a bounded wait gave up (a peer died)
+  uint32_t* ticket = nullptr;      // [2] tile ticket / tiles done of the routing kernel
   // Routing scratch, preallocated (nothing is allocated or freed inside a step) and double-buffered by step parity: with a
-  // separate ingest stream the routing of step e+1 runs while step e is still being evaluated and un-routed.
+  // separate ingest stream the routing of step e+1 runs while step e is still being evaluated and collected.
   struct Route {
-    uint8_t* owner = nullptr;      // [cap]
-    uint32_t* tile_off = nullptr;  // [(cap / ROUTE_TILE + 1) * MAX_SHARDS]
+    unsigned long long* tile_agg = nullptr;  // [(cap / RT_THREADS + 1) * MAX_SHARDS]
     uint32_t* counts = nullptr;    // [MAX_SHARDS]
     uint32_t* perm = nullptr;      // [cap]
-    cudaEvent_t routed = nullptr;     // this parity's scatter has been issued and completed (ingest stream)
-    cudaEvent_t step_done = nullptr;  // this parity's un-route has completed (evaluation stream)
+    uint8_t* true_owner = nullptr; // [cap] (GLOBAL mode)
+    cudaEvent_t routed = nullptr;     // this parity's routing has been issued (ingest stream)
+    cudaEvent_t step_done = nullptr;  // this parity's collect has completed (evaluation stream)
     bool step_done_valid = false;
   } rt[2];
+  // GLOBAL behaviour (gub_p2p_enable_global): device queues + tick buffers
+  gub_gq *hits_q = nullptr, *updates_q = nullptr;
+  uint32_t gcap = 0;
+  gub_req *g_reqs = nullptr; gub_resp* g_resps = nullptr; gub_item *g_items = nullptr, *g_gather = nullptr;
+  uint32_t* g_count = nullptr;     // [4] device counters (hits drained, queries drained, items made, spare)
+  uint32_t* g_counts_all = nullptr;  // [MAX_SHARDS] device: items per rank
+  uint64_t seq = 0;
+  void* nccl = nullptr;            // ncclComm_t
+  uint64_t tick_bytes = 0;         // bytes all-gathered by the last tick
 };
 
 namespace {
@@ -1017,6 +1129,10 @@ gub::P2PView p2p_view(void* base, uint32_t W, uint32_t cap) {
   v.resp_flag = v.req_flag + 2 * W;
   return v;
 }
+
+// A bounded device-side wait gave up during an earlier step (a peer died or hung): surfaced here, at the next call, without
+// adding a host round trip to the step itself.  The flag is host-mapped... it is device memory; reading it costs a sync, so
+// callers poll it with gub_p2p_status() at their own cadence.
 }  // namespace
 
 extern "C" {
@@ -1026,20 +1142,24 @@ void gub_p2p_destroy(gub_p2p* p) {
   cudaSetDevice(p->t->device);
   cudaDeviceSynchronize();
   for (uint32_t r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
-  void* ptrs[] = {p->block, p->inbox, p->inbox_resp, p->seg_off, p->m_dev, p->done_ctr, p->error};
+  void* ptrs[] = {p->block, p->error, p->ticket, p->g_reqs, p->g_resps, p->g_items, p->g_gather, p->g_count, p->g_counts_all};
   for (void* q : ptrs) if (q) cudaFree(q);
   for (auto& r : p->rt) {
-    void* rp[] = {r.owner, r.tile_off, r.counts, r.perm};
+    void* rp[] = {r.tile_agg, r.counts, r.perm, r.true_owner};
     for (void* q : rp) if (q) cudaFree(q);
     if (r.routed) cudaEventDestroy(r.routed);
     if (r.step_done) cudaEventDestroy(r.step_done);
   }
+  if (p->hits_q) gub_gq_destroy(p->hits_q);
+  if (p->updates_q) gub_gq_destroy(p->updates_q);
+  gub_nccl_comm_destroy_(p->nccl);
   delete p;
 }
 
 int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t cap, gub_p2p** out) {
   const uint32_t world = ring ? (uint32_t)gub_ring_size(ring) : 0;
-  if (!t || !out || world == 0 || world > (uint32_t)gub::MAX_SHARDS || rank >= world || cap == 0) return fail("gub_p2p_create: bad argument");
+  if (!t || !out || world == 0 || world > (uint32_t)gub::MAX_SHARDS || rank >= world || cap == 0 || cap >= (1u << 24))
+    return fail("gub_p2p_create: bad argument");
   CK(cudaSetDevice(t->device));
   {
     std::lock_guard<std::mutex> lk(t->mu);
@@ -1050,23 +1170,21 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t c
   p->block_bytes = p2p_req_bytes(world, cap) + p2p_resp_bytes(world, cap) + (size_t)4 * world * 8;
   cudaError_t e = cudaMalloc(&p->block, p->block_bytes);
   if (e == cudaSuccess) e = cudaMemset(p->block, 0, p->block_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&p->seg_off, (gub::MAX_SHARDS + 1) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&p->m_dev, 4);
-  if (e == cudaSuccess) e = cudaMalloc(&p->done_ctr, 8);
   if (e == cudaSuccess) e = cudaMalloc(&p->error, 4);
-  if (e == cudaSuccess) e = cudaMemset(p->done_ctr, 0, 8);
   if (e == cudaSuccess) e = cudaMemset(p->error, 0, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&p->ticket, 8);
+  if (e == cudaSuccess) e = cudaMemset(p->ticket, 0, 8);
+  const size_t agg = ((size_t)cap / gub::RT_THREADS + 1) * gub::MAX_SHARDS;
   for (auto& r : p->rt) {
-    if (e == cudaSuccess) e = cudaMalloc(&r.owner, cap);
-    if (e == cudaSuccess) e = cudaMalloc(&r.tile_off, ((size_t)cap / gub::ROUTE_TILE + 1) * gub::MAX_SHARDS * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&r.tile_agg, agg * 8);
+    if (e == cudaSuccess) e = cudaMemset(r.tile_agg, 0, agg * 8);
     if (e == cudaSuccess) e = cudaMalloc(&r.counts, gub::MAX_SHARDS * 4);
+    if (e == cudaSuccess) e = cudaMemset(r.counts, 0, gub::MAX_SHARDS * 4);
     if (e == cudaSuccess) e = cudaMalloc(&r.perm, (size_t)cap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&r.true_owner, (size_t)cap);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.routed, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.step_done, cudaEventDisableTiming);
   }
-  p->inbox_cap = (size_t)world * cap;  // worst case every shard sends us its whole batch
-  if (e == cudaSuccess) e = cudaMalloc(&p->inbox, p->inbox_cap * sizeof(gub_req));
-  if (e == cudaSuccess) e = cudaMalloc(&p->inbox_resp, p->inbox_cap * sizeof(gub_resp));
   if (e != cudaSuccess) { gub_p2p_destroy(p); return fail(std::string("gub_p2p_create: ") + cudaGetErrorString(e)); }
   for (uint32_t r = 0; r < world; r++) p->views[r] = p2p_view(p->block, world, cap);  // until connected: everything loops back
   CK(cudaDeviceSynchronize());
@@ -1100,15 +1218,81 @@ int gub_p2p_connect(gub_p2p* p, const void* handles) {
   return 0;
 }
 
+// All shards in this process (the reference daemon is one process: daemon.go:73): the mailboxes are shared by pointer, and
+// shards on different devices get peer access to each other's memory enabled here.
 int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers) {
   if (!p || !peers) return fail("gub_p2p_connect_local: null argument");
+  CK(cudaSetDevice(p->t->device));
   for (uint32_t r = 0; r < p->world; r++) {
     if (!peers[r] || peers[r]->world != p->world || peers[r]->cap != p->cap) return fail("gub_p2p_connect_local: mismatched peer");
+    const int dev = peers[r]->t->device;
+    if (dev != p->t->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, p->t->device, dev));
+      if (!can) return fail("gub_p2p_connect_local: device " + std::to_string(p->t->device) + " cannot access device " + std::to_string(dev));
+      cudaError_t e = cudaDeviceEnablePeerAccess(dev, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+    }
     p->views[r] = p2p_view(peers[r]->block, p->world, p->cap);
   }
   p->connected = true;
   return 0;
 }
+
+int gub_p2p_status(gub_p2p* p, int* error_out) {
+  if (!p || !error_out) return fail("gub_p2p_status: null argument");
+  CK(cudaSetDevice(p->t->device));
+  uint32_t e1 = 0, e2 = 0;
+  CK(cudaMemcpy(&e1, p->error, 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&e2, &p->t->ctl->error, 4, cudaMemcpyDeviceToHost));
+  *error_out = (int)(e1 | e2);
+  if (e1 | e2) return fail("gub_p2p: a bounded device-side wait gave up (peer flag / grid barrier): a shard of the ring is not answering");
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+void p2p_args(gub_p2p* p, gub::P2PArgs& A) {
+  for (uint32_t r = 0; r < p->world; r++) A.peers[r] = p->views[r];
+  A.world = p->world; A.rank = p->rank; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = nullptr; A.error = p->error;
+}
+
+// The three launches of a step.  d_n (optional): the ingest batch's size lives on the device (<= n).  self_global >= 0: GLOBAL
+// requests this shard does not own are answered here (and their true owners recorded for the hits queue).
+int p2p_route(gub_p2p* p, gub_p2p::Route* rt, const gub::P2PArgs& A, const gub_req* d_reqs, uint32_t n, const uint32_t* d_n, int self_global, cudaStream_t si) {
+  gub_table* t = p->t;
+  gub::RouteArgs R;
+  R.P = A; R.reqs = d_reqs; R.n = n; R.n_dev = d_n; R.pts = t->d_ring_pts; R.pt_peer = t->d_ring_peers; R.lut = t->d_ring_lut; R.npts = t->ring_npts;
+  R.self_global = self_global; R.true_owner = self_global >= 0 ? rt->true_owner : nullptr; R.tile_agg = rt->tile_agg; R.counts = rt->counts; R.perm = rt->perm;
+  R.ticket = p->ticket;
+  const uint32_t tiles = std::max<uint32_t>(1u, (n + gub::RT_THREADS - 1) / gub::RT_THREADS);
+  gub::k_p2p_route<<<tiles, gub::RT_THREADS, 0, si>>>(R);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int p2p_evaluate(gub_p2p* p, const gub::P2PArgs& A, const gub_clock* clk, cudaStream_t st) {
+  gub_table* t = p->t;
+  gub::FArgs F;
+  fused_base_args(t, clk, F);
+  const uint32_t par = p->epoch & 1u;
+  for (uint32_t s = 0; s < p->world; s++) {
+    F.seg[s].reqs = A.peers[p->rank].req_mb + ((size_t)par * p->world + s) * p->cap;         // what source s stored into our mailbox
+    F.seg[s].flag = &A.peers[p->rank].req_flag[(size_t)par * p->world + s];
+    F.seg[s].out = A.peers[s].resp_mb + ((size_t)par * p->world + p->rank) * p->cap;         // NVLink stores into source s's response mailbox
+    F.seg[s].n = p->cap;
+    F.resp_flag[s] = &A.peers[s].resp_flag[(size_t)par * p->world + p->rank];
+  }
+  F.nseg = p->world; F.n_resp_flags = p->world; F.flag_epoch = p->epoch;
+  return launch_fused(t, F, 0, st);
+}
+
+}  // namespace
+
+extern "C" {
 
 int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream, void* stream) {
   if (!p || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
@@ -1116,53 +1300,247 @@ int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_
   const gub_ring* ring = p->ring;
   if (p->t->ring_cached != ring || p->t->ring_version != gub_ring_version_(ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
   gub_table* t = p->t;
+  if (!t->fused) return fail("gub_p2p_step: needs the fused batch kernel (GUB_FUSED=0 is a single-GPU measurement switch)");
   cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)ingest_stream;
   const bool two = si != st;
-  uint32_t ntiles = 0;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  p->epoch++;
+  gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
   gub::P2PArgs A;
-  gub_p2p::Route* rt = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(t->mu);
-    CK(cudaSetDevice(t->device));
-    p->epoch++;
-    rt = &p->rt[p->epoch & 1u];
-    for (uint32_t r = 0; r < p->world; r++) A.peers[r] = p->views[r];
-    A.world = p->world; A.rank = p->rank; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = p->done_ctr; A.error = p->error;
-    // ---- ingest stream: partition by owner and store the records into the owners' mailboxes.  This parity's scratch and
-    // mailbox halves were last used two steps ago; that step's un-route (on the evaluation stream) must have finished, which
-    // also means every peer has drained what we sent it then.
-    if (two && rt->step_done_valid) CK(cudaStreamWaitEvent(si, rt->step_done, 0));
-    if (n) {
-      ntiles = (uint32_t)((n + gub::ROUTE_TILE - 1) / gub::ROUTE_TILE);
-      gub::k_route_count<<<ntiles, 256, 0, si>>>(d_reqs, (uint32_t)n, t->d_ring_pts, t->d_ring_peers, t->ring_npts, p->world, rt->owner,
-                                                rt->tile_off, ntiles, -1, nullptr);
-      gub::k_route_scan<<<1, 1024, 0, si>>>(rt->tile_off, p->world * ntiles, p->world, ntiles, rt->counts);
-      gub::k_p2p_scatter<<<ntiles, 256, 0, si>>>(A, d_reqs, (uint32_t)n, rt->owner, rt->tile_off, ntiles, rt->counts, rt->perm);
-    } else {
-      gub::k_p2p_publish_empty<<<1, 32, 0, si>>>(A);
-    }
-    if (two) CK(cudaEventRecord(rt->routed, si));
-    // ---- evaluation stream: the gather synchronises with every source (ourselves included) through the mailbox flags
-    gub::k_p2p_gather<<<148, 256, 0, st>>>(A, p->inbox, p->seg_off, p->m_dev);
-    CK(cudaGetLastError());
+  p2p_args(p, A);
+  // ---- ingest stream: partition by owner and store the records into the owners' mailboxes.  This parity's scratch and
+  // mailbox halves were last used two steps ago; that step's collect (on the evaluation stream) must have finished, which
+  // also means every peer has drained what we sent it then.
+  if (two && rt->step_done_valid) CK(cudaStreamWaitEvent(si, rt->step_done, 0));
+  const int self_global = p->hits_q ? (int)p->rank : -1;
+  if (p2p_route(p, rt, A, d_reqs, (uint32_t)n, nullptr, self_global, si)) return -1;
+  if (p->hits_q && n) {  // a non-owner queues the hits of its GLOBAL requests (gubernator.go:402-404, global.go:74-78)
+    if (gq_accumulate(p->hits_q, d_reqs, n, nullptr, rt->true_owner, p->rank, p->seq, si)) return -1;
   }
-  // How many records we own is only known on the device (p->m_dev): the evaluation launches are sized for what a shard may
-  // receive at most and trim themselves, so the step needs no host round trip at all.
-  if (gub_submit_device_n(t, p->inbox, (size_t)p->world * p->cap, p->m_dev, clk, p->inbox_resp, stream)) return -1;
-  {
-    std::lock_guard<std::mutex> lk(t->mu);
-    gub::k_p2p_push_resp<<<148, 256, 0, st>>>(A, p->inbox_resp, p->seg_off);
-    if (two) CK(cudaStreamWaitEvent(st, rt->routed, 0));  // the un-route reads this parity's offsets and permutation
-    if (n) gub::k_p2p_unroute<<<148, 256, 0, st>>>(A, rt->tile_off, ntiles, rt->perm, (uint32_t)n, d_out);
-    else gub::k_p2p_wait_resp_only<<<1, 32, 0, st>>>(A);
-    if (two) { CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true; }
-    CK(cudaGetLastError());
+  if (two) CK(cudaEventRecord(rt->routed, si));
+  // ---- evaluation stream: the batch kernel synchronises with every source (ourselves included) through the mailbox flags,
+  // evaluates straight out of the mailboxes and stores the responses into the sources' response mailboxes
+  if (order_after_last(t, st)) return -1;
+  if (p2p_evaluate(p, A, clk, st)) return -1;
+  t->last_stream = st; t->last_pending = true;
+  if (p->updates_q) {  // GLOBAL requests just evaluated as owner (gubernator.go:604-606, global.go:80-84)
+    if (gq_accumulate_segments(p, A, st)) return -1;
   }
+  if (two) CK(cudaStreamWaitEvent(st, rt->routed, 0));  // the collect reads this parity's permutation
+  gub::k_p2p_collect<<<std::max<unsigned>(1u, std::min<unsigned>(148u, (unsigned)((n + 255) / 256))), 256, 0, st>>>(A, rt->perm, (uint32_t)n, nullptr, d_out);
+  if (two) { CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true; }
+  CK(cudaGetLastError());
+  p->seq += (uint64_t)1 << 32;
   return 0;
 }
 
 int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream) {
   return gub_p2p_step_streams(p, d_reqs, n, clk, d_out, stream, stream);
+}
+
+}  // extern "C"
+
+
+// ---- GLOBAL behaviour behind the C ABI: queues fed by the step, and the sync tick (global.go:91-283) with NCCL -----------------
+namespace {
+
+int gq_accumulate_segments(gub_p2p* p, const gub::P2PArgs& A, cudaStream_t st) {
+  gub_gq* g = p->updates_q;
+  const size_t total = (size_t)p->world * p->cap;
+  if (gq_reserve(g, total, st)) return -1;
+  gub::GqSegs G;
+  const uint32_t par = p->epoch & 1u;
+  for (uint32_t s = 0; s < p->world; s++) {
+    G.reqs[s] = A.peers[p->rank].req_mb + ((size_t)par * p->world + s) * p->cap;
+    G.flag[s] = &A.peers[p->rank].req_flag[(size_t)par * p->world + s];
+  }
+  G.nseg = p->world; G.cap = p->cap;
+  gub::k_gq_claim_segs<<<148, 256, 0, st>>>(g->q, G, (unsigned long long)p->seq, g->slot_of);
+  gub::k_gq_fill_segs<<<148, 256, 0, st>>>(g->q, G, (unsigned long long)p->seq, g->slot_of);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// NCCL is loaded at run time (libnccl.so.2, the one torch bundles when the host process is Python): a single-GPU deployment
+// needs no NCCL at all.  Minimal prototypes of nccl.h (2.27): ncclResult_t is an int enum, ncclComm_t an opaque pointer.
+struct Id128 { char b[128]; };
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.ok) return 0;
+  const char* names[] = {getenv("GUB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    if (!nm) continue;
+    g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return fail("NCCL not found (dlopen libnccl.so.2): GLOBAL sync across GPUs needs it");
+#define SYM(field, name)                                                              \
+  *reinterpret_cast<void**>(&g_nccl.field) = dlsym(g_nccl.h, name);                   \
+  if (!g_nccl.field) return fail(std::string("NCCL symbol missing: ") + name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllGather, "ncclAllGather");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.ok = true;
+  return 0;
+}
+#define NCK(call)                                                                                                  \
+  do {                                                                                                             \
+    int r__ = (call);                                                                                              \
+    if (r__ != 0) return fail(std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error")); \
+  } while (0)
+}  // namespace
+
+extern "C" {
+
+void gub_nccl_comm_destroy_(void* comm) {
+  if (comm && g_nccl.ok) g_nccl.CommDestroy(comm);
+}
+
+/* ncclGetUniqueId: 128 bytes the host application hands to every rank (its own channel: the Go daemon's peer discovery, torch.distributed, a file) */
+int gub_nccl_unique_id(void* out128) {
+  if (!out128) return fail("gub_nccl_unique_id: null argument");
+  if (nccl_load()) return -1;
+  NCK(g_nccl.GetUniqueId(out128));
+  return 0;
+}
+
+/* One communicator per shard (rank = the shard's index in the ring).  Collective across the ring's processes. */
+int gub_p2p_nccl_init(gub_p2p* p, const void* id128) {
+  if (!p || !id128) return fail("gub_p2p_nccl_init: null argument");
+  if (nccl_load()) return -1;
+  CK(cudaSetDevice(p->t->device));
+  Id128 id;
+  std::memcpy(&id, id128, sizeof id);
+  NCK(g_nccl.CommInitRank(&p->nccl, (int)p->world, id, (int)p->rank));
+  return 0;
+}
+
+/* All shards in one process: the communicators are created inside one NCCL group. */
+int gub_p2p_nccl_init_local(gub_p2p* const* ps, uint32_t world) {
+  if (!ps || world == 0) return fail("gub_p2p_nccl_init_local: bad argument");
+  if (nccl_load()) return -1;
+  Id128 id;
+  NCK(g_nccl.GetUniqueId(&id));
+  NCK(g_nccl.GroupStart());
+  for (uint32_t r = 0; r < world; r++) {
+    CK(cudaSetDevice(ps[r]->t->device));
+    NCK(g_nccl.CommInitRank(&ps[r]->nccl, (int)world, id, (int)ps[r]->rank));
+  }
+  NCK(g_nccl.GroupEnd());
+  return 0;
+}
+
+/* Turns GLOBAL handling on for this shard's steps: GLOBAL requests it does not own are answered from the local replica
+ * (gubernator.go:257-269,408-411) and their hits queued (global.go:74-111); GLOBAL requests it evaluates as owner are queued for
+ * the broadcast (global.go:80-84,201).  capacity = most distinct GLOBAL keys per sync window (drops are counted in gq_dropped). */
+int gub_p2p_enable_global(gub_p2p* p, uint32_t capacity) {
+  if (!p || capacity < 64) return fail("gub_p2p_enable_global: bad argument");
+  if (p->hits_q) return 0;
+  CK(cudaSetDevice(p->t->device));
+  if (gub_gq_create(p->t->device, capacity, 0, &p->hits_q)) return -1;
+  if (gub_gq_create(p->t->device, capacity, 1, &p->updates_q)) return -1;
+  p->hits_q->q.dropped = p->t->counters + gub::C_GQ_DROPPED;
+  p->updates_q->q.dropped = p->t->counters + gub::C_GQ_DROPPED;
+  p->gcap = std::min<uint32_t>(next_pow2(capacity), p->cap);
+  CK(cudaMalloc(&p->g_reqs, (size_t)p->gcap * sizeof(gub_req)));
+  CK(cudaMalloc(&p->g_resps, (size_t)p->gcap * sizeof(gub_resp)));
+  CK(cudaMalloc(&p->g_items, (size_t)p->gcap * sizeof(gub_item)));
+  CK(cudaMalloc(&p->g_gather, (size_t)p->gcap * p->world * sizeof(gub_item)));
+  CK(cudaMalloc(&p->g_count, 16));
+  CK(cudaMemset(p->g_count, 0, 16));
+  CK(cudaMalloc(&p->g_counts_all, gub::MAX_SHARDS * 4));
+  if (gq_reserve(p->updates_q, (size_t)p->world * p->cap, 0)) return -1;
+  if (gq_reserve(p->hits_q, p->cap, 0)) return -1;
+  return 0;
+}
+
+/* One GLOBAL sync: sendHits (global.go:144-190), then broadcastPeers (global.go:234-283) as an NCCL all-gather of the owners'
+ * UpdatePeerGlobal items, installed by every other shard (UpdatePeerGlobals, gubernator.go:425-459).  Collective: every shard
+ * of the ring calls it the same number of times, interleaved the same way with its steps.  now_ms = MillisecondNow() of the
+ * receivers (CreatedAt / UpdatedAt of the installed items).  Everything is enqueued on `stream`; the one host round trip is the
+ * per-shard item counts (a tick runs every GlobalSyncWait = 500 ms, not per batch).
+ * stats (optional, 4 x uint64): hit records sent to owners, update items broadcast by this shard, items installed here, bytes gathered. */
+int gub_global_tick(gub_p2p* p, const gub_clock* clk, int64_t now_ms, void* stream, uint64_t* stats) {
+  if (!p || !clk) return fail("gub_global_tick: null argument");
+  if (!p->hits_q) return fail("gub_global_tick: gub_p2p_enable_global has not been called");
+  if (p->world > 1 && !p->nccl) return fail("gub_global_tick: no NCCL communicator (gub_p2p_nccl_init)");
+  gub_table* t = p->t;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t h_counts[4] = {0, 0, 0, 0};
+  {
+    std::lock_guard<std::mutex> lk(t->mu);
+    CK(cudaSetDevice(t->device));
+    // 1. the window's aggregated hits -> their owners, over the same NVLink mailboxes as a step (plain routing: these records go to
+    //    the owner), evaluated there with DRAIN_OVER_LIMIT as owner (gubernator.go:510-512); the responses are dropped like sendHits does
+    CK(cudaMemsetAsync(p->g_count, 0, 16, st));
+    gub::k_gq_drain<<<148, 256, 0, st>>>(p->hits_q->q, p->g_reqs, p->gcap, p->g_count + 0, 0u);
+    p->epoch++;
+    gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
+    if (rt->step_done_valid) CK(cudaStreamWaitEvent(st, rt->step_done, 0));
+    gub::P2PArgs A;
+    p2p_args(p, A);
+    if (p2p_route(p, rt, A, p->g_reqs, p->gcap, p->g_count + 0, -1, st)) return -1;
+    if (order_after_last(t, st)) return -1;
+    if (p2p_evaluate(p, A, clk, st)) return -1;
+    t->last_stream = st; t->last_pending = true;
+    if (gq_accumulate_segments(p, A, st)) return -1;
+    gub::k_p2p_collect<<<64, 256, 0, st>>>(A, rt->perm, p->gcap, p->g_count + 0, p->g_resps);
+    CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true;
+    p->seq += (uint64_t)1 << 32;
+    // 2. owners re-read every key touched by GLOBAL traffic with Hits = 0 (global.go:243-245) and build the UpdatePeerGlobal items
+    gub::k_gq_drain<<<148, 256, 0, st>>>(p->updates_q->q, p->g_reqs, p->gcap, p->g_count + 1, 1u);
+    gub::FArgs F;
+    fused_base_args(t, clk, F);
+    F.seg[0].reqs = p->g_reqs; F.seg[0].out = p->g_resps; F.seg[0].n = p->gcap; F.seg[0].n_dev = p->g_count + 1; F.nseg = 1;
+    if (launch_fused(t, F, 0, st)) return -1;
+    gub::k_make_updates<<<(p->gcap + 255) / 256, 256, 0, st>>>(p->g_reqs, p->g_resps, p->gcap, p->g_count + 1, p->g_items, p->g_count + 2);
+    CK(cudaGetLastError());
+    // 3. all-gather: counts first (the host needs them to size the item gather), then the items, padded to the largest count
+    std::vector<uint32_t> all(p->world, 0);
+    if (p->world > 1) {
+      NCK(g_nccl.AllGather(p->g_count + 2, p->g_counts_all, 1, /* ncclUint32 */ 3, p->nccl, st));
+      CK(cudaMemcpyAsync(all.data(), p->g_counts_all, p->world * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(h_counts, p->g_count, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint32_t pad = 0;
+    for (uint32_t r = 0; r < p->world; r++) pad = std::max(pad, std::min(all[r], p->gcap));
+    uint64_t installed = 0;
+    p->tick_bytes = 0;
+    if (p->world > 1 && pad) {
+      NCK(g_nccl.AllGather(p->g_items, p->g_gather, (size_t)pad * sizeof(gub_item), /* ncclUint8 */ 1, p->nccl, st));
+      p->tick_bytes = (uint64_t)pad * sizeof(gub_item) * p->world;
+      for (uint32_t r = 0; r < p->world; r++) {
+        const uint32_t k = std::min(all[r], p->gcap);
+        if (r == p->rank || !k) continue;  // "Exclude ourselves from the update" (global.go:263-265)
+        k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters);
+        installed += k;
+      }
+      CK(cudaGetLastError());
+    }
+    if (stats) { stats[0] = std::min(h_counts[0], p->gcap); stats[1] = std::min(h_counts[2], p->gcap); stats[2] = installed; stats[3] = p->tick_bytes; }
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -68,7 +68,7 @@ struct OvfItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags, _pad; };  // 
 
 struct FCtl {
   uint32_t bar_cnt, bar_gen;            // grid barrier
-  uint32_t ord_bump;                    // allocator of `ordbuf` (member lists of non-uniform groups), reset every round
+  uint32_t _spare;
   uint32_t done_ctr;                    // CTAs that have stored all their responses (multi-GPU: the last one publishes the flags)
   uint32_t error;                       // a flag wait timed out (a peer died)
   uint32_t ovf_count;                   // pending items in `ovf`
@@ -83,9 +83,8 @@ struct FArgs {
   uint32_t flag_epoch;                  // epoch the segments' flags must show
   GEntry* aux;
   uint32_t* presence;                   // [FB_AUX_ENTRIES][FB_PRES_WORDS]
-  uint16_t* fragsize;                   // [FB_AUX_ENTRIES][FB_ROW]
-  uint32_t* gpos;                       // [FB_MAX_GRID * FB_THREADS] group entry of every request of the round
-  uint32_t* ordbuf;                     // [FB_MAX_GRID * FB_THREADS]
+  uint32_t* fragrow;                    // [FB_AUX_ENTRIES][FB_ROW] per tile: (offset of the fragment's members in the tile's list << 16) | fragment size
+  uint16_t* members;                    // [FB_MAX_GRID * FB_THREADS] per tile: the members of each of its fragments, contiguous, in index order
   FCtl* ctl;
   OvfItem* ovf;                         // [FB_OVF_CAP]
   unsigned long long* counters;
@@ -93,19 +92,25 @@ struct FArgs {
   unsigned long long* resp_flag[FB_MAX_SEGS];
   uint32_t n_resp_flags;
   uint32_t sweep_chunk;                 // slots each CTA sweeps per round (0 = off)
+  unsigned long long* trace;            // optional [gridDim.x][FB_TRACE_MARKS]: %globaltimer of every CTA at the phase boundaries (diagnostic)
   gub_clock clk;
 };
+constexpr int FB_TRACE_MARKS = 12;
 
 // What the rarely taken, out-of-line parts of the kernel need of FArgs, kept in shared memory (a non-inlined function taking the
 // kernel's parameter struct by reference would force a 1 KB local copy of it).  Same member names as FArgs.
 struct FCtx {
   Slot* table;
   uint64_t capacity;
-  uint32_t* gpos;
+  GEntry* aux;
+  uint32_t* presence;
+  uint32_t* fragrow;
+  uint16_t* members;
   FCtl* ctl;
   OvfItem* ovf;
   unsigned long long* counters;
-  uint32_t nseg, sweep_chunk;
+  unsigned long long* trace;
+  uint32_t nseg, sweep_chunk, n_resp_flags, _pad;
   gub_clock clk;
 };
 
@@ -147,7 +152,19 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   return v;
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void spin_pause() { __nanosleep(20); }
+__device__ __forceinline__ void spin_pause() {}
+#endif
+
+#if defined(GUB_EMULATE)
+__device__ __forceinline__ void trace_mark(const FCtx&, int) {}
+#else
+__device__ __forceinline__ void trace_mark(const FCtx& A, int k) {
+  if (A.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    A.trace[(size_t)blockIdx.x * FB_TRACE_MARKS + k] = t;
+  }
+}
 #endif
 
 // Every CTA of the grid is resident (one per SM, cooperative launch), so a counter + generation barrier is safe.  The
@@ -173,16 +190,27 @@ __device__ __forceinline__ void grid_barrier(FCtl* ctl) {
 }
 
 // ---- shared memory of one CTA --------------------------------------------------------------------------------------
-struct FMixed {                      // scratch of the segment walk (non-uniform groups)
-  uint32_t np, covered, nseg, serial;
-  uint32_t wsum[FB_WARPS];
-  uint16_t seg[FB_THREADS + 1];
-  Piece pieces[MAX_PIECES];
+// Scratch of one team (a warp, or the whole CTA) evaluating a non-uniform group: the tiles holding its members, the starts of
+// its runs of identical requests (segments) and the bucket state entering each segment.
+template <int TILES, int SEGS>
+struct MixScratch {
+  uint32_t nseg, ntile;
+  uint32_t cum[TILES + 1];       // members in the tiles before slot j
+  uint16_t tile[TILES], off[TILES];
+  uint32_t seg[SEGS + 1];        // first member (rank within the group) of every segment, ascending; seg[nseg] = members
+  uint8_t kind[SEGS];            // 1: the segment's requests were applied one by one by the planner (no closed form)
+  Bucket state[SEGS];            // bucket entering the segment
 };
+constexpr int MIX_WARP_TILES = 32, MIX_WARP_SEGS = 12, MIX_CTA_SEGS = 96;
+constexpr uint32_t MIX_WARP_MAX = 32;  // groups of up to this many members are taken by one warp each, larger ones by the CTA
+using MixWarp = MixScratch<MIX_WARP_TILES, MIX_WARP_SEGS>;
+using MixCta = MixScratch<FB_MAX_GRID, MIX_CTA_SEGS>;
+
+struct TileInfo { uint32_t seg, off, n; };
 
 struct __align__(128) FSmem {
-  gub_req req[FB_THREADS];               // the tile (TMA destination); later: staging of a non-uniform group's requests
-  ulonglong2 snap[FB_THREADS][4];        // per fragment: the slot as found; later: staging of a non-uniform group's responses
+  gub_req req[FB_THREADS];               // the tile (TMA destination); later: scratch of the CTA-wide evaluation of large non-uniform groups
+  ulonglong2 snap[FB_THREADS][4];        // per fragment: the slot as found; later: per-warp scratch of the evaluation of small non-uniform groups
   unsigned long long key[FB_HT];         // tile-local key table
   uint8_t wcnt[FB_HT][FB_WARPS];         // [key slot][warp]: members of the key among the warp's lanes
   long long fslot[FB_THREADS];           // per fragment: slot index when found, else first reusable slot of the window (or -1)
@@ -196,10 +224,14 @@ struct __align__(128) FSmem {
   uint16_t sp[FB_THREADS];               // per request: key slot
   uint16_t local[FB_THREADS];            // per request: rank within the fragment
   uint16_t fin[FB_THREADS];              // fragments whose group this CTA finishes
+  uint32_t fdone[FB_THREADS];            // per fragment: members that have answered
+  uint8_t fready[FB_THREADS];            // per fragment: its first member has published the slot snapshot and the base rank
   uint8_t ffound[FB_THREADS];            // per fragment: key is in the table
   uint8_t fmixed[FB_THREADS];            // per fragment: its members differ (or can never settle): the group takes the segment walk
-  FMixed mx;
   FCtx cx;
+  uint16_t foff[FB_THREADS];             // per fragment: offset of its members in the tile's member list
+  uint32_t moff, wq, last, parity;
+  TileInfo ti;                           // this CTA's tile of the current round
   // the batch's segments
   const gub_req* seg_reqs[FB_MAX_SEGS];
   gub_resp* seg_out[FB_MAX_SEGS];
@@ -211,7 +243,6 @@ struct __align__(128) FSmem {
   MBar mbar;
 };
 
-struct TileInfo { uint32_t seg, off, n; };
 __device__ __forceinline__ TileInfo tile_info(const FSmem& S, uint32_t nseg, uint32_t tl) {
   TileInfo ti;
   uint32_t s = 0;
@@ -249,13 +280,18 @@ __device__ __forceinline__ gub_req global_req(const gub_req* p) {  // written ea
 }
 
 // ---- the batch-wide group table ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gentry_join(const FArgs& A, uint64_t key, bool* claimed) {
+__device__ __forceinline__ uint32_t gentry_join(const FCtx& A, uint64_t key, bool look_first, bool* claimed) {
   uint32_t pos = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (FB_AUX_ENTRIES - 1);
   *claimed = false;
 #pragma unroll 1
   for (;;) {
-    const unsigned long long old = atomicCAS(&A.aux[pos].key, 0ull, (unsigned long long)key);
-    if (old == 0ull) { *claimed = true; break; }
+    // a key with several members in this tile is probably in many tiles: 148 CTAs doing a CAS on one address serialise in L2,
+    // so look first (reads of one address do not) and only CAS what looks free
+    unsigned long long old = look_first ? __ldcg(&A.aux[pos].key) : 0ull;
+    if (old == 0ull) {
+      old = atomicCAS(&A.aux[pos].key, 0ull, (unsigned long long)key);
+      if (old == 0ull) { *claimed = true; break; }
+    }
     if (old == key) break;
     pos = (pos + 1) & (FB_AUX_ENTRIES - 1);
   }
@@ -268,10 +304,8 @@ __device__ __forceinline__ void gentry_clear(GEntry* e) {
 }
 
 // Sum of the fragment sizes of the tiles before `tt` that hold members of group `pos`.
-__device__ __forceinline__ uint32_t fragment_base2(const FArgs& A, uint32_t pos, uint32_t tt) {
-  const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
-  const uint16_t* row = A.fragsize + (size_t)pos * FB_ROW;
-  const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
+__device__ __forceinline__ uint32_t fragment_base2(const FCtx& A, uint32_t pos, uint32_t tt, const uint4& p0, const uint4& p1) {
+  const uint32_t* row = A.fragrow + (size_t)pos * FB_ROW;
   uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
   const uint32_t last = tt >> 5, keep = (1u << (tt & 31)) - 1u;
   uint32_t base = 0;
@@ -280,66 +314,27 @@ __device__ __forceinline__ uint32_t fragment_base2(const FArgs& A, uint32_t pos,
     uint32_t x = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u);
     if (!x) continue;
     if (__popc(x) <= 4) {
-      while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)__ldcg(row + w * 32 + k); }
-    } else {  // all 32 sizes of the word's tiles (64 bytes), masked
+      while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += __ldcg(row + w * 32 + k) & 0xFFFFu; }
+    } else {  // the entries of all 32 tiles of the word (128 bytes), masked
       const uint4* r4 = reinterpret_cast<const uint4*>(row + w * 32);
-      const uint4 v0 = __ldcg(r4), v1 = __ldcg(r4 + 1), v2 = __ldcg(r4 + 2), v3 = __ldcg(r4 + 3);
-      const uint32_t v[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const uint32_t m = (x >> (2 * k)) & 3u;
-        base += ((m & 1u) ? (v[k] & 0xFFFFu) : 0u) + ((m & 2u) ? (v[k] >> 16) : 0u);
+      for (int h = 0; h < 2; h++) {  // four 16-byte loads in flight at a time
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = __ldcg(r4 + 4 * h + k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint32_t m = (x >> (4 * (4 * h + k))) & 0xFu;
+          base += ((m & 1u) ? (v[k].x & 0xFFFFu) : 0u) + ((m & 2u) ? (v[k].y & 0xFFFFu) : 0u) + ((m & 4u) ? (v[k].z & 0xFFFFu) : 0u) +
+                  ((m & 8u) ? (v[k].w & 0xFFFFu) : 0u);
+        }
       }
     }
   }
   return base;
 }
 
-// ---- warp-cooperative table probe ---------------------------------------------------------------------------------------
-// Fragments [0, F) of the tile are looked up four lanes at a time: lane q of a quad loads bytes [16q, 16q+16) of the probed
-// slot (one coalesced 64-byte transaction per quad, eight slots per warp instruction), lane 0's words (key, tag|flags) are
-// broadcast inside the quad, and the quads of a warp probe linearly until every one of them has hit, or met an empty slot.
-__device__ __forceinline__ void probe_fragments(const FArgs& A, FSmem& S, uint32_t F) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane & 3, quad0 = lane & ~3u;
-#pragma unroll 1
-  for (uint32_t j0 = warp * 8; j0 < F; j0 += FB_WARPS * 8) {
-    const uint32_t j = j0 + (lane >> 2);
-    bool done = j >= F;
-    uint64_t key = 0, tag = 0, idx = 0;
-    long long reuse = -1;
-    bool found = false;
-    if (!done) {
-      const gub_req* lr = &S.req[S.flead[j]];
-      key = remap_key(lr->key_xxh64); tag = lr->key_fnv1 >> 8;
-      idx = __umul64hi(key, A.capacity);
-    }
-#pragma unroll 1
-    for (int p = 0; p < MAX_PROBE; p++) {
-      ulonglong2 v = make_ulonglong2(0ull, 0ull);
-      if (!done) v = __ldcg(reinterpret_cast<const ulonglong2*>(A.table + idx) + q);
-      const unsigned long long w0 = __shfl_sync(0xFFFFFFFFu, v.x, quad0), w1 = __shfl_sync(0xFFFFFFFFu, v.y, quad0);
-      if (!done) {
-        if (w0 == key && (w1 >> 8) == tag) {
-          S.snap[j][q] = v;
-          found = true; done = true;
-        } else if (w0 == KEY_EMPTY) {
-          if (reuse < 0) reuse = (long long)idx;
-          done = true;
-        } else {
-          if (w0 == KEY_TOMB && reuse < 0) reuse = (long long)idx;
-          idx = (idx + 1 == A.capacity) ? 0 : idx + 1;
-        }
-      }
-      if (__all_sync(0xFFFFFFFFu, done)) break;
-    }
-    if (j < F && q == 0) {
-      S.fslot[j] = found ? (long long)idx : reuse;
-      S.ffound[j] = found ? 1 : 0;
-    }
-  }
-}
-
-__device__ __forceinline__ void cursor_from_snapshot(const FArgs& A, const FSmem& S, uint32_t f, uint64_t key, uint64_t tag, Cursor& c) {
+__device__ __forceinline__ void cursor_from_snapshot(const FCtx& A, const FSmem& S, uint32_t f, uint64_t key, uint64_t tag, Cursor& c) {
   c.home = __umul64hi(key, A.capacity);
   c.found = S.ffound[f] != 0;
   c.slot = S.fslot[f];
@@ -369,130 +364,190 @@ __device__ __forceinline__ void close_or_park(const Ctx& A, Cursor& cur, Tally& 
   }
 }
 
-// ---- groups whose requests differ: walked in index order, segment by segment ---------------------------------------------
-// ord[0..cnt) = round-local indices of the group's members in index order.  The group is taken in chunks of FB_THREADS members:
-// the chunk's requests are staged in shared memory, runs of identical requests (segments) are found in parallel, and then either
-// thread 0 plans every segment with plan_run() (closed forms) and all threads evaluate and store the responses, or — when the
-// chunk is mostly one-request segments, where planning buys nothing — thread 0 simply applies the chunk's requests one after
-// another.  The slot is opened once and written once.
-__device__ __noinline__ void mixed_walk(const FCtx& A, FSmem& S, const uint32_t* ord, uint32_t cnt, uint32_t round, Tally& t) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  gub_resp* stage = reinterpret_cast<gub_resp*>(&S.snap[0][0]);
-  Cursor cur;
-  bool open = false;
-  uint64_t ck = 0, ct = 0;
-#pragma unroll 1
-  for (uint32_t c0 = 0; c0 < cnt; c0 += FB_THREADS) {
-    const uint32_t m = min((uint32_t)FB_THREADS, cnt - c0);
-    __syncthreads();  // the staging areas are free again
-    uint32_t my_i = 0;
-    if (tid < m) {
-      my_i = __ldcg(ord + c0 + tid);
-      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(req_at(S, A.nseg, round, my_i));
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&S.req[tid]);
-      dst[0] = __ldcg(src); dst[1] = __ldcg(src + 1); dst[2] = __ldcg(src + 2); dst[3] = __ldcg(src + 3);
+// ---- groups whose requests differ ---------------------------------------------------------------------------------------------
+// A group's members, in index order, are its fragments in tile order; tile t keeps the members of each of its fragments
+// contiguous in members[t * 512 + off ..] (off and size are in the group's fragrow[t]).  The group is a sequence of SEGMENTS
+// (runs of identical requests).  A team — one warp for groups of up to 32 members, the whole CTA for larger ones — finds the
+// segment starts in parallel (each member compares its request with its predecessor's), one thread then folds the segments in
+// order (closed forms: O(1) per segment) keeping the bucket state ENTERING each, writes the final state back, and every member
+// evaluates run_to_rank(entering state, request, rank within the segment) by itself.  More segments than the scratch holds
+// (or segments whose requests can never settle) are applied one request at a time by the folding thread.
+template <int NT> struct TeamOps;
+template <> struct TeamOps<32> {
+  static __device__ __forceinline__ uint32_t tid() { return threadIdx.x & 31u; }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+template <> struct TeamOps<FB_THREADS> {
+  static __device__ __forceinline__ uint32_t tid() { return threadIdx.x; }
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+
+template <class SC>
+__device__ __forceinline__ uint32_t member_at(const FCtx& A, const SC& sc, uint32_t k) {  // round-local index of the group's k-th member
+  uint32_t lo = 0, hi = sc.ntile;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sc.cum[mid] <= k) lo = mid; else hi = mid; }
+  const uint32_t t = sc.tile[lo];
+  return t * FB_THREADS + (uint32_t)__ldcg(A.members + t * FB_THREADS + sc.off[lo] + (k - sc.cum[lo]));
+}
+
+template <int NT, class SC>
+__device__ __noinline__ void mixed_group(const FCtx& A, FSmem& S, SC& sc, uint32_t pos, uint32_t total, const uint32_t* bits /* FB_PRES_WORDS */,
+                                        uint32_t round, Tally& t) {
+  using T = TeamOps<NT>;
+  const uint32_t tid = T::tid();
+  constexpr uint32_t TILES = sizeof(sc.tile) / sizeof(sc.tile[0]), SEGS = sizeof(sc.kind);
+  // 1. the tiles that hold members, in order, with their member counts
+  if (tid == 0) { sc.nseg = 0; sc.ntile = 0; }
+  T::sync();
+  const uint32_t* row = A.fragrow + (size_t)pos * FB_ROW;
+  for (uint32_t b = tid; b < (uint32_t)FB_MAX_GRID; b += NT) {
+    if (!((bits[b >> 5] >> (b & 31)) & 1u)) continue;
+    uint32_t slot = __popc(bits[b >> 5] & ((1u << (b & 31)) - 1u));
+    for (uint32_t w = 0; w < (b >> 5); w++) slot += __popc(bits[w]);
+    if (slot < TILES) {
+      const uint32_t r = __ldcg(row + b);
+      sc.tile[slot] = (uint16_t)b; sc.off[slot] = (uint16_t)(r >> 16); sc.cum[slot + 1] = r & 0xFFFFu;
     }
-    __syncthreads();
-    // segment starts, in order
-    bool boundary = false;
-    if (tid < m) boundary = tid == 0 || !req_same(smem_req(&S.req[tid]), smem_req(&S.req[tid - 1]));
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, boundary);
-    if (lane == 0) S.mx.wsum[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, nseg = 0;
-#pragma unroll
-    for (int w = 0; w < FB_WARPS; w++) { const uint32_t c = S.mx.wsum[w]; nseg += c; before += ((uint32_t)w < warp) ? c : 0u; }
-    if (boundary) S.mx.seg[before + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)tid;
-    if (tid == 0) S.mx.seg[nseg] = (uint16_t)m;
-    __syncthreads();
-    const bool serial = nseg * 4 > m && m > 8;  // short segments: planning costs more than applying
-    if (serial) {
-      if (tid == 0) {
-#pragma unroll 1
-        for (uint32_t k = 0; k < m; k++) {
-          const gub_req rq = smem_req(&S.req[k]);
-          const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-          if (!open || key != ck || tag != ct) {
-            if (open) close_or_park(A, cur, t);
-            cursor_open(cur, A.table, A.capacity, key, tag);
-            open = true; ck = key; ct = tag;
-          }
-          Delta d = {0, 0, 0};
-          const gub_resp r = apply_one(cur.b, rq, A.clk, d);
-          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-          stage[k] = r;
-        }
-        atomicAdd(A.counters + C_SERIAL, 1ull);
+    atomicAdd(&sc.ntile, 1u);
+  }
+  T::sync();
+  if (tid == 0) {
+    sc.cum[0] = 0;
+    const uint32_t nt = min(sc.ntile, TILES);
+    sc.ntile = nt;
+    for (uint32_t j = 0; j < nt; j++) sc.cum[j + 1] += sc.cum[j];
+  }
+  T::sync();
+  // 2. segment starts: members whose request differs from their predecessor's
+  for (uint32_t k = tid; k < total; k += NT) {
+    bool boundary = k == 0;
+    if (!boundary) {
+      const gub_req a = global_req(req_at(S, A.nseg, round, member_at(A, sc, k))), b = global_req(req_at(S, A.nseg, round, member_at(A, sc, k - 1)));
+      boundary = !req_same(a, b);
+    }
+    if (boundary) { const uint32_t q = atomicAdd(&sc.nseg, 1u); if (q < SEGS) sc.seg[q] = k; }
+  }
+  T::sync();
+  const uint32_t nseg = sc.nseg;
+  // 3. one thread folds the segments in order
+  if (tid == 0) {
+    Cursor cur;
+    bool open = false;
+    uint64_t ck = 0, ct = 0;
+    if (nseg <= SEGS) {
+      for (uint32_t a = 1; a < nseg; a++) {  // the starts arrived in any order
+        const uint32_t v = sc.seg[a];
+        int b = (int)a - 1;
+        while (b >= 0 && sc.seg[b] > v) { sc.seg[b + 1] = sc.seg[b]; b--; }
+        sc.seg[b + 1] = v;
       }
-      __syncthreads();
-      if (tid < m) store_resp(resp_at(S, A.nseg, round, my_i), stage[tid]);
-      continue;
+      sc.seg[nseg] = total;
     }
+    const uint32_t steps = nseg <= SEGS ? nseg : 1u;
 #pragma unroll 1
-    for (uint32_t s = 0; s < nseg; s++) {
-      const uint32_t lo = S.mx.seg[s], hi = S.mx.seg[s + 1], len = hi - lo;
-      if (tid == 0) {
-        const gub_req rq = smem_req(&S.req[lo]);
+    for (uint32_t sgi = 0; sgi < steps; sgi++) {
+      const uint32_t lo = nseg <= SEGS ? sc.seg[sgi] : 0u, hi = nseg <= SEGS ? sc.seg[sgi + 1] : total;
+      gub_req rq = global_req(req_at(S, A.nseg, round, member_at(A, sc, lo)));
+      const bool closed_form = nseg <= SEGS && req_regular(rq);
+      if (nseg <= SEGS) sc.kind[sgi] = closed_form ? 0 : 1;
+#pragma unroll 1
+      for (uint32_t k = lo; k < hi; k++) {  // closed form: one pass for the whole segment; else one pass per request
+        uint32_t i_k = 0;
+        if (!closed_form) { i_k = member_at(A, sc, k); if (k > lo) rq = global_req(req_at(S, A.nseg, round, i_k)); }
         const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-        if (!open || key != ck || tag != ct) {
+        if (!open || key != ck || tag != ct) {  // (the key only changes when two keys share their XXH64)
           if (open) close_or_park(A, cur, t);
           cursor_open(cur, A.table, A.capacity, key, tag);
           open = true; ck = key; ct = tag;
         }
         Delta d = {0, 0, 0};
-        uint32_t np = 0;
-        const uint32_t covered = plan_run(cur.b, rq, len, A.clk, d, S.mx.pieces, MAX_PIECES, &np);
-        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-        // ranks the piece buffer could not hold (no regular regime, e.g. RESET_REMAINING flip-flops): applied one by one
-        for (uint32_t k = covered; k < len; k++) {
-          Delta d2 = {0, 0, 0};
-          stage[lo + k] = apply_one(cur.b, rq, A.clk, d2);
-          t.over += d2.over; t.hit += d2.hit; t.miss += d2.miss;
+        if (closed_form) {
+          sc.state[sgi] = cur.b;
+          run_to_rank(cur.b, rq, hi - lo - 1, A.clk, d);
+          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+          break;
         }
-        S.mx.np = np; S.mx.covered = covered;
+        const gub_resp r = apply_one(cur.b, rq, A.clk, d);
+        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+        store_resp(resp_at(S, A.nseg, round, i_k), r);
       }
-      __syncthreads();
-      const uint32_t np = S.mx.np, covered = S.mx.covered;
-      for (uint32_t k = tid; k < covered; k += FB_THREADS) {
-        uint32_t pi = 0;
-        while (pi + 1 < np && S.mx.pieces[pi + 1].start <= k) pi++;
-        stage[lo + k] = eval_piece(S.mx.pieces[pi], k);
-      }
-      __syncthreads();
     }
-    if (tid < m) store_resp(resp_at(S, A.nseg, round, my_i), stage[tid]);
+    if (nseg > SEGS) atomicAdd(A.counters + C_SERIAL, 1ull);
+    if (open) close_or_park(A, cur, t);
   }
-  if (tid == 0 && open) close_or_park(A, cur, t);
-  __syncthreads();
+  T::sync();
+  // 4. every member of a closed-form segment answers for itself
+  if (nseg <= SEGS) {
+    for (uint32_t k = tid; k < total; k += NT) {
+      uint32_t lo = 0, hi = nseg;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sc.seg[mid] <= k) lo = mid; else hi = mid; }
+      if (sc.kind[lo]) continue;
+      const uint32_t i_k = member_at(A, sc, k);
+      const gub_req rq = global_req(req_at(S, A.nseg, round, i_k));
+      Bucket b = sc.state[lo];
+      Delta d = {0, 0, 0};
+      store_resp(resp_at(S, A.nseg, round, i_k), run_to_rank(b, rq, k - sc.seg[lo], A.clk, d));
+    }
+  }
+  T::sync();
 }
 
-// Members of group `pos` in the tiles `bits` marks (round-local tile numbers), listed in index order into `ord`.
-// Returns the number listed (== the group's member count).
-__device__ __noinline__ uint32_t list_members(const FCtx& A, FSmem& S, uint32_t pos, const uint32_t bits[FB_PRES_WORDS], uint32_t round, uint32_t* ord) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t listed = 0;
-#pragma unroll 1
-  for (uint32_t w = 0; w < (uint32_t)FB_PRES_WORDS; w++) {
-    uint32_t x = bits[w];
-#pragma unroll 1
-    while (x) {
-      const uint32_t tt = w * 32 + (__ffs(x) - 1);
-      x &= x - 1;
-      const TileInfo ti = tile_info(S, A.nseg, round * gridDim.x + tt);
-      const bool mine = tid < ti.n && __ldcg(A.gpos + tt * FB_THREADS + tid) == pos;
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
-      __syncthreads();
-      if (lane == 0) S.mx.wsum[warp] = __popc(bal);
-      __syncthreads();
-      uint32_t before = 0, tot = 0;
+// The tiles of a group that is being finished: its presence bitmap, or just this tile.
+__device__ __forceinline__ void group_bits(const FCtx& A, uint32_t pos, bool spread, uint32_t bits[FB_PRES_WORDS]) {
 #pragma unroll
-      for (int k = 0; k < FB_WARPS; k++) { const uint32_t c = S.mx.wsum[k]; tot += c; before += ((uint32_t)k < warp) ? c : 0u; }
-      if (mine) __stcg(ord + listed + before + __popc(bal & ((1u << lane) - 1u)), tt * FB_THREADS + tid);
-      listed += tot;
-    }
+  for (int w = 0; w < FB_PRES_WORDS; w++) bits[w] = 0;
+  if (spread) {
+    const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
+    const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
+    bits[0] = p0.x; bits[1] = p0.y; bits[2] = p0.z; bits[3] = p0.w; bits[4] = p1.x; bits[5] = p1.y; bits[6] = p1.z; bits[7] = p1.w;
+  } else {
+    bits[blockIdx.x >> 5] = 1u << (blockIdx.x & 31);
+  }
+}
+__device__ __forceinline__ void group_release(const FCtx& A, uint32_t pos) {  // hands the entry and its bitmap back clean
+  ulonglong2* pz = reinterpret_cast<ulonglong2*>(A.presence + (size_t)pos * FB_PRES_WORDS);
+  __stcg(pz, make_ulonglong2(0ull, 0ull)); __stcg(pz + 1, make_ulonglong2(0ull, 0ull));
+  gentry_clear(&A.aux[pos]);
+}
+
+// All non-uniform groups this CTA finishes (S.fin, entries 0xFFFF are done): small ones are dealt to the warps, large ones
+// take the whole CTA one after another.
+__device__ __noinline__ void finish_mixed_groups(FSmem& S, uint32_t nfin, uint32_t round, Tally& t, uint32_t& dup, uint32_t& mixed_groups) {
+  const FCtx& A = S.cx;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) S.wq = 0;
+  __syncthreads();
+  static_assert(sizeof(MixWarp) * FB_WARPS <= sizeof(S.snap), "per-warp scratch lives in the snapshot area");
+  static_assert(sizeof(MixCta) <= sizeof(S.req), "CTA scratch lives in the tile area");
+  MixWarp& wsc = reinterpret_cast<MixWarp*>(&S.snap[0][0])[warp];
+  for (;;) {
+    uint32_t k = 0;
+    if (lane == 0) k = atomicAdd(&S.wq, 1u);
+    k = __shfl_sync(0xFFFFFFFFu, k, 0);
+    if (k >= nfin) break;
+    const uint32_t ff = S.fin[k];
+    if (ff == 0xFFFFu || S.ftotal[ff] > MIX_WARP_MAX) continue;
+    const uint32_t pos = S.fpos[ff];
+    const bool spread = S.fnfrag[ff] > 1;
+    uint32_t bits[FB_PRES_WORDS];
+    group_bits(A, pos, spread, bits);
+    mixed_group<32>(A, S, wsc, pos, S.ftotal[ff], bits, round, t);
+    if (lane == 0) { dup++; mixed_groups++; if (spread) group_release(A, pos); }
   }
   __syncthreads();
-  return listed;
+  MixCta& csc = *reinterpret_cast<MixCta*>(&S.req[0]);
+#pragma unroll 1
+  for (uint32_t k = 0; k < nfin; k++) {
+    const uint32_t ff = S.fin[k];
+    if (ff == 0xFFFFu || S.ftotal[ff] <= MIX_WARP_MAX) continue;
+    const uint32_t pos = S.fpos[ff];
+    const bool spread = S.fnfrag[ff] > 1;
+    uint32_t bits[FB_PRES_WORDS];
+    group_bits(A, pos, spread, bits);
+    mixed_group<FB_THREADS>(A, S, csc, pos, S.ftotal[ff], bits, round, t);
+    if (tid == 0) { dup++; mixed_groups++; if (spread) group_release(A, pos); }
+  }
+  __syncthreads();
 }
 
 // ---- maintenance inside the batch kernel (both run before the grid barrier, when nothing reads the table) -------------------
@@ -592,15 +647,247 @@ __device__ __forceinline__ uint32_t segment_count(const FArgs& A, uint32_t s) {
   return g.n;
 }
 
+// Folds a phase's counter deltas into the CTA's shared-memory tally.
+__device__ __forceinline__ void tally_to_smem(FSmem& S, const Tally& t, uint32_t dup, uint32_t mixed_groups, uint32_t swept) {
+  const uint32_t v[8] = {t.over, t.hit, t.miss, t.inserts, t.full, dup, mixed_groups, swept};
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&S.tally[k], s);
+  }
+}
+
+// ---- phase 1 of a round: stage the tile, group it by key, register the fragments (see the header of this file) ----------------
+__device__ __noinline__ void batch_phase1(FSmem& S, uint32_t round) {
+  const FCtx& A = S.cx;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ntiles = S.ntiles;
+  Tally t = {0, 0, 0, 0, 0};
+  uint32_t swept = 0;
+  // =============================== phase 1: stage, group, register ===============================
+  const uint32_t tl = round * gridDim.x + blockIdx.x;
+  TileInfo ti = {0, 0, 0};
+  if (tl < ntiles) ti = tile_info(S, A.nseg, tl);
+  const uint32_t n_t = ti.n;
+  if (tid == 0) S.ti = ti;
+  if (tid == 0 && n_t) tile_load(&S.req[0], S.seg_reqs[ti.seg] + ti.off, n_t * (uint32_t)sizeof(gub_req), &S.mbar);
+  {
+    ulonglong2* kz = reinterpret_cast<ulonglong2*>(&S.key[0]);  // 8 KB
+    kz[tid] = make_ulonglong2(0ull, 0ull);
+    ulonglong2* wz = reinterpret_cast<ulonglong2*>(&S.wcnt[0][0]);  // 16 KB
+    wz[tid] = make_ulonglong2(0ull, 0ull);
+    wz[tid + FB_THREADS] = make_ulonglong2(0ull, 0ull);
+    S.fmixed[tid] = 0; S.fready[tid] = 0; S.fdone[tid] = 0;
+  }
+  if (tid == 0) S.moff = 0;
+  __syncthreads();
+  if (round == 0) trace_mark(A, 1);
+  if (n_t) mbar_wait(&S.mbar, S.parity);
+  if (round == 0) trace_mark(A, 2);
+  const bool valid = tid < n_t;
+  uint64_t key = 0;
+  uint32_t sp = 0xFFFFu;
+  if (valid) {
+    key = remap_key(S.req[tid].key_xxh64);
+    const uint64_t home = __umul64hi(key, A.capacity);
+    prefetch_l2(A.table + home);
+    prefetch_l2(A.table + (home + 1 == A.capacity ? 0 : home + 1));
+    sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54);  // top 10 bits -> FB_HT
+#pragma unroll 1
+    for (;;) {
+      const unsigned long long old = atomicCAS(&S.key[sp], 0ull, (unsigned long long)key);
+      if (old == 0ull || old == key) break;
+      sp = (sp + 1) & (FB_HT - 1);
+    }
+  }
+  __syncthreads();
+  // index-ordered rank inside the tile: members in earlier warps + earlier lanes of my warp
+  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? sp : (0x10000u | lane));
+  if (valid && lane == (uint32_t)(__ffs(peers) - 1)) S.wcnt[sp][warp] = (uint8_t)__popc(peers);
+  __syncthreads();
+  uint32_t local = 0;
+  if (valid) {
+    const uint4 wc = *reinterpret_cast<const uint4*>(&S.wcnt[sp][0]);
+    const uint32_t wv[4] = {wc.x, wc.y, wc.z, wc.w};
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < FB_WARPS; w++) {
+      const uint32_t c = (wv[w >> 2] >> (8 * (w & 3))) & 0xFFu;
+      total += c;
+      before += ((uint32_t)w < warp) ? c : 0u;
+    }
+    local = before + __popc(peers & ((1u << lane) - 1u));
+    S.sp[tid] = (uint16_t)sp; S.local[tid] = (uint16_t)local;
+    if (local == 0) {  // the fragment's first member registers it
+      const uint32_t f = atomicAdd(&S.nfrag, 1u);
+      S.f_of_sp[sp] = (uint16_t)f; S.flead[f] = (uint16_t)tid; S.fcnt[f] = (uint16_t)total;
+      bool claimed;
+      const uint32_t pos = gentry_join(A, key, total > 1, &claimed);
+      atomicAdd(&A.aux[pos].cnt, (1ull << 32) | (unsigned long long)total);
+      if (claimed) A.aux[pos].rep = blockIdx.x * FB_THREADS + tid;
+      atomicOr(&A.presence[(size_t)pos * FB_PRES_WORDS + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
+      const uint32_t foff = atomicAdd(&S.moff, total);  // this fragment's place in the tile's member list
+      S.foff[f] = (uint16_t)foff;
+      A.fragrow[(size_t)pos * FB_ROW + blockIdx.x] = (foff << 16) | total;
+      S.fpos[f] = pos;
+    }
+  }
+  // maintenance: nothing reads the table before the barrier
+  if (blockIdx.x == 0 && warp == 0 && __ldcg(&A.ctl->ovf_count)) drain_overflow(S.cx, t);
+  if (A.sweep_chunk && warp == FB_WARPS - 1 && !__ldcg(&A.ctl->ovf_count)) sweep_slice(S.cx, &swept);  // (a pending placement may pick a slot the sweep is freeing)
+
+  tally_to_smem(S, t, 0, 0, swept);
+}
+
+// ---- phase 2 of a round: probe, evaluate, finish ---------------------------------------------------------------------------------
+__device__ __noinline__ void batch_phase2(FSmem& S, uint32_t round) {
+  const FCtx& A = S.cx;
+  const uint32_t tid = threadIdx.x;
+  const TileInfo ti = S.ti;
+  const bool valid = tid < ti.n;
+  const uint32_t sp = S.sp[tid], local = S.local[tid];
+  const uint64_t key = valid ? remap_key(S.req[tid].key_xxh64) : 0;
+  Tally t = {0, 0, 0, 0, 0};
+  uint32_t dup = 0, mixed_groups = 0;
+  // =============================== phase 2: probe, evaluate, finish ===============================
+  // No block-wide barrier from here to the end of the evaluation: every warp runs on its own.  A fragment's first member
+  // (its leader) reads the group entry, computes the base rank, probes the table and publishes the slot for its siblings
+  // through shared memory (flag per fragment; siblings sit in the same or a later warp).  Every member answers for itself.
+  // The member that completes a fragment (shared-memory counter) checks the fragment in on the group entry; the last
+  // fragment to arrive finishes the group.
+  if (A.sweep_chunk && blockIdx.x == 0 && tid == 0) A.ctl->sweep_cursor = (A.ctl->sweep_cursor + (uint64_t)gridDim.x * A.sweep_chunk) % A.capacity;
+  uint32_t f = 0, lead = 0, cnt = 0, nfrag = 1, total = 1, base = 0;
+  gub_req rq;
+  Cursor cur;
+  bool have_cur = false;
+  if (valid) {
+    rq = smem_req(&S.req[tid]);
+    f = S.f_of_sp[sp]; lead = S.flead[f]; cnt = S.fcnt[f];
+    if (tid == lead) {
+      const uint32_t pos = S.fpos[f];
+      // the group entry, its presence bitmap, and the probe: all issued before any is consumed
+      const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
+      const uint32_t e_rep = __ldcg(&A.aux[pos].rep);
+      const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
+      const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
+      cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
+      have_cur = true;
+      total = (uint32_t)(e0.y & 0xFFFFFFFFull); nfrag = (uint32_t)(e0.y >> 32);
+      if (nfrag > 1) {
+        gub_req rr;
+        const bool cmp = e_rep != blockIdx.x * FB_THREADS + tid;  // uniformity across tiles: every fragment's first member == the representative
+        if (cmp) rr = global_req(req_at(S, A.nseg, round, e_rep));
+        base = fragment_base2(A, pos, blockIdx.x, p0, p1);
+        if (cmp && !req_same(rq, rr)) atomicOr(&A.aux[pos].flags, G_NONUNIFORM);
+      } else {  // the key lives in this tile only: hand the entry and the bitmap word back now
+        A.presence[(size_t)pos * FB_PRES_WORDS + (blockIdx.x >> 5)] = 0;
+        gentry_clear(&A.aux[pos]);
+      }
+      S.fbase[f] = base; S.ftotal[f] = total; S.fnfrag[f] = (uint16_t)nfrag;
+      if (cnt > 1 || nfrag > 1) {  // somebody else (a sibling, or whoever finishes the group from this CTA) needs the slot as found
+        const Bucket& b = cur.b;
+        S.snap[f][0] = make_ulonglong2(b.key, (b.tag << 8) | (uint64_t)(b.flags & 0xFF));
+        S.snap[f][1] = make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration);
+        S.snap[f][2] = make_ulonglong2(b.rem, (uint64_t)b.stamp);
+        S.snap[f][3] = make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire);
+        S.fslot[f] = cur.slot; S.ffound[f] = cur.found ? 1 : 0;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint8_t*>(&S.fready[f]) = 1;
+      }
+    }
+  }
+  __syncwarp();  // a leader and its siblings in this warp: published before anybody below waits
+  if (round == 0) trace_mark(A, 5);
+  if (valid) {
+    if (!have_cur) {
+      while (*reinterpret_cast<volatile uint8_t*>(&S.fready[f]) == 0) spin_pause();
+      __threadfence_block();
+      cursor_from_snapshot(A, S, f, key, rq.key_fnv1 >> 8, cur);
+      base = S.fbase[f]; total = S.ftotal[f]; nfrag = S.fnfrag[f];
+    }
+    // uniformity inside the fragment: every member == the fragment's first, and can settle
+    bool irregular = false;
+    if (total > 1) {
+      irregular = !req_regular(rq);
+      if (tid != lead && !irregular) irregular = !req_same(rq, smem_req(&S.req[lead]));
+      if (irregular) *reinterpret_cast<volatile uint8_t*>(&S.fmixed[f]) = 1;
+      A.members[blockIdx.x * FB_THREADS + S.foff[f] + local] = (uint16_t)tid;  // the group's member list, should it need one
+    }
+    Delta d = {0, 0, 0};
+    if (!irregular) store_resp(S.seg_out[ti.seg] + ti.off + tid, run_to_rank(cur.b, rq, base + local, A.clk, d));
+    // the member that completes the fragment speaks for it
+    bool completer = true;
+    if (cnt > 1) { __threadfence_block(); completer = atomicAdd(&S.fdone[f], 1u) + 1u == cnt; }
+    if (completer) {
+      const bool mixedf = cnt > 1 ? *reinterpret_cast<volatile uint8_t*>(&S.fmixed[f]) != 0 : irregular;
+      const uint32_t pos = S.fpos[f];
+      uint32_t fin_kind = 0;  // 1: finish a uniform group from the snapshot, 2: a group whose requests differ
+      if (nfrag == 1) {
+        if (mixedf) fin_kind = 2;
+        else if (cnt == 1) {  // a key seen once: its state is in my registers
+          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+          close_or_park(A, cur, t);
+        } else fin_kind = 1;
+      } else {
+        if (mixedf) atomicOr(&A.aux[pos].flags, G_NONUNIFORM);
+        if (A.n_resp_flags) __threadfence_system(); else __threadfence();  // this CTA's slot reads and response stores precede the check-in
+        if (atomicAdd(&A.aux[pos].arrived, 1u) == nfrag - 1) {  // every other fragment has read the slot and answered: finish the group
+          __threadfence();
+          fin_kind = (__ldcg(&A.aux[pos].flags) & G_NONUNIFORM) ? 2u : 1u;
+        }
+      }
+      if (fin_kind) S.fin[atomicAdd(&S.nfin, 1u)] = (uint16_t)(f | (fin_kind == 2 ? 0x8000u : 0u));
+    }
+  }
+  if (round == 0) trace_mark(A, 7);
+  tally_to_smem(S, t, dup, mixed_groups, 0);
+}
+
+// ---- end of a round: groups this CTA finishes ---------------------------------------------------------------------------------------
+__device__ __noinline__ void batch_finish(FSmem& S, uint32_t round) {
+  const FCtx& A = S.cx;
+  const uint32_t tid = threadIdx.x;
+  Tally t = {0, 0, 0, 0, 0};
+  uint32_t dup = 0, mixed_groups = 0;
+  __syncthreads();
+  if (round == 0) trace_mark(A, 8);
+  // (a) repeated keys whose requests are all the same: one thread each evaluates the run's last rank from the slot as found
+  //     and writes the final state; (b) groups whose requests differ (rare): the teams of this CTA evaluate them
+  {
+    const uint32_t nfin = S.nfin;
+    bool mixed_here = false;
+    for (uint32_t k = tid; k < nfin; k += FB_THREADS) {
+      const uint32_t e = S.fin[k], ff = e & 0x7FFFu;
+      if (e & 0x8000u) { S.fin[k] = (uint16_t)ff; mixed_here = true; continue; }
+      S.fin[k] = 0xFFFFu;
+      const gub_req lr = smem_req(&S.req[S.flead[ff]]);
+      Cursor c2;
+      cursor_from_snapshot(A, S, ff, remap_key(lr.key_xxh64), lr.key_fnv1 >> 8, c2);
+      Delta d2 = {0, 0, 0};
+      run_to_rank(c2.b, lr, S.ftotal[ff] - 1, A.clk, d2);
+      t.over += d2.over; t.hit += d2.hit; t.miss += d2.miss;
+      close_or_park(A, c2, t);
+      dup++;
+      if (S.fnfrag[ff] > 1) group_release(S.cx, S.fpos[ff]);
+    }
+    if (round == 0) trace_mark(A, 9);
+    if (__syncthreads_or(mixed_here)) finish_mixed_groups(S, nfin, round, t, dup, mixed_groups);
+  }
+  tally_to_smem(S, t, dup, mixed_groups, 0);
+}
+
 __global__ void __launch_bounds__(FB_THREADS, 1) k_batch(const FArgs A) {
   FSmem& S = *reinterpret_cast<FSmem*>(GUB_DYN_SMEM());
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    mbar_init(&S.mbar); S.nfrag = 0; S.nfin = 0;
-    S.cx.table = A.table; S.cx.capacity = A.capacity; S.cx.gpos = A.gpos; S.cx.ctl = A.ctl; S.cx.ovf = A.ovf; S.cx.counters = A.counters;
-    S.cx.nseg = A.nseg; S.cx.sweep_chunk = A.sweep_chunk; S.cx.clk = A.clk;
+    mbar_init(&S.mbar); S.nfrag = 0; S.nfin = 0; S.parity = 0;
+    S.cx.table = A.table; S.cx.capacity = A.capacity; S.cx.fragrow = A.fragrow; S.cx.members = A.members; S.cx.presence = A.presence; S.cx.aux = A.aux; S.cx.ctl = A.ctl;
+    S.cx.ovf = A.ovf; S.cx.counters = A.counters; S.cx.trace = A.trace; S.cx.nseg = A.nseg; S.cx.sweep_chunk = A.sweep_chunk; S.cx.n_resp_flags = A.n_resp_flags;
+    S.cx.clk = A.clk;
   }
   if (tid < 8) S.tally[tid] = 0;
+  __syncthreads();
+  trace_mark(S.cx, 0);
   pdl_wait();     // everything earlier in the stream (the producer of the records, the previous batch) is complete and visible
   pdl_release();
   if (tid < A.nseg) {
@@ -626,9 +913,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_batch(const FArgs A) {
   __syncthreads();
   const uint32_t ntiles = S.ntiles;
   const uint32_t rounds = (ntiles + gridDim.x - 1) / gridDim.x;
-  Tally t = {0, 0, 0, 0, 0};
-  uint32_t dup = 0, mixed_groups = 0, swept = 0;
-  uint32_t parity = 0;
   if (blockIdx.x == 0 && tid == 0) {
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)S.total);
     atomicAdd(A.counters + C_BATCHES, 1ull);
@@ -636,228 +920,32 @@ __global__ void __launch_bounds__(FB_THREADS, 1) k_batch(const FArgs A) {
 
 #pragma unroll 1
   for (uint32_t round = 0; round < max(rounds, 1u); round++) {
-    // =============================== phase 1: stage, group, register ===============================
-    const uint32_t tl = round * gridDim.x + blockIdx.x;
-    TileInfo ti = {0, 0, 0};
-    if (tl < ntiles) ti = tile_info(S, A.nseg, tl);
-    const uint32_t n_t = ti.n;
-    if (tid == 0 && n_t) tile_load(&S.req[0], S.seg_reqs[ti.seg] + ti.off, n_t * (uint32_t)sizeof(gub_req), &S.mbar);
-    {
-      ulonglong2* kz = reinterpret_cast<ulonglong2*>(&S.key[0]);  // 8 KB
-      kz[tid] = make_ulonglong2(0ull, 0ull);
-      ulonglong2* wz = reinterpret_cast<ulonglong2*>(&S.wcnt[0][0]);  // 16 KB
-      wz[tid] = make_ulonglong2(0ull, 0ull);
-      wz[tid + FB_THREADS] = make_ulonglong2(0ull, 0ull);
-      S.fmixed[tid] = 0;
-    }
-    if (blockIdx.x == 0 && tid == 0) A.ctl->ord_bump = 0;
-    __syncthreads();
-    if (n_t) { mbar_wait(&S.mbar, parity); parity ^= 1u; }
-    const bool valid = tid < n_t;
-    uint64_t key = 0;
-    uint32_t sp = 0xFFFFu;
-    if (valid) {
-      key = remap_key(S.req[tid].key_xxh64);
-      const uint64_t home = __umul64hi(key, A.capacity);
-      prefetch_l2(A.table + home);
-      prefetch_l2(A.table + (home + 1 == A.capacity ? 0 : home + 1));
-      sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 54);  // top 10 bits -> FB_HT
-#pragma unroll 1
-      for (;;) {
-        const unsigned long long old = atomicCAS(&S.key[sp], 0ull, (unsigned long long)key);
-        if (old == 0ull || old == key) break;
-        sp = (sp + 1) & (FB_HT - 1);
-      }
-    }
-    __syncthreads();
-    // index-ordered rank inside the tile: members in earlier warps + earlier lanes of my warp
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? sp : (0x10000u | lane));
-    if (valid && lane == (uint32_t)(__ffs(peers) - 1)) S.wcnt[sp][warp] = (uint8_t)__popc(peers);
-    __syncthreads();
-    uint32_t local = 0;
-    if (valid) {
-      const uint4 wc = *reinterpret_cast<const uint4*>(&S.wcnt[sp][0]);
-      const uint32_t wv[4] = {wc.x, wc.y, wc.z, wc.w};
-      uint32_t before = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < FB_WARPS; w++) {
-        const uint32_t c = (wv[w >> 2] >> (8 * (w & 3))) & 0xFFu;
-        total += c;
-        before += ((uint32_t)w < warp) ? c : 0u;
-      }
-      local = before + __popc(peers & ((1u << lane) - 1u));
-      S.sp[tid] = (uint16_t)sp; S.local[tid] = (uint16_t)local;
-      if (local == 0) {  // the fragment's first member registers it
-        const uint32_t f = atomicAdd(&S.nfrag, 1u);
-        S.f_of_sp[sp] = (uint16_t)f; S.flead[f] = (uint16_t)tid; S.fcnt[f] = (uint16_t)total;
-        bool claimed;
-        const uint32_t pos = gentry_join(A, key, &claimed);
-        atomicAdd(&A.aux[pos].cnt, (1ull << 32) | (unsigned long long)total);
-        if (claimed) A.aux[pos].rep = blockIdx.x * FB_THREADS + tid;
-        atomicOr(&A.presence[(size_t)pos * FB_PRES_WORDS + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
-        A.fragsize[(size_t)pos * FB_ROW + blockIdx.x] = (uint16_t)total;
-        S.fpos[f] = pos;
-      }
-    }
-    __syncthreads();
-    if (valid) A.gpos[blockIdx.x * FB_THREADS + tid] = S.fpos[S.f_of_sp[sp]];
-    // maintenance: nothing reads the table before the barrier
-    if (blockIdx.x == 0 && warp == 0 && __ldcg(&A.ctl->ovf_count)) drain_overflow(S.cx, t);
-    if (A.sweep_chunk && warp == FB_WARPS - 1 && !__ldcg(&A.ctl->ovf_count)) sweep_slice(S.cx, &swept);  // (a pending placement may pick a slot the sweep is freeing)
-
+    batch_phase1(S, round);
+    if (round == 0) trace_mark(S.cx, 3);
     grid_barrier(A.ctl);
-
-    // =============================== phase 2: probe, evaluate, finish ===============================
-    if (A.sweep_chunk && blockIdx.x == 0 && tid == 0) A.ctl->sweep_cursor = (A.ctl->sweep_cursor + (uint64_t)gridDim.x * A.sweep_chunk) % A.capacity;
-    const uint32_t F = S.nfrag;
-    uint32_t e_pos = 0, e_total = 0, e_nfrag = 0, e_rep = 0;
-    if (tid < F) {  // the fragment's group entry: issued ahead of the probe, consumed after it
-      e_pos = S.fpos[tid];
-      const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[e_pos]));
-      e_rep = __ldcg(&A.aux[e_pos].rep);
-      e_total = (uint32_t)(e0.y & 0xFFFFFFFFull); e_nfrag = (uint32_t)(e0.y >> 32);
-    }
-    probe_fragments(A, S, F);
-    if (tid < F) {
-      uint32_t base = 0;
-      if (e_nfrag > 1) {
-        base = fragment_base2(A, e_pos, blockIdx.x);
-        const uint32_t lead = S.flead[tid];
-        if (e_rep != blockIdx.x * FB_THREADS + lead) {  // uniformity across tiles: every fragment's first member == the representative
-          const gub_req rr = global_req(req_at(S, A.nseg, round, e_rep));
-          if (!req_same(smem_req(&S.req[lead]), rr)) atomicOr(&A.aux[e_pos].flags, G_NONUNIFORM);
-        }
-      } else {  // the key lives in this tile only: hand the entry and the bitmap word back now
-        A.presence[(size_t)e_pos * FB_PRES_WORDS + (blockIdx.x >> 5)] = 0;
-        gentry_clear(&A.aux[e_pos]);
-      }
-      S.fbase[tid] = base; S.ftotal[tid] = e_total; S.fnfrag[tid] = (uint16_t)e_nfrag;
-    }
+    if (round == 0) trace_mark(S.cx, 4);
+    batch_phase2(S, round);
+    batch_finish(S, round);
     __syncthreads();
-    // uniformity inside the fragment: every member == the fragment's first
-    gub_req rq;
-    uint32_t f = 0, lead = 0;
-    if (valid) {
-      rq = smem_req(&S.req[tid]);
-      f = S.f_of_sp[sp]; lead = S.flead[f];
-      if (S.ftotal[f] > 1) {
-        bool irregular = !req_regular(rq);
-        if (tid != lead && !irregular) irregular = !req_same(rq, smem_req(&S.req[lead]));
-        if (irregular) S.fmixed[f] = 1;
-      }
-    }
-    __syncthreads();
-    if (valid) {
-      const uint32_t nfrag = S.fnfrag[f];
-      if (!S.fmixed[f]) {
-        Cursor cur;
-        cursor_from_snapshot(A, S, f, key, rq.key_fnv1 >> 8, cur);
-        Delta d = {0, 0, 0};
-        const gub_resp r = run_to_rank(cur.b, rq, S.fbase[f] + local, A.clk, d);
-        store_resp(S.seg_out[ti.seg] + ti.off + tid, r);
-        if (nfrag == 1 && local + 1 == S.fcnt[f]) {  // the key's last request of the batch: I hold its final state and counter totals
-          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-          close_or_park(A, cur, t);
-          if (S.fcnt[f] > 1) dup++;
-        }
-      } else if (nfrag > 1 && tid == lead) {
-        atomicOr(&A.aux[S.fpos[f]].flags, G_NONUNIFORM);
-      }
-    }
-    __threadfence_system();  // responses (possibly in peer memory) before the check-in below
-    __syncthreads();
-    // check in: the last fragment of a group to arrive finishes it
-    if (tid < F) {
-      const uint32_t nfrag = S.fnfrag[tid];
-      bool finish = false;
-      if (nfrag > 1) {
-        finish = atomicAdd(&A.aux[S.fpos[tid]].arrived, 1u) == nfrag - 1;
-        if (finish) __threadfence();
-      } else {
-        finish = S.fmixed[tid] != 0;
-      }
-      if (finish) S.fin[atomicAdd(&S.nfin, 1u)] = (uint16_t)tid;
-    }
-    __syncthreads();
-    const uint32_t nfin = S.nfin;
-    // (a) uniform groups spread over tiles: one thread each computes the run's final state from its own snapshot and writes it
-    for (uint32_t k = tid; k < nfin; k += FB_THREADS) {
-      const uint32_t ff = S.fin[k];
-      if (S.fnfrag[ff] <= 1) continue;
-      const uint32_t pos = S.fpos[ff];
-      if (__ldcg(&A.aux[pos].flags) & G_NONUNIFORM) continue;
-      const gub_req lr = smem_req(&S.req[S.flead[ff]]);
-      Cursor cur;
-      cursor_from_snapshot(A, S, ff, remap_key(lr.key_xxh64), lr.key_fnv1 >> 8, cur);
-      Delta d = {0, 0, 0};
-      run_to_rank(cur.b, lr, S.ftotal[ff] - 1, A.clk, d);
-      t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-      close_or_park(A, cur, t);
-      dup++;
-      ulonglong2* pz = reinterpret_cast<ulonglong2*>(A.presence + (size_t)pos * FB_PRES_WORDS);
-      __stcg(pz, make_ulonglong2(0ull, 0ull)); __stcg(pz + 1, make_ulonglong2(0ull, 0ull));
-      gentry_clear(&A.aux[pos]);
-      S.fin[k] = 0xFFFFu;
-    }
-    __syncthreads();
-    // (b) groups whose requests differ: the whole CTA walks each in index order
-#pragma unroll 1
-    for (uint32_t k = 0; k < nfin; k++) {
-      const uint32_t ff = S.fin[k];
-      if (ff == 0xFFFFu) continue;
-      const uint32_t pos = S.fpos[ff], total = S.ftotal[ff];
-      const bool spread = S.fnfrag[ff] > 1;
-      uint32_t bits[FB_PRES_WORDS];
-#pragma unroll
-      for (int w = 0; w < FB_PRES_WORDS; w++) bits[w] = 0;
-      if (spread) {
-        const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
-        const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
-        bits[0] = p0.x; bits[1] = p0.y; bits[2] = p0.z; bits[3] = p0.w; bits[4] = p1.x; bits[5] = p1.y; bits[6] = p1.z; bits[7] = p1.w;
-      } else {
-        bits[blockIdx.x >> 5] = 1u << (blockIdx.x & 31);
-      }
-      __syncthreads();
-      if (tid == 0) S.mx.np = atomicAdd(&A.ctl->ord_bump, total);
-      __syncthreads();
-      uint32_t* ord = A.ordbuf + S.mx.np;
-      list_members(S.cx, S, pos, bits, round, ord);
-      mixed_walk(S.cx, S, ord, total, round, t);
-      if (tid == 0) {
-        dup++; mixed_groups++;
-        if (spread) {
-          ulonglong2* pz = reinterpret_cast<ulonglong2*>(A.presence + (size_t)pos * FB_PRES_WORDS);
-          __stcg(pz, make_ulonglong2(0ull, 0ull)); __stcg(pz + 1, make_ulonglong2(0ull, 0ull));
-          gentry_clear(&A.aux[pos]);
-        }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) { S.nfrag = 0; S.nfin = 0; }
+    if (tid == 0) { S.nfrag = 0; S.nfin = 0; if (S.ti.n) S.parity ^= 1u; }
     if (round + 1 < rounds) grid_barrier(A.ctl);  // the next round's groups start from a clean group table and the updated slots
   }
 
+  trace_mark(S.cx, 10);
   // ---- counters: summed per CTA first ----
-  {
-    const uint32_t v[8] = {t.over, t.hit, t.miss, t.inserts, t.full, dup, mixed_groups, swept};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const uint32_t s = __reduce_add_sync(0xFFFFFFFFu, v[k]);
-      if (lane == 0 && s) atomicAdd(&S.tally[k], s);
-    }
-    __syncthreads();
-    if (tid < 8 && S.tally[tid]) {
-      const int slot[8] = {C_OVER, C_HIT, C_MISS, C_INSERTS, C_FULL, C_DUP_GROUPS, C_MIXED_GROUPS, C_SWEPT};
-      atomicAdd(A.counters + slot[tid], (unsigned long long)S.tally[tid]);
-    }
+  __syncthreads();
+  if (tid < 8 && S.tally[tid]) {
+    const int slot[8] = {C_OVER, C_HIT, C_MISS, C_INSERTS, C_FULL, C_DUP_GROUPS, C_MIXED_GROUPS, C_SWEPT};
+    atomicAdd(A.counters + slot[tid], (unsigned long long)S.tally[tid]);
   }
+  trace_mark(S.cx, 11);
   // ---- multi-GPU: the last CTA to finish tells every source that its responses are in place ----
   if (A.n_resp_flags) {
     __threadfence_system();
     __syncthreads();
-    if (tid == 0) S.mx.serial = atomicAdd(&A.ctl->done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (tid == 0) S.last = atomicAdd(&A.ctl->done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
-    if (S.mx.serial) {
+    if (S.last) {
       if (tid < A.n_resp_flags) {
         __threadfence_system();
         st_release_sys(A.resp_flag[tid], (unsigned long long)A.flag_epoch << 32);
@@ -872,7 +960,7 @@ __global__ void k_drain_overflow(const FArgs A) {
   Tally t = {0, 0, 0, 0, 0};
   __shared__ FCtx cx;
   if (threadIdx.x == 0) {
-    cx.table = A.table; cx.capacity = A.capacity; cx.gpos = A.gpos; cx.ctl = A.ctl; cx.ovf = A.ovf; cx.counters = A.counters;
+    cx.table = A.table; cx.capacity = A.capacity; cx.fragrow = A.fragrow; cx.members = A.members; cx.presence = A.presence; cx.aux = A.aux; cx.ctl = A.ctl; cx.ovf = A.ovf; cx.counters = A.counters;
     cx.nseg = A.nseg; cx.sweep_chunk = 0; cx.clk = A.clk;
   }
   __syncthreads();

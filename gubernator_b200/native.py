@@ -35,7 +35,8 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_ring_get", "gub_ring_get_by_hash", "gub_ring_points", "gub_route_device", "gub_unroute_device", "gub_gq_create",
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
            "gub_route_owner_device", "gub_route_global_device", "gub_p2p_create", "gub_p2p_destroy", "gub_p2p_export", "gub_p2p_connect",
-           "gub_p2p_connect_local", "gub_p2p_step", "gub_p2p_step_streams"]
+           "gub_p2p_connect_local", "gub_p2p_step", "gub_p2p_step_streams", "gub_p2p_status", "gub_p2p_enable_global", "gub_nccl_unique_id",
+           "gub_p2p_nccl_init", "gub_p2p_nccl_init_local", "gub_global_tick", "gub_gq_dropped", "gub_set_sweep", "gub_set_trace", "gub_get_trace", "gub_get_trace_raw"]
 
 
 class Config(C.Structure):
@@ -108,6 +109,17 @@ def lib():
         L.gub_p2p_step.argtypes = [vp, vp, sz, vp, vp, vp]
         L.gub_probe_random_access.argtypes = [vp, C.c_uint64, C.POINTER(C.c_double)]
         L.gub_p2p_step_streams.argtypes = [vp, vp, sz, vp, vp, vp, vp]
+        L.gub_p2p_status.argtypes = [vp, C.POINTER(C.c_int)]
+        L.gub_p2p_enable_global.argtypes = [vp, C.c_uint32]
+        L.gub_nccl_unique_id.argtypes = [vp]
+        L.gub_p2p_nccl_init.argtypes = [vp, vp]
+        L.gub_p2p_nccl_init_local.argtypes = [C.POINTER(vp), C.c_uint32]
+        L.gub_global_tick.argtypes = [vp, vp, i64, vp, vp]
+        L.gub_gq_dropped.argtypes = [vp, C.POINTER(u64)]
+        L.gub_set_sweep.argtypes = [vp, C.c_uint32]
+        L.gub_set_trace.argtypes = [vp, i32]
+        L.gub_get_trace.argtypes = [vp, vp, vp]
+        L.gub_get_trace_raw.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -287,6 +299,25 @@ class Table:
     def hash_keys_device(self, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr=None, stream=0):
         _check(lib().gub_hash_keys_device(self._h, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr, stream), "gub_hash_keys_device")
 
+    def set_sweep(self, slots_per_cta):
+        _check(lib().gub_set_sweep(self._h, int(slots_per_cta)), "gub_set_sweep")
+
+    def set_trace(self, on):
+        _check(lib().gub_set_trace(self._h, 1 if on else 0), "gub_set_trace")
+
+    TRACE_MARKS = ("entry", "tile_issued", "tile_landed", "phase1_done", "barrier_passed", "probe_done", "entries_read", "evaluated",
+                   "checked_in", "uniform_finished", "mixed_finished", "counters_flushed")
+
+    def get_trace(self):
+        mx, mean = np.zeros(12), np.zeros(12)
+        _check(lib().gub_get_trace(self._h, mx.ctypes.data, mean.ctypes.data), "gub_get_trace")
+        return {"max_us": dict(zip(self.TRACE_MARKS, (round(float(v), 2) for v in mx))), "mean_us": dict(zip(self.TRACE_MARKS, (round(float(v), 2) for v in mean)))}
+
+    def get_trace_raw(self):
+        raw = np.zeros((256, 12), dtype=np.uint64)
+        _check(lib().gub_get_trace_raw(self._h, raw.ctypes.data), "gub_get_trace_raw")
+        return raw
+
     def set_profiling(self, on):
         _check(lib().gub_set_profiling(self._h, 1 if on else 0), "gub_set_profiling")
 
@@ -345,6 +376,24 @@ class P2P:
         else:
             _check(lib().gub_p2p_step_streams(self._h, d_reqs_ptr, n, clk.ctypes.data, d_out_ptr, ingest_stream, stream), "gub_p2p_step_streams")
 
+    def status(self):
+        """Raises when a bounded device-side wait of an earlier step gave up (a shard of the ring is not answering)."""
+        e = C.c_int(0)
+        _check(lib().gub_p2p_status(self._h, C.byref(e)), "gub_p2p_status")
+        return e.value
+
+    def enable_global(self, capacity=1 << 16):
+        _check(lib().gub_p2p_enable_global(self._h, int(capacity)), "gub_p2p_enable_global")
+
+    def nccl_init(self, unique_id: bytes):
+        _check(lib().gub_p2p_nccl_init(self._h, C.create_string_buffer(unique_id, 128)), "gub_p2p_nccl_init")
+
+    def tick(self, clk, now_ms, stream=0):
+        """One GLOBAL sync (gub_global_tick).  Returns dict(hits_sent, updates_made, installed, gathered_bytes)."""
+        st = (C.c_uint64 * 4)()
+        _check(lib().gub_global_tick(self._h, clk.ctypes.data, int(now_ms), stream, st), "gub_global_tick")
+        return dict(hits_sent=int(st[0]), updates_made=int(st[1]), installed=int(st[2]), gathered_bytes=int(st[3]))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().gub_p2p_destroy(self._h)
@@ -355,6 +404,17 @@ class P2P:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().gub_nccl_unique_id(buf), "gub_nccl_unique_id")
+    return buf.raw
+
+
+def p2p_nccl_init_local(p2ps):
+    arr = (C.c_void_p * len(p2ps))(*[p._h for p in p2ps])
+    _check(lib().gub_p2p_nccl_init_local(arr, len(p2ps)), "gub_p2p_nccl_init_local")
 
 
 class GlobalQueue:

@@ -57,7 +57,8 @@ enum {
   GUB_ERR_INVALID_ALGORITHM = 3,  /* workers.go:318 */
   GUB_ERR_GREGORIAN_WEEKS = 4,    /* interval.go:93,134 */
   GUB_ERR_GREGORIAN_INVALID = 5,  /* interval.go:107,147 */
-  GUB_ERR_TABLE_FULL = 6          /* no reference analogue: the LRU would have evicted (lrucache.go:98) */
+  GUB_ERR_TABLE_FULL = 6,         /* no longer produced by the batch path (a full probe window evicts, like lrucache.go:98); gub_add_items only */
+  GUB_ERR_PEER_TIMEOUT = 7        /* the owning shard did not answer within the bounded wait (peer_client.go:169-189 returns the RPC error in-band) */
 };
 
 /* One RateLimitReq (gubernator.proto:137-183) after HashKey() (client.go:39-41) and hashing.  64 bytes. */
@@ -198,6 +199,18 @@ int gub_size(gub_table* t, size_t* n_out);
 int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed);
 int gub_get_counters(gub_table* t, gub_counters* out);
 
+/* Incremental expiry sweep inside the batch kernel: every CTA frees the removed / expired entries of `slots_per_cta` table slots
+ * per batch (tombstones; tombstone runs that end at an empty slot become empty again), so that a long-running service does not
+ * fill its probe windows with dead keys (the reference frees lazily on access, lrucache.go:115, and by eviction, :138).
+ * Default: the whole table once every ~65536 batches.  0 = off. */
+int gub_set_sweep(gub_table* t, uint32_t slots_per_cta);
+/* Diagnostic: per-CTA timestamps at the phase boundaries of the batch kernel, for the last launch (12 marks: entry, tile issued,
+ * tile landed, phase 1 done, grid barrier passed, probe done, entries read, evaluated, checked in, uniform groups finished,
+ * non-uniform groups finished, counters flushed): us since the first CTA entered; max and mean over CTAs. */
+int gub_set_trace(gub_table* t, int on);
+int gub_get_trace(gub_table* t, double* max_us /* 12 */, double* mean_us /* 12 */);
+int gub_get_trace_raw(gub_table* t, uint64_t* out /* 256 CTAs x 12 marks, ns; 0 = CTA not launched */);
+
 /* Diagnostic: random 64-byte read-modify-write rate of the device over the table's own slots (contents unchanged), in GB/s
  * moved (64 B read + 64 B written per access): the "HBM random access" ceiling bench.py reports the path against. */
 int gub_probe_random_access(gub_table* t, uint64_t accesses, double* gbs);
@@ -252,6 +265,8 @@ void gub_gq_destroy(gub_gq* q);
  * evaluated still carries GLOBAL, gubernator.go:604-606).  `seq_base` orders requests across calls (first / latest). */
 int gub_gq_accumulate_device(gub_gq* q, const gub_req* d_reqs, size_t n, const uint8_t* d_owner, uint32_t self,
                              uint64_t seq_base, void* stream);
+/* Requests that were not queued because the queue was full within one window (the reference's maps are unbounded: size for the hot set). */
+int gub_gq_dropped(gub_gq* q, uint64_t* dropped);
 /* Drains the queue into request records and clears it: as_status_query = 0 -> hit requests for the owner (Hits = window
  * sum, DRAIN_OVER_LIMIT | IS_OWNER set, gubernator.go:510-512); 1 -> Hits = 0 status queries, IsOwner = false
  * (global.go:238-245).  *d_count (device uint32) receives the number of records (<= cap are written). */
@@ -268,9 +283,16 @@ int gub_route_owner_device(gub_table* t, const gub_ring* ring, const gub_req* d_
 int gub_route_global_device(gub_table* t, const gub_ring* ring, uint32_t self, const gub_req* d_reqs, size_t n, gub_req* d_out_reqs,
                             uint32_t* d_perm, uint32_t* d_counts, uint8_t* d_owner_out, void* stream);
 
-/* ---- fused routing over NVLink peer memory (one process per GPU, or W shards in one process for tests) ---------------
- * gub_p2p_step = route + exchange + evaluate + return of one ingest batch, with the request / response records stored
- * directly into the owning / originating shard's mailbox by the routing kernels (no NCCL, no host-side split sizes).
+/* ---- the ring of GPUs inside one box: fused routing over NVLink peer memory, GLOBAL sync with NCCL -----------------------------
+ * (replaces gubernator.go:257-283 peer forwarding + peer_client.go:284 batching + global.go inside one NVSwitch domain)
+ * One gub_p2p per shard (GPU): one process per GPU (gub_p2p_export / gub_p2p_connect swap cudaIpc handles), or all shards in
+ * one process like the reference daemon (gub_p2p_connect_local enables peer access between the devices).
+ * gub_p2p_step = three launches:
+ *   k_p2p_route   partitions the ingest batch by owning shard (replicated_hash.go:104-119, stable: per-key order survives) and
+ *                 stores every 64-byte record straight into the owner's mailbox; the last tile publishes the per-owner counts;
+ *   k_batch       the owner's batch kernel waits for the W flags, evaluates straight out of the mailboxes (segment order = source
+ *                 rank, then source index) and stores every 32-byte response into the source's response mailbox; publishes;
+ *   k_p2p_collect the source waits for the owners' flags and puts the responses back in request order.
  * Collective: every shard of the ring must call gub_p2p_step the same number of times.  n <= cap. */
 typedef struct gub_p2p gub_p2p;
 #define GUB_P2P_HANDLE_BYTES 64
@@ -278,14 +300,29 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring /* one address per shard; 
 void gub_p2p_destroy(gub_p2p* p);
 int gub_p2p_export(gub_p2p* p, void* handle_out /* GUB_P2P_HANDLE_BYTES: a cudaIpcMemHandle_t */);
 int gub_p2p_connect(gub_p2p* p, const void* handles /* world x GUB_P2P_HANDLE_BYTES, rank order; own entry ignored */);
-int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers /* world pointers, same process */);
+int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers /* world pointers, same process; devices may differ */);
 int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
-/* Same step on two streams: the routing kernels (partition + NVLink stores into the owners' mailboxes) run on
- * `ingest_stream`, the stream d_reqs was produced on; gather, evaluation, response return and un-route run on `stream`,
+/* Same step on two streams: the routing kernel (partition + NVLink stores into the owners' mailboxes) runs on
+ * `ingest_stream`, the stream d_reqs was produced on; evaluation, response return and collect run on `stream`,
  * where d_out becomes valid.  Routing touches no bucket state, so the routing of step e+1 overlaps the evaluation of step
  * e (the reference overlaps forwarding and evaluation the same way: peer_client.go:284 runs in its own goroutine). */
 int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream,
                          void* stream);
+/* Device-side waits are bounded (a dead peer must not hang the GPU); a wait that gave up marks the step: *error_out != 0 and the
+ * call fails with text in gub_last_error().  Requests whose owner never answered carry GUB_ERR_PEER_TIMEOUT in-band.  Costs a
+ * device synchronisation: poll at your own cadence. */
+int gub_p2p_status(gub_p2p* p, int* error_out);
+
+/* GLOBAL behaviour (global.go, gubernator.go:395-459) for the ring.  After gub_p2p_enable_global, a step answers GLOBAL
+ * requests this shard does not own from the local replica (GLOBAL cleared, NO_BATCHING set, IsOwner = false) and queues their
+ * hits; GLOBAL requests evaluated as owner are queued for the broadcast.  gub_global_tick is the reference's GlobalSyncWait
+ * timer made explicit: hits go to their owners (applied with DRAIN_OVER_LIMIT), owners re-read the touched keys with Hits = 0,
+ * and an NCCL all-gather delivers the UpdatePeerGlobal items to every other shard, which overwrites its replica. */
+int gub_p2p_enable_global(gub_p2p* p, uint32_t capacity /* most distinct GLOBAL keys per sync window */);
+int gub_nccl_unique_id(void* out128 /* 128 bytes: ncclUniqueId, to be handed to every shard by the host application */);
+int gub_p2p_nccl_init(gub_p2p* p, const void* id128);                     /* one process per GPU; collective */
+int gub_p2p_nccl_init_local(gub_p2p* const* ps, uint32_t world);           /* all shards in this process */
+int gub_global_tick(gub_p2p* p, const gub_clock* clk, int64_t now_ms, void* stream, uint64_t* stats /* optional, 4 values */);
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,7 @@ def lib(early_singles=1, onepass=0, class_sort=0):
         L.emu_make_updates.argtypes = [vp, vp, u32, vp]; L.emu_make_updates.restype = u32
         L.emu_p2p_create.argtypes = [u32, u32, u64, u32, vp, vp, u32]; L.emu_p2p_create.restype = vp
         L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
-        L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp]
+        L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         assert L.emu_counter_count() == len(COUNTER_NAMES)
         _libs[variant] = L
     return _libs[variant]
@@ -158,7 +158,7 @@ class EmuP2PCluster:
         n = np.array([len(b) for b in batches], dtype=np.uint32)
         self._L.emu_set_finish_cap(self._finish_cap)
         try:
-            rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op)
+            rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op, 0, None)
         finally:
             self._L.emu_set_finish_cap(148)
         assert rc == 0, "a mailbox flag wait timed out"

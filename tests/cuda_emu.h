@@ -57,6 +57,7 @@ struct Block {
   std::vector<Warp> warps;
   uint3 idx{0, 0, 0};
   void* dyn_smem = nullptr;
+  unsigned or_acc = 0;
 };
 struct Fiber {
   ucontext_t ctx;
@@ -208,8 +209,19 @@ void launch_coop(K kernel, unsigned grid, unsigned block, size_t smem_bytes, Arg
 #define gridDim (emu::st().grid_dim)
 
 inline void __syncthreads() { emu::arrive_and_wait(emu::st().cur->blk->sync); }
+inline int __syncthreads_or(int pred) {
+  emu::Block* b = emu::st().cur->blk;
+  if (pred) b->or_acc = 1;
+  __syncthreads();
+  const int r = b->or_acc != 0;
+  __syncthreads();
+  b->or_acc = 0;
+  __syncthreads();
+  return r;
+}
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::arrive_and_wait(emu::my_warp().sync); }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 
 inline unsigned __match_any_sync(unsigned, unsigned long long v) {

@@ -41,8 +41,8 @@ struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   unsigned long long* counters = nullptr;
   // the fused batch kernel (gub_batch.cuh)
   GEntry* gaux = nullptr;
-  uint32_t *gpres = nullptr, *gpos = nullptr, *ordbuf = nullptr;
-  uint16_t* gfrag = nullptr;
+  uint32_t *gpres = nullptr, *gfrag = nullptr;
+  uint16_t* gmembers = nullptr;
   FCtl* ctl = nullptr;
   OvfItem* ovf = nullptr;
   uint32_t grid = 6, sweep_chunk = 0;
@@ -76,9 +76,8 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
   t->counters = zalloc<unsigned long long>(C_COUNT);
   t->gaux = zalloc<GEntry>(FB_AUX_ENTRIES);
   t->gpres = zalloc<uint32_t>((size_t)FB_AUX_ENTRIES * FB_PRES_WORDS);
-  t->gfrag = zalloc<uint16_t>((size_t)FB_AUX_ENTRIES * FB_ROW);
-  t->gpos = zalloc<uint32_t>((size_t)FB_MAX_GRID * FB_THREADS);
-  t->ordbuf = zalloc<uint32_t>((size_t)FB_MAX_GRID * FB_THREADS);
+  t->gfrag = zalloc<uint32_t>((size_t)FB_AUX_ENTRIES * FB_ROW);
+  t->gmembers = zalloc<uint16_t>((size_t)FB_MAX_GRID * FB_THREADS);
   t->ctl = zalloc<FCtl>(1);
   t->ovf = zalloc<OvfItem>(FB_OVF_CAP);
   return t;
@@ -87,7 +86,7 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
 void emu_destroy(void* tv) {
   EmuTable* t = static_cast<EmuTable*>(tv);
   void* ptrs[] = {t->table, t->aux, t->presence, t->fragsize, t->commit, t->commit_ent, t->ent, t->meta, t->rank, t->order, t->mixed_ent, t->ctr, t->counters,
-                  t->gaux, t->gpres, t->gfrag, t->gpos, t->ordbuf, t->ctl, t->ovf};
+                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf};
   for (void* p : ptrs) std::free(p);
   delete t;
 }
@@ -101,7 +100,7 @@ void emu_set_sweep(void* tv, uint32_t chunk) { static_cast<EmuTable*>(tv)->sweep
 
 static void fused_args(EmuTable* t, const gub_clock* clk, FArgs& A) {
   std::memset(&A, 0, sizeof A);
-  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragsize = t->gfrag; A.gpos = t->gpos; A.ordbuf = t->ordbuf;
+  A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragrow = t->gfrag; A.members = t->gmembers;
   A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.clk = *clk;
 }
 
@@ -241,6 +240,7 @@ void* emu_gq_create(uint32_t capacity, uint32_t keep_latest) {
   g->q.slots = zalloc<gub_req>(g->capacity);
   g->q.seq = zalloc<unsigned long long>(g->capacity);
   g->q.count = zalloc<unsigned long long>(1);
+  g->q.dropped = zalloc<unsigned long long>(1);
   g->q.capacity_mask = g->capacity - 1;
   g->q.mode = keep_latest ? GQ_KEEP_LAST : GQ_KEEP_FIRST;
   return g;
@@ -250,8 +250,8 @@ void emu_gq_accumulate(void* gv, const gub_req* reqs, uint32_t n, const uint8_t*
   EmuGq* g = static_cast<EmuGq*>(gv);
   if (!n) return;
   std::vector<uint32_t> slot_of(n);
-  emu::launch(k_gq_claim, (n + 255) / 256, 256u, g->q, reqs, n, owner, self, owner ? 1u : 0u, seq_base, slot_of.data());
-  emu::launch(k_gq_fill, (n + 255) / 256, 256u, g->q, reqs, n, seq_base, (const uint32_t*)slot_of.data());
+  emu::launch(k_gq_claim, (n + 255) / 256, 256u, g->q, reqs, n, (const uint32_t*)nullptr, owner, self, owner ? 1u : 0u, seq_base, slot_of.data());
+  emu::launch(k_gq_fill, (n + 255) / 256, 256u, g->q, reqs, n, (const uint32_t*)nullptr, seq_base, (const uint32_t*)slot_of.data());
 }
 uint32_t emu_gq_drain(void* gv, gub_req* out, uint32_t cap, uint32_t as_status_query) {
   EmuGq* g = static_cast<EmuGq*>(gv);
@@ -261,7 +261,7 @@ uint32_t emu_gq_drain(void* gv, gub_req* out, uint32_t cap, uint32_t as_status_q
 }
 uint32_t emu_make_updates(const gub_req* queries, const gub_resp* resps, uint32_t n, gub_item* out) {
   uint32_t count = 0;
-  if (n) emu::launch(k_make_updates, (n + 255) / 256, 256u, queries, resps, n, out, &count);
+  if (n) emu::launch(k_make_updates, (n + 255) / 256, 256u, queries, resps, n, (const uint32_t*)nullptr, out, &count);
   return count;
 }
 
@@ -272,12 +272,12 @@ uint32_t emu_make_updates(const gub_req* queries, const gub_resp* resps, uint32_
 struct EmuP2P {
   uint32_t world = 0, cap = 0, epoch = 0;
   std::vector<EmuTable*> tabs;
-  std::vector<uint64_t> pts; std::vector<int32_t> peers;
+  std::vector<uint64_t> pts; std::vector<int32_t> peers; std::vector<uint16_t> lut;
   struct Rank {
     P2PView view;
-    gub_req* inbox; gub_resp* inbox_resp;
-    uint32_t *seg_off, *m_dev, *done_ctr, *error, *tile_off, *counts, *perm;
-    uint8_t* owner;
+    unsigned long long* tile_agg;
+    uint32_t *error, *counts, *perm, *ticket;
+    uint8_t* true_owner;
   };
   std::vector<Rank> ranks;
 };
@@ -286,59 +286,71 @@ void* emu_p2p_create(uint32_t world, uint32_t cap, uint64_t capacity_slots, uint
   EmuP2P* p = new EmuP2P();
   p->world = world; p->cap = cap;
   p->pts.assign(pts, pts + npts); p->peers.assign(peers, peers + npts);
+  p->lut.resize(65536);
+  size_t k = 0;
+  for (uint32_t b = 0; b < 65536; b++) {  // ensure_ring of gub_api.cu
+    const uint64_t lo = (uint64_t)b << 48;
+    while (k < npts && pts[k] < lo) k++;
+    p->lut[b] = (uint16_t)k;
+  }
   for (uint32_t r = 0; r < world; r++) {
     p->tabs.push_back(static_cast<EmuTable*>(emu_create(capacity_slots, max_batch)));
-    EmuP2P::Rank k;
-    k.view.req_mb = zalloc<gub_req>((size_t)2 * world * cap);
-    k.view.resp_mb = zalloc<gub_resp>((size_t)2 * world * cap);
-    k.view.req_flag = zalloc<unsigned long long>((size_t)2 * world);
-    k.view.resp_flag = zalloc<unsigned long long>((size_t)2 * world);
-    k.inbox = zalloc<gub_req>((size_t)world * cap); k.inbox_resp = zalloc<gub_resp>((size_t)world * cap);
-    k.seg_off = zalloc<uint32_t>(MAX_SHARDS + 1); k.m_dev = zalloc<uint32_t>(1); k.done_ctr = zalloc<uint32_t>(2); k.error = zalloc<uint32_t>(1);
-    k.tile_off = zalloc<uint32_t>(((size_t)cap / ROUTE_TILE + 1) * MAX_SHARDS); k.counts = zalloc<uint32_t>(MAX_SHARDS); k.perm = zalloc<uint32_t>(cap);
-    k.owner = zalloc<uint8_t>(cap);
-    p->ranks.push_back(k);
+    EmuP2P::Rank k2;
+    k2.view.req_mb = zalloc<gub_req>((size_t)2 * world * cap);
+    k2.view.resp_mb = zalloc<gub_resp>((size_t)2 * world * cap);
+    k2.view.req_flag = zalloc<unsigned long long>((size_t)2 * world);
+    k2.view.resp_flag = zalloc<unsigned long long>((size_t)2 * world);
+    k2.tile_agg = zalloc<unsigned long long>(((size_t)cap / RT_THREADS + 1) * MAX_SHARDS);
+    k2.error = zalloc<uint32_t>(1); k2.counts = zalloc<uint32_t>(MAX_SHARDS); k2.perm = zalloc<uint32_t>(cap); k2.ticket = zalloc<uint32_t>(2);
+    k2.true_owner = zalloc<uint8_t>(cap);
+    p->ranks.push_back(k2);
   }
   return p;
 }
 
 void* emu_p2p_table(void* pv, uint32_t rank) { return static_cast<EmuP2P*>(pv)->tabs[rank]; }
 
-int emu_p2p_step(void* pv, const gub_req* const* reqs, const uint32_t* n, const gub_clock* clk, gub_resp* const* outs) {
+// gub_p2p_step_streams of gub_api.cu for W shards in one process, phase by phase: every shard routes (k_p2p_route), then every
+// shard evaluates straight out of its mailboxes (k_batch over W flagged segments, responses into the sources' mailboxes), then
+// every shard collects.  self_global != 0: GLOBAL requests a shard does not own stay with it (rewritten).
+int emu_p2p_step(void* pv, const gub_req* const* reqs, const uint32_t* n, const gub_clock* clk, gub_resp* const* outs, uint32_t self_global,
+                 uint8_t* const* true_owner_out) {
   EmuP2P* p = static_cast<EmuP2P*>(pv);
   p->epoch++;
   std::vector<P2PArgs> args(p->world);
-  std::vector<uint32_t> ntiles(p->world, 0);
   for (uint32_t r = 0; r < p->world; r++) {
     P2PArgs& A = args[r];
     for (uint32_t q = 0; q < p->world; q++) A.peers[q] = p->ranks[q].view;
-    A.world = p->world; A.rank = r; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = p->ranks[r].done_ctr; A.error = p->ranks[r].error;
+    A.world = p->world; A.rank = r; A.cap = p->cap; A.epoch = p->epoch; A.done_ctr = nullptr; A.error = p->ranks[r].error;
   }
-  for (uint32_t r = 0; r < p->world; r++) {  // phase 1: partition by owner, store into the owners' mailboxes, publish counts
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 1
     EmuP2P::Rank& k = p->ranks[r];
-    if (n[r]) {
-      ntiles[r] = (n[r] + ROUTE_TILE - 1) / ROUTE_TILE;
-      emu::launch(k_route_count, ntiles[r], 256u, reqs[r], n[r], (const uint64_t*)p->pts.data(), (const int32_t*)p->peers.data(), (uint32_t)p->pts.size(), p->world,
-                  k.owner, k.tile_off, ntiles[r], -1, (uint8_t*)nullptr);
-      emu::launch(k_route_scan, 1u, 1024u, k.tile_off, p->world * ntiles[r], p->world, ntiles[r], k.counts);
-      emu::launch(k_p2p_scatter, ntiles[r], 256u, args[r], reqs[r], n[r], (const uint8_t*)k.owner, (const uint32_t*)k.tile_off, ntiles[r], (const uint32_t*)k.counts,
-                  k.perm);
-    } else {
-      emu::launch(k_p2p_publish_empty, 1u, 32u, args[r]);
+    RouteArgs R;
+    R.P = args[r]; R.reqs = reqs[r]; R.n = n[r]; R.n_dev = nullptr; R.pts = p->pts.data(); R.pt_peer = p->peers.data(); R.lut = p->lut.data();
+    R.npts = (uint32_t)p->pts.size(); R.self_global = self_global ? (int32_t)r : -1; R.true_owner = self_global ? k.true_owner : nullptr;
+    R.tile_agg = k.tile_agg; R.counts = k.counts; R.perm = k.perm; R.ticket = k.ticket;
+    emu::launch(k_p2p_route, std::max<uint32_t>(1u, (n[r] + RT_THREADS - 1) / RT_THREADS), (unsigned)RT_THREADS, R);
+    if (self_global && true_owner_out && n[r]) std::memcpy(true_owner_out[r], k.true_owner, n[r]);
+  }
+  const uint32_t par = p->epoch & 1u;
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 2
+    FSeg segs[MAX_SHARDS];
+    unsigned long long* rflags[MAX_SHARDS];
+    std::memset(segs, 0, sizeof segs);
+    for (uint32_t s = 0; s < p->world; s++) {
+      segs[s].reqs = args[r].peers[r].req_mb + ((size_t)par * p->world + s) * p->cap;
+      segs[s].flag = &args[r].peers[r].req_flag[(size_t)par * p->world + s];
+      segs[s].out = args[r].peers[s].resp_mb + ((size_t)par * p->world + r) * p->cap;
+      segs[s].n = p->cap;
+      rflags[s] = &args[r].peers[s].resp_flag[(size_t)par * p->world + r];
     }
-  }
-  for (uint32_t r = 0; r < p->world; r++) {  // phase 2: gather, evaluate what we own (batch size on the "device"), return responses
-    EmuP2P::Rank& k = p->ranks[r];
-    emu::launch(k_p2p_gather, 4u, 256u, args[r], k.inbox, k.seg_off, k.m_dev);
-    submit_impl(p->tabs[r], k.inbox, (size_t)p->world * p->cap, k.m_dev, clk, k.inbox_resp);
-    emu::launch(k_p2p_push_resp, 4u, 256u, args[r], (const gub_resp*)k.inbox_resp, (const uint32_t*)k.seg_off);
+    submit_fused(p->tabs[r], segs, p->world, p->epoch, clk, rflags, p->world);
   }
   int err = 0;
-  for (uint32_t r = 0; r < p->world; r++) {  // phase 3: responses back in request order
+  for (uint32_t r = 0; r < p->world; r++) {  // phase 3
     EmuP2P::Rank& k = p->ranks[r];
-    if (n[r]) emu::launch(k_p2p_unroute, 4u, 256u, args[r], (const uint32_t*)k.tile_off, ntiles[r], (const uint32_t*)k.perm, n[r], outs[r]);
-    else emu::launch(k_p2p_wait_resp_only, 1u, 32u, args[r]);
-    err |= (int)*k.error;
+    emu::launch(k_p2p_collect, 4u, 256u, args[r], (const uint32_t*)k.perm, n[r], (const uint32_t*)nullptr, outs[r]);
+    err |= (int)*k.error | (int)p->tabs[r]->ctl->error;
   }
   return err;
 }
