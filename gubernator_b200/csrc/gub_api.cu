@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -42,6 +43,8 @@ struct PipeSlot {
   gub_req* d_req = nullptr;
   gub_resp* d_resp = nullptr;
   gub_creq* d_creq = nullptr;       // compact submissions: what arrives over PCIe
+  uint8_t* d_packed = nullptr;      // key-string submissions: [gub_kreq x n][offsets x (n+1)][key bytes]
+  size_t packed_cap = 0;
   gub_params* d_params = nullptr;
   size_t cap = 0, params_cap = 0;
   cudaEvent_t in_done = nullptr, out_done = nullptr;
@@ -79,7 +82,8 @@ struct gub_table {
   int num_sms = 0;
   uint32_t sweep_chunk = 0;           // slots every CTA sweeps per batch (incremental expiry sweep), 0 = off
   gub::GEntry* gaux = nullptr;
-  uint32_t *gpres = nullptr, *gfrag = nullptr;
+  uint32_t* gpres = nullptr;
+  unsigned long long* gfrag = nullptr;
   uint16_t* gmembers = nullptr;
   gub::FCtl* ctl = nullptr;
   gub::OvfItem* ovf = nullptr;
@@ -377,6 +381,7 @@ void gub_destroy(gub_table* t) {
     if (s.d_req) cudaFree(s.d_req);
     if (s.d_resp) cudaFree(s.d_resp);
     if (s.d_creq) cudaFree(s.d_creq);
+    if (s.d_packed) cudaFree(s.d_packed);
     if (s.d_params) cudaFree(s.d_params);
     if (s.in_done) cudaEventDestroy(s.in_done);
     if (s.out_done) cudaEventDestroy(s.out_done);
@@ -442,7 +447,7 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   if (const char* e = getenv("GUB_COOP")) t->coop = std::atoi(e) != 0;
   ALLOC(t->gaux, (size_t)gub::FB_AUX_ENTRIES * sizeof(gub::GEntry));
   ALLOC(t->gpres, (size_t)gub::FB_AUX_ENTRIES * gub::FB_PRES_WORDS * 4);
-  ALLOC(t->gfrag, (size_t)gub::FB_AUX_ENTRIES * gub::FB_ROW * 4);
+  ALLOC(t->gfrag, (size_t)gub::FB_AUX_ENTRIES * gub::FB_ROW * 8);
   ALLOC(t->gmembers, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 2);
   ALLOC(t->ctl, sizeof(gub::FCtl));
   ALLOC(t->ovf, (size_t)gub::FB_OVF_CAP * sizeof(gub::OvfItem));
@@ -573,6 +578,62 @@ int gub_submit_compact_async(gub_table* t, const gub_creq* reqs, size_t n, const
   CK(cudaEventRecord(s.out_done, t->s_d2h));
   if (tr && trace_mark(t, t->s_d2h)) return -1;
   if (tr && t->trace_ev.size() >= TRACE_MAX * 6) trace_dump(t);
+  s.busy = true;
+  return 0;
+}
+
+/* Key strings in, responses out: the host ships raw key bytes and 16-byte request records; hashing (XXH64 + FNV-1), the
+ * expansion of the per-limit parameters and the evaluation all run on the device.  `packed` = [gub_kreq x n][uint32 offsets x
+ * (n + 1)][key bytes] in one buffer (one host-to-device copy per batch: small separate copies cost the copy stream far more than
+ * their size, profiles/r01_e2e_pipeline.md); gub_keys_layout() gives the offsets of the three parts. */
+int gub_keys_layout(size_t n, size_t key_bytes, size_t* offsets_at, size_t* bytes_at, size_t* total) {
+  if (!offsets_at || !bytes_at || !total) return fail("gub_keys_layout: null argument");
+  *offsets_at = n * sizeof(gub_kreq);
+  *bytes_at = *offsets_at + (n + 1) * 4;
+  *total = (*bytes_at + key_bytes + 15) & ~(size_t)15;
+  return 0;
+}
+
+int gub_submit_keys_async(gub_table* t, const void* packed, size_t packed_bytes, size_t n, const gub_params* params, size_t n_params, int64_t created_base,
+                          const gub_clock* clk, gub_resp* out, int* ticket) {
+  if (!t || !clk || !ticket || (n && (!packed || !out || !params))) return fail("gub_submit_keys_async: null argument");
+  if (n > 0x7FFFFFFFull || n_params > 0xFFFFFFFFull) return fail("gub_submit_keys_async: too large");
+  if (n && packed_bytes < n * sizeof(gub_kreq) + (n + 1) * 4) return fail("gub_submit_keys_async: packed buffer too small");
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  const int si = t->next_slot;
+  t->next_slot = (t->next_slot + 1) % PIPE_DEPTH;
+  PipeSlot& s = t->pipe[si];
+  if (s.busy) { CK(cudaEventSynchronize(s.out_done)); s.busy = false; }
+  *ticket = si;
+  if (n == 0) { CK(cudaEventRecord(s.out_done, t->s_d2h)); s.busy = true; return 0; }
+  if (ensure_slot(s, n)) return -1;
+  if (s.packed_cap < packed_bytes) {
+    if (s.d_packed) cudaFree(s.d_packed);
+    s.d_packed = nullptr;
+    s.packed_cap = std::max<size_t>(packed_bytes + packed_bytes / 4, (size_t)1 << 20);
+    CK(cudaMalloc(&s.d_packed, s.packed_cap));
+  }
+  const bool inl = n_params <= gub::INLINE_PARAMS;
+  if (!inl && (s.params_cap < n_params || !s.d_params)) {
+    if (s.d_params) cudaFree(s.d_params);
+    s.d_params = nullptr;
+    s.params_cap = std::max<size_t>(n_params, 1024);
+    CK(cudaMalloc(&s.d_params, s.params_cap * sizeof(gub_params)));
+  }
+  CK(cudaMemcpyAsync(s.d_packed, packed, packed_bytes, cudaMemcpyHostToDevice, t->s_h2d));
+  if (!inl) CK(cudaMemcpyAsync(s.d_params, params, n_params * sizeof(gub_params), cudaMemcpyHostToDevice, t->s_h2d));
+  CK(cudaEventRecord(s.in_done, t->s_h2d));
+  CK(cudaStreamWaitEvent(t->s_compute, s.in_done, 0));
+  gub::InlineParams P;
+  std::memset(&P, 0, sizeof P);
+  if (inl) std::memcpy(&P, params, n_params * sizeof(gub_params));
+  gub::k_hash_expand<<<(unsigned)((n + 255) / 256), 256, 0, t->s_compute>>>(s.d_packed, (uint32_t)n, P, (uint32_t)n_params, inl ? nullptr : s.d_params, created_base, s.d_req);
+  if (launch_batch(t, s.d_req, n, clk, s.d_resp, t->s_compute)) return -1;
+  CK(cudaEventRecord(t->compute_done[si], t->s_compute));
+  CK(cudaStreamWaitEvent(t->s_d2h, t->compute_done[si], 0));
+  CK(cudaMemcpyAsync(out, s.d_resp, n * sizeof(gub_resp), cudaMemcpyDeviceToHost, t->s_d2h));
+  CK(cudaEventRecord(s.out_done, t->s_d2h));
   s.busy = true;
   return 0;
 }
@@ -1113,6 +1174,11 @@ struct gub_p2p {
   uint32_t* g_count = nullptr;     // [4] device counters (hits drained, queries drained, items made, spare)
   uint32_t* g_counts_all = nullptr;  // [MAX_SHARDS] device: items per rank
   uint64_t seq = 0;
+  // all shards in one process (gub_p2p_connect_local): peers by pointer + a host-side rendezvous for the GLOBAL tick
+  struct LocalGroup { std::mutex mu; std::condition_variable cv; uint32_t arrived = 0, gen = 0; } own_group;
+  LocalGroup* group = nullptr;
+  gub_p2p* local_peers[gub::MAX_SHARDS] = {};
+  uint32_t* h_counts = nullptr;    // pinned: {hits drained, queries drained, items made, spare} of the tick in flight
   void* nccl = nullptr;            // ncclComm_t
   uint64_t tick_bytes = 0;         // bytes all-gathered by the last tick
 };
@@ -1144,6 +1210,7 @@ void gub_p2p_destroy(gub_p2p* p) {
   for (uint32_t r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
   void* ptrs[] = {p->block, p->error, p->ticket, p->g_reqs, p->g_resps, p->g_items, p->g_gather, p->g_count, p->g_counts_all};
   for (void* q : ptrs) if (q) cudaFree(q);
+  if (p->h_counts) cudaFreeHost(p->h_counts);
   for (auto& r : p->rt) {
     void* rp[] = {r.tile_agg, r.counts, r.perm, r.true_owner};
     for (void* q : rp) if (q) cudaFree(q);
@@ -1235,7 +1302,9 @@ int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers) {
       else if (e != cudaSuccess) return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
     }
     p->views[r] = p2p_view(peers[r]->block, p->world, p->cap);
+    p->local_peers[r] = peers[r];
   }
+  p->group = &peers[0]->own_group;
   p->connected = true;
   return 0;
 }
@@ -1294,24 +1363,30 @@ int p2p_evaluate(gub_p2p* p, const gub::P2PArgs& A, const gub_clock* clk, cudaSt
 
 extern "C" {
 
-int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int p2p_step_check(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out) {
   if (!p || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
   if (n > p->cap) return fail("gub_p2p_step: n exceeds the mailbox capacity");
-  const gub_ring* ring = p->ring;
-  if (p->t->ring_cached != ring || p->t->ring_version != gub_ring_version_(ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
+  if (p->t->ring_cached != p->ring || p->t->ring_version != gub_ring_version_(p->ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
+  if (!p->t->fused) return fail("gub_p2p_step: needs the fused batch kernel (GUB_FUSED=0 is a single-GPU measurement switch)");
+  return 0;
+}
+
+// Phase 1 of a step, on the ingest stream: partition by owner and store the records into the owners' mailboxes.  This parity's
+// scratch and mailbox halves were last used two steps ago; that step's collect (on the evaluation stream) must have finished,
+// which also means every peer has drained what we sent it then.
+int p2p_phase_route(gub_p2p* p, const gub_req* d_reqs, size_t n, cudaStream_t si, cudaStream_t st) {
   gub_table* t = p->t;
-  if (!t->fused) return fail("gub_p2p_step: needs the fused batch kernel (GUB_FUSED=0 is a single-GPU measurement switch)");
-  cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)ingest_stream;
-  const bool two = si != st;
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
+  const bool two = si != st;
   p->epoch++;
   gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
   gub::P2PArgs A;
   p2p_args(p, A);
-  // ---- ingest stream: partition by owner and store the records into the owners' mailboxes.  This parity's scratch and
-  // mailbox halves were last used two steps ago; that step's collect (on the evaluation stream) must have finished, which
-  // also means every peer has drained what we sent it then.
   if (two && rt->step_done_valid) CK(cudaStreamWaitEvent(si, rt->step_done, 0));
   const int self_global = p->hits_q ? (int)p->rank : -1;
   if (p2p_route(p, rt, A, d_reqs, (uint32_t)n, nullptr, self_global, si)) return -1;
@@ -1319,19 +1394,65 @@ int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_
     if (gq_accumulate(p->hits_q, d_reqs, n, nullptr, rt->true_owner, p->rank, p->seq, si)) return -1;
   }
   if (two) CK(cudaEventRecord(rt->routed, si));
-  // ---- evaluation stream: the batch kernel synchronises with every source (ourselves included) through the mailbox flags,
-  // evaluates straight out of the mailboxes and stores the responses into the sources' response mailboxes
+  return 0;
+}
+
+// Phase 2, on the evaluation stream: the batch kernel synchronises with every source (ourselves included) through the mailbox
+// flags, evaluates straight out of the mailboxes and stores the responses into the sources' response mailboxes.
+int p2p_phase_evaluate(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  gub::P2PArgs A;
+  p2p_args(p, A);
   if (order_after_last(t, st)) return -1;
   if (p2p_evaluate(p, A, clk, st)) return -1;
   t->last_stream = st; t->last_pending = true;
   if (p->updates_q) {  // GLOBAL requests just evaluated as owner (gubernator.go:604-606, global.go:80-84)
     if (gq_accumulate_segments(p, A, st)) return -1;
   }
+  return 0;
+}
+
+// Phase 3: wait for the owners' flags, responses back in request order.
+int p2p_phase_collect(gub_p2p* p, size_t n, gub_resp* d_out, cudaStream_t si, cudaStream_t st) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  const bool two = si != st;
+  gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
+  gub::P2PArgs A;
+  p2p_args(p, A);
   if (two) CK(cudaStreamWaitEvent(st, rt->routed, 0));  // the collect reads this parity's permutation
   gub::k_p2p_collect<<<std::max<unsigned>(1u, std::min<unsigned>(148u, (unsigned)((n + 255) / 256))), 256, 0, st>>>(A, rt->perm, (uint32_t)n, nullptr, d_out);
   if (two) { CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true; }
   CK(cudaGetLastError());
   p->seq += (uint64_t)1 << 32;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream, void* stream) {
+  if (p2p_step_check(p, d_reqs, n, clk, d_out)) return -1;
+  cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)ingest_stream;
+  if (p2p_phase_route(p, d_reqs, n, si, st)) return -1;
+  if (p2p_phase_evaluate(p, clk, st)) return -1;
+  return p2p_phase_collect(p, n, d_out, si, st);
+}
+
+/* One step of every shard of this process, driven by ONE host thread (the shape of the reference daemon: one process): the
+ * phases are enqueued shard by shard — all routings, then all evaluations, then all collects — so that no shard's kernels wait
+ * for work the host has not enqueued yet (on ONE device that would deadlock: the batch kernel occupies every SM). */
+int gub_p2p_step_local_all(gub_p2p* const* ps, uint32_t world, const gub_req* const* d_reqs, const size_t* n, const gub_clock* clk,
+                           gub_resp* const* d_out, void* const* streams) {
+  if (!ps || !d_reqs || !n || !d_out || !streams || world == 0) return fail("gub_p2p_step_local_all: bad argument");
+  for (uint32_t r = 0; r < world; r++) if (p2p_step_check(ps[r], d_reqs[r], n[r], clk, d_out[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) if (p2p_phase_route(ps[r], d_reqs[r], n[r], (cudaStream_t)streams[r], (cudaStream_t)streams[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) if (p2p_phase_evaluate(ps[r], clk, (cudaStream_t)streams[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) if (p2p_phase_collect(ps[r], n[r], d_out[r], (cudaStream_t)streams[r], (cudaStream_t)streams[r])) return -1;
   return 0;
 }
 
@@ -1469,76 +1590,180 @@ int gub_p2p_enable_global(gub_p2p* p, uint32_t capacity) {
   CK(cudaMalloc(&p->g_count, 16));
   CK(cudaMemset(p->g_count, 0, 16));
   CK(cudaMalloc(&p->g_counts_all, gub::MAX_SHARDS * 4));
+  CK(cudaHostAlloc(&p->h_counts, 16, cudaHostAllocDefault));
+  std::memset(p->h_counts, 0, 16);
   if (gq_reserve(p->updates_q, (size_t)p->world * p->cap, 0)) return -1;
   if (gq_reserve(p->hits_q, p->cap, 0)) return -1;
   return 0;
 }
 
-/* One GLOBAL sync: sendHits (global.go:144-190), then broadcastPeers (global.go:234-283) as an NCCL all-gather of the owners'
- * UpdatePeerGlobal items, installed by every other shard (UpdatePeerGlobals, gubernator.go:425-459).  Collective: every shard
- * of the ring calls it the same number of times, interleaved the same way with its steps.  now_ms = MillisecondNow() of the
- * receivers (CreatedAt / UpdatedAt of the installed items).  Everything is enqueued on `stream`; the one host round trip is the
- * per-shard item counts (a tick runs every GlobalSyncWait = 500 ms, not per batch).
- * stats (optional, 4 x uint64): hit records sent to owners, update items broadcast by this shard, items installed here, bytes gathered. */
+/* One GLOBAL sync: sendHits (global.go:144-190), then broadcastPeers (global.go:234-283): the owners' UpdatePeerGlobal items reach
+ * every other shard, which installs them (UpdatePeerGlobals, gubernator.go:425-459).  Transport of the broadcast: an NCCL
+ * all-gather when the shard has a communicator (one process per GPU); direct peer reads when all shards live in this process
+ * (gub_p2p_connect_local), where the calling threads — one per shard — rendezvous on the host.  Collective: every shard of the
+ * ring calls it the same number of times, interleaved the same way with its steps.  now_ms = MillisecondNow() of the receivers
+ * (CreatedAt / UpdatedAt of the installed items).  The one host round trip is the per-shard item counts (a tick runs every
+ * GlobalSyncWait = 500 ms, not per batch).
+ * stats (optional, 4 x uint64): hit records sent to owners, update items broadcast by this shard, items installed here, bytes moved. */
+}  // extern "C"
+
+namespace {
+
+// A tick in three enqueue-only phases (no host synchronisation inside), so that one host thread can drive all the shards of a
+// process phase by phase (see gub_p2p_step_local_all).
+// A: the window's aggregated hits -> their owners' mailboxes (plain routing: these records go to the owner).
+int tick_phase_a(gub_p2p* p, cudaStream_t st) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  CK(cudaMemsetAsync(p->g_count, 0, 16, st));
+  gub::k_gq_drain<<<148, 256, 0, st>>>(p->hits_q->q, p->g_reqs, p->gcap, p->g_count + 0, 0u);
+  p->epoch++;
+  gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
+  if (rt->step_done_valid) CK(cudaStreamWaitEvent(st, rt->step_done, 0));
+  gub::P2PArgs A;
+  p2p_args(p, A);
+  return p2p_route(p, rt, A, p->g_reqs, p->gcap, p->g_count + 0, -1, st);
+}
+// B: owners apply the hits with DRAIN_OVER_LIMIT as owner (gubernator.go:510-512); the responses are dropped like sendHits does.
+int tick_phase_b(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
+  gub::P2PArgs A;
+  p2p_args(p, A);
+  if (order_after_last(t, st)) return -1;
+  if (p2p_evaluate(p, A, clk, st)) return -1;
+  t->last_stream = st; t->last_pending = true;
+  if (gq_accumulate_segments(p, A, st)) return -1;
+  gub::k_p2p_collect<<<64, 256, 0, st>>>(A, rt->perm, p->gcap, p->g_count + 0, p->g_resps);
+  CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true;
+  p->seq += (uint64_t)1 << 32;
+  CK(cudaGetLastError());
+  return 0;
+}
+// C: owners re-read every key touched by GLOBAL traffic with Hits = 0 (global.go:243-245) and build the UpdatePeerGlobal items.
+int tick_phase_c(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  gub::k_gq_drain<<<148, 256, 0, st>>>(p->updates_q->q, p->g_reqs, p->gcap, p->g_count + 1, 1u);
+  gub::FArgs F;
+  fused_base_args(t, clk, F);
+  F.seg[0].reqs = p->g_reqs; F.seg[0].out = p->g_resps; F.seg[0].n = p->gcap; F.seg[0].n_dev = p->g_count + 1; F.nseg = 1;
+  if (launch_fused(t, F, 0, st)) return -1;
+  gub::k_make_updates<<<(p->gcap + 255) / 256, 256, 0, st>>>(p->g_reqs, p->g_resps, p->gcap, p->g_count + 1, p->g_items, p->g_count + 2);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(p->h_counts, p->g_count, 16, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+int tick_enqueue(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
+  if (tick_phase_a(p, st)) return -1;
+  if (tick_phase_b(p, clk, st)) return -1;
+  return tick_phase_c(p, clk, st);
+}
+
+void group_barrier(gub_p2p::LocalGroup* g, uint32_t world) {
+  std::unique_lock<std::mutex> lk(g->mu);
+  const uint32_t my = g->gen;
+  if (++g->arrived == world) { g->arrived = 0; g->gen++; g->cv.notify_all(); }
+  else g->cv.wait(lk, [&] { return g->gen != my; });
+}
+
+// Installs the items every other shard of this process has made (their g_items, read in place: same device or peer memory).
+int tick_install_local(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* installed) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  p->tick_bytes = 0;
+  for (uint32_t r = 0; r < p->world; r++) {
+    if (r == p->rank) continue;  // "Exclude ourselves from the update" (global.go:263-265)
+    const gub_p2p* q = p->local_peers[r];
+    const uint32_t k = std::min(q->h_counts[2], q->gcap);
+    if (!k) continue;
+    k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, q->g_items, k, now_ms, t->counters);
+    *installed += k;
+    p->tick_bytes += (uint64_t)k * sizeof(gub_item);
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));  // the peers may overwrite their items at their next tick
+  return 0;
+}
+
+int tick_install_nccl(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* installed) {
+  gub_table* t = p->t;
+  std::lock_guard<std::mutex> lk(t->mu);
+  CK(cudaSetDevice(t->device));
+  // all-gather: counts first (the host needs them to size the item gather), then the items, padded to the largest count
+  std::vector<uint32_t> all(p->world, 0);
+  NCK(g_nccl.AllGather(p->g_count + 2, p->g_counts_all, 1, /* ncclUint32 */ 3, p->nccl, st));
+  CK(cudaMemcpyAsync(all.data(), p->g_counts_all, p->world * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  uint32_t pad = 0;
+  for (uint32_t r = 0; r < p->world; r++) pad = std::max(pad, std::min(all[r], p->gcap));
+  p->tick_bytes = 0;
+  if (pad) {
+    NCK(g_nccl.AllGather(p->g_items, p->g_gather, (size_t)pad * sizeof(gub_item), /* ncclUint8 */ 1, p->nccl, st));
+    p->tick_bytes = (uint64_t)pad * sizeof(gub_item) * p->world;
+    for (uint32_t r = 0; r < p->world; r++) {
+      const uint32_t k = std::min(all[r], p->gcap);
+      if (r == p->rank || !k) continue;  // "Exclude ourselves from the update" (global.go:263-265)
+      k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters);
+      *installed += k;
+    }
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+void tick_stats(gub_p2p* p, uint64_t installed, uint64_t* stats) {
+  if (!stats) return;
+  stats[0] = std::min(p->h_counts[0], p->gcap); stats[1] = std::min(p->h_counts[2], p->gcap); stats[2] = installed; stats[3] = p->tick_bytes;
+}
+
+}  // namespace
+
+extern "C" {
+
 int gub_global_tick(gub_p2p* p, const gub_clock* clk, int64_t now_ms, void* stream, uint64_t* stats) {
   if (!p || !clk) return fail("gub_global_tick: null argument");
   if (!p->hits_q) return fail("gub_global_tick: gub_p2p_enable_global has not been called");
-  if (p->world > 1 && !p->nccl) return fail("gub_global_tick: no NCCL communicator (gub_p2p_nccl_init)");
-  gub_table* t = p->t;
+  if (p->world > 1 && !p->nccl && !p->group) return fail("gub_global_tick: no NCCL communicator (gub_p2p_nccl_init) and the shards are not local to this process");
   cudaStream_t st = (cudaStream_t)stream;
-  uint32_t h_counts[4] = {0, 0, 0, 0};
-  {
-    std::lock_guard<std::mutex> lk(t->mu);
-    CK(cudaSetDevice(t->device));
-    // 1. the window's aggregated hits -> their owners, over the same NVLink mailboxes as a step (plain routing: these records go to
-    //    the owner), evaluated there with DRAIN_OVER_LIMIT as owner (gubernator.go:510-512); the responses are dropped like sendHits does
-    CK(cudaMemsetAsync(p->g_count, 0, 16, st));
-    gub::k_gq_drain<<<148, 256, 0, st>>>(p->hits_q->q, p->g_reqs, p->gcap, p->g_count + 0, 0u);
-    p->epoch++;
-    gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
-    if (rt->step_done_valid) CK(cudaStreamWaitEvent(st, rt->step_done, 0));
-    gub::P2PArgs A;
-    p2p_args(p, A);
-    if (p2p_route(p, rt, A, p->g_reqs, p->gcap, p->g_count + 0, -1, st)) return -1;
-    if (order_after_last(t, st)) return -1;
-    if (p2p_evaluate(p, A, clk, st)) return -1;
-    t->last_stream = st; t->last_pending = true;
-    if (gq_accumulate_segments(p, A, st)) return -1;
-    gub::k_p2p_collect<<<64, 256, 0, st>>>(A, rt->perm, p->gcap, p->g_count + 0, p->g_resps);
-    CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true;
-    p->seq += (uint64_t)1 << 32;
-    // 2. owners re-read every key touched by GLOBAL traffic with Hits = 0 (global.go:243-245) and build the UpdatePeerGlobal items
-    gub::k_gq_drain<<<148, 256, 0, st>>>(p->updates_q->q, p->g_reqs, p->gcap, p->g_count + 1, 1u);
-    gub::FArgs F;
-    fused_base_args(t, clk, F);
-    F.seg[0].reqs = p->g_reqs; F.seg[0].out = p->g_resps; F.seg[0].n = p->gcap; F.seg[0].n_dev = p->g_count + 1; F.nseg = 1;
-    if (launch_fused(t, F, 0, st)) return -1;
-    gub::k_make_updates<<<(p->gcap + 255) / 256, 256, 0, st>>>(p->g_reqs, p->g_resps, p->gcap, p->g_count + 1, p->g_items, p->g_count + 2);
-    CK(cudaGetLastError());
-    // 3. all-gather: counts first (the host needs them to size the item gather), then the items, padded to the largest count
-    std::vector<uint32_t> all(p->world, 0);
-    if (p->world > 1) {
-      NCK(g_nccl.AllGather(p->g_count + 2, p->g_counts_all, 1, /* ncclUint32 */ 3, p->nccl, st));
-      CK(cudaMemcpyAsync(all.data(), p->g_counts_all, p->world * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaMemcpyAsync(h_counts, p->g_count, 16, cudaMemcpyDeviceToHost, st));
+  if (tick_enqueue(p, clk, st)) return -1;
+  uint64_t installed = 0;
+  if (p->world > 1 && p->nccl) {
+    if (tick_install_nccl(p, now_ms, st, &installed)) return -1;
     CK(cudaStreamSynchronize(st));
-    uint32_t pad = 0;
-    for (uint32_t r = 0; r < p->world; r++) pad = std::max(pad, std::min(all[r], p->gcap));
-    uint64_t installed = 0;
-    p->tick_bytes = 0;
-    if (p->world > 1 && pad) {
-      NCK(g_nccl.AllGather(p->g_items, p->g_gather, (size_t)pad * sizeof(gub_item), /* ncclUint8 */ 1, p->nccl, st));
-      p->tick_bytes = (uint64_t)pad * sizeof(gub_item) * p->world;
-      for (uint32_t r = 0; r < p->world; r++) {
-        const uint32_t k = std::min(all[r], p->gcap);
-        if (r == p->rank || !k) continue;  // "Exclude ourselves from the update" (global.go:263-265)
-        k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters);
-        installed += k;
-      }
-      CK(cudaGetLastError());
+  } else {
+    CK(cudaSetDevice(p->t->device));
+    CK(cudaStreamSynchronize(st));  // my items and their count are final
+    if (p->world > 1) {
+      group_barrier(p->group, p->world);  // ... and so are everybody else's
+      const int rc = tick_install_local(p, now_ms, st, &installed);
+      group_barrier(p->group, p->world);  // nobody still reads my items
+      if (rc) return -1;
     }
-    if (stats) { stats[0] = std::min(h_counts[0], p->gcap); stats[1] = std::min(h_counts[2], p->gcap); stats[2] = installed; stats[3] = p->tick_bytes; }
+  }
+  tick_stats(p, installed, stats);
+  return 0;
+}
+
+/* The same for a single host thread driving all the shards of this process (gub_p2p_connect_local): phases run shard by shard. */
+int gub_global_tick_local_all(gub_p2p* const* ps, uint32_t world, const gub_clock* clk, int64_t now_ms, void* const* streams, uint64_t* stats /* world x 4, optional */) {
+  if (!ps || !clk || !streams || world == 0) return fail("gub_global_tick_local_all: bad argument");
+  for (uint32_t r = 0; r < world; r++) {
+    if (!ps[r] || !ps[r]->hits_q || ps[r]->world != world || (world > 1 && !ps[r]->group)) return fail("gub_global_tick_local_all: shards must be local, connected and GLOBAL-enabled");
+  }
+  for (uint32_t r = 0; r < world; r++) if (tick_phase_a(ps[r], (cudaStream_t)streams[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) if (tick_phase_b(ps[r], clk, (cudaStream_t)streams[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) if (tick_phase_c(ps[r], clk, (cudaStream_t)streams[r])) return -1;
+  for (uint32_t r = 0; r < world; r++) { CK(cudaSetDevice(ps[r]->t->device)); CK(cudaStreamSynchronize((cudaStream_t)streams[r])); }
+  for (uint32_t r = 0; r < world; r++) {
+    uint64_t installed = 0;
+    if (world > 1 && tick_install_local(ps[r], now_ms, (cudaStream_t)streams[r], &installed)) return -1;
+    tick_stats(ps[r], installed, stats ? stats + 4 * r : nullptr);
   }
   return 0;
 }

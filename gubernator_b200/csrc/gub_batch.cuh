@@ -41,7 +41,7 @@ constexpr int FB_PRES_WORDS = 8;     // presence bitmap: one bit per tile of a r
 constexpr int FB_MAX_GRID = FB_PRES_WORDS * 32;
 constexpr int FB_ROW = FB_MAX_GRID;  // fragment-size row (uint16) per group entry
 constexpr int FB_MAX_SEGS = MAX_SHARDS;
-constexpr uint32_t FB_AUX_ENTRIES = 1u << 18;  // batch-wide group table (a round holds <= 256 x 512 keys)
+constexpr uint32_t FB_AUX_ENTRIES = 1u << 17;  // batch-wide group table (a round of 148 tiles holds <= 75 776 keys)
 constexpr uint32_t G_NONUNIFORM = 1u;
 constexpr int FB_OVF_CAP = 1024;     // items whose insert found the probe window full; placed (with eviction) at the next batch
 
@@ -52,7 +52,7 @@ struct __align__(32) GEntry {
   uint32_t rep;             // round-local index of one member: every fragment's first member is compared with it
   uint32_t flags;           // G_NONUNIFORM
   uint32_t arrived;         // fragments that have read the slot and answered
-  uint32_t _pad;
+  uint32_t scanned;         // the base ranks of the group's fragments are in its row
 };
 
 struct FSeg {                           // one run of request records, evaluated in order after the previous segment
@@ -83,7 +83,8 @@ struct FArgs {
   uint32_t flag_epoch;                  // epoch the segments' flags must show
   GEntry* aux;
   uint32_t* presence;                   // [FB_AUX_ENTRIES][FB_PRES_WORDS]
-  uint32_t* fragrow;                    // [FB_AUX_ENTRIES][FB_ROW] per tile: (offset of the fragment's members in the tile's list << 16) | fragment size
+  unsigned long long* fragrow;          // [FB_AUX_ENTRIES][FB_ROW] per tile: [63:32] rank of the fragment's first member within the group (written by the
+                                        // group's scanner) [31:16] offset of the fragment's members in the tile's list [15:0] fragment size
   uint16_t* members;                    // [FB_MAX_GRID * FB_THREADS] per tile: the members of each of its fragments, contiguous, in index order
   FCtl* ctl;
   OvfItem* ovf;                         // [FB_OVF_CAP]
@@ -104,7 +105,7 @@ struct FCtx {
   uint64_t capacity;
   GEntry* aux;
   uint32_t* presence;
-  uint32_t* fragrow;
+  unsigned long long* fragrow;
   uint16_t* members;
   FCtl* ctl;
   OvfItem* ovf;
@@ -123,6 +124,7 @@ __device__ __forceinline__ void mbar_wait(MBar*, uint32_t) {}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) { return *p; }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { *p = v; }
 __device__ __forceinline__ void spin_pause() { emu::spin_yield(); }
+__device__ __forceinline__ uint32_t atomic_add_acq_rel_gpu(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 #else
 struct __align__(8) MBar { uint64_t w; };
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,6 +155,11 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void spin_pause() {}
+__device__ __forceinline__ uint32_t atomic_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+}
 #endif
 
 #if defined(GUB_EMULATE)
@@ -173,10 +180,8 @@ __device__ __forceinline__ void grid_barrier(FCtl* ctl) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t gen = ld_acquire_gpu(&ctl->bar_gen);
-    __threadfence();
-    if (atomicAdd(&ctl->bar_cnt, 1u) == gridDim.x - 1) {
+    if (atomic_add_acq_rel_gpu(&ctl->bar_cnt, 1u) == gridDim.x - 1) {  // release: everything this CTA wrote (cumulative over the barrier above)
       ctl->bar_cnt = 0;
-      __threadfence();
       st_release_gpu(&ctl->bar_gen, gen + 1);
     } else {
       // bounded (seconds): a CTA that never arrives (a fault, a grid that is not co-resident) must not hang the device
@@ -184,7 +189,6 @@ __device__ __forceinline__ void grid_barrier(FCtl* ctl) {
       while (ld_acquire_gpu(&ctl->bar_gen) == gen && ++it < (1u << 26)) spin_pause();
       if (it >= (1u << 26)) atomicExch(&ctl->error, 2u);
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -304,34 +308,42 @@ __device__ __forceinline__ void gentry_clear(GEntry* e) {
 }
 
 // Sum of the fragment sizes of the tiles before `tt` that hold members of group `pos`.
-__device__ __forceinline__ uint32_t fragment_base2(const FCtx& A, uint32_t pos, uint32_t tt, const uint4& p0, const uint4& p1) {
-  const uint32_t* row = A.fragrow + (size_t)pos * FB_ROW;
-  uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  const uint32_t last = tt >> 5, keep = (1u << (tt & 31)) - 1u;
-  uint32_t base = 0;
+// ---- base ranks: one scan per group, not one per fragment ----------------------------------------------------------------------
+// A fragment's members rank base + 0, base + 1, ... within the group, base = members in the tiles before it.  Every fragment
+// summing the row itself costs O(fragments^2) loads per group (a hot key has a fragment in every tile).  Instead ONE fragment of
+// each group — picked by key hash among the tiles the group occupies, so the duty spreads evenly over the CTAs — scans the row
+// once, warp-cooperatively (64 tiles per step, coalesced), stores every fragment's base next to its size and raises the entry's
+// `scanned` flag; the other fragments wait for the flag and read one number.
+__device__ __forceinline__ uint32_t kth_set_bit(const uint32_t bits[FB_PRES_WORDS], uint32_t k) {  // position of the k-th (0-based) set bit
+  uint32_t w = 0;
+#pragma unroll 1
+  for (; w < (uint32_t)FB_PRES_WORDS - 1; w++) { const uint32_t c = __popc(bits[w]); if (k < c) break; k -= c; }
+  uint32_t x = bits[w];
+  for (; k > 0; k--) x &= x - 1;
+  return w * 32 + (uint32_t)(__ffs(x) - 1);
+}
+
+__device__ __forceinline__ void scan_group_row(const FCtx& A, uint32_t pos, const uint32_t bits[FB_PRES_WORDS]) {  // whole warp
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned long long* row = A.fragrow + (size_t)pos * FB_ROW;
+  uint32_t carry = 0;
+#pragma unroll 1
+  for (uint32_t c = 0; c < (uint32_t)FB_PRES_WORDS / 2; c++) {  // 64 tiles per step: lane -> tiles 64c + 2 lane, + 1
+    const uint32_t w0 = bits[2 * c], w1 = bits[2 * c + 1];
+    if (!(w0 | w1)) continue;
+    const uint32_t pair = lane < 16 ? (w0 >> (2 * lane)) & 3u : (w1 >> (2 * (lane - 16))) & 3u;
+    ulonglong2 e = make_ulonglong2(0ull, 0ull);
+    if (pair) e = __ldcg(reinterpret_cast<const ulonglong2*>(row + 64 * c + 2 * lane));
+    const uint32_t v0 = (pair & 1u) ? (uint32_t)(e.x & 0xFFFFull) : 0u, v1 = (pair & 2u) ? (uint32_t)(e.y & 0xFFFFull) : 0u;
+    uint32_t incl = v0 + v1;
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
-    uint32_t x = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u);
-    if (!x) continue;
-    if (__popc(x) <= 4) {
-      while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += __ldcg(row + w * 32 + k) & 0xFFFFu; }
-    } else {  // the entries of all 32 tiles of the word (128 bytes), masked
-      const uint4* r4 = reinterpret_cast<const uint4*>(row + w * 32);
-#pragma unroll
-      for (int h = 0; h < 2; h++) {  // four 16-byte loads in flight at a time
-        uint4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = __ldcg(r4 + 4 * h + k);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const uint32_t m = (x >> (4 * (4 * h + k))) & 0xFu;
-          base += ((m & 1u) ? (v[k].x & 0xFFFFu) : 0u) + ((m & 2u) ? (v[k].y & 0xFFFFu) : 0u) + ((m & 4u) ? (v[k].z & 0xFFFFu) : 0u) +
-                  ((m & 8u) ? (v[k].w & 0xFFFFu) : 0u);
-        }
-      }
-    }
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
+    const uint32_t excl = carry + incl - (v0 + v1);
+    uint32_t* hi = reinterpret_cast<uint32_t*>(row + 64 * c + 2 * lane);
+    if (pair & 1u) __stcg(hi + 1, excl);
+    if (pair & 2u) __stcg(hi + 3, excl + v0);
+    carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
   }
-  return base;
 }
 
 __device__ __forceinline__ void cursor_from_snapshot(const FCtx& A, const FSmem& S, uint32_t f, uint64_t key, uint64_t tag, Cursor& c) {
@@ -399,13 +411,13 @@ __device__ __noinline__ void mixed_group(const FCtx& A, FSmem& S, SC& sc, uint32
   // 1. the tiles that hold members, in order, with their member counts
   if (tid == 0) { sc.nseg = 0; sc.ntile = 0; }
   T::sync();
-  const uint32_t* row = A.fragrow + (size_t)pos * FB_ROW;
+  const unsigned long long* row = A.fragrow + (size_t)pos * FB_ROW;
   for (uint32_t b = tid; b < (uint32_t)FB_MAX_GRID; b += NT) {
     if (!((bits[b >> 5] >> (b & 31)) & 1u)) continue;
     uint32_t slot = __popc(bits[b >> 5] & ((1u << (b & 31)) - 1u));
     for (uint32_t w = 0; w < (b >> 5); w++) slot += __popc(bits[w]);
     if (slot < TILES) {
-      const uint32_t r = __ldcg(row + b);
+      const uint32_t r = (uint32_t)(__ldcg(row + b) & 0xFFFFFFFFull);
       sc.tile[slot] = (uint16_t)b; sc.off[slot] = (uint16_t)(r >> 16); sc.cum[slot + 1] = r & 0xFFFFu;
     }
     atomicAdd(&sc.ntile, 1u);
@@ -756,44 +768,66 @@ __device__ __noinline__ void batch_phase2(FSmem& S, uint32_t round) {
   // The member that completes a fragment (shared-memory counter) checks the fragment in on the group entry; the last
   // fragment to arrive finishes the group.
   if (A.sweep_chunk && blockIdx.x == 0 && tid == 0) A.ctl->sweep_cursor = (A.ctl->sweep_cursor + (uint64_t)gridDim.x * A.sweep_chunk) % A.capacity;
-  uint32_t f = 0, lead = 0, cnt = 0, nfrag = 1, total = 1, base = 0;
+  uint32_t f = 0, lead = 0, cnt = 0, nfrag = 1, total = 1, base = 0, lpos = 0;
   gub_req rq;
   Cursor cur;
-  bool have_cur = false;
+  bool have_cur = false, is_scanner = false;
+  uint32_t pbits[FB_PRES_WORDS];
+#pragma unroll
+  for (int w = 0; w < FB_PRES_WORDS; w++) pbits[w] = 0;
   if (valid) {
     rq = smem_req(&S.req[tid]);
     f = S.f_of_sp[sp]; lead = S.flead[f]; cnt = S.fcnt[f];
     if (tid == lead) {
-      const uint32_t pos = S.fpos[f];
+      lpos = S.fpos[f];
       // the group entry, its presence bitmap, and the probe: all issued before any is consumed
-      const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
-      const uint32_t e_rep = __ldcg(&A.aux[pos].rep);
-      const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
+      const ulonglong2 e0 = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[lpos]));
+      const uint32_t e_rep = __ldcg(&A.aux[lpos].rep);
+      const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)lpos * FB_PRES_WORDS);
       const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
       cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
       have_cur = true;
       total = (uint32_t)(e0.y & 0xFFFFFFFFull); nfrag = (uint32_t)(e0.y >> 32);
       if (nfrag > 1) {
-        gub_req rr;
-        const bool cmp = e_rep != blockIdx.x * FB_THREADS + tid;  // uniformity across tiles: every fragment's first member == the representative
-        if (cmp) rr = global_req(req_at(S, A.nseg, round, e_rep));
-        base = fragment_base2(A, pos, blockIdx.x, p0, p1);
-        if (cmp && !req_same(rq, rr)) atomicOr(&A.aux[pos].flags, G_NONUNIFORM);
+        pbits[0] = p0.x; pbits[1] = p0.y; pbits[2] = p0.z; pbits[3] = p0.w; pbits[4] = p1.x; pbits[5] = p1.y; pbits[6] = p1.z; pbits[7] = p1.w;
+        is_scanner = kth_set_bit(pbits, (uint32_t)(key >> 17) % nfrag) == blockIdx.x;
+        if (e_rep != blockIdx.x * FB_THREADS + tid) {  // uniformity across tiles: every fragment's first member == the representative
+          const gub_req rr = global_req(req_at(S, A.nseg, round, e_rep));
+          if (!req_same(rq, rr)) atomicOr(&A.aux[lpos].flags, G_NONUNIFORM);
+        }
       } else {  // the key lives in this tile only: hand the entry and the bitmap word back now
-        A.presence[(size_t)pos * FB_PRES_WORDS + (blockIdx.x >> 5)] = 0;
-        gentry_clear(&A.aux[pos]);
+        A.presence[(size_t)lpos * FB_PRES_WORDS + (blockIdx.x >> 5)] = 0;
+        gentry_clear(&A.aux[lpos]);
       }
-      S.fbase[f] = base; S.ftotal[f] = total; S.fnfrag[f] = (uint16_t)nfrag;
-      if (cnt > 1 || nfrag > 1) {  // somebody else (a sibling, or whoever finishes the group from this CTA) needs the slot as found
-        const Bucket& b = cur.b;
-        S.snap[f][0] = make_ulonglong2(b.key, (b.tag << 8) | (uint64_t)(b.flags & 0xFF));
-        S.snap[f][1] = make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration);
-        S.snap[f][2] = make_ulonglong2(b.rem, (uint64_t)b.stamp);
-        S.snap[f][3] = make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire);
-        S.fslot[f] = cur.slot; S.ffound[f] = cur.found ? 1 : 0;
-        __threadfence_block();
-        *reinterpret_cast<volatile uint8_t*>(&S.fready[f]) = 1;
-      }
+    }
+  }
+  // the groups this warp scans (see scan_group_row)
+  for (uint32_t m = __ballot_sync(0xFFFFFFFFu, is_scanner); m; m &= m - 1) {
+    const uint32_t src = __ffs(m) - 1;
+    uint32_t bits[FB_PRES_WORDS];
+#pragma unroll
+    for (int w = 0; w < FB_PRES_WORDS; w++) bits[w] = __shfl_sync(0xFFFFFFFFu, pbits[w], src);
+    const uint32_t spos = __shfl_sync(0xFFFFFFFFu, lpos, src);
+    scan_group_row(A, spos, bits);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { __threadfence(); st_release_gpu(&A.aux[spos].scanned, 1u); }
+  }
+  if (valid && tid == lead) {
+    if (nfrag > 1) {
+      uint32_t it = 0;
+      while (ld_acquire_gpu(&A.aux[lpos].scanned) == 0 && ++it < (1u << 26)) spin_pause();
+      base = __ldcg(reinterpret_cast<const uint32_t*>(A.fragrow + (size_t)lpos * FB_ROW + blockIdx.x) + 1);
+    }
+    S.fbase[f] = base; S.ftotal[f] = total; S.fnfrag[f] = (uint16_t)nfrag;
+    if (cnt > 1 || nfrag > 1) {  // somebody else (a sibling, or whoever finishes the group from this CTA) needs the slot as found
+      const Bucket& b = cur.b;
+      S.snap[f][0] = make_ulonglong2(b.key, (b.tag << 8) | (uint64_t)(b.flags & 0xFF));
+      S.snap[f][1] = make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration);
+      S.snap[f][2] = make_ulonglong2(b.rem, (uint64_t)b.stamp);
+      S.snap[f][3] = make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire);
+      S.fslot[f] = cur.slot; S.ffound[f] = cur.found ? 1 : 0;
+      __threadfence_block();
+      *reinterpret_cast<volatile uint8_t*>(&S.fready[f]) = 1;
     }
   }
   __syncwarp();  // a leader and its siblings in this warp: published before anybody below waits

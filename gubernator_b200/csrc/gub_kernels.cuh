@@ -894,18 +894,11 @@ __device__ __forceinline__ uint64_t load_u64_le(const uint8_t* p) {
 }
 __device__ __forceinline__ uint64_t xxh_lane(uint64_t acc, uint64_t w) { return rotl64(acc + w * 0xC2B2AE3D27D4EB4Full, 31) * 0x9E3779B185EBCA87ull; }
 
-__global__ void __launch_bounds__(256) k_hash_keys(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint64_t* xxh_out, uint64_t* fnv_out,
-                                                   gub_req* reqs_out /* optional: fill key_xxh64 / key_fnv1 of request i */) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void hash_key_bytes(const uint8_t* p, uint32_t len, uint64_t* xxh, uint64_t* fnv) {
   constexpr uint64_t P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull, P4 = 0x85EBCA77C2B2AE63ull,
                      P5 = 0x27D4EB2F165667C5ull;
-  const uint8_t* p = bytes + offsets[i];
-  const uint64_t len = offsets[i + 1] - offsets[i];
-  // FNV-1 64 over the whole key
   uint64_t f = 0xCBF29CE484222325ull;
-  for (uint64_t k = 0; k < len; k++) f = (f * 0x100000001B3ull) ^ p[k];
-  // XXH64, seed 0
+  for (uint32_t k = 0; k < len; k++) f = (f * 0x100000001B3ull) ^ p[k];
   const uint8_t* q = p;
   const uint8_t* const end = p + len;
   uint64_t h;
@@ -932,6 +925,15 @@ __global__ void __launch_bounds__(256) k_hash_keys(const uint8_t* bytes, const u
   h = (h ^ (h >> 33)) * P2;
   h = (h ^ (h >> 29)) * P3;
   h ^= h >> 32;
+  *xxh = h; *fnv = f;
+}
+
+__global__ void __launch_bounds__(256) k_hash_keys(const uint8_t* bytes, const uint64_t* offsets, uint32_t n, uint64_t* xxh_out, uint64_t* fnv_out,
+                                                   gub_req* reqs_out /* optional: fill key_xxh64 / key_fnv1 of request i */) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t h, f;
+  hash_key_bytes(bytes + offsets[i], (uint32_t)(offsets[i + 1] - offsets[i]), &h, &f);
   if (xxh_out) xxh_out[i] = h;
   if (fnv_out) fnv_out[i] = f;
   if (reqs_out) { reqs_out[i].key_xxh64 = h; reqs_out[i].key_fnv1 = f; }
@@ -980,6 +982,29 @@ __global__ void __launch_bounds__(256) k_expand_inline(const gub_creq* creqs, ui
   const bool known = pi < n_params;
   const uint32_t k = known ? pi : 0u;
   expand_one(creqs, i, P.q[k][0], P.q[k][1], known, a, b, created_base, out);
+}
+
+// ---- key strings -> gub_req records: HashKey (client.go:39-41) + XXH64 (workers.go:153) + FNV-1 (replicated_hash.go:108) on the
+// device, fused with the expansion of the per-limit parameters.  One packed buffer per batch: [gub_kreq x n][uint32 offsets x (n+1)]
+// [key bytes], key i = bytes[offsets[i] .. offsets[i+1]).
+__global__ void __launch_bounds__(256) k_hash_expand(const uint8_t* packed, uint32_t n, const InlineParams P, uint32_t n_params, const gub_params* params_far,
+                                                     int64_t created_base, gub_req* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ulonglong2 kr = __ldcs(reinterpret_cast<const ulonglong2*>(packed) + i);  // hits | params, created_delta
+  const uint32_t* offsets = reinterpret_cast<const uint32_t*>(packed + (size_t)n * 16);
+  const uint8_t* bytes = packed + (size_t)n * 16 + ((size_t)n + 1) * 4;
+  const uint32_t lo = __ldg(offsets + i), hi = __ldg(offsets + i + 1);
+  uint64_t xxh, fnv;
+  hash_key_bytes(bytes + lo, hi - lo, &xxh, &fnv);
+  const uint32_t pi = (uint32_t)(kr.y & 0xFFFFFFFFull);
+  const bool known = pi < n_params;
+  ulonglong2 q0 = make_ulonglong2(0, 0), q1 = q0;
+  if (known) {
+    if (params_far) { const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(params_far + pi); q0 = __ldg(pp); q1 = __ldg(pp + 1); }
+    else { q0 = P.q[pi][0]; q1 = P.q[pi][1]; }
+  }
+  expand_one(nullptr, i, q0, q1, known, make_ulonglong2(xxh, fnv), kr, created_base, out);
 }
 
 // ---- maintenance kernels -------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ TOKEN_BUCKET, LEAKY_BUCKET = 0, 1
 UNDER_LIMIT, OVER_LIMIT = 0, 1
 NO_BATCHING, GLOBAL, DURATION_IS_GREGORIAN, RESET_REMAINING, MULTI_REGION, DRAIN_OVER_LIMIT = 1, 2, 4, 8, 16, 32
 REQ_IS_OWNER = 0x100
-ERR_UNIQUE_KEY_EMPTY, ERR_NAMESPACE_EMPTY, ERR_INVALID_ALGORITHM, ERR_GREGORIAN_WEEKS, ERR_GREGORIAN_INVALID, ERR_TABLE_FULL = 1, 2, 3, 4, 5, 6
+ERR_UNIQUE_KEY_EMPTY, ERR_NAMESPACE_EMPTY, ERR_INVALID_ALGORITHM, ERR_GREGORIAN_WEEKS, ERR_GREGORIAN_INVALID, ERR_TABLE_FULL, ERR_PEER_TIMEOUT = 1, 2, 3, 4, 5, 6, 7
 
 REQ_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("hits", "<i8"), ("limit", "<i8"), ("duration", "<i8"),
                       ("burst", "<i8"), ("created_at", "<i8"), ("algorithm", "<u4"), ("behavior", "<u4")])
@@ -36,7 +36,7 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
            "gub_route_owner_device", "gub_route_global_device", "gub_p2p_create", "gub_p2p_destroy", "gub_p2p_export", "gub_p2p_connect",
            "gub_p2p_connect_local", "gub_p2p_step", "gub_p2p_step_streams", "gub_p2p_status", "gub_p2p_enable_global", "gub_nccl_unique_id",
-           "gub_p2p_nccl_init", "gub_p2p_nccl_init_local", "gub_global_tick", "gub_gq_dropped", "gub_set_sweep", "gub_set_trace", "gub_get_trace", "gub_get_trace_raw"]
+           "gub_p2p_nccl_init", "gub_p2p_nccl_init_local", "gub_global_tick", "gub_gq_dropped", "gub_set_sweep", "gub_set_trace", "gub_get_trace", "gub_get_trace_raw", "gub_keys_layout", "gub_submit_keys_async", "gub_global_tick_local_all", "gub_p2p_step_local_all"]
 
 
 class Config(C.Structure):
@@ -115,11 +115,15 @@ def lib():
         L.gub_p2p_nccl_init.argtypes = [vp, vp]
         L.gub_p2p_nccl_init_local.argtypes = [C.POINTER(vp), C.c_uint32]
         L.gub_global_tick.argtypes = [vp, vp, i64, vp, vp]
+        L.gub_p2p_step_local_all.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(vp), C.POINTER(sz), vp, C.POINTER(vp), C.POINTER(vp)]
+        L.gub_global_tick_local_all.argtypes = [C.POINTER(vp), C.c_uint32, vp, i64, C.POINTER(vp), vp]
         L.gub_gq_dropped.argtypes = [vp, C.POINTER(u64)]
         L.gub_set_sweep.argtypes = [vp, C.c_uint32]
         L.gub_set_trace.argtypes = [vp, i32]
         L.gub_get_trace.argtypes = [vp, vp, vp]
         L.gub_get_trace_raw.argtypes = [vp, vp]
+        L.gub_submit_keys_async.argtypes = [vp, vp, sz, sz, vp, sz, i64, vp, vp, C.POINTER(C.c_int)]
+        L.gub_keys_layout.argtypes = [sz, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         _lib = L
     return _lib
 
@@ -299,6 +303,13 @@ class Table:
     def hash_keys_device(self, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr=None, stream=0):
         _check(lib().gub_hash_keys_device(self._h, d_bytes_ptr, d_offsets_ptr, n, d_xxh_ptr, d_fnv_ptr, d_reqs_ptr, stream), "gub_hash_keys_device")
 
+    def submit_keys_async(self, packed_ptr, packed_bytes, n, params_ptr, n_params, created_base, clk, out_ptr):
+        """Key strings in (packed: see pack_keys), responses out; hashing runs on the device.  Returns a ticket for wait()."""
+        tk = C.c_int(-1)
+        _check(lib().gub_submit_keys_async(self._h, packed_ptr, packed_bytes, n, params_ptr, n_params, int(created_base), clk.ctypes.data, out_ptr, C.byref(tk)),
+               "gub_submit_keys_async")
+        return tk.value
+
     def set_sweep(self, slots_per_cta):
         _check(lib().gub_set_sweep(self._h, int(slots_per_cta)), "gub_set_sweep")
 
@@ -406,10 +417,44 @@ class P2P:
             pass
 
 
+KREQ_DTYPE = np.dtype([("hits", "<i8"), ("params", "<u4"), ("created_delta", "<i4")])
+
+
+def pack_keys(keys, hits, params_idx, created_delta):
+    """The one-buffer layout of gub_submit_keys_async: [gub_kreq x n][uint32 offsets x (n + 1)][key bytes] -> np.uint8 array."""
+    n = len(keys)
+    lens = np.fromiter((len(k) for k in keys), dtype=np.int64, count=n)
+    blob = b"".join(keys)
+    o_at, b_at, tot = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    _check(lib().gub_keys_layout(n, len(blob), C.byref(o_at), C.byref(b_at), C.byref(tot)), "gub_keys_layout")
+    buf = np.zeros(tot.value, dtype=np.uint8)
+    kr = buf[:n * 16].view(KREQ_DTYPE)
+    kr["hits"] = hits; kr["params"] = params_idx; kr["created_delta"] = created_delta
+    offs = buf[o_at.value:o_at.value + 4 * (n + 1)].view(np.uint32)
+    offs[1:] = np.cumsum(lens)
+    buf[b_at.value:b_at.value + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+    return buf
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     _check(lib().gub_nccl_unique_id(buf), "gub_nccl_unique_id")
     return buf.raw
+
+
+def p2p_step_local_all(p2ps, req_ptrs, ns, clk, out_ptrs, streams):
+    """One step of every shard of this process from one host thread (gub_p2p_step_local_all)."""
+    W = len(p2ps)
+    _check(lib().gub_p2p_step_local_all((C.c_void_p * W)(*[p._h for p in p2ps]), W, (C.c_void_p * W)(*req_ptrs), (C.c_size_t * W)(*ns), clk.ctypes.data,
+                                        (C.c_void_p * W)(*out_ptrs), (C.c_void_p * W)(*streams)), "gub_p2p_step_local_all")
+
+
+def global_tick_local_all(p2ps, clk, now_ms, streams):
+    W = len(p2ps)
+    st = (C.c_uint64 * (4 * W))()
+    _check(lib().gub_global_tick_local_all((C.c_void_p * W)(*[p._h for p in p2ps]), W, clk.ctypes.data, int(now_ms), (C.c_void_p * W)(*streams), st),
+           "gub_global_tick_local_all")
+    return [dict(hits_sent=int(st[4 * r]), updates_made=int(st[4 * r + 1]), installed=int(st[4 * r + 2]), gathered_bytes=int(st[4 * r + 3])) for r in range(W)]
 
 
 def p2p_nccl_init_local(p2ps):

@@ -175,6 +175,20 @@ int gub_submit_compact_async(gub_table* t, const gub_creq* reqs, size_t n, const
 int gub_submit_compact(gub_table* t, const gub_creq* reqs, size_t n, const gub_params* params, size_t n_params,
                        int64_t created_base, const gub_clock* clk, gub_resp* out);
 
+/* ---- key strings: the step right before the path (client.go:39-41 HashKey, workers.go:153 XXH64, replicated_hash.go:108 FNV-1)
+ * runs on the device too.  The host ships the raw key bytes ("Name_UniqueKey") and one 16-byte record per request; a kernel hashes
+ * the keys and builds the gub_req records (parameter table as for the compact path), then the normal path runs.  Results are
+ * identical to hashing on the host and submitting the full records. */
+typedef struct {
+  int64_t hits;
+  uint32_t params;        /* index into the batch's gub_params table */
+  int32_t created_delta;  /* created_at = created_base + created_delta (ms) */
+} gub_kreq;               /* 16 bytes */
+/* One buffer per batch: [gub_kreq x n][uint32 offsets x (n + 1)][key bytes]; key i = bytes[offsets[i] .. offsets[i+1]). */
+int gub_keys_layout(size_t n, size_t key_bytes, size_t* offsets_at, size_t* bytes_at, size_t* total);
+int gub_submit_keys_async(gub_table* t, const void* packed, size_t packed_bytes, size_t n, const gub_params* params, size_t n_params,
+                          int64_t created_base, const gub_clock* clk, gub_resp* out, int* ticket);
+
 /* Page-locked host memory for request/response buffers: with these the H2D/D2H copies of gub_submit_async are truly
  * asynchronous (a Go shim allocates its batch arenas here once).  Any other host memory works too, just slower. */
 void* gub_host_alloc(size_t bytes);
@@ -308,6 +322,10 @@ int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* c
  * e (the reference overlaps forwarding and evaluation the same way: peer_client.go:284 runs in its own goroutine). */
 int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream,
                          void* stream);
+/* One step of every shard of this process, driven by ONE host thread (the reference daemon is one process, daemon.go:73): all
+ * routings are enqueued, then all evaluations, then all collects.  streams[r] = the stream of shard r (on its device). */
+int gub_p2p_step_local_all(gub_p2p* const* ps, uint32_t world, const gub_req* const* d_reqs, const size_t* n, const gub_clock* clk,
+                           gub_resp* const* d_out, void* const* streams);
 /* Device-side waits are bounded (a dead peer must not hang the GPU); a wait that gave up marks the step: *error_out != 0 and the
  * call fails with text in gub_last_error().  Requests whose owner never answered carry GUB_ERR_PEER_TIMEOUT in-band.  Costs a
  * device synchronisation: poll at your own cadence. */
@@ -323,6 +341,9 @@ int gub_nccl_unique_id(void* out128 /* 128 bytes: ncclUniqueId, to be handed to 
 int gub_p2p_nccl_init(gub_p2p* p, const void* id128);                     /* one process per GPU; collective */
 int gub_p2p_nccl_init_local(gub_p2p* const* ps, uint32_t world);           /* all shards in this process */
 int gub_global_tick(gub_p2p* p, const gub_clock* clk, int64_t now_ms, void* stream, uint64_t* stats /* optional, 4 values */);
+/* All shards in this process, driven by ONE host thread (gub_global_tick itself expects one calling thread per local shard). */
+int gub_global_tick_local_all(gub_p2p* const* ps, uint32_t world, const gub_clock* clk, int64_t now_ms, void* const* streams,
+                              uint64_t* stats /* optional, world x 4 */);
 
 #ifdef __cplusplus
 }

@@ -877,6 +877,39 @@ static void mt_free(struct mt_ctx* m) {
   for (size_t i = 0; i < k; i++) free(m->lists[i]);
   free(m->lists); free(m->counts); free(m->caps); free(m->th); free(m);
 }
+/* Same, starting from the key strings: every thread first hashes the keys of its slice — XXH64 as the worker pool does
+ * (workers.go:153-155) and FNV-1 as the peer picker does (replicated_hash.go:108) — into `scratch` (a copy of reqs whose hash
+ * fields are filled in), then the batch runs as above.  key i = bytes[offsets[i] .. offsets[i+1]). */
+struct key_job { const char* bytes; const uint64_t* offsets; gubo_hreq* scratch; size_t n; int T; };
+static void* key_hash_main(void* vp) {
+  void** a = (void**)vp;
+  struct key_job* j = (struct key_job*)a[0];
+  int t = (int)(intptr_t)a[1];
+  size_t lo = j->n * (size_t)t / (size_t)j->T, hi = j->n * (size_t)(t + 1) / (size_t)j->T;
+  for (size_t i = lo; i < hi; i++) {
+    const char* k = j->bytes + j->offsets[i];
+    size_t len = (size_t)(j->offsets[i + 1] - j->offsets[i]);
+    j->scratch[i].key_xxh64 = gubo_xxh64(k, len, 0);
+    j->scratch[i].key_fnv1 = gubo_fnv1_64(k, len);
+  }
+  return NULL;
+}
+double gubo_submit_hashed_mt(gubo_pool* p, const gubo_hreq* reqs, size_t n, gubo_hresp* out, int threads);
+double gubo_submit_keys_mt(gubo_pool* p, const char* bytes, const uint64_t* offsets, gubo_hreq* scratch, size_t n, gubo_hresp* out, int threads) {
+  if (threads < 1) threads = 1;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  struct key_job job = {bytes, offsets, scratch, n, threads};
+  pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+  void** args = (void**)calloc((size_t)threads * 2, sizeof(void*));
+  for (int t = 0; t < threads; t++) { args[2 * t] = &job; args[2 * t + 1] = (void*)(intptr_t)t; pthread_create(&th[t], NULL, key_hash_main, &args[2 * t]); }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th); free(args);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  double hash_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return hash_s + gubo_submit_hashed_mt(p, scratch, n, out, threads);
+}
+
 double gubo_submit_hashed_mt(gubo_pool* p, const gubo_hreq* reqs, size_t n, gubo_hresp* out, int threads) {
   if (threads < 1) threads = 1;
   if (p->mt && p->mt->T != threads) { mt_free(p->mt); p->mt = NULL; }

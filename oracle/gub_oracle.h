@@ -172,6 +172,8 @@ void gubo_submit_hashed(gubo_pool*, const gubo_hreq* reqs, size_t n, gubo_hresp*
  * XXH64>>1 / step (workers.go:180-184) to single-threaded shards and applied in index order per shard.
  * Returns elapsed seconds for the batch. */
 double gubo_submit_hashed_mt(gubo_pool*, const gubo_hreq* reqs, size_t n, gubo_hresp* out, int threads);
+/* the same from key strings: hashing (XXH64 + FNV-1 per key) happens inside the timed call */
+double gubo_submit_keys_mt(gubo_pool* p, const char* bytes, const uint64_t* offsets, gubo_hreq* scratch, size_t n, gubo_hresp* out, int threads);
 
 #ifdef __cplusplus
 }

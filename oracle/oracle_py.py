@@ -89,6 +89,7 @@ def lib():
         L.gubo_ring_free.argtypes = [vp]
         L.gubo_submit_hashed.argtypes = [vp, vp, sz, vp]
         L.gubo_submit_hashed_mt.restype = C.c_double; L.gubo_submit_hashed_mt.argtypes = [vp, vp, sz, vp, C.c_int]
+        L.gubo_submit_keys_mt.restype = C.c_double; L.gubo_submit_keys_mt.argtypes = [vp, vp, vp, vp, sz, vp, C.c_int]
         _lib = L
     return _lib
 
@@ -175,6 +176,14 @@ class Pool:
             self.last_mt_seconds = lib().gubo_submit_hashed_mt(self._p, reqs.ctypes.data, len(reqs), out.ctypes.data, threads)
         else:
             lib().gubo_submit_hashed(self._p, reqs.ctypes.data, len(reqs), out.ctypes.data)
+        return out
+
+    def submit_keys(self, key_bytes: np.ndarray, offsets: np.ndarray, reqs: np.ndarray, threads=1):
+        """reqs: HREQ_DTYPE records whose hash fields are ignored; the keys are hashed inside the (timed) call."""
+        assert reqs.dtype == HREQ_DTYPE and offsets.dtype == np.uint64 and key_bytes.dtype == np.uint8
+        out = np.zeros(len(reqs), dtype=HRESP_DTYPE)
+        scratch = reqs.copy()
+        self.last_mt_seconds = lib().gubo_submit_keys_mt(self._p, key_bytes.ctypes.data, offsets.ctypes.data, scratch.ctypes.data, len(reqs), out.ctypes.data, max(1, threads))
         return out
 
     def worker_index_for_hash63(self, h):

@@ -41,7 +41,8 @@ struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   unsigned long long* counters = nullptr;
   // the fused batch kernel (gub_batch.cuh)
   GEntry* gaux = nullptr;
-  uint32_t *gpres = nullptr, *gfrag = nullptr;
+  uint32_t* gpres = nullptr;
+  unsigned long long* gfrag = nullptr;
   uint16_t* gmembers = nullptr;
   FCtl* ctl = nullptr;
   OvfItem* ovf = nullptr;
@@ -76,7 +77,7 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
   t->counters = zalloc<unsigned long long>(C_COUNT);
   t->gaux = zalloc<GEntry>(FB_AUX_ENTRIES);
   t->gpres = zalloc<uint32_t>((size_t)FB_AUX_ENTRIES * FB_PRES_WORDS);
-  t->gfrag = zalloc<uint32_t>((size_t)FB_AUX_ENTRIES * FB_ROW);
+  t->gfrag = zalloc<unsigned long long>((size_t)FB_AUX_ENTRIES * FB_ROW);
   t->gmembers = zalloc<uint16_t>((size_t)FB_MAX_GRID * FB_THREADS);
   t->ctl = zalloc<FCtl>(1);
   t->ovf = zalloc<OvfItem>(FB_OVF_CAP);

@@ -1,6 +1,9 @@
-"""GLOBAL behaviour on the GPU: a W-shard cluster in ONE process on one GPU (W tables, collectives replaced by the
-in-process LocalExchange — the shape of the reference's cluster.StartWith fixture), checked against the oracle-side
-model in tests/global_model.py and against the reference's own GLOBAL scenarios (functional_test.go:959-1341)."""
+"""GLOBAL behaviour on the GPU: a W-shard cluster in ONE process on one GPU (the shape of the reference's cluster.StartWith
+fixture), checked against the oracle-side model in tests/global_model.py and against the reference's own GLOBAL scenarios
+(functional_test.go:959-1341, :1690-2097).  Two drivers of the same device code: "c" = everything behind the C ABI
+(gub_p2p_step_local_all with gub_p2p_enable_global, gub_global_tick_local_all: NVLink-mailbox routing, queues fed by the step, the
+tick's broadcast read from the peers in place); "python" = the torch.distributed-shaped orchestration of
+gubernator_b200.sharded.ShardedStep over the same kernels (collectives replaced by the in-process LocalExchange)."""
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -58,6 +61,26 @@ class GpuCluster:
         return self._all(run)
 
 
+class CCluster:
+    """The same surface over tests/local_ring.LocalRing (C ABI drivers)."""
+
+    def __init__(self, world, now_ms, capacity=1 << 14):
+        from local_ring import LocalRing
+        self.lr = LocalRing(world, capacity=capacity, cap=4096, global_capacity=4096)
+        self.W, self.tabs = world, self.lr.tabs
+
+    def step(self, batches, now_ms):
+        return self.lr.step(batches, now_ms)
+
+    def tick(self, now_ms):
+        return self.lr.tick(now_ms)
+
+
+@pytest.fixture(params=["c", "python"])
+def make_cluster(request):
+    return CCluster if request.param == "c" else GpuCluster
+
+
 def _req(name_id, hits, limit, duration, algorithm=0, behavior=O.GLOBAL, created_at=T0):
     r = np.zeros(1, dtype=O.HREQ_DTYPE)
     xx, fv = key_hashes([name_id], name="glob")
@@ -77,11 +100,11 @@ def _send(cl, model, shard, req, now):
     return a
 
 
-def test_reference_global_scenarios():
+def test_reference_global_scenarios(make_cluster):
     """TestGlobalRateLimits (functional_test.go:959-1032) and TestGlobalRateLimitsPeerOverLimit (:1093-1142), with the
     reference's wall-clock waits for the async send/broadcast replaced by explicit ticks."""
     W = 6
-    cl, model = GpuCluster(W, T0), OracleCluster(W, T0)
+    cl, model = make_cluster(W, T0), OracleCluster(W, T0)
     rq = lambda hits: _req(1, hits, 5, 180000)
     owner = int(model.owners(rq(1))[0])
     peers = [r for r in range(W) if r != owner]
@@ -113,10 +136,10 @@ def test_reference_global_scenarios():
     assert tuple(_send(cl, model, p0, rq2(0), now)[["status", "remaining"]]) == (1, 0)
 
 
-def test_reference_global_reset_remaining():
+def test_reference_global_reset_remaining(make_cluster):
     """TestGlobalResetRemaining (functional_test.go:1258-1341): leaky bucket, every peer takes 50, reset propagates."""
     W = 4
-    cl, model = GpuCluster(W, T0), OracleCluster(W, T0)
+    cl, model = make_cluster(W, T0), OracleCluster(W, T0)
     rq = lambda hits, beh=O.GLOBAL: _req(3, hits, 100, 60000 * 1000, algorithm=1, behavior=beh)
     owner = int(model.owners(rq(1))[0])
     peers = [r for r in range(W) if r != owner]
@@ -131,9 +154,9 @@ def test_reference_global_reset_remaining():
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_global_random_traffic_matches_model(world):
+def test_global_random_traffic_matches_model(world, make_cluster):
     rng = np.random.default_rng(500 + world)
-    cl, model = GpuCluster(world, T0), OracleCluster(world, T0)
+    cl, model = make_cluster(world, T0), OracleCluster(world, T0)
     now = T0
     n_keys = 300
     for step in range(14):
@@ -174,3 +197,37 @@ def test_global_random_traffic_matches_model(world):
                 assert np.float64(s["remaining_f"]).view(np.uint64) == np.float64(it.remaining_f).view(np.uint64)
             else:
                 assert int(s["remaining"]) == it.remaining_i and int(s["status"]) == it.status
+
+
+@pytest.mark.parametrize("hits", [1, 10])
+@pytest.mark.parametrize("where", ["owner", "non_owner", "distributed"])
+def test_reference_global_behavior(where, hits):
+    """TestGlobalBehavior (functional_test.go:1690-2097), with the reference's metric counters read from the tick's statistics:
+    hits on the owner -> no hit update from anybody, exactly one broadcast item from the owner, installed once on every other peer;
+    hits on one non-owner -> exactly one hit-update record, from that peer; hits spread over the non-owners -> one hit-update
+    record from each peer that took hits; and in every case all peers then report the same Remaining (:1816-1821)."""
+    W, limit = 6, 1000
+    cl, model = CCluster(W, T0), OracleCluster(W, T0)
+    rq = lambda h: _req({"owner": 11, "non_owner": 12, "distributed": 13}[where] * 100 + hits, h, limit, 180000)
+    owner = int(model.owners(rq(1))[0])
+    peers = [r for r in range(W) if r != owner]
+    now = T0
+    took = set()
+    for i in range(hits):
+        shard = owner if where == "owner" else (peers[0] if where == "non_owner" else peers[i % len(peers)])
+        r = _send(cl, model, shard, rq(1), now)
+        assert r["status"] == 0
+        if where != "distributed":
+            assert r["remaining"] == limit - 1 - i  # sendHit(..., 999 - i)
+        if shard != owner:
+            took.add(shard)
+    cl.tick(now); model.tick(now)
+    st = cl.lr.last_tick
+    assert [st[r]["hits_sent"] for r in range(W)] == [1 if r in took else 0 for r in range(W)]       # gubernator_global_send_duration_count
+    assert [st[r]["updates_made"] for r in range(W)] == [1 if r == owner else 0 for r in range(W)]   # gubernator_broadcast_duration_count
+    assert [st[r]["installed"] for r in range(W)] == [0 if r == owner else 1 for r in range(W)]      # UpdatePeerGlobals once per other peer
+    for r in range(W):
+        got = _send(cl, model, r, rq(0), now)
+        assert (got["status"], got["remaining"]) == (0, limit - hits)
+    cl.tick(now); model.tick(now)  # nothing queued: Hits = 0 requests are never queued (global.go:74-84)
+    assert all(x["hits_sent"] == 0 and x["updates_made"] == 0 and x["installed"] == 0 for x in cl.lr.last_tick)

@@ -1,124 +1,102 @@
-"""Fused NVLink-mailbox routing (gub_p2p_step) on ONE GPU: W shards in one process, each on its own stream, mailboxes
-shared by pointer (gub_p2p_connect_local); responses checked against one oracle per shard applied in the documented
-order (source rank, then source index).  The cross-process cudaIpc variant runs in tests/test_gpu_sharded.py."""
-from concurrent.futures import ThreadPoolExecutor
-
+"""The ring inside one box through the C ABI (gub_p2p_*): W shards in one process driven by one host thread
+(gub_p2p_step_local_all), records stored by the routing kernel straight into the owners' mailboxes, evaluated out of the
+mailboxes by the batch kernel, responses stored into the sources' mailboxes; checked against one oracle per shard applied in
+the documented order (source rank, then source index).  On a one-GPU box all shards share the device; with >= 2 GPUs the second
+test spreads them (peer memory over NVLink).  The one-process-per-GPU cudaIpc variant runs in tests/test_gpu_sharded.py."""
 import numpy as np
 import pytest
 
 import oracle_py as O
+from local_ring import LocalRing, per_shard_oracle_results
 from workloads import T0, adversarial_batch, bench_requests, zipf_ids
 
 pytestmark = pytest.mark.gpu
 
+SIZES = [[3000, 1, 0, 8192, 5], [2000, 0, 0, 8192, 700], [1, 4000, 0, 100, 8192], [8192, 0, 0, 7, 300]]
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_p2p_step_matches_per_shard_oracles(world):
-    import torch
-    import gubernator_b200 as g
-    from gubernator_b200.sharded import P2PStep, shard_addresses
-    dev = torch.device("cuda", 0)
-    ring, oring = g.Ring(0, 512), O.Ring(0, 512)
+
+def _batches(world, step, now, cap):
+    out = []
+    for r in range(world):
+        rng = np.random.default_rng(77 * step + r)
+        n = min(SIZES[r % 4][step % 5], cap)
+        if n == 0:
+            out.append(np.zeros(0, dtype=O.HREQ_DTYPE))
+        elif step % 2:
+            out.append(adversarial_batch(rng, n, 41, now))
+        else:
+            out.append(bench_requests(zipf_ids(rng, n, 3000, 1.1), now))
+    return out
+
+
+def _oring(world):
+    from gubernator_b200.sharded import shard_addresses
+    oring = O.Ring(0, 512)
     for a in shard_addresses(world):
-        ring.add(a); oring.add(a)
-    tabs = [g.Table(1 << 16, max_batch=65536, device=0) for _ in range(world)]
-    steppers = [P2PStep(tabs[r], ring, world, r, cap=8192) for r in range(world)]
-    for s in steppers:
-        s.connect_local(steppers)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+        oring.add(a)
+    return oring
+
+
+@pytest.mark.parametrize("spread", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_p2p_step_matches_per_shard_oracles(world, spread):
+    import torch
+    if spread and (torch.cuda.device_count() < 2 or world == 1):
+        pytest.skip("needs >= 2 GPUs")
+    cl = LocalRing(world, spread_devices=spread)
+    oring = _oring(world)
     sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(world)]
-    pool = ThreadPoolExecutor(world)
-    sizes = [[3000, 1, 0, 8192, 5], [2000, 0, 0, 8192, 700], [1, 4000, 0, 100, 8192], [8192, 0, 0, 7, 300]]
     for step in range(10):
         now = T0 + step
-        rngs = [np.random.default_rng(77 * step + r) for r in range(world)]
-        batches = []
-        for r in range(world):
-            n = sizes[r % 4][step % 5]
-            if n == 0:
-                batches.append(np.zeros(0, dtype=O.HREQ_DTYPE))
-            elif step % 2:
-                batches.append(adversarial_batch(rngs[r], n, 41, now))
-            else:
-                batches.append(bench_requests(zipf_ids(rngs[r], n, 3000, 1.1), now))
-        clk = g.clock_fill(now)
-
-        def run(r):
-            torch.cuda.set_device(0)
-            b, n = batches[r], len(batches[r])
-            with torch.cuda.stream(streams[r]):
-                buf = torch.from_numpy(b.view(np.uint8).reshape(n, 64).copy()).to(dev) if n else torch.empty((1, 64), dtype=torch.uint8, device=dev)
-                out = torch.zeros((max(n, 1), 32), dtype=torch.uint8, device=dev)
-                steppers[r].step(buf, n, clk, out, stream=streams[r].cuda_stream)
-                streams[r].synchronize()
-                return out[:n].cpu().numpy().reshape(-1).view(O.HRESP_DTYPE)
-        got = [f.result() for f in [pool.submit(run, r) for r in range(world)]]
-        owners = [np.array([oring.get_by_hash(int(h)) for h in b["key_fnv1"]], dtype=np.int64) for b in batches]
-        want = [np.zeros(len(b), dtype=O.HRESP_DTYPE) for b in batches]
-        for gi in range(world):
-            sim[gi].set_now(now)
-            for s in range(world):
-                idx = np.nonzero(owners[s] == gi)[0]
-                if len(idx):
-                    want[s][idx] = sim[gi].submit_hashed(np.ascontiguousarray(batches[s][idx]))
+        batches = _batches(world, step, now, cl.cap)
+        got = cl.step(batches, now)
+        want = per_shard_oracle_results(oring, sim, batches, now)
         for r in range(world):
             assert np.array_equal(got[r], want[r]), f"step {step} shard {r}: {int((got[r] != want[r]).sum())} differ"
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_p2p_two_stream_pipeline(world):
-    """gub_p2p_step_streams: routing on an ingest stream, evaluation on another; eight steps enqueued back to back per shard
-    with no synchronisation in between (step e+1 is being routed while step e is evaluated), then every response of every
-    step is compared with the per-shard oracles."""
-    import torch
-    import gubernator_b200 as g
-    from gubernator_b200.sharded import P2PStep, shard_addresses
-    dev = torch.device("cuda", 0)
-    ring, oring = g.Ring(0, 512), O.Ring(0, 512)
-    for a in shard_addresses(world):
-        ring.add(a); oring.add(a)
-    tabs = [g.Table(1 << 16, max_batch=65536, device=0) for _ in range(world)]
-    steppers = [P2PStep(tabs[r], ring, world, r, cap=4096) for r in range(world)]
-    for s in steppers:
-        s.connect_local(steppers)
-    s_in = [torch.cuda.Stream(device=dev) for _ in range(world)]
-    s_ev = [torch.cuda.Stream(device=dev) for _ in range(world)]
+def test_p2p_steps_back_to_back(world):
+    """Eight steps enqueued back to back with no host synchronisation in between (mailbox halves and routing scratch are reused
+    every second step), then every response of every step is compared with the per-shard oracles."""
+    cl = LocalRing(world, cap=4096)
+    oring = _oring(world)
     STEPS = 8
-    sizes = [[3000, 1, 0, 4096, 5, 2000, 4096, 17], [2000, 0, 0, 4096, 700, 1, 4096, 4096], [1, 4000, 0, 100, 4096, 9, 0, 3], [4096, 0, 0, 7, 300, 4096, 1, 1]]
-    batches = [[None] * world for _ in range(STEPS)]
+    batches = [_batches(world, step, T0 + step, 4096) for step in range(STEPS)]
+    staged = [cl.upload(b) for b in batches]
     for step in range(STEPS):
-        for r in range(world):
-            rng = np.random.default_rng(991 * step + r)
-            n = sizes[r % 4][step]
-            if n == 0:
-                batches[step][r] = np.zeros(0, dtype=O.HREQ_DTYPE)
-            elif step % 2:
-                batches[step][r] = adversarial_batch(rng, n, 41, T0 + step)
-            else:
-                batches[step][r] = bench_requests(zipf_ids(rng, n, 3000, 1.1), T0 + step)
-    bufs = [[torch.from_numpy(b.view(np.uint8).reshape(len(b), 64).copy()).to(dev) if len(b) else torch.empty((1, 64), dtype=torch.uint8, device=dev)
-             for b in row] for row in batches]
-    outs = [[torch.zeros((max(len(b), 1), 32), dtype=torch.uint8, device=dev) for b in row] for row in batches]
-    clks = [g.clock_fill(T0 + step) for step in range(STEPS)]
-    torch.cuda.synchronize()
-
-    def run(r):
-        torch.cuda.set_device(0)
-        for step in range(STEPS):
-            steppers[r].step(bufs[step][r], len(batches[step][r]), clks[step], outs[step][r], stream=s_ev[r].cuda_stream,
-                             ingest_stream=s_in[r].cuda_stream)
-    with ThreadPoolExecutor(world) as pool:
-        for f in [pool.submit(run, r) for r in range(world)]:
-            f.result()
-    torch.cuda.synchronize()
+        cl.enqueue(staged[step][0], [len(b) for b in batches[step]], T0 + step, staged[step][1])
+    cl.sync()
     sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(world)]
     for step in range(STEPS):
-        owners = [np.array([oring.get_by_hash(int(h)) for h in b["key_fnv1"]], dtype=np.int64) for b in batches[step]]
-        for gi in range(world):
-            sim[gi].set_now(T0 + step)
-            for s in range(world):
-                idx = np.nonzero(owners[s] == gi)[0]
-                if len(idx):
-                    want = sim[gi].submit_hashed(np.ascontiguousarray(batches[step][s][idx]))
-                    got = outs[step][s][:len(batches[step][s])].cpu().numpy().reshape(-1).view(O.HRESP_DTYPE)[idx]
-                    assert np.array_equal(got, want), f"step {step} source {s} owner {gi}: {int((got != want).sum())} differ"
+        want = per_shard_oracle_results(oring, sim, batches[step], T0 + step)
+        for r in range(world):
+            got = staged[step][1][r][:len(batches[step][r])].cpu().numpy().reshape(-1).view(O.HRESP_DTYPE)
+            assert np.array_equal(got, want[r]), f"step {step} shard {r}: {int((got != want[r]).sum())} differ"
+
+
+def test_a_silent_peer_is_reported_not_waited_for_forever():
+    """Device-side waits are bounded: a shard whose peer never steps gets GUB_ERR_PEER_TIMEOUT in-band for the requests that peer
+    owns, and gub_p2p_status reports the step (the flag used to be set and never read)."""
+    import torch
+    import gubernator_b200 as g
+    from gubernator_b200.sharded import shard_addresses
+    world = 2
+    ring = g.Ring(0, 512)
+    for a in shard_addresses(world):
+        ring.add(a)
+    tabs = [g.Table(1 << 12, device=0) for _ in range(world)]
+    p2ps = [g.native.P2P(tabs[r], ring, r, 1024) for r in range(world)]
+    for p in p2ps:
+        p.connect_local(p2ps)
+    reqs = bench_requests(np.arange(600), T0)
+    buf = torch.from_numpy(reqs.view(np.uint8).reshape(-1, 64).copy()).cuda()
+    out = torch.zeros((600, 32), dtype=torch.uint8, device="cuda")
+    p2ps[0].step(buf.data_ptr(), 600, g.clock_fill(T0), out.data_ptr(), torch.cuda.current_stream().cuda_stream)  # shard 1 never steps
+    torch.cuda.synchronize()
+    with pytest.raises(g.native.GubError):
+        p2ps[0].status()
+    got = out.cpu().numpy().reshape(-1).view(O.HRESP_DTYPE)
+    oring = _oring(world)
+    owner = np.array([oring.get_by_hash(int(h)) for h in reqs["key_fnv1"]])
+    assert np.all(got["err_code"][owner == 1] == g.native.ERR_PEER_TIMEOUT) and (owner == 1).any()
