@@ -59,6 +59,7 @@ enum : uint32_t {
   F_LEAKY = 1u,  // Value is *LeakyBucketItem (else *TokenBucketItem)
   F_OVER = 2u,   // TokenBucketItem.Status == OVER_LIMIT (sticky, :168)
   F_LIVE = 4u,   // the cache holds an item for this key
+  F_INVALID_AT = 8u,  // CacheItem.InvalidAt != 0 (set by Store / Loader plugins only): the value lives in the table's side index
 };
 
 struct Bucket {

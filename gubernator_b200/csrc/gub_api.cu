@@ -61,23 +61,21 @@ struct gub_table {
   gub::Slot* table = nullptr;
   uint64_t capacity = 0;
   uint32_t max_batch = 0;
-  // per-batch scratch, two sets: k_group/k_rank of batch b+1 (prep stream) overlap k_eval/k_finish of batch b
+  // per-batch scratch of the four-kernel pipeline (gub_kernels.cuh)
   struct Scratch {
     gub::AuxEntry* aux = nullptr;
     uint32_t *ent = nullptr, *meta = nullptr, *rank = nullptr, *order = nullptr, *mixed_ent = nullptr, *presence = nullptr;
     uint8_t* fragsize = nullptr;
     ulonglong2* commit = nullptr;
-    uint32_t* commit_ent = nullptr;
     gub::BatchCtr* ctr = nullptr;
     uint32_t epoch = 0;
-    cudaEvent_t prep_done = nullptr;   // stage 1 (k_group, k_rank) finished on the prep stream
-    cudaEvent_t eval_done = nullptr;   // stage 2 (k_eval, k_finish) finished: the set may be reused
-    bool used = false;
-  } scr[2];
-  uint32_t next_set = 0;
+  } scr;
   uint32_t aux_entries = 0, pres_words = 0, max_blocks = 0;
   // the fused batch kernel (gub_batch.cuh): one scratch set, one cooperative launch per batch
-  bool fused = true;                  // GUB_FUSED=0: the four-kernel path (kept for A/B measurements)
+  // Which kernels evaluate a single table's batches (gub_submit*): the four-kernel pipeline (default: consecutive batches overlap,
+  // 31.7 us per 65 536-request step on B200) or the single persistent kernel (GUB_PATH=fused: ~65 us latency, no overlap between
+  // batches; profiles/README.md).  Rings (gub_p2p_*) always evaluate out of the mailboxes with the persistent kernel.
+  bool fused = false;
   bool coop = true;                   // cooperative launch (co-residency of the grid guaranteed by the driver)
   int num_sms = 0;
   uint32_t sweep_chunk = 0;           // slots every CTA sweeps per batch (incremental expiry sweep), 0 = off
@@ -87,11 +85,9 @@ struct gub_table {
   uint16_t* gmembers = nullptr;
   gub::FCtl* ctl = nullptr;
   gub::OvfItem* ovf = nullptr;
+  gub::InvIndex inv{};                // CacheItem.InvalidAt side index
   unsigned long long* trace = nullptr; // per-CTA phase timestamps of the last k_batch launch (gub_set_trace)
   unsigned long long* counters = nullptr;
-  cudaStream_t s_prep = nullptr;
-  cudaEvent_t inputs_ready = nullptr;
-  bool overlap = true;                // GUB_OVERLAP=0: everything on the caller's stream
   // ordering between streams that touch the shared scratch
   cudaEvent_t last_done = nullptr;
   cudaStream_t last_stream = nullptr; // stream of the most recent table-touching work
@@ -173,24 +169,10 @@ cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cuda
   return cudaLaunchKernelEx(&cfg, kernel, A);
 }
 
-int launch_finish(gub_table* t, const gub::BatchArgs& A, uint32_t n, cudaStream_t st) {
-  // commit records (one thread each, at most n/2) + non-uniform groups (one block each, grid-stride; normally none)
-  const uint32_t mixed_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
-  const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(148u, (n / 2 + gub::MIXED_THREADS - 1) / gub::MIXED_THREADS));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(mixed_blocks + commit_blocks); cfg.blockDim = dim3(gub::MIXED_THREADS); cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
-  CK(cudaLaunchKernelEx(&cfg, gub::k_finish, A, mixed_blocks));
-  return 0;
-}
-
 void fused_base_args(gub_table* t, const gub_clock* clk, gub::FArgs& A) {
   std::memset(&A, 0, sizeof A);
   A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragrow = t->gfrag; A.members = t->gmembers;
-  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.trace = t->trace; A.clk = *clk;
+  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.trace = t->trace; A.inv = t->inv; A.clk = *clk;
 }
 
 // One launch of k_batch over the segments in A (A.seg / A.nseg / flags filled by the caller).  `total_hint` = number of requests
@@ -227,24 +209,15 @@ int launch_fused(gub_table* t, const gub::FArgs& A, uint64_t total_hint, cudaStr
   return 0;
 }
 
-// One batch (<= max_batch requests).  Stage 1 (k_group, k_rank) never touches bucket state, so it runs on the prep
-// stream and overlaps stage 2 (k_eval, k_finish) of the previous batch, which runs on the caller's stream.
+// One batch (<= max_batch requests) through the four-kernel pipeline, chained with programmatic dependent launch.
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
                  const uint32_t* n_dev = nullptr, uint32_t n_off = 0) {
-  const bool overlap = t->overlap && !t->prof && !gub::EARLY_SINGLES;  // k_rank touches the table in the early-singles build
-  gub_table::Scratch& sc = t->scr[overlap ? t->next_set : 0u];  // one set is enough when batches do not overlap
-  if (overlap) t->next_set ^= 1u;
-  cudaStream_t sp = overlap ? t->s_prep : st;
-  if (overlap) {
-    CK(cudaEventRecord(t->inputs_ready, st));          // whatever produced d_reqs on the caller's stream
-    CK(cudaStreamWaitEvent(sp, t->inputs_ready, 0));
-    if (sc.used) CK(cudaStreamWaitEvent(sp, sc.eval_done, 0));  // the batch that last used this scratch set is done with it
-  }
+  gub_table::Scratch& sc = t->scr;
   if (sc.epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
-    CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), sp));
+    CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), st));
     // 65535 -> 1 keeps the parity: the batch after the wrap reuses ctr[1], which k_rank (it only resets the OTHER parity) left
     // holding batch 65535's allocators.  Clear both.
-    CK(cudaMemsetAsync(sc.ctr, 0, 2 * sizeof(gub::BatchCtr), sp));
+    CK(cudaMemsetAsync(sc.ctr, 0, 2 * sizeof(gub::BatchCtr), st));
     sc.epoch = 0;
   }
   sc.epoch++;
@@ -252,8 +225,8 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.n_dev = n_dev; A.n_off = n_off; A.epoch = sc.epoch;
   A.aux = sc.aux; A.aux_mask = t->aux_entries - 1; A.presence = sc.presence; A.fragsize = sc.fragsize;
   A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = sc.ent; A.meta = sc.meta; A.rank = sc.rank;
-  A.commit = sc.commit; A.commit_ent = sc.commit_ent; A.order = sc.order; A.mixed_ent = sc.mixed_ent; A.ctr = sc.ctr;
-  A.counters = t->counters;
+  A.commit = sc.commit; A.order = sc.order; A.mixed_ent = sc.mixed_ent; A.ctr = sc.ctr;
+  A.counters = t->counters; A.ovf = t->ovf; A.ovf_count = &t->ctl->ovf_count; A.inv = t->inv;
   A.clk = *clk;
   const uint32_t blocks = (n + 255) / 256;
   cudaEvent_t* pe = nullptr;
@@ -266,19 +239,15 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
     t->prof_pending++;
     CK(cudaEventRecord(pe[0], st));
   }
-  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, sp, A));
+  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[1], st));
-  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, sp, A));
+  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[2], st));
-  if (overlap) {
-    CK(cudaEventRecord(sc.prep_done, sp));
-    CK(cudaStreamWaitEvent(st, sc.prep_done, 0));
-  }
   CK(launch_k(t, gub::k_eval, blocks, gub::GROUP_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[3], st));
-  if (launch_finish(t, A, n, st)) return -1;
+  // non-uniform groups, one block each (grid-stride; normally none: the blocks return at once)
+  CK(launch_k(t, gub::k_finish, std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, st, A));
   if (pe) CK(cudaEventRecord(pe[4], st));
-  if (overlap) { CK(cudaEventRecord(sc.eval_done, st)); sc.used = true; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -339,6 +308,7 @@ gub::DevItem to_dev(const gub_item& it) {
   d.w[0] = (uint64_t)it.limit; d.w[1] = (uint64_t)it.duration;
   if (leaky) std::memcpy(&d.w[2], &it.remaining_f, 8); else d.w[2] = (uint64_t)it.remaining;
   d.w[3] = (uint64_t)it.stamp; d.w[4] = leaky ? (uint64_t)it.burst : 0; d.w[5] = (uint64_t)it.expire_at;
+  d.invalid_at = it.invalid_at;
   return d;
 }
 gub_item from_dev(const gub::DevItem& d) {
@@ -351,6 +321,7 @@ gub_item from_dev(const gub::DevItem& d) {
   it.limit = (int64_t)d.w[0]; it.duration = (int64_t)d.w[1];
   if (leaky) std::memcpy(&it.remaining_f, &d.w[2], 8); else it.remaining = (int64_t)d.w[2];
   it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5];
+  it.invalid_at = d.invalid_at;
   return it;
 }
 
@@ -367,16 +338,13 @@ void gub_destroy(gub_table* t) {
   cudaDeviceSynchronize();
   trace_dump(t);
   void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_ring_lut, t->d_owner, t->d_tile_counts,
-                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf, t->trace};
+                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf, t->trace, t->inv.e};
   for (void* p : ptrs) if (p) cudaFree(p);
-  for (auto& sc : t->scr) {
-    void* sp[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.commit_ent, sc.ctr};
+  {
+    auto& sc = t->scr;
+    void* sp[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.ctr};
     for (void* p : sp) if (p) cudaFree(p);
-    if (sc.prep_done) cudaEventDestroy(sc.prep_done);
-    if (sc.eval_done) cudaEventDestroy(sc.eval_done);
   }
-  if (t->s_prep) cudaStreamDestroy(t->s_prep);
-  if (t->inputs_ready) cudaEventDestroy(t->inputs_ready);
   for (auto& s : t->pipe) {
     if (s.d_req) cudaFree(s.d_req);
     if (s.d_resp) cudaFree(s.d_resp);
@@ -429,12 +397,12 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     cudaMemset((ptr), 0, (bytes));                                           \
   } while (0)
   ALLOC(t->table, t->capacity * sizeof(gub::Slot));
-  for (auto& sc : t->scr) {
+  {
+    auto& sc = t->scr;
     ALLOC(sc.aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
     ALLOC(sc.presence, (size_t)t->aux_entries * t->pres_words * 4);
     ALLOC(sc.fragsize, (size_t)t->aux_entries * t->max_blocks);
     ALLOC(sc.commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
-    ALLOC(sc.commit_ent, ((size_t)B / 2 + 1) * 4);
     ALLOC(sc.ent, (size_t)B * 4);
     ALLOC(sc.meta, (size_t)B * 4);
     ALLOC(sc.rank, (size_t)B * 4);
@@ -443,7 +411,7 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     ALLOC(sc.ctr, 2 * sizeof(gub::BatchCtr));
   }
   t->num_sms = std::min<int>(prop.multiProcessorCount, gub::FB_MAX_GRID);
-  if (const char* e = getenv("GUB_FUSED")) t->fused = std::atoi(e) != 0;
+  if (const char* e = getenv("GUB_PATH")) t->fused = std::string(e) == "fused";
   if (const char* e = getenv("GUB_COOP")) t->coop = std::atoi(e) != 0;
   ALLOC(t->gaux, (size_t)gub::FB_AUX_ENTRIES * sizeof(gub::GEntry));
   ALLOC(t->gpres, (size_t)gub::FB_AUX_ENTRIES * gub::FB_PRES_WORDS * 4);
@@ -451,6 +419,8 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   ALLOC(t->gmembers, (size_t)gub::FB_MAX_GRID * gub::FB_THREADS * 2);
   ALLOC(t->ctl, sizeof(gub::FCtl));
   ALLOC(t->ovf, (size_t)gub::FB_OVF_CAP * sizeof(gub::OvfItem));
+  ALLOC(t->inv.e, (size_t)65536 * sizeof(gub::InvEntry));
+  t->inv.mask = 65535;
   {
     // incremental expiry sweep: the whole table once every ~65536 batches (GUB_SWEEP=<slots per CTA per batch>, 0 = off)
     uint64_t chunk = (t->capacity + (uint64_t)t->num_sms * 65536 - 1) / ((uint64_t)t->num_sms * 65536);
@@ -462,13 +432,6 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   ALLOC(t->counters, gub::C_COUNT * sizeof(unsigned long long));
   ALLOC(t->d_scalar, 4 * sizeof(unsigned long long));
 #undef ALLOC
-  CK(cudaStreamCreateWithFlags(&t->s_prep, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&t->inputs_ready, cudaEventDisableTiming));
-  for (auto& sc : t->scr) {
-    CK(cudaEventCreateWithFlags(&sc.prep_done, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&sc.eval_done, cudaEventDisableTiming));
-  }
-  if (const char* e = getenv("GUB_OVERLAP")) t->overlap = std::atoi(e) != 0;
   CK(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&t->s_compute, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
@@ -673,6 +636,20 @@ void* gub_host_alloc(size_t bytes) {
 }
 void gub_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+namespace {
+// Items parked by a batch whose probe window was full are placed before anything else reads or writes the table.
+int drain_pending(gub_table* t) {
+  gub_clock clk;
+  std::memset(&clk, 0, sizeof clk);
+  clk.now_ms = INT64_MIN;  // nothing counts as expired here: only free, removed and then the earliest-expiring entries give way
+  gub::FArgs A;
+  fused_base_args(t, &clk, A);
+  gub::k_drain_overflow<<<1, 32>>>(A);
+  CK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 int gub_add_items(gub_table* t, const gub_item* items, size_t n) {
   if (!t || (n && !items)) return fail("gub_add_items: null argument");
   if (n == 0) return 0;
@@ -693,6 +670,7 @@ int gub_add_items(gub_table* t, const gub_item* items, size_t n) {
   }
   if (dev.empty()) return 0;
   CK(cudaDeviceSynchronize());
+  if (drain_pending(t)) return -1;
   gub::DevItem* d_items = nullptr;
   CK(cudaMalloc(&d_items, dev.size() * sizeof(gub::DevItem)));
   cudaError_t e = cudaMemcpy(d_items, dev.data(), dev.size() * sizeof(gub::DevItem), cudaMemcpyHostToDevice);
@@ -700,7 +678,7 @@ int gub_add_items(gub_table* t, const gub_item* items, size_t n) {
   uint32_t failed = 0;
   if (e == cudaSuccess) {
     gub::k_add_items<<<(unsigned)((dev.size() + 255) / 256), 256>>>(t->table, t->capacity, d_items, (uint32_t)dev.size(), t->counters,
-                                                                    reinterpret_cast<uint32_t*>(t->d_scalar));
+                                                                    reinterpret_cast<uint32_t*>(t->d_scalar), t->inv);
     e = cudaDeviceSynchronize();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&failed, t->d_scalar, 4, cudaMemcpyDeviceToHost);
@@ -716,6 +694,7 @@ int gub_get_items(gub_table* t, const uint64_t* kx, const uint64_t* kf, size_t n
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
   CK(cudaDeviceSynchronize());
+  if (drain_pending(t)) return -1;
   uint64_t *d_kx = nullptr, *d_kf = nullptr; gub::DevItem* d_out = nullptr; uint8_t* d_found = nullptr;
   std::vector<gub::DevItem> host(n);
   cudaError_t e = cudaMalloc(&d_kx, n * 8);
@@ -725,7 +704,7 @@ int gub_get_items(gub_table* t, const uint64_t* kx, const uint64_t* kf, size_t n
   if (e == cudaSuccess) e = cudaMemcpy(d_kx, kx, n * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_kf, kf, n * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    gub::k_get_items<<<(unsigned)((n + 255) / 256), 256>>>(t->table, t->capacity, d_kx, d_kf, (uint32_t)n, now_ms, d_out, d_found);
+    gub::k_get_items<<<(unsigned)((n + 255) / 256), 256>>>(t->table, t->capacity, d_kx, d_kf, (uint32_t)n, now_ms, d_out, d_found, t->inv);
     e = cudaDeviceSynchronize();
   }
   if (e == cudaSuccess) e = cudaMemcpy(host.data(), d_out, n * sizeof(gub::DevItem), cudaMemcpyDeviceToHost);
@@ -741,12 +720,13 @@ int gub_scan(gub_table* t, gub_item* out, size_t cap, size_t* n_out) {
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
   CK(cudaDeviceSynchronize());
+  if (drain_pending(t)) return -1;
   gub::DevItem* d_out = nullptr;
   if (cap) CK(cudaMalloc(&d_out, cap * sizeof(gub::DevItem)));
   unsigned long long total = 0;
   cudaError_t e = cudaMemset(t->d_scalar, 0, 8);
   if (e == cudaSuccess) {
-    gub::k_scan<<<148 * 8, 256>>>(t->table, t->capacity, d_out, (unsigned long long)cap, t->d_scalar);
+    gub::k_scan<<<148 * 8, 256>>>(t->table, t->capacity, d_out, (unsigned long long)cap, t->d_scalar, t->inv);
     e = cudaDeviceSynchronize();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&total, t->d_scalar, 8, cudaMemcpyDeviceToHost);
@@ -1093,7 +1073,7 @@ int gub_make_updates_device(gub_table* t, const gub_req* d_queries, const gub_re
   return 0;
 }
 
-__global__ void k_add_items_pub(gub::Slot* table, uint64_t cap, const gub_item* items, uint32_t n, int64_t now_ms, unsigned long long* counters) {
+__global__ void k_add_items_pub(gub::Slot* table, uint64_t cap, const gub_item* items, uint32_t n, int64_t now_ms, unsigned long long* counters, gub::InvIndex inv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const gub_item it = items[i];
@@ -1103,7 +1083,8 @@ __global__ void k_add_items_pub(gub::Slot* table, uint64_t cap, const gub_item* 
   gub::cursor_open(cur, table, cap, key, tag);
   const bool leaky = it.algorithm == GUB_LEAKY_BUCKET;
   cur.b.key = key; cur.b.tag = tag;
-  cur.b.flags = gub::F_LIVE | (leaky ? gub::F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? gub::F_OVER : 0u);
+  cur.b.flags = gub::F_LIVE | (leaky ? gub::F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? gub::F_OVER : 0u) | (it.invalid_at != 0 ? gub::F_INVALID_AT : 0u);
+  if (it.invalid_at != 0) gub::inv_store(inv, key, tag, it.invalid_at);
   cur.b.limit = it.limit; cur.b.duration = it.duration;
   cur.b.rem = leaky ? gub::f2bits(it.remaining_f) : (uint64_t)it.remaining;
   cur.b.stamp = now_ms; cur.b.burst = leaky ? it.burst : 0; cur.b.expire = it.expire_at;
@@ -1119,7 +1100,7 @@ int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_
   CK(cudaSetDevice(t->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (order_after_last(t, st)) return -1;
-  k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters);
+  k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters, t->inv);
   CK(cudaGetLastError());
   t->last_stream = st; t->last_pending = true;
   return 0;
@@ -1178,6 +1159,7 @@ struct gub_p2p {
   struct LocalGroup { std::mutex mu; std::condition_variable cv; uint32_t arrived = 0, gen = 0; } own_group;
   LocalGroup* group = nullptr;
   gub_p2p* local_peers[gub::MAX_SHARDS] = {};
+  cudaEvent_t phase_ev = nullptr;  // single-thread drivers: 'this shard's phase has been enqueued and completed' (see local_phase_sync)
   uint32_t* h_counts = nullptr;    // pinned: {hits drained, queries drained, items made, spare} of the tick in flight
   void* nccl = nullptr;            // ncclComm_t
   uint64_t tick_bytes = 0;         // bytes all-gathered by the last tick
@@ -1211,6 +1193,7 @@ void gub_p2p_destroy(gub_p2p* p) {
   void* ptrs[] = {p->block, p->error, p->ticket, p->g_reqs, p->g_resps, p->g_items, p->g_gather, p->g_count, p->g_counts_all};
   for (void* q : ptrs) if (q) cudaFree(q);
   if (p->h_counts) cudaFreeHost(p->h_counts);
+  if (p->phase_ev) cudaEventDestroy(p->phase_ev);
   for (auto& r : p->rt) {
     void* rp[] = {r.tile_agg, r.counts, r.perm, r.true_owner};
     for (void* q : rp) if (q) cudaFree(q);
@@ -1371,7 +1354,6 @@ int p2p_step_check(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock*
   if (!p || !clk || (n && (!d_reqs || !d_out))) return fail("gub_p2p_step: null argument");
   if (n > p->cap) return fail("gub_p2p_step: n exceeds the mailbox capacity");
   if (p->t->ring_cached != p->ring || p->t->ring_version != gub_ring_version_(p->ring)) return fail("gub_p2p_step: the table's ring changed since gub_p2p_create");
-  if (!p->t->fused) return fail("gub_p2p_step: needs the fused batch kernel (GUB_FUSED=0 is a single-GPU measurement switch)");
   return 0;
 }
 
@@ -1443,6 +1425,29 @@ int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_
   return p2p_phase_collect(p, n, d_out, si, st);
 }
 
+}  // extern "C"
+
+namespace {
+// Between the phases of the single-thread drivers: every shard's stream waits for the phase just enqueued on every other shard's
+// stream.  The kernels of the next phase then find their mailbox flags already published and never spin: on a device shared by
+// several shards a spinning kernel could keep another shard's (cooperative, all-SM) batch kernel from ever becoming resident.
+int local_phase_sync(gub_p2p* const* ps, uint32_t world, void* const* streams) {
+  if (world < 2) return 0;
+  for (uint32_t r = 0; r < world; r++) {
+    CK(cudaSetDevice(ps[r]->t->device));
+    if (!ps[r]->phase_ev) CK(cudaEventCreateWithFlags(&ps[r]->phase_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ps[r]->phase_ev, (cudaStream_t)streams[r]));
+  }
+  for (uint32_t r = 0; r < world; r++) {
+    CK(cudaSetDevice(ps[r]->t->device));
+    for (uint32_t q = 0; q < world; q++) if (q != r) CK(cudaStreamWaitEvent((cudaStream_t)streams[r], ps[q]->phase_ev, 0));
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
 /* One step of every shard of this process, driven by ONE host thread (the shape of the reference daemon: one process): the
  * phases are enqueued shard by shard — all routings, then all evaluations, then all collects — so that no shard's kernels wait
  * for work the host has not enqueued yet (on ONE device that would deadlock: the batch kernel occupies every SM). */
@@ -1451,7 +1456,9 @@ int gub_p2p_step_local_all(gub_p2p* const* ps, uint32_t world, const gub_req* co
   if (!ps || !d_reqs || !n || !d_out || !streams || world == 0) return fail("gub_p2p_step_local_all: bad argument");
   for (uint32_t r = 0; r < world; r++) if (p2p_step_check(ps[r], d_reqs[r], n[r], clk, d_out[r])) return -1;
   for (uint32_t r = 0; r < world; r++) if (p2p_phase_route(ps[r], d_reqs[r], n[r], (cudaStream_t)streams[r], (cudaStream_t)streams[r])) return -1;
+  if (local_phase_sync(ps, world, streams)) return -1;
   for (uint32_t r = 0; r < world; r++) if (p2p_phase_evaluate(ps[r], clk, (cudaStream_t)streams[r])) return -1;
+  if (local_phase_sync(ps, world, streams)) return -1;
   for (uint32_t r = 0; r < world; r++) if (p2p_phase_collect(ps[r], n[r], d_out[r], (cudaStream_t)streams[r], (cudaStream_t)streams[r])) return -1;
   return 0;
 }
@@ -1625,21 +1632,17 @@ int tick_phase_a(gub_p2p* p, cudaStream_t st) {
   p2p_args(p, A);
   return p2p_route(p, rt, A, p->g_reqs, p->gcap, p->g_count + 0, -1, st);
 }
-// B: owners apply the hits with DRAIN_OVER_LIMIT as owner (gubernator.go:510-512); the responses are dropped like sendHits does.
+// B: owners apply the hits with DRAIN_OVER_LIMIT as owner (gubernator.go:510-512).
 int tick_phase_b(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
   gub_table* t = p->t;
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
-  gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
   gub::P2PArgs A;
   p2p_args(p, A);
   if (order_after_last(t, st)) return -1;
   if (p2p_evaluate(p, A, clk, st)) return -1;
   t->last_stream = st; t->last_pending = true;
   if (gq_accumulate_segments(p, A, st)) return -1;
-  gub::k_p2p_collect<<<64, 256, 0, st>>>(A, rt->perm, p->gcap, p->g_count + 0, p->g_resps);
-  CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true;
-  p->seq += (uint64_t)1 << 32;
   CK(cudaGetLastError());
   return 0;
 }
@@ -1648,6 +1651,16 @@ int tick_phase_c(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
   gub_table* t = p->t;
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
+  {  // the owners' answers to our hit records are dropped (sendHits ignores them), but the flags are consumed: epochs stay aligned.
+     // (Enqueued here, after EVERY shard's evaluation: on a device shared by several shards a collect spinning ahead of another
+     // shard's batch kernel would keep that cooperative kernel from ever becoming resident.)
+    gub_p2p::Route* rt = &p->rt[p->epoch & 1u];
+    gub::P2PArgs A;
+    p2p_args(p, A);
+    gub::k_p2p_collect<<<64, 256, 0, st>>>(A, rt->perm, p->gcap, p->g_count + 0, p->g_resps);
+    CK(cudaEventRecord(rt->step_done, st)); rt->step_done_valid = true;
+    p->seq += (uint64_t)1 << 32;
+  }
   gub::k_gq_drain<<<148, 256, 0, st>>>(p->updates_q->q, p->g_reqs, p->gcap, p->g_count + 1, 1u);
   gub::FArgs F;
   fused_base_args(t, clk, F);
@@ -1682,7 +1695,7 @@ int tick_install_local(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* in
     const gub_p2p* q = p->local_peers[r];
     const uint32_t k = std::min(q->h_counts[2], q->gcap);
     if (!k) continue;
-    k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, q->g_items, k, now_ms, t->counters);
+    k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, q->g_items, k, now_ms, t->counters, t->inv);
     *installed += k;
     p->tick_bytes += (uint64_t)k * sizeof(gub_item);
   }
@@ -1709,7 +1722,7 @@ int tick_install_nccl(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* ins
     for (uint32_t r = 0; r < p->world; r++) {
       const uint32_t k = std::min(all[r], p->gcap);
       if (r == p->rank || !k) continue;  // "Exclude ourselves from the update" (global.go:263-265)
-      k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters);
+      k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters, t->inv);
       *installed += k;
     }
     CK(cudaGetLastError());
@@ -1757,7 +1770,9 @@ int gub_global_tick_local_all(gub_p2p* const* ps, uint32_t world, const gub_cloc
     if (!ps[r] || !ps[r]->hits_q || ps[r]->world != world || (world > 1 && !ps[r]->group)) return fail("gub_global_tick_local_all: shards must be local, connected and GLOBAL-enabled");
   }
   for (uint32_t r = 0; r < world; r++) if (tick_phase_a(ps[r], (cudaStream_t)streams[r])) return -1;
+  if (local_phase_sync(ps, world, streams)) return -1;
   for (uint32_t r = 0; r < world; r++) if (tick_phase_b(ps[r], clk, (cudaStream_t)streams[r])) return -1;
+  if (local_phase_sync(ps, world, streams)) return -1;
   for (uint32_t r = 0; r < world; r++) if (tick_phase_c(ps[r], clk, (cudaStream_t)streams[r])) return -1;
   for (uint32_t r = 0; r < world; r++) { CK(cudaSetDevice(ps[r]->t->device)); CK(cudaStreamSynchronize((cudaStream_t)streams[r])); }
   for (uint32_t r = 0; r < world; r++) {

@@ -43,7 +43,7 @@ constexpr int FB_ROW = FB_MAX_GRID;  // fragment-size row (uint16) per group ent
 constexpr int FB_MAX_SEGS = MAX_SHARDS;
 constexpr uint32_t FB_AUX_ENTRIES = 1u << 17;  // batch-wide group table (a round of 148 tiles holds <= 75 776 keys)
 constexpr uint32_t G_NONUNIFORM = 1u;
-constexpr int FB_OVF_CAP = 1024;     // items whose insert found the probe window full; placed (with eviction) at the next batch
+constexpr int FB_OVF_CAP = OVF_CAP;  // items whose insert found the probe window full; placed (with eviction) at the next batch
 
 // Batch-wide group entry.  All zero between batches: whoever finishes a group hands the entry back clean.
 struct __align__(32) GEntry {
@@ -52,7 +52,7 @@ struct __align__(32) GEntry {
   uint32_t rep;             // round-local index of one member: every fragment's first member is compared with it
   uint32_t flags;           // G_NONUNIFORM
   uint32_t arrived;         // fragments that have read the slot and answered
-  uint32_t scanned;         // the base ranks of the group's fragments are in its row
+  uint32_t _pad;
 };
 
 struct FSeg {                           // one run of request records, evaluated in order after the previous segment
@@ -63,8 +63,6 @@ struct FSeg {                           // one run of request records, evaluated
   uint32_t n;                           // count when neither is given
   uint32_t _pad;
 };
-
-struct OvfItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags, _pad; };  // 72 bytes
 
 struct FCtl {
   uint32_t bar_cnt, bar_gen;            // grid barrier
@@ -93,6 +91,7 @@ struct FArgs {
   unsigned long long* resp_flag[FB_MAX_SEGS];
   uint32_t n_resp_flags;
   uint32_t sweep_chunk;                 // slots each CTA sweeps per round (0 = off)
+  InvIndex inv;                         // CacheItem.InvalidAt side index (see gub_kernels.cuh)
   unsigned long long* trace;            // optional [gridDim.x][FB_TRACE_MARKS]: %globaltimer of every CTA at the phase boundaries (diagnostic)
   gub_clock clk;
 };
@@ -111,6 +110,7 @@ struct FCtx {
   OvfItem* ovf;
   unsigned long long* counters;
   unsigned long long* trace;
+  InvIndex inv;
   uint32_t nseg, sweep_chunk, n_resp_flags, _pad;
   gub_clock clk;
 };
@@ -124,6 +124,10 @@ __device__ __forceinline__ void mbar_wait(MBar*, uint32_t) {}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) { return *p; }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { *p = v; }
 __device__ __forceinline__ void spin_pause() { emu::spin_yield(); }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) { return *p; }
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) { *p = v; }
+__device__ __forceinline__ uint32_t atomic_add_release_gpu(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+__device__ __forceinline__ void fence_acquire_gpu() {}
 __device__ __forceinline__ uint32_t atomic_add_acq_rel_gpu(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
 #else
 struct __align__(8) MBar { uint64_t w; };
@@ -155,6 +159,18 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void spin_pause() {}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atomic_add_release_gpu(uint32_t* p, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint32_t atomic_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
   uint32_t o;
   asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
@@ -312,8 +328,8 @@ __device__ __forceinline__ void gentry_clear(GEntry* e) {
 // A fragment's members rank base + 0, base + 1, ... within the group, base = members in the tiles before it.  Every fragment
 // summing the row itself costs O(fragments^2) loads per group (a hot key has a fragment in every tile).  Instead ONE fragment of
 // each group — picked by key hash among the tiles the group occupies, so the duty spreads evenly over the CTAs — scans the row
-// once, warp-cooperatively (64 tiles per step, coalesced), stores every fragment's base next to its size and raises the entry's
-// `scanned` flag; the other fragments wait for the flag and read one number.
+// once, warp-cooperatively (64 tiles per step, coalesced), and stores every fragment's base (+ 1: non-zero = published) next to its
+// size; the other fragments poll their own row entry: one word is both the flag and the data, so no fence is involved.
 __device__ __forceinline__ uint32_t kth_set_bit(const uint32_t bits[FB_PRES_WORDS], uint32_t k) {  // position of the k-th (0-based) set bit
   uint32_t w = 0;
 #pragma unroll 1
@@ -340,8 +356,8 @@ __device__ __forceinline__ void scan_group_row(const FCtx& A, uint32_t pos, cons
     for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (uint32_t)o) incl += u; }
     const uint32_t excl = carry + incl - (v0 + v1);
     uint32_t* hi = reinterpret_cast<uint32_t*>(row + 64 * c + 2 * lane);
-    if (pair & 1u) __stcg(hi + 1, excl);
-    if (pair & 2u) __stcg(hi + 3, excl + v0);
+    if (pair & 1u) st_relaxed_gpu(hi + 1, excl + 1u);        // base + 1: non-zero = published (the finisher of the group zeroes it again)
+    if (pair & 2u) st_relaxed_gpu(hi + 3, excl + v0 + 1u);
     carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
   }
 }
@@ -358,22 +374,10 @@ __device__ __forceinline__ void cursor_from_snapshot(const FCtx& A, const FSmem&
   c.old = c.b;
 }
 
-// Writes a key's final state.  A new key whose probe window has no free slot is parked in the overflow list: the next batch
-// places it before anything reads the table, evicting the entry of the window that expires first (the reference's LRU would
-// have evicted as well: lrucache.go:98,138-149).
+// Writes a key's final state; a new key whose probe window has no free slot is parked (gub_kernels.cuh: close_or_park).
 template <class Ctx>
 __device__ __forceinline__ void close_or_park(const Ctx& A, Cursor& cur, Tally& t) {
-  if (cursor_close(cur, A.table, A.capacity, t.inserts)) return;
-  const uint32_t k = atomicAdd(&A.ctl->ovf_count, 1u);
-  if (k < (uint32_t)FB_OVF_CAP) {
-    OvfItem it;
-    it.key = cur.b.key; it.tag = cur.b.tag; it.flags = cur.b.flags; it._pad = 0;
-    it.w[0] = (uint64_t)cur.b.limit; it.w[1] = (uint64_t)cur.b.duration; it.w[2] = cur.b.rem; it.w[3] = (uint64_t)cur.b.stamp;
-    it.w[4] = (uint64_t)cur.b.burst; it.w[5] = (uint64_t)cur.b.expire;
-    A.ovf[k] = it;
-  } else {
-    t.full++;  // more than FB_OVF_CAP keys without a slot in one batch: the state of this one is dropped (counted)
-  }
+  close_or_park(cur, A.table, A.capacity, A.ovf, &A.ctl->ovf_count, t);
 }
 
 // ---- groups whose requests differ ---------------------------------------------------------------------------------------------
@@ -470,6 +474,7 @@ __device__ __noinline__ void mixed_group(const FCtx& A, FSmem& S, SC& sc, uint32
         if (!open || key != ck || tag != ct) {  // (the key only changes when two keys share their XXH64)
           if (open) close_or_park(A, cur, t);
           cursor_open(cur, A.table, A.capacity, key, tag);
+          apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
           open = true; ck = key; ct = tag;
         }
         Delta d = {0, 0, 0};
@@ -516,9 +521,15 @@ __device__ __forceinline__ void group_bits(const FCtx& A, uint32_t pos, bool spr
     bits[blockIdx.x >> 5] = 1u << (blockIdx.x & 31);
   }
 }
-__device__ __forceinline__ void group_release(const FCtx& A, uint32_t pos) {  // hands the entry and its bitmap back clean
-  ulonglong2* pz = reinterpret_cast<ulonglong2*>(A.presence + (size_t)pos * FB_PRES_WORDS);
-  __stcg(pz, make_ulonglong2(0ull, 0ull)); __stcg(pz + 1, make_ulonglong2(0ull, 0ull));
+__device__ __forceinline__ void group_release(const FCtx& A, uint32_t pos) {  // hands the entry, its bitmap and the published bases back clean
+  uint4* pz = reinterpret_cast<uint4*>(A.presence + (size_t)pos * FB_PRES_WORDS);
+  const uint4 p0 = __ldcg(pz), p1 = __ldcg(pz + 1);
+  const uint32_t bits[FB_PRES_WORDS] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  uint32_t* row = reinterpret_cast<uint32_t*>(A.fragrow + (size_t)pos * FB_ROW);
+#pragma unroll 1
+  for (uint32_t w = 0; w < (uint32_t)FB_PRES_WORDS; w++)
+    for (uint32_t x = bits[w]; x; x &= x - 1) st_relaxed_gpu(row + 2 * (w * 32 + (uint32_t)__ffs(x) - 1) + 1, 0u);
+  __stcg(pz, make_uint4(0u, 0u, 0u, 0u)); __stcg(pz + 1, make_uint4(0u, 0u, 0u, 0u));
   gentry_clear(&A.aux[pos]);
 }
 
@@ -563,46 +574,9 @@ __device__ __noinline__ void finish_mixed_groups(FSmem& S, uint32_t nfin, uint32
 }
 
 // ---- maintenance inside the batch kernel (both run before the grid barrier, when nothing reads the table) -------------------
-// Items parked by close_or_park(): one warp places them, evicting when the window is still full.
-__device__ __noinline__ void drain_overflow(const FCtx& A, Tally& t) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t n = min(__ldcg(&A.ctl->ovf_count), (uint32_t)FB_OVF_CAP);
-#pragma unroll 1
-  for (uint32_t k = 0; k < n; k++) {
-    const OvfItem it = A.ovf[k];
-    const uint64_t home = __umul64hi(it.key, A.capacity);
-    // every lane inspects 16 slots of the window: best = reusable, else dead / expired, else the smallest ExpireAt
-    uint64_t best_rank = ~0ull, best_idx = 0;
-#pragma unroll 1
-    for (uint32_t p = lane; p < (uint32_t)MAX_PROBE; p += 32) {
-      const uint64_t idx = (home + p) % A.capacity;  // (a table smaller than the window wraps more than once)
-      const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(A.table + idx));
-      const int64_t exp = (int64_t)__ldcg(&A.table[idx].w[7]);
-      uint64_t rank;
-      if (a.x == it.key && (a.y >> 8) == it.tag) rank = 0;                                   // the key itself (re-created meanwhile)
-      else if (a.x <= KEY_TOMB) rank = 1;                                                    // free
-      else if (!(a.y & F_LIVE) || exp < A.clk.now_ms) rank = 2;                              // removed or expired
-      else rank = 3 + ((uint64_t)exp ^ 0x8000000000000000ull) / 4;                           // live: earliest ExpireAt first
-      rank = (rank << 9 | (uint64_t)p) & ~0ull;                                              // ties: nearest to home
-      if (rank < best_rank) { best_rank = rank; best_idx = idx; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint64_t r2 = __shfl_sync(0xFFFFFFFFu, (unsigned long long)best_rank, lane ^ o), i2 = __shfl_sync(0xFFFFFFFFu, (unsigned long long)best_idx, lane ^ o);
-      if (r2 < best_rank) { best_rank = r2; best_idx = i2; }
-    }
-    if (lane == 0) {
-      if ((best_rank >> 9) >= 3) atomicAdd(A.counters + C_EVICT_UNEXPIRED, 1ull);
-      if ((best_rank >> 9) >= 1) t.inserts++;
-      ulonglong2* p = reinterpret_cast<ulonglong2*>(A.table + best_idx);
-      __stcg(p, make_ulonglong2(it.key, (it.tag << 8) | (uint64_t)(it.flags & 0xFF)));
-      __stcg(p + 1, make_ulonglong2(it.w[0], it.w[1]));
-      __stcg(p + 2, make_ulonglong2(it.w[2], it.w[3]));
-      __stcg(p + 3, make_ulonglong2(it.w[4], it.w[5]));
-    }
-    __syncwarp();
-  }
-  if (lane == 0 && n) A.ctl->ovf_count = 0;
+// Items parked by close_or_park(): one warp places them (gub_kernels.cuh: drain_parked).
+__device__ __forceinline__ void drain_overflow(const FCtx& A, Tally& t) {
+  drain_parked(A.table, A.capacity, A.ovf, &A.ctl->ovf_count, A.clk.now_ms, A.counters, &t.inserts);
 }
 
 // Incremental expiry sweep: every CTA frees the removed / expired entries of a few slots per round (tombstones; a tombstone
@@ -786,6 +760,7 @@ __device__ __noinline__ void batch_phase2(FSmem& S, uint32_t round) {
       const uint4* pres = reinterpret_cast<const uint4*>(A.presence + (size_t)lpos * FB_PRES_WORDS);
       const uint4 p0 = __ldcg(pres), p1 = __ldcg(pres + 1);
       cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
+      apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
       have_cur = true;
       total = (uint32_t)(e0.y & 0xFFFFFFFFull); nfrag = (uint32_t)(e0.y >> 32);
       if (nfrag > 1) {
@@ -809,14 +784,13 @@ __device__ __noinline__ void batch_phase2(FSmem& S, uint32_t round) {
     for (int w = 0; w < FB_PRES_WORDS; w++) bits[w] = __shfl_sync(0xFFFFFFFFu, pbits[w], src);
     const uint32_t spos = __shfl_sync(0xFFFFFFFFu, lpos, src);
     scan_group_row(A, spos, bits);
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) { __threadfence(); st_release_gpu(&A.aux[spos].scanned, 1u); }
   }
   if (valid && tid == lead) {
-    if (nfrag > 1) {
-      uint32_t it = 0;
-      while (ld_acquire_gpu(&A.aux[lpos].scanned) == 0 && ++it < (1u << 26)) spin_pause();
-      base = __ldcg(reinterpret_cast<const uint32_t*>(A.fragrow + (size_t)lpos * FB_ROW + blockIdx.x) + 1);
+    if (nfrag > 1) {  // the group's scanner (maybe a lane of this very warp, above) publishes base + 1 in our row entry
+      const uint32_t* hi = reinterpret_cast<const uint32_t*>(A.fragrow + (size_t)lpos * FB_ROW + blockIdx.x) + 1;
+      uint32_t v = ld_relaxed_gpu(hi), it = 0;
+      while (v == 0 && ++it < (1u << 26)) { spin_pause(); v = ld_relaxed_gpu(hi); }
+      base = v - 1u;
     }
     S.fbase[f] = base; S.ftotal[f] = total; S.fnfrag[f] = (uint16_t)nfrag;
     if (cnt > 1 || nfrag > 1) {  // somebody else (a sibling, or whoever finishes the group from this CTA) needs the slot as found
@@ -864,9 +838,10 @@ __device__ __noinline__ void batch_phase2(FSmem& S, uint32_t round) {
         } else fin_kind = 1;
       } else {
         if (mixedf) atomicOr(&A.aux[pos].flags, G_NONUNIFORM);
-        if (A.n_resp_flags) __threadfence_system(); else __threadfence();  // this CTA's slot reads and response stores precede the check-in
-        if (atomicAdd(&A.aux[pos].arrived, 1u) == nfrag - 1) {  // every other fragment has read the slot and answered: finish the group
-          __threadfence();
+        if (A.n_resp_flags) __threadfence_system();  // responses in peer memory: system scope
+        // release: this CTA's slot reads and response stores precede the check-in (cumulative over the shared-memory counter above)
+        if (atomic_add_release_gpu(&A.aux[pos].arrived, 1u) == nfrag - 1) {  // every other fragment has read the slot and answered: finish the group
+          fence_acquire_gpu();
           fin_kind = (__ldcg(&A.aux[pos].flags) & G_NONUNIFORM) ? 2u : 1u;
         }
       }
@@ -912,11 +887,11 @@ __device__ __noinline__ void batch_finish(FSmem& S, uint32_t round) {
 
 __global__ void __launch_bounds__(FB_THREADS, 1) k_batch(const FArgs A) {
   FSmem& S = *reinterpret_cast<FSmem*>(GUB_DYN_SMEM());
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.mbar); S.nfrag = 0; S.nfin = 0; S.parity = 0;
     S.cx.table = A.table; S.cx.capacity = A.capacity; S.cx.fragrow = A.fragrow; S.cx.members = A.members; S.cx.presence = A.presence; S.cx.aux = A.aux; S.cx.ctl = A.ctl;
-    S.cx.ovf = A.ovf; S.cx.counters = A.counters; S.cx.trace = A.trace; S.cx.nseg = A.nseg; S.cx.sweep_chunk = A.sweep_chunk; S.cx.n_resp_flags = A.n_resp_flags;
+    S.cx.ovf = A.ovf; S.cx.counters = A.counters; S.cx.trace = A.trace; S.cx.inv = A.inv; S.cx.nseg = A.nseg; S.cx.sweep_chunk = A.sweep_chunk; S.cx.n_resp_flags = A.n_resp_flags;
     S.cx.clk = A.clk;
   }
   if (tid < 8) S.tally[tid] = 0;

@@ -162,7 +162,7 @@ __global__ void k_make_updates(const gub_req* queries, const gub_resp* resps, ui
   gub_item it;
   it.key_xxh64 = r.key_xxh64; it.key_fnv1 = r.key_fnv1; it.algorithm = (int32_t)r.algorithm; it.status = (int32_t)s.status;
   it.limit = s.limit; it.duration = r.duration; it.remaining = s.remaining; it.remaining_f = (double)s.remaining;
-  it.stamp = 0; it.burst = s.limit; it.expire_at = s.reset_time;
+  it.stamp = 0; it.burst = s.limit; it.expire_at = s.reset_time; it.invalid_at = 0;
   out[k] = it;
 }
 

@@ -19,17 +19,18 @@
 //            distinct (block, key) "fragment" joins the batch-wide group entry (count += members), sets the block's bit
 //            in the group's presence bitmap and stores the fragment size.  Prefetches every request's home slot into L2.
 //   k_rank   members of repeated keys get rank = (sum of earlier blocks' fragment sizes) + local rank and compare their
-//            request with the group's representative; any difference marks the group non-uniform.  In the default build
-//            (GUB_EARLY_SINGLES=1) keys seen once — most keys — are also evaluated right here (probe, apply_one, write-back,
-//            response) and the rank-0 member of a repeated key parks the slot as found in a snapshot.
+//            request with the group's representative; any difference marks the group non-uniform.  Keys seen once — most keys —
+//            are evaluated right here (probe, apply_one, write-back, response) and the rank-0 member of a repeated key parks the
+//            slot as found in a snapshot.
 //   k_eval   every member of a uniform run evaluates run_to_rank(snapshot, request, rank) and answers; the last rank writes
 //            the slot back.  Members of non-uniform runs only file themselves: order[base + rank] = index.
 //   k_finish one block per non-uniform group: split the ordered run into segments of identical requests, plan each with
 //            plan_run() on one thread, evaluate/scatter with all threads (serial walk when there are too many segments).
-// With GUB_EARLY_SINGLES=0, k_group and k_rank never touch bucket state (everything is evaluated in k_eval, repeated keys
-// are written back by k_finish from commit records), so stage 1 of batch b+1 may overlap stage 2 of batch b.
-// The four kernels are chained with programmatic dependent launch; block requests are partitioned by algorithm so that a
-// warp runs one bucket algorithm's code path.
+// The four kernels are chained with programmatic dependent launch (consecutive batches overlap: the small, high-occupancy kernels of
+// batch b+1 start while the tail of batch b drains — this pipeline's throughput advantage over the single persistent kernel of
+// gub_batch.cuh, measured in profiles/README.md); block requests are partitioned by algorithm so that a warp runs one bucket
+// algorithm's code path.  Variants measured on B200 and removed (profiles/r02_ab_round1_switches.json): dealing requests to threads
+// by class in k_rank (no gain), a table-free k_rank with commit records (slower).
 #pragma once
 #if !defined(GUB_EMULATE)  // tests/kernel_emu_harness.cpp compiles this header for the CPU on top of tests/cuda_emu.h
 #include <cuda_runtime.h>
@@ -49,37 +50,6 @@ constexpr int MIXED_THREADS = 256;
 constexpr int MAX_SEG = 96;          // uniform segments of a non-uniform group planned in parallel; more => serial walk
 constexpr int MAX_PIECES = 16;
 
-// Two placements of the singleton evaluation (compile-time; -DGUB_EARLY_SINGLES=0/1):
-//   1: keys seen once are evaluated in k_rank (their probe overlaps the rank work of repeated keys); the rank-0 member of
-//      a repeated key parks the slot as found in a snapshot, siblings read that in k_eval and the last rank writes the
-//      table directly.  Fewer instructions in the longest kernel; k_rank touches the table, so batches cannot overlap.
-//   0: k_rank stays table-free (stage 1 of batch b+1 may overlap stage 2 of batch b); everything is evaluated in k_eval and
-//      repeated keys are written back by k_finish from commit records.
-#ifndef GUB_EARLY_SINGLES
-#define GUB_EARLY_SINGLES 1
-#endif
-constexpr bool EARLY_SINGLES = GUB_EARLY_SINGLES != 0;
-
-// Experimental (-DGUB_GROUP_ONEPASS=1, default 0 until measured on a B200): k_group ranks a block's requests with one barrier
-// instead of eight warp turns, and the blocks of k_finish that have nothing to do return before the counter flush.  ncu (profiles/r01_ncu_full_v7_raw.csv) attributes most of k_group's issue stalls to those
-// barriers (17.5 stalled warps per issued instruction on `barrier`, against 9.9 on memory).  Each warp counts its members per
-// key (match.any) into s_wcnt[slot][warp]; after one barrier a member's local rank is the sum over earlier warps + its rank
-// inside the warp.  Same results (checked on the CPU emulation, tests/test_kernels_emulated.py).
-#ifndef GUB_GROUP_ONEPASS
-#define GUB_GROUP_ONEPASS 0
-#endif
-
-// Experimental (-DGUB_RANK_CLASS_SORT=1, default 0 until measured; needs GUB_EARLY_SINGLES=1): k_rank deals a block's requests to its
-// threads by class — keys seen once (token, then leaky), then members of repeated keys — instead of by algorithm only.  A warp of
-// the default build holds both kinds and walks both dependent chains one after the other (slot probe + update for the singletons;
-// bitmap -> size row -> rank, representative compare for the members): ncu shows 11.6 of 32 lanes active per instruction in k_rank.
-// The class is only known after the group entry has been read, so the deal happens after the wait, with the group data staged
-// through shared memory.
-#ifndef GUB_RANK_CLASS_SORT
-#define GUB_RANK_CLASS_SORT 0
-#endif
-static_assert(!(GUB_RANK_CLASS_SORT && !GUB_EARLY_SINGLES), "GUB_RANK_CLASS_SORT needs the default GUB_EARLY_SINGLES=1 build");
-
 struct __align__(64) Slot { uint64_t w[8]; };
 
 struct __align__(32) AuxEntry {
@@ -94,7 +64,14 @@ __host__ __device__ inline uint32_t aux_count(unsigned long long w) { return (ui
 __host__ __device__ inline uint32_t aux_epoch(unsigned long long w) { return (uint32_t)(w >> 48); }
 __host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint32_t)((w >> 24) & 0xFFFFFFull); }
 
-struct BatchCtr { uint32_t n_mixed, order_bump, n_commit, _pad1; };
+struct BatchCtr { uint32_t n_mixed, order_bump, _pad0, _pad1; };
+
+// Items whose insert found the probe window full are parked here and placed — evicting the entry of the window that expires first,
+// like the reference's LRU would have evicted (lrucache.go:98,138-149) — before the next batch reads the table.
+constexpr int OVF_CAP = 1024;
+struct OvfItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags, _pad; };  // 72 bytes
+struct InvEntry { unsigned long long key, tag; long long invalid_at, _pad; };
+struct InvIndex { InvEntry* e; uint32_t mask; };
 
 enum { C_OVER = 0, C_HIT, C_MISS, C_INSERTS, C_FULL, C_REQUESTS, C_BATCHES, C_DUP_GROUPS, C_MIXED_GROUPS, C_SERIAL, C_EVICT_UNEXPIRED, C_SWEPT, C_GQ_DROPPED,
        C_COUNT };
@@ -116,12 +93,14 @@ struct BatchArgs {
   uint32_t* ent;           // [n] group entry of request i
   uint32_t* meta;          // [n] (shared-memory slot of the fragment << 16) | local rank
   uint32_t* rank;          // [n] rank within the group (repeated keys only)
-  ulonglong2* commit;      // [entries * 6] repeated keys: final state + slot cursor parked by the run's last rank for k_finish
-  uint32_t* commit_ent;    // [max_batch / 2] entries that have a commit record
+  ulonglong2* commit;      // [entries * 6] repeated keys: the slot as the run's rank-0 member found it (snapshot for its siblings)
   uint32_t* order;         // [max_batch] rank-ordered member indices of non-uniform groups
   uint32_t* mixed_ent;     // [max_batch / 2] entries of non-uniform groups
   BatchCtr* ctr;           // [2], indexed by epoch parity
   unsigned long long* counters;  // [C_COUNT]
+  OvfItem* ovf;            // [OVF_CAP] parked inserts
+  uint32_t* ovf_count;
+  InvIndex inv;            // CacheItem.InvalidAt side index
   gub_clock clk;
 };
 
@@ -183,6 +162,39 @@ struct Cursor {  // one key's slot while requests are applied to it
   uint64_t home;
   bool found;
 };
+
+// CacheItem.InvalidAt (cache.go:40,47) is only ever set by Store / Loader plugins, so it does not get a word of the 64-byte
+// slot: slots that have one carry F_INVALID_AT and the value sits in a small side index (open addressing by key, a few probes;
+// a full neighbourhood overwrites its home entry: the item then merely falls back to ExpireAt).
+constexpr int INV_PROBES = 16;
+__device__ __forceinline__ int64_t inv_lookup(const InvIndex& I, uint64_t key, uint64_t tag) {
+  uint32_t pos = (uint32_t)(key ^ (key >> 33)) & I.mask;
+  for (int p = 0; p < INV_PROBES; p++) {
+    const unsigned long long k = __ldcg(&I.e[pos].key);
+    if (k == key && __ldcg(&I.e[pos].tag) == tag) return (int64_t)__ldcg(&I.e[pos].invalid_at);
+    if (k == 0ull) break;
+    pos = (pos + 1) & I.mask;
+  }
+  return 0;
+}
+__device__ __forceinline__ void inv_store(const InvIndex& I, uint64_t key, uint64_t tag, int64_t invalid_at) {
+  const uint32_t home = (uint32_t)(key ^ (key >> 33)) & I.mask;
+  uint32_t pos = home;
+  for (int p = 0; p < INV_PROBES; p++) {
+    const unsigned long long old = atomicCAS(&I.e[pos].key, 0ull, (unsigned long long)key);
+    if (old == 0ull || (old == key && I.e[pos].tag == tag) || old == key) { I.e[pos].tag = tag; I.e[pos].invalid_at = invalid_at; return; }
+    pos = (pos + 1) & I.mask;
+  }
+  I.e[home].key = key; I.e[home].tag = tag; I.e[home].invalid_at = invalid_at;
+}
+// IsExpired's first clause: an item past its InvalidAt counts as expired (removed, reported as a miss; the caller's apply_one sees a
+// bucket that is not live).
+__device__ __forceinline__ void apply_invalid_at(const InvIndex& I, Bucket& b, bool found, int64_t now_ms) {
+  if (found && (b.flags & F_INVALID_AT)) {
+    const int64_t inv = inv_lookup(I, b.key, b.tag);
+    if (inv != 0 && inv < now_ms) b.flags &= ~(F_LIVE | F_INVALID_AT);
+  }
+}
 
 // Looks `key` up.  On a hit the slot is loaded into cur.b.  On a miss cur.b is an empty (not live) bucket and cur.slot
 // is the first reusable slot (tombstone or empty) seen, if any.
@@ -264,6 +276,66 @@ __device__ __forceinline__ uint32_t snap_load(const ulonglong2* sp, Cursor& c) {
   return (uint32_t)g.y;
 }
 
+struct Tally { uint32_t over, hit, miss, inserts, full; };
+
+// Writes a key's final state.  A new key whose probe window has no free slot is parked (see OvfItem).
+__device__ __forceinline__ void close_or_park(Cursor& cur, Slot* table, uint64_t cap, OvfItem* ovf, uint32_t* ovf_count, Tally& t) {
+  if (cursor_close(cur, table, cap, t.inserts)) return;
+  const uint32_t k = atomicAdd(ovf_count, 1u);
+  if (k < (uint32_t)OVF_CAP) {
+    OvfItem it;
+    it.key = cur.b.key; it.tag = cur.b.tag; it.flags = cur.b.flags; it._pad = 0;
+    it.w[0] = (uint64_t)cur.b.limit; it.w[1] = (uint64_t)cur.b.duration; it.w[2] = cur.b.rem; it.w[3] = (uint64_t)cur.b.stamp;
+    it.w[4] = (uint64_t)cur.b.burst; it.w[5] = (uint64_t)cur.b.expire;
+    ovf[k] = it;
+  } else {
+    t.full++;  // more than OVF_CAP keys without a slot in one batch: the state of this one is dropped (counted)
+  }
+}
+
+// One warp places the parked items, evicting when the window is still full.  Runs when nothing reads the table.
+__device__ __noinline__ void drain_parked(Slot* table, uint64_t capacity, OvfItem* ovf, uint32_t* ovf_count, int64_t now_ms, unsigned long long* counters,
+                                          uint32_t* inserts) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n = min(__ldcg(ovf_count), (uint32_t)OVF_CAP);
+#pragma unroll 1
+  for (uint32_t k = 0; k < n; k++) {
+    const OvfItem it = ovf[k];
+    const uint64_t home = __umul64hi(it.key, capacity);
+    // every lane inspects 16 slots of the window: best = the key itself, else free, else removed / expired, else the smallest ExpireAt
+    uint64_t best_rank = ~0ull, best_idx = 0;
+#pragma unroll 1
+    for (uint32_t p = lane; p < (uint32_t)MAX_PROBE; p += 32) {
+      const uint64_t idx = (home + p) % capacity;  // (a table smaller than the window wraps more than once)
+      const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(table + idx));
+      const int64_t exp = (int64_t)__ldcg(&table[idx].w[7]);
+      uint64_t rank;
+      if (a.x == it.key && (a.y >> 8) == it.tag) rank = 0;
+      else if (a.x <= KEY_TOMB) rank = 1;
+      else if (!(a.y & F_LIVE) || exp < now_ms) rank = 2;
+      else rank = 3 + ((uint64_t)exp ^ 0x8000000000000000ull) / 4;  // live: earliest ExpireAt first
+      rank = (rank << 9) | (uint64_t)p;                               // ties: nearest to home
+      if (rank < best_rank) { best_rank = rank; best_idx = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t r2 = __shfl_sync(0xFFFFFFFFu, (unsigned long long)best_rank, lane ^ o), i2 = __shfl_sync(0xFFFFFFFFu, (unsigned long long)best_idx, lane ^ o);
+      if (r2 < best_rank) { best_rank = r2; best_idx = i2; }
+    }
+    if (lane == 0) {
+      if ((best_rank >> 9) >= 3) atomicAdd(counters + C_EVICT_UNEXPIRED, 1ull);
+      if ((best_rank >> 9) >= 1) (*inserts)++;
+      ulonglong2* p = reinterpret_cast<ulonglong2*>(table + best_idx);
+      __stcg(p, make_ulonglong2(it.key, (it.tag << 8) | (uint64_t)(it.flags & 0xFF)));
+      __stcg(p + 1, make_ulonglong2(it.w[0], it.w[1]));
+      __stcg(p + 2, make_ulonglong2(it.w[2], it.w[3]));
+      __stcg(p + 3, make_ulonglong2(it.w[4], it.w[5]));
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && n) *ovf_count = 0;
+}
+
 __device__ __forceinline__ gub_req load_req(const gub_req* p) {
   const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
   ulonglong2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
@@ -277,8 +349,6 @@ __device__ __forceinline__ void store_resp(gub_resp* p, const gub_resp& r) {
   __stcs(q, make_ulonglong2((uint64_t)r.status | ((uint64_t)r.err_code << 32), (uint64_t)r.limit));
   __stcs(q + 1, make_ulonglong2((uint64_t)r.remaining, (uint64_t)r.reset_time));
 }
-
-struct Tally { uint32_t over, hit, miss, inserts, full; };
 
 // Counter deltas are summed per block in shared memory first: a grid-wide atomicAdd per warp on five fixed addresses
 // serialises in L2 and costs more than the probes themselves.
@@ -303,6 +373,13 @@ __device__ __forceinline__ void tally_flush_block(const Tally& t, unsigned long 
   }
 }
 
+// cursor_open + the InvalidAt clause of IsExpired (cache.go:47), and the write-back with parking, in terms of BatchArgs
+__device__ __forceinline__ void open_slot(const BatchArgs& A, Cursor& cur, uint64_t key, uint64_t tag) {
+  cursor_open(cur, A.table, A.capacity, key, tag);
+  apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
+}
+__device__ __forceinline__ void close_slot(const BatchArgs& A, Cursor& cur, Tally& t) { close_or_park(cur, A.table, A.capacity, A.ovf, A.ovf_count, t); }
+
 // Applies the requests reqs[idx[0..cnt)] (ascending batch order) one after another, keeping the current key's slot in
 // registers and switching slots only when the key changes (it never does unless two keys collide on the 24-bit group tag).
 template <typename IdxFn>
@@ -319,20 +396,16 @@ __device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, Id
     if (j + 1 < cnt) { i_next = idx_of(j + 1); rq_next = load_req(A.reqs + i_next); }  // overlap the next request's load with this update
     const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
     if (!open || key != ck || tag != ct) {
-      if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;  // state of the previous key is lost: counted
-      cursor_open(cur, A.table, A.capacity, key, tag);
+      if (open) close_slot(A, cur, t);
+      open_slot(A, cur, key, tag);
       open = true; ck = key; ct = tag;
     }
     Delta d = {0, 0, 0};
-    gub_resp r = apply_one(cur.b, rq, A.clk, d);
-    if (!cur.found && (cur.b.flags & F_LIVE)) {
-      // a new key: claim its slot now so that a full table is reported on the request that created the item
-      if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); cur.b.flags = 0; t.full++; }
-    }
+    const gub_resp r = apply_one(cur.b, rq, A.clk, d);
     t.over += d.over; t.hit += d.hit; t.miss += d.miss;
     store_resp(A.out + i, r);
   }
-  if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
+  if (open) close_slot(A, cur, t);
 }
 
 // ---- kernel 1: group the batch by key, rank members inside each block --------------------------------------------
@@ -396,22 +469,30 @@ __device__ void merge_colliding_fragments(const BatchArgs& A, const uint32_t* s_
 
 __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ unsigned long long s_key[GROUP_SLOTS];
-  __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block (running, in warp order)
+  __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block
   __shared__ uint32_t s_pos[GROUP_SLOTS];  // batch-wide entry position
   __shared__ uint32_t s_conflict;          // two fragments of this block joined the same group entry (see merge_colliding_fragments)
+  // [key slot][warp]: members of the key among the warp's lanes (<= 32).  Every warp counts its members per key (match.any); after one
+  // barrier a member's index-ordered local rank is the sum over earlier warps + its rank inside the warp.  (Measured against eight
+  // warp turns with a barrier each: 31.7 vs 40.5 us per 65 536-request step, profiles/r02_ab_round1_switches.json.)
+  __shared__ __align__(16) uint8_t s_wcnt[GROUP_SLOTS][GROUP_THREADS / 32];
+  static_assert(sizeof(s_wcnt) == GROUP_THREADS * sizeof(uint4), "one 16-byte store per thread clears it");
   for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
   if (threadIdx.x == 0) s_conflict = 0u;
-#if GUB_GROUP_ONEPASS
-  __shared__ __align__(16) uint8_t s_wcnt[GROUP_SLOTS][GROUP_THREADS / 32];  // [key slot][warp]: members of the key among the warp's lanes (<= 32)
-  static_assert(sizeof(s_wcnt) == GROUP_THREADS * sizeof(uint4), "one 16-byte store per thread clears it");
   reinterpret_cast<uint4*>(&s_wcnt[0][0])[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
-#endif
   pdl_wait();
   pdl_release();
   __syncthreads();
+  // Inserts a previous batch could not place (probe window full) are placed now, with eviction: this kernel never reads the table
+  // and the previous batch is complete, so nothing can observe a half-moved entry.
+  if (blockIdx.x == 0 && threadIdx.x < 32 && __ldcg(A.ovf_count)) {
+    uint32_t ins = 0;
+    drain_parked(A.table, A.capacity, A.ovf, A.ovf_count, A.clk.now_ms, A.counters, &ins);
+    if (threadIdx.x == 0 && ins) atomicAdd(A.counters + C_INSERTS, (unsigned long long)ins);
+  }
   const uint32_t i = blockIdx.x * GROUP_THREADS + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t n = batch_n(A);  // after the wait: a gather kernel may have just written it
+  const uint32_t n = batch_n(A);  // after the wait: an earlier kernel may have just written it
   if (blockIdx.x * GROUP_THREADS >= n) return;  // whole block beyond the batch (uniform: no barrier is skipped by part of a block)
   const bool valid = i < n;
   uint32_t sp = 0xFFFFu;  // shared-memory slot of my key (0xFFFF: no request)
@@ -420,7 +501,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   if (valid) {
     key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
     first = __ldcg(&A.aux[aux_home(A, key)].word);  // consumed much later, by the fragment's first member only
-    prefetch_l2(A.table + __umul64hi(key, A.capacity));  // the slot k_eval will probe
+    prefetch_l2(A.table + __umul64hi(key, A.capacity));  // the slot k_rank / k_eval will probe
     sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
 #pragma unroll 1
     for (;;) {
@@ -431,8 +512,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   }
   __syncthreads();
   uint32_t local = 0;
-#if GUB_GROUP_ONEPASS
-  // every warp records how many of its lanes hold each key; a member's local rank = members in earlier warps + earlier lanes
   {
     constexpr int NW = GROUP_THREADS / 32;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sp);
@@ -448,21 +527,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     }
     __syncthreads();
   }
-#else
-  // local rank in index order: warps take turns in order; inside a warp the lanes sharing a key are ranked by lane id
-#pragma unroll 1
-  for (uint32_t w = 0; w < GROUP_THREADS / 32; w++) {
-    if (warp == w) {
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sp);
-      const uint32_t leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (valid && lane == leader) { base = s_cnt[sp]; s_cnt[sp] = base + __popc(peers); }
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      local = base + __popc(peers & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-  }
-#endif
   // the first member of each fragment joins the batch-wide group
   if (valid && local == 0) {
     const uint32_t c = s_cnt[sp];
@@ -575,83 +639,31 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
   return blockIdx.x * GROUP_THREADS + s_perm[tid];
 }
 
-#if GUB_RANK_CLASS_SORT
-// Stable partition of the block's threads by class (0..3); returns the thread whose request this thread takes over.
-__device__ __forceinline__ uint32_t partition_by_class(uint32_t cls) {
-  __shared__ uint16_t s_src[GROUP_THREADS];
-  __shared__ uint32_t s_cnt4[GROUP_THREADS / 32][4];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1), b2 = __ballot_sync(0xFFFFFFFFu, cls == 2),
-                 b3 = ~(b0 | b1 | b2);
-  if (lane < 4) s_cnt4[warp][lane] = __popc(lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3)));
-  __syncthreads();
-  uint32_t start = 0, before = 0;
-#pragma unroll
-  for (int w = 0; w < GROUP_THREADS / 32; w++) {
-#pragma unroll
-    for (uint32_t c = 0; c < 4; c++) {
-      const uint32_t k = s_cnt4[w][c];
-      if (c < cls) start += k;
-      if (c == cls && (uint32_t)w < warp) before += k;
-    }
-  }
-  const uint32_t mine = cls == 0 ? b0 : (cls == 1 ? b1 : (cls == 2 ? b2 : b3));
-  s_src[start + before + __popc(mine & ((1u << lane) - 1u))] = (uint16_t)tid;
-  __syncthreads();
-  return s_src[tid];
-}
-#endif
 
-__global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
+#ifndef GUB_EVAL_MINBLOCKS
+#define GUB_EVAL_MINBLOCKS 2  // resident blocks per SM the register budget of k_rank / k_eval is sized for
+#endif
+__global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
-#if GUB_RANK_CLASS_SORT
-  __shared__ uint32_t s_pre_pos[GROUP_THREADS], s_pre_meta[GROUP_THREADS];
-  __shared__ ulonglong2 s_pre_ent[GROUP_THREADS];
-  const uint32_t j = blockIdx.x * GROUP_THREADS + threadIdx.x;  // the request whose group data this thread fetches
-  uint32_t algo_j = 2;
-  if (j < n) algo_j = __ldg(&A.reqs[j].algorithm);  // safe ahead of the wait, like the records
-  Tally t = {0, 0, 0, 0, 0};
-  pdl_wait();
-  pdl_release();
-  uint32_t cls = 3;  // no request
-  if (j < n) {
-    const uint32_t pj = A.ent[j];
-    const ulonglong2 ej = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pj]));
-    s_pre_pos[threadIdx.x] = pj; s_pre_meta[threadIdx.x] = A.meta[j]; s_pre_ent[threadIdx.x] = ej;
-    cls = aux_count(ej.x) > 1 ? 2u : (algo_j == 1u ? 1u : 0u);
-  }
-  const uint32_t src = partition_by_class(cls);  // two barriers: the staged group data is visible afterwards
-  const uint32_t i = blockIdx.x * GROUP_THREADS + src;
-  const bool valid = i < n;
-  gub_req rq;
-  if (valid) rq = load_req(A.reqs + i);
-#else
-  const uint32_t i = EARLY_SINGLES ? partition_by_algorithm(A.reqs, n) : blockIdx.x * GROUP_THREADS + threadIdx.x;
+  const uint32_t i = partition_by_algorithm(A.reqs, n);
   Tally t = {0, 0, 0, 0, 0};
   const bool valid = i < n;
   gub_req rq;
   if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
   pdl_wait();
   pdl_release();
-#endif
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
-    nxt->n_mixed = 0; nxt->order_bump = 0; nxt->n_commit = 0;
+    nxt->n_mixed = 0; nxt->order_bump = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
   uint32_t pos = 0, cnt = 0, sp = 0, local = 0;
   if (valid) {
-#if GUB_RANK_CLASS_SORT
-    pos = s_pre_pos[src];
-    const uint32_t m = s_pre_meta[src];
-    const ulonglong2 e = s_pre_ent[src];
-#else
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
-#endif
     const uint64_t key = remap_key(rq.key_xxh64);
     sp = m >> 16; local = m & 0xFFFFu;
     cnt = aux_count(e.x);
@@ -665,9 +677,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
       if (local == 0) {
         const uint32_t base = fragment_base(A, pos, blockIdx.x);
         s_base[sp] = base;
-        if (EARLY_SINGLES && base == 0) {  // rank 0 of the run: look the key up once for everybody
+        if (base == 0) {  // rank 0 of the run: look the key up once for everybody
           Cursor cur;
-          cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
+          open_slot(A, cur, key, rq.key_fnv1 >> 8);
           snap_store(A.commit + (size_t)pos * 6, cur, i);
         }
       }
@@ -680,17 +692,15 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
           A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
         }
       }
-    } else if (cnt == 1) {
+    } else if (cnt == 1) {  // a key seen once — most keys: evaluated right here (its slot was prefetched into L2 by k_group)
       A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
-      if (EARLY_SINGLES) {
-        Cursor cur;
-        cursor_open(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8);
-        Delta d = {0, 0, 0};
-        gub_resp r = apply_one(cur.b, rq, A.clk, d);
-        if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
-        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-        store_resp(A.out + i, r);
-      }
+      Cursor cur;
+      open_slot(A, cur, key, rq.key_fnv1 >> 8);
+      Delta d = {0, 0, 0};
+      const gub_resp r = apply_one(cur.b, rq, A.clk, d);
+      close_slot(A, cur, t);
+      t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+      store_resp(A.out + i, r);
     }
   }
   __syncthreads();
@@ -699,7 +709,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_rank(const BatchArgs A) {
 }
 
 // ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
-__global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
+__global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_eval(const BatchArgs A) {
   const uint32_t n = batch_n(A);
   const uint32_t i = partition_by_algorithm(A.reqs, n);
   Tally t = {0, 0, 0, 0, 0};
@@ -710,34 +720,26 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_eval(const BatchArgs A) {
   pdl_release();
   if (i < n) {
     const uint32_t pos = A.ent[i];
-    uint32_t rank = A.rank[i];                   // garbage for singletons; replaced below
+    const uint32_t rank = A.rank[i];             // garbage for keys seen once: not used
     const AuxEntry* e = &A.aux[pos];
     const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
     const uint32_t cnt = aux_count(ev.x);
     const bool mixed = cnt > 1 && ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
-    if (cnt == 1) rank = 0;
     if (cnt > 1 && rank == 0) {  // hand the presence bitmap back clean
       uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
       for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
     }
     if (mixed) {
       A.order[__ldcg(&e->gbase) + rank] = i;
-    } else if (!(EARLY_SINGLES && cnt == 1)) {
+    } else if (cnt > 1) {
       Cursor cur;
-      if (EARLY_SINGLES) snap_load(A.commit + (size_t)pos * 6, cur);  // the slot as k_rank found it (the last rank may already be writing the table)
-      else cursor_open(cur, A.table, A.capacity, remap_key(rq.key_xxh64), rq.key_fnv1 >> 8);
+      snap_load(A.commit + (size_t)pos * 6, cur);  // the slot as k_rank found it (the last rank may already be writing the table)
       Delta d = {0, 0, 0};
-      gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
+      const gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
       if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
         t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-        if (cnt == 1 || EARLY_SINGLES) {
-          if (!cursor_close(cur, A.table, A.capacity, t.inserts)) { r = mk_err(GUB_ERR_TABLE_FULL); t.full++; }
-          dup = cnt > 1 ? 1u : 0u;
-        } else {  // siblings may still be reading the slot: k_finish writes it
-          snap_store(A.commit + (size_t)pos * 6, cur, i);
-          A.commit_ent[atomicAdd(&A.ctr[A.epoch & 1].n_commit, 1u)] = pos;
-          dup = 1;
-        }
+        close_slot(A, cur, t);
+        dup = 1;
       }
       store_resp(A.out + i, r);
     }
@@ -756,69 +758,82 @@ struct MixedShared {
   Piece pieces[MAX_PIECES];
 };
 
+// A group is taken in chunks of MIXED_CHUNK members: per chunk the runs of identical requests (segments) are found in parallel; up
+// to MAX_SEG of them are planned one by one by thread 0 (closed forms) and evaluated by everybody; a chunk with more segments than
+// that is mostly one-request runs, where planning buys nothing: thread 0 applies its requests one after another.  The slot is
+// opened once and written once for the whole group (thread 0 carries the cursor across chunks).
+constexpr uint32_t MIXED_CHUNK = 4096;
+
 __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Tally& t) {
   const uint32_t tid = threadIdx.x;
-  const uint32_t cnt = aux_count(__ldcg(&A.aux[pos].word));
-  const uint32_t* ord = A.order + __ldcg(&A.aux[pos].gbase);
-  if (tid == 0) S.nseg = 0;
-  __syncthreads();
-  // segment boundaries: ranks whose request differs from the previous member's
-  for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
-    bool boundary = (k == 0);
-    if (!boundary) {
-      const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
-      boundary = !req_same(a, b);
-    }
-    if (boundary) { const uint32_t s = atomicAdd(&S.nseg, 1u); if (s < (uint32_t)MAX_SEG) S.seg[s] = k; }
-  }
-  __syncthreads();
-  const uint32_t nseg = S.nseg;
-  if (nseg > (uint32_t)MAX_SEG) {  // too irregular to plan: one thread walks the group in order
-    if (tid == 0) {
-      serial_walk(A, cnt, [ord](uint32_t j) { return ord[j]; }, t);
-      atomicAdd(A.counters + C_SERIAL, 1ull);
-    }
-    __syncthreads();
-    return;
-  }
-  if (tid == 0) {  // tiny insertion sort of the segment starts
-    for (uint32_t a = 1; a < nseg; a++) {
-      const uint32_t v = S.seg[a];
-      int b = (int)a - 1;
-      while (b >= 0 && S.seg[b] > v) { S.seg[b + 1] = S.seg[b]; b--; }
-      S.seg[b + 1] = v;
-    }
-  }
-  __syncthreads();
-  // per segment: thread 0 plans, everybody evaluates
+  const uint32_t total = aux_count(__ldcg(&A.aux[pos].word));
+  const uint32_t* ord_all = A.order + __ldcg(&A.aux[pos].gbase);
   Cursor cur;
   bool open = false;
   uint64_t ck = 0, ct = 0;
 #pragma unroll 1
-  for (uint32_t s = 0; s < nseg; s++) {
-    const uint32_t lo = S.seg[s], hi = (s + 1 < nseg) ? S.seg[s + 1] : cnt, m = hi - lo;
-    if (tid == 0) {
-      const gub_req rq = load_req(A.reqs + ord[lo]);
-      const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-      if (!open || key != ck || tag != ct) {
-        if (open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
-        cursor_open(cur, A.table, A.capacity, key, tag);
-        open = true; ck = key; ct = tag;
+  for (uint32_t c0 = 0; c0 < total; c0 += MIXED_CHUNK) {
+    const uint32_t* ord = ord_all + c0;
+    const uint32_t cnt = min(MIXED_CHUNK, total - c0);
+    __syncthreads();
+    if (tid == 0) S.nseg = 0;
+    __syncthreads();
+    // segment boundaries: ranks whose request differs from the previous member's (the chunk's first member starts one)
+    for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
+      bool boundary = (k == 0);
+      if (!boundary) {
+        const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
+        boundary = !req_same(a, b);
       }
-      Delta d = {0, 0, 0};
-      uint32_t np = 0, covered;
-      const bool was_found = cur.found;
-      Bucket before = cur.b;
-      covered = plan_run(cur.b, rq, m, A.clk, d, S.pieces, MAX_PIECES, &np);
-      bool full = false;
-      if (!was_found && (cur.b.flags & F_LIVE)) {
-        if (!cursor_close(cur, A.table, A.capacity, t.inserts)) full = true;
+      if (boundary) { const uint32_t q = atomicAdd(&S.nseg, 1u); if (q < (uint32_t)MAX_SEG) S.seg[q] = k; }
+    }
+    __syncthreads();
+    const uint32_t nseg = S.nseg;
+    if (nseg > (uint32_t)MAX_SEG) {  // mostly one-request runs: applied one by one
+      if (tid == 0) {
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; j++) {
+          const uint32_t i = ord[j];
+          const gub_req rq = load_req(A.reqs + i);
+          const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
+          if (!open || key != ck || tag != ct) {
+            if (open) close_slot(A, cur, t);
+            open_slot(A, cur, key, tag);
+            open = true; ck = key; ct = tag;
+          }
+          Delta d = {0, 0, 0};
+          const gub_resp r = apply_one(cur.b, rq, A.clk, d);
+          t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+          store_resp(A.out + i, r);
+        }
+        atomicAdd(A.counters + C_SERIAL, 1ull);
       }
-      if (full) {  // no slot for a new key: every request of the segment reports it, nothing is stored
-        cur.b = before; cur.b.flags = 0;
-        S.pieces[0].start = 0; S.pieces[0].kind = P_FIXED; S.pieces[0].resp = mk_err(GUB_ERR_TABLE_FULL);
-        np = 1; covered = m; t.full += m;
-      } else {
+      continue;
+    }
+    if (tid == 0) {  // tiny insertion sort of the segment starts
+      for (uint32_t a = 1; a < nseg; a++) {
+        const uint32_t v = S.seg[a];
+        int b = (int)a - 1;
+        while (b >= 0 && S.seg[b] > v) { S.seg[b + 1] = S.seg[b]; b--; }
+        S.seg[b + 1] = v;
+      }
+    }
+    __syncthreads();
+    // per segment: thread 0 plans, everybody evaluates
+#pragma unroll 1
+    for (uint32_t sgi = 0; sgi < nseg; sgi++) {
+      const uint32_t lo = S.seg[sgi], hi = (sgi + 1 < nseg) ? S.seg[sgi + 1] : cnt, m = hi - lo;
+      if (tid == 0) {
+        const gub_req rq = load_req(A.reqs + ord[lo]);
+        const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
+        if (!open || key != ck || tag != ct) {
+          if (open) close_slot(A, cur, t);
+          open_slot(A, cur, key, tag);
+          open = true; ck = key; ct = tag;
+        }
+        Delta d = {0, 0, 0};
+        uint32_t np = 0;
+        const uint32_t covered = plan_run(cur.b, rq, m, A.clk, d, S.pieces, MAX_PIECES, &np);
         t.over += d.over; t.hit += d.hit; t.miss += d.miss;
         // ranks the piece buffer could not hold (no regular regime, e.g. RESET_REMAINING flip-flops): walk them
         for (uint32_t k = covered; k < m; k++) {
@@ -827,57 +842,36 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
           t.over += d2.over; t.hit += d2.hit; t.miss += d2.miss;
           store_resp(A.out + ord[lo + k], rr);
         }
+        S.np = np; S.covered = covered;
       }
-      S.np = np; S.covered = covered;
+      __syncthreads();
+      const uint32_t np = S.np, covered = S.covered;
+      for (uint32_t k = tid; k < covered; k += MIXED_THREADS) {
+        uint32_t pi = 0;
+        while (pi + 1 < np && S.pieces[pi + 1].start <= k) pi++;
+        store_resp(A.out + ord[lo + k], eval_piece(S.pieces[pi], k));
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    const uint32_t np = S.np, covered = S.covered;
-    for (uint32_t k = tid; k < covered; k += MIXED_THREADS) {
-      uint32_t pi = 0;
-      while (pi + 1 < np && S.pieces[pi + 1].start <= k) pi++;
-      store_resp(A.out + ord[lo + k], eval_piece(S.pieces[pi], k));
-    }
-    __syncthreads();
   }
-  if (tid == 0 && open && !cursor_close(cur, A.table, A.capacity, t.inserts)) t.full++;
+  if (tid == 0 && open) close_slot(A, cur, t);
 }
 
-// Blocks [0, mixed_blocks): non-uniform groups, one block each (grid-stride).  The rest: commit records, one thread each.
-__global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A, uint32_t mixed_blocks) {
+// Non-uniform groups, one block each (grid-stride).  A launch with nothing to finish — the usual case — returns at once.
+__global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A) {
   __shared__ MixedShared S;
   Tally t = {0, 0, 0, 0, 0};
   pdl_wait();
   pdl_release();
   const BatchCtr ctr = A.ctr[A.epoch & 1];
-#if GUB_GROUP_ONEPASS  // same experimental switch: a launch with nothing to finish (the usual case) skips the counter flush's barriers
-  if (blockIdx.x < mixed_blocks ? ctr.n_mixed == 0 : ctr.n_commit == 0) return;
-#endif
-  if (blockIdx.x < mixed_blocks) {
-    for (uint32_t g = blockIdx.x; g < ctr.n_mixed; g += mixed_blocks) {
-      mixed_group(A, A.mixed_ent[g], S, t);
-      __syncthreads();
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && ctr.n_mixed) {
-      atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.n_mixed);
-      atomicAdd(A.counters + C_MIXED_GROUPS, (unsigned long long)ctr.n_mixed);
-    }
-  } else {
-    const uint32_t stride = (gridDim.x - mixed_blocks) * blockDim.x;
-    for (uint32_t k = (blockIdx.x - mixed_blocks) * blockDim.x + threadIdx.x; k < ctr.n_commit; k += stride) {
-      Cursor cur;
-      const uint32_t who = snap_load(A.commit + (size_t)A.commit_ent[k] * 6, cur);
-      if (cur.found) {  // existing slot: store the whole 64 bytes (cheaper than re-reading it to find what changed)
-        const Bucket& b = cur.b;
-        ulonglong2* p = reinterpret_cast<ulonglong2*>(A.table + cur.slot);
-        __stcg(p, make_ulonglong2(b.key, (b.tag << 8) | (uint64_t)(b.flags & 0xFF)));
-        __stcg(p + 1, make_ulonglong2((uint64_t)b.limit, (uint64_t)b.duration));
-        __stcg(p + 2, make_ulonglong2(b.rem, (uint64_t)b.stamp));
-        __stcg(p + 3, make_ulonglong2((uint64_t)b.burst, (uint64_t)b.expire));
-      } else if (!cursor_close(cur, A.table, A.capacity, t.inserts)) {
-        store_resp(A.out + who, mk_err(GUB_ERR_TABLE_FULL));
-        t.full++;
-      }
-    }
+  if (ctr.n_mixed == 0) return;
+  for (uint32_t g = blockIdx.x; g < ctr.n_mixed; g += gridDim.x) {
+    mixed_group(A, A.mixed_ent[g], S, t);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)ctr.n_mixed);
+    atomicAdd(A.counters + C_MIXED_GROUPS, (unsigned long long)ctr.n_mixed);
   }
   tally_flush_block(t, A.counters);
 }
@@ -1009,15 +1003,16 @@ __global__ void __launch_bounds__(256) k_hash_expand(const uint8_t* packed, uint
 
 // ---- maintenance kernels -------------------------------------------------------------------------------------
 // Upsert whole items: WorkerPool.AddCacheItem / Load / UpdatePeerGlobals.  Keys are unique within one launch.
-struct DevItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags; uint32_t _pad; };
+struct DevItem { uint64_t key, tag; uint64_t w[6]; uint32_t flags; uint32_t _pad; int64_t invalid_at; };
 
-__global__ void k_add_items(Slot* table, uint64_t cap, const DevItem* items, uint32_t n, unsigned long long* counters, uint32_t* failed) {
+__global__ void k_add_items(Slot* table, uint64_t cap, const DevItem* items, uint32_t n, unsigned long long* counters, uint32_t* failed, InvIndex inv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const DevItem it = items[i];
   Cursor cur;
   cursor_open(cur, table, cap, it.key, it.tag);
-  cur.b.key = it.key; cur.b.tag = it.tag; cur.b.flags = it.flags;
+  cur.b.key = it.key; cur.b.tag = it.tag; cur.b.flags = it.flags | (it.invalid_at != 0 ? F_INVALID_AT : 0u);
+  if (it.invalid_at != 0) inv_store(inv, it.key, it.tag, it.invalid_at);
   cur.b.limit = (int64_t)it.w[0]; cur.b.duration = (int64_t)it.w[1]; cur.b.rem = it.w[2]; cur.b.stamp = (int64_t)it.w[3];
   cur.b.burst = (int64_t)it.w[4]; cur.b.expire = (int64_t)it.w[5];
   uint32_t ins = 0;
@@ -1026,22 +1021,23 @@ __global__ void k_add_items(Slot* table, uint64_t cap, const DevItem* items, uin
 }
 
 __global__ void k_get_items(const Slot* table, uint64_t cap, const uint64_t* keys, const uint64_t* fnv, uint32_t n, int64_t now_ms,
-                            DevItem* out, uint8_t* found) {
+                            DevItem* out, uint8_t* found, InvIndex inv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Cursor cur;
   cursor_open(cur, table, cap, remap_key(keys[i]), fnv[i] >> 8);
-  const bool ok = cur.found && (cur.b.flags & F_LIVE) && !(cur.b.expire < now_ms);  // lrucache.go:111-128
+  const int64_t inv_at = (cur.found && (cur.b.flags & F_INVALID_AT)) ? inv_lookup(inv, cur.b.key, cur.b.tag) : 0;
+  const bool ok = cur.found && (cur.b.flags & F_LIVE) && !(cur.b.expire < now_ms) && !(inv_at != 0 && inv_at < now_ms);  // lrucache.go:111-128, cache.go:43-57
   found[i] = ok ? 1 : 0;
   DevItem o;
-  o.key = keys[i]; o.tag = cur.b.tag; o.flags = cur.b.flags; o._pad = 0;
+  o.key = keys[i]; o.tag = cur.b.tag; o.flags = cur.b.flags; o._pad = 0; o.invalid_at = inv_at;
   o.w[0] = (uint64_t)cur.b.limit; o.w[1] = (uint64_t)cur.b.duration; o.w[2] = cur.b.rem; o.w[3] = (uint64_t)cur.b.stamp;
   o.w[4] = (uint64_t)cur.b.burst; o.w[5] = (uint64_t)cur.b.expire;
   out[i] = o;
 }
 
 // Cache.Each: every live item (expired ones included until something removes them, like the reference's map walk).
-__global__ void k_scan(const Slot* table, uint64_t cap, DevItem* out, unsigned long long out_cap, unsigned long long* n_out) {
+__global__ void k_scan(const Slot* table, uint64_t cap, DevItem* out, unsigned long long out_cap, unsigned long long* n_out, InvIndex inv) {
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
     const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2*>(table + s));
     if (a.x > KEY_TOMB && (a.y & F_LIVE)) {
@@ -1051,6 +1047,7 @@ __global__ void k_scan(const Slot* table, uint64_t cap, DevItem* out, unsigned l
         slot_load(table + s, a2, b, c, d);
         DevItem o;
         o.key = a.x; o.tag = a.y >> 8; o.flags = (uint32_t)(a.y & 0xFF); o._pad = 0;
+        o.invalid_at = (o.flags & F_INVALID_AT) ? inv_lookup(inv, o.key, o.tag) : 0;
         o.w[0] = b.x; o.w[1] = b.y; o.w[2] = c.x; o.w[3] = c.y; o.w[4] = d.x; o.w[5] = d.y;
         out[k] = o;
       }

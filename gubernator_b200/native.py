@@ -20,13 +20,13 @@ RESP_DTYPE = np.dtype([("status", "<u4"), ("err_code", "<u4"), ("limit", "<i8"),
 CLOCK_DTYPE = np.dtype([("now_ms", "<i8"), ("greg_expire", "<i8", (6,)), ("greg_duration", "<i8", (6,))])
 ITEM_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("algorithm", "<i4"), ("status", "<i4"), ("limit", "<i8"),
                        ("duration", "<i8"), ("remaining", "<i8"), ("remaining_f", "<f8"), ("stamp", "<i8"), ("burst", "<i8"),
-                       ("expire_at", "<i8")])
+                       ("expire_at", "<i8"), ("invalid_at", "<i8")])
 COUNTER_FIELDS = ("over_limit", "cache_hit", "cache_miss", "inserts", "table_full", "requests", "batches", "dup_groups",
                   "mixed_groups", "serial_fallbacks", "unexpired_evictions", "swept", "gq_dropped")
 CREQ_DTYPE = np.dtype([("key_xxh64", "<u8"), ("key_fnv1", "<u8"), ("hits", "<i8"), ("params", "<u4"), ("created_delta", "<i4")])
 PARAMS_DTYPE = np.dtype([("limit", "<i8"), ("duration", "<i8"), ("burst", "<i8"), ("algorithm", "<u4"), ("behavior", "<u4")])
 assert CREQ_DTYPE.itemsize == 32 and PARAMS_DTYPE.itemsize == 32
-assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 80
+assert REQ_DTYPE.itemsize == 64 and RESP_DTYPE.itemsize == 32 and CLOCK_DTYPE.itemsize == 104 and ITEM_DTYPE.itemsize == 88
 
 EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gub_submit", "gub_submit_device", "gub_submit_device_n", "gub_submit_compact", "gub_submit_compact_async",
            "gub_pipeline_depth", "gub_submit_async", "gub_wait", "gub_host_alloc", "gub_host_free", "gub_clock_fill",

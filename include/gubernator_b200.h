@@ -105,6 +105,7 @@ typedef struct {
   int64_t stamp;         /* TokenBucketItem.CreatedAt | LeakyBucketItem.UpdatedAt */
   int64_t burst;         /* LeakyBucketItem.Burst */
   int64_t expire_at;     /* CacheItem.ExpireAt */
+  int64_t invalid_at;    /* CacheItem.InvalidAt (cache.go:40): 0 = none; set by Store / Loader plugins only; an item past it is a miss (cache.go:47) */
 } gub_item;
 
 /* Mirrors metricOverLimitCounter (gubernator.go:74), metricCacheAccess hit/miss (lrucache.go:52) + table stats */

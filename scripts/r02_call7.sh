@@ -1,0 +1,14 @@
+set -x
+O=gpurun_out/r02_call7; mkdir -p $O
+timeout 400 python bench.py --steps 1000 --warmup 50 --no-cpu-baseline --no-e2e --no-traffic > $O/bench.json 2> $O/bench.err
+python -c "
+import json
+d=json.loads(open('$O/bench.json').read().strip().splitlines()[-1])
+print('fused', round(d['value']/1e9,3), round(d['ms_per_step']*1e3,2), 'big', d['larger_calls']['value']/1e9)
+t=d['phase_trace']
+for k in t['max_us']: print('  %-18s max %7.2f mean %7.2f'%(k,t['max_us'][k],t['mean_us'][k]))
+print(t['slowest_cta']); print(t['median_cta_us'])" || tail -5 $O/bench.err
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_batch -c 2 -o $O/ncu_kbatch python bench.py --traffic-probe > $O/ncu.log 2>&1
+tail -2 $O/ncu.log
+timeout 600 python -m pytest tests/test_gpu_global.py tests/test_gpu_parity.py -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" >> $O/pytest.log
+tail -8 $O/pytest.log

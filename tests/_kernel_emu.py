@@ -20,17 +20,12 @@ COUNTER_NAMES = ["over_limit", "cache_hit", "cache_miss", "inserts", "table_full
 _libs = {}
 
 
-def lib(early_singles=1, onepass=0, class_sort=0):
-    """Build variants of the kernels: early_singles = GUB_EARLY_SINGLES (1 = default build, 0 = table-free k_rank + commit records),
-    onepass = GUB_GROUP_ONEPASS (0 = default, 1 = k_group ranks a block with one barrier), class_sort = GUB_RANK_CLASS_SORT (0 = default,
-    1 = k_rank deals requests to threads by class)."""
-    variant = (early_singles, onepass, class_sort)
-    if variant not in _libs:
-        so = SO if variant == (1, 0, 0) else SO.replace(".so", f"_es{early_singles}_op{onepass}_cs{class_sort}.so")
+def lib():
+    if "L" not in _libs:
+        so = SO
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in SRC):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-msse2", "-ffp-contract=off", "-Wno-unknown-pragmas",
-                                   f"-DGUB_EARLY_SINGLES={early_singles}", f"-DGUB_GROUP_ONEPASS={onepass}", f"-DGUB_RANK_CLASS_SORT={class_sort}", "-I", os.path.join(ROOT, "include"),
-                                   "-x", "c++", SRC[0], "-o", so])
+                                   "-I", os.path.join(ROOT, "include"), "-x", "c++", SRC[0], "-o", so])
         L = C.CDLL(so)
         vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
         L.emu_create.argtypes = [u64, u32]; L.emu_create.restype = vp
@@ -57,27 +52,35 @@ def lib(early_singles=1, onepass=0, class_sort=0):
         L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
         L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp, u32, vp]
         assert L.emu_counter_count() == len(COUNTER_NAMES)
-        _libs[variant] = L
-    return _libs[variant]
+        _libs["L"] = L
+    return _libs["L"]
 
 
 class EmuTable:
     """Same surface as gubernator_b200.native.Table for what the CPU tests need."""
 
-    def __init__(self, capacity_slots, max_batch=65536, early_singles=1, onepass=0, class_sort=0):
-        self._L = lib(early_singles, onepass, class_sort)
+    def __init__(self, capacity_slots, max_batch=65536, fused=False, grid=6, sweep=0):
+        """fused: evaluate with the persistent kernel k_batch (what rings use) instead of the four-kernel pipeline; grid = its CTAs
+        (every emulated CTA costs 512 fibers; the kernel takes any grid, more rounds make up for it); sweep = slots every CTA of
+        k_batch sweeps per round."""
+        self._L = lib()
         self._h = self._L.emu_create(int(capacity_slots), int(max_batch))
         self.capacity = int(capacity_slots)
+        self.fused = bool(fused)
+        self._L.emu_set_grid(self._h, int(grid))
+        self._L.emu_set_sweep(self._h, int(sweep))
 
     def submit(self, reqs, clk, resp_dtype):
         out = np.zeros(len(reqs), dtype=resp_dtype)
         reqs = np.ascontiguousarray(reqs)
         assert reqs.dtype.itemsize == 64 and out.dtype.itemsize == 32
+        self._L.emu_set_fused(1 if self.fused else 0)
         self._L.emu_submit(self._h, reqs.ctypes.data, len(reqs), clk.ctypes.data, out.ctypes.data)
         return out
 
     def submit_compact(self, creqs, params, created_base, clk, resp_dtype):
         out = np.zeros(len(creqs), dtype=resp_dtype)
+        self._L.emu_set_fused(1 if self.fused else 0)
         self._L.emu_submit_compact(self._h, creqs.ctypes.data, len(creqs), params.ctypes.data, len(params), int(created_base), clk.ctypes.data,
                                  out.ctypes.data)
         return out

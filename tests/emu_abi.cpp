@@ -29,6 +29,7 @@ DevItem to_dev(const gub_item& it) {  // same mapping as gub_api.cu
   d.w[0] = (uint64_t)it.limit; d.w[1] = (uint64_t)it.duration;
   if (leaky) std::memcpy(&d.w[2], &it.remaining_f, 8); else d.w[2] = (uint64_t)it.remaining;
   d.w[3] = (uint64_t)it.stamp; d.w[4] = leaky ? (uint64_t)it.burst : 0; d.w[5] = (uint64_t)it.expire_at;
+  d.invalid_at = it.invalid_at;
   return d;
 }
 gub_item from_dev(const DevItem& d) {
@@ -41,6 +42,7 @@ gub_item from_dev(const DevItem& d) {
   it.limit = (int64_t)d.w[0]; it.duration = (int64_t)d.w[1];
   if (leaky) std::memcpy(&it.remaining_f, &d.w[2], 8); else it.remaining = (int64_t)d.w[2];
   it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5];
+  it.invalid_at = d.invalid_at;
   return it;
 }
 }  // namespace
@@ -110,7 +112,7 @@ int gub_add_items(gub_table* t, const gub_item* items, size_t n) {
   if (dev.empty()) return 0;
   uint32_t failed = 0;
   emu::launch(k_add_items, (unsigned)((dev.size() + 255) / 256), 256u, t->e->table, t->e->capacity, (const DevItem*)dev.data(), (uint32_t)dev.size(), t->e->counters,
-              &failed);
+              &failed, t->e->inv);
   if (failed) return fail("gub_add_items: table full for " + std::to_string(failed) + " items");
   return 0;
 }
@@ -120,7 +122,7 @@ int gub_get_items(gub_table* t, const uint64_t* kx, const uint64_t* kf, size_t n
   if (n == 0) return 0;
   std::lock_guard<std::mutex> lk(g_emu_mu);
   std::vector<DevItem> host(n);
-  emu::launch(k_get_items, (unsigned)((n + 255) / 256), 256u, (const Slot*)t->e->table, t->e->capacity, kx, kf, (uint32_t)n, now_ms, host.data(), found);
+  emu::launch(k_get_items, (unsigned)((n + 255) / 256), 256u, (const Slot*)t->e->table, t->e->capacity, kx, kf, (uint32_t)n, now_ms, host.data(), found, t->e->inv);
   for (size_t i = 0; i < n; i++) { out[i] = from_dev(host[i]); out[i].key_xxh64 = kx[i]; out[i].key_fnv1 = kf[i]; }
   return 0;
 }
@@ -130,7 +132,7 @@ int gub_scan(gub_table* t, gub_item* out, size_t cap, size_t* n_out) {
   std::lock_guard<std::mutex> lk(g_emu_mu);
   std::vector<DevItem> dev(std::max<size_t>(cap, 1));
   unsigned long long total = 0;
-  emu::launch(k_scan, 4u, 256u, (const Slot*)t->e->table, t->e->capacity, dev.data(), (unsigned long long)cap, &total);
+  emu::launch(k_scan, 4u, 256u, (const Slot*)t->e->table, t->e->capacity, dev.data(), (unsigned long long)cap, &total, t->e->inv);
   for (size_t i = 0; i < std::min<size_t>(cap, (size_t)total); i++) out[i] = from_dev(dev[i]);
   *n_out = (size_t)total;
   return 0;
@@ -151,7 +153,7 @@ int gub_get_counters(gub_table* t, gub_counters* out) {
   const unsigned long long* c = t->e->counters;
   out->over_limit = c[C_OVER]; out->cache_hit = c[C_HIT]; out->cache_miss = c[C_MISS]; out->inserts = c[C_INSERTS]; out->table_full = c[C_FULL];
   out->requests = c[C_REQUESTS]; out->batches = c[C_BATCHES]; out->dup_groups = c[C_DUP_GROUPS]; out->mixed_groups = c[C_MIXED_GROUPS];
-  out->serial_fallbacks = c[C_SERIAL];
+  out->serial_fallbacks = c[C_SERIAL]; out->unexpired_evictions = c[C_EVICT_UNEXPIRED]; out->swept = c[C_SWEPT]; out->gq_dropped = c[C_GQ_DROPPED];
   return 0;
 }
 

@@ -36,6 +36,7 @@ run("test_missing_fields_and_batch_cap")
 run("test_error_strings_and_order")
 run("test_update_peer_globals_items")
 run("test_add_get_scan_items")
+run("test_invalid_at_of_loaded_items")
 run("test_rpc_aggregator_coalesces_concurrent_calls")
 for algo in (0, 1):
     run("test_store_plugin_call_sequences", algo)

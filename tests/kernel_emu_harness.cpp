@@ -46,10 +46,11 @@ struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   uint16_t* gmembers = nullptr;
   FCtl* ctl = nullptr;
   OvfItem* ovf = nullptr;
+  InvIndex inv{};
   uint32_t grid = 6, sweep_chunk = 0;
 };
 
-uint32_t g_fused = 1;  // emu_set_fused(0): the four-kernel path
+uint32_t g_fused = 0;  // emu_set_fused(1): the persistent kernel k_batch instead of the four-kernel pipeline (rings always use it)
 
 }  // namespace
 
@@ -81,6 +82,7 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
   t->gmembers = zalloc<uint16_t>((size_t)FB_MAX_GRID * FB_THREADS);
   t->ctl = zalloc<FCtl>(1);
   t->ovf = zalloc<OvfItem>(FB_OVF_CAP);
+  t->inv.e = zalloc<InvEntry>(65536); t->inv.mask = 65535;
   return t;
 }
 
@@ -102,7 +104,7 @@ void emu_set_sweep(void* tv, uint32_t chunk) { static_cast<EmuTable*>(tv)->sweep
 static void fused_args(EmuTable* t, const gub_clock* clk, FArgs& A) {
   std::memset(&A, 0, sizeof A);
   A.table = t->table; A.capacity = t->capacity; A.aux = t->gaux; A.presence = t->gpres; A.fragrow = t->gfrag; A.members = t->gmembers;
-  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.clk = *clk;
+  A.ctl = t->ctl; A.ovf = t->ovf; A.counters = t->counters; A.sweep_chunk = t->sweep_chunk; A.inv = t->inv; A.clk = *clk;
 }
 
 // launch_fused of gub_api.cu: one cooperative launch of k_batch over the batch's segments (here with a small grid: every emulated
@@ -137,18 +139,14 @@ static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_
     A.table = t->table; A.capacity = t->capacity; A.reqs = reqs + off; A.out = out + off; A.n = m; A.n_dev = n_dev; A.n_off = (uint32_t)off; A.epoch = t->epoch;
     A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
     A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank;
-    A.commit = t->commit; A.commit_ent = t->commit_ent; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
-    A.counters = t->counters;
+    A.commit = t->commit; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
+    A.counters = t->counters; A.ovf = t->ovf; A.ovf_count = &t->ctl->ovf_count; A.inv = t->inv;
     A.clk = *clk;
     const uint32_t blocks = (m + 255) / 256;
     emu::launch(k_group, blocks, GROUP_THREADS, A);
     emu::launch(k_rank, blocks, GROUP_THREADS, A);
     emu::launch(k_eval, blocks, GROUP_THREADS, A);
-    // gub_api.cu caps both at 148 (one per SM); the cap only changes how the grid-stride loops of k_finish are split, and every
-    // emulated block costs 256 fibers, so tests may lower it (emu_set_finish_cap)
-    const uint32_t mixed_blocks = std::min<uint32_t>(g_finish_cap, std::max<uint32_t>(1u, m / 2));
-    const uint32_t commit_blocks = std::max<uint32_t>(1u, std::min<uint32_t>(g_finish_cap, (m / 2 + MIXED_THREADS - 1) / MIXED_THREADS));
-    emu::launch(k_finish, mixed_blocks + commit_blocks, MIXED_THREADS, A, mixed_blocks);
+    emu::launch(k_finish, std::min<uint32_t>(g_finish_cap, std::max<uint32_t>(1u, m / 2)), MIXED_THREADS, A);  // gub_api.cu caps the grid at 148
   }
   return 0;
 }
@@ -181,7 +179,7 @@ uint64_t emu_scan(void* tv, gub_item* out, uint64_t cap) {
   EmuTable* t = static_cast<EmuTable*>(tv);
   std::vector<DevItem> dev(std::max<uint64_t>(cap, 1));
   unsigned long long n = 0;
-  emu::launch(k_scan, 4u, 256u, (const Slot*)t->table, t->capacity, dev.data(), (unsigned long long)cap, &n);
+  emu::launch(k_scan, 4u, 256u, (const Slot*)t->table, t->capacity, dev.data(), (unsigned long long)cap, &n, t->inv);
   const uint64_t m = std::min<uint64_t>(n, cap);
   for (uint64_t i = 0; i < m; i++) {
     const DevItem& d = dev[i];
@@ -193,7 +191,7 @@ uint64_t emu_scan(void* tv, gub_item* out, uint64_t cap) {
     it.status = (d.flags & F_OVER) ? GUB_OVER_LIMIT : GUB_UNDER_LIMIT;
     it.limit = (int64_t)d.w[0]; it.duration = (int64_t)d.w[1];
     if (leaky) std::memcpy(&it.remaining_f, &d.w[2], 8); else it.remaining = (int64_t)d.w[2];
-    it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5];
+    it.stamp = (int64_t)d.w[3]; it.burst = (int64_t)d.w[4]; it.expire_at = (int64_t)d.w[5]; it.invalid_at = d.invalid_at;
     out[i] = it;
   }
   return n;

@@ -86,8 +86,62 @@ if USE_GPU:
     backend = GpuBackend(tab, ring, W, dev, 131072)
 else:
     backend = CpuBackend(O.Pool(workers=2, cache_size=10**7, now_ms=T0))
-USE_P2P = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") in ("p2p", "p2p2")
-PIPELINED = USE_GPU and os.environ.get("GUB_ROUTE", "nccl") == "p2p2"  # two streams, all steps in flight before any is checked
+ROUTE = os.environ.get("GUB_ROUTE", "nccl")
+if USE_GPU and ROUTE == "p2pg":
+    # GLOBAL behaviour across processes, everything behind the C ABI: gub_p2p_step with gub_p2p_enable_global, gub_global_tick with
+    # the NCCL all-gather of the UpdatePeerGlobal items; every rank replays the whole cluster in the oracle-side model
+    from global_model import OracleCluster
+    from workloads import key_hashes
+    p2p = g.native.P2P(tab, ring, rank, 8192)
+    handles = [None] * W
+    dist.all_gather_object(handles, p2p.export())
+    p2p.connect(handles)
+    p2p.enable_global(4096)
+    uid = [g.native.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    p2p.nccl_init(uid[0])
+    dist.barrier()
+    model = OracleCluster(W, T0)
+    rng = np.random.default_rng(4242)  # the same stream on every rank: everybody generates everybody's batches
+    now = T0
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(14):
+        now += int(rng.choice([0, 1, 5, 400]))
+        batches = []
+        for r in range(W):
+            n = int(rng.choice([0, 1, 700, 3000]))
+            ids = rng.integers(0, 300, n)
+            b = np.zeros(n, dtype=O.HREQ_DTYPE)
+            xx, fv = key_hashes(ids, name="glob")
+            b["key_xxh64"], b["key_fnv1"] = xx, fv
+            b["limit"] = 20 + (ids % 7) * 10; b["duration"] = 30000 + (ids % 3) * 30000; b["algorithm"] = (ids >> 1) & 1
+            b["hits"] = np.where(ids % 11 == 0, 0, 1 + (ids % 3)); b["created_at"] = now
+            glob = (ids % 5) < 2
+            b["behavior"] = np.where(glob, O.GLOBAL, 0).astype(np.uint32) | np.uint32(O.REQ_IS_OWNER)
+            if step == 7:
+                b["behavior"] |= np.where(glob & (ids % 13 == 0), O.RESET_REMAINING, 0).astype(np.uint32)
+            batches.append(b)
+        mine, n = batches[rank], len(batches[rank])
+        buf = torch.from_numpy(mine.view(np.uint8).reshape(n, 64).copy()).to(dev) if n else torch.empty((1, 64), dtype=torch.uint8, device=dev)
+        out = torch.zeros((max(n, 1), 32), dtype=torch.uint8, device=dev)
+        p2p.step(buf.data_ptr(), n, g.clock_fill(now), out.data_ptr(), st)
+        torch.cuda.synchronize()
+        got = out[:n].cpu().numpy().reshape(-1).view(O.HRESP_DTYPE)
+        want = model.step(batches, now)[rank]
+        if not np.array_equal(got, want):
+            bad = np.nonzero(got != want)[0]
+            raise AssertionError(f"rank {rank} step {step}: {len(bad)} responses differ; first {bad[0]}: {got[bad[0]]} vs {want[bad[0]]}")
+        if step % 3 == 2:
+            p2p.tick(g.clock_fill(now), now, st)
+            torch.cuda.synchronize()
+            model.tick(now)
+    p2p.status()
+    dist.barrier()
+    print(f"rank {rank} ok")
+    dist.destroy_process_group()
+    sys.exit(0)
+USE_P2P = USE_GPU and ROUTE in ("p2p", "p2p2")
+PIPELINED = USE_GPU and ROUTE == "p2p2"  # two streams, all steps in flight before any is checked
 if USE_P2P:  # records travel by NVLink stores from the routing kernels (cudaIpc mailboxes) instead of NCCL all-to-all
     from gubernator_b200.sharded import P2PStep
     stepper = P2PStep(tab, ring, W, rank, cap=65536)

@@ -13,6 +13,14 @@ from workloads import T0, adversarial_batch, bench_batch, bench_requests, extrem
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+def eval_path(request, monkeypatch):
+    """Every test runs on both evaluation paths of a single table: the four-kernel pipeline (the default of gub_submit*) and the
+    persistent kernel k_batch (what rings use; GUB_PATH=fused selects it for a plain table too)."""
+    monkeypatch.setenv("GUB_PATH", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def G():
     import gubernator_b200 as g
@@ -460,6 +468,41 @@ def test_epoch_wrap(G):
         if b in checkpoints:
             torch.cuda.synchronize()
             _cmp(d_out.cpu().numpy().reshape(-1).view(G.RESP_DTYPE), want, f"batch {b}")
+
+
+def test_invalid_at_of_loaded_items(G):
+    """CacheItem.InvalidAt (cache.go:40,47) — only ever set by Store / Loader plugins — travels with gub_add_items: an item past its
+    InvalidAt is a miss for GetCacheItem and for the batch path (removed and re-created, like the oracle given the same items),
+    one that is not yet invalid keeps its InvalidAt across updates, and Store (gub_scan) reports it."""
+    n = 40
+    tab, pool = G.Table(1 << 12), O.Pool(now_ms=T0)
+    xx, fv = key_hashes(np.arange(n), name="inv")
+    items = np.zeros(n, dtype=G.ITEM_DTYPE)
+    items["key_xxh64"], items["key_fnv1"] = xx, fv
+    items["algorithm"] = np.arange(n) & 1
+    items["limit"] = 10; items["duration"] = 60000; items["remaining"] = 4; items["remaining_f"] = 4.0; items["stamp"] = T0
+    items["burst"] = 10; items["expire_at"] = T0 + 60000
+    items["invalid_at"] = np.where(np.arange(n) % 4 == 0, 0, T0 + 1000 * (np.arange(n) % 4))  # none, +1 s, +2 s, +3 s
+    tab.add_items(items)
+    for i in range(n):
+        it = O.Item()
+        it.algorithm = int(items["algorithm"][i]); it.value_kind = 2 if items["algorithm"][i] else 1
+        it.expire_at = T0 + 60000; it.invalid_at = int(items["invalid_at"][i]); it.limit = 10; it.duration = 60000
+        it.remaining_i = 4; it.remaining_f = 4.0; it.stamp = T0; it.burst = 10 if items["algorithm"][i] else 0
+        pool.add_item_hashed(xx[i], fv[i], it)
+    got, found = tab.get_items(xx, fv, T0 + 1500)
+    assert np.array_equal(found.astype(bool), ~((items["invalid_at"] != 0) & (items["invalid_at"] < T0 + 1500)))
+    assert np.array_equal(got["invalid_at"], items["invalid_at"])
+    assert np.array_equal(np.sort(tab.scan()["invalid_at"]), np.sort(items["invalid_at"]))
+    reqs = np.zeros(2 * n, dtype=G.REQ_DTYPE)
+    reqs["key_xxh64"], reqs["key_fnv1"] = np.tile(xx, 2), np.tile(fv, 2)
+    reqs["hits"] = 1; reqs["limit"] = 10; reqs["duration"] = 60000; reqs["algorithm"] = np.tile(items["algorithm"], 2).astype(np.uint32)
+    reqs["behavior"] = G.native.REQ_IS_OWNER
+    for now in (T0 + 1500, T0 + 2500, T0 + 9000):
+        reqs["created_at"] = now
+        pool.set_now(now)
+        _cmp(tab.submit(reqs, G.clock_fill(now)), pool.submit_hashed(reqs), f"now = T0 + {now - T0}")
+    _cmp_counters(tab, pool)
 
 
 def test_device_key_hashing_matches_host(G):

@@ -1,4 +1,4 @@
-"""The CUDA kernel source itself, on the CPU: gubernator_b200/csrc/gub_kernels.cuh compiled with g++ on top of tests/cuda_emu.h
+"""The CUDA kernel source itself, on the CPU: gubernator_b200/csrc/gub_kernels.cuh and gub_batch.cuh compiled with g++ on top of tests/cuda_emu.h
 (fibers standing in for the threads of a block; tests/kernel_emu_harness.cpp drives the launches exactly like gub_api.cu) and
 checked against the oracle — responses, counters and final table, bit for bit.  This is NOT a product path (the library has no
 CPU fallback) and not a replacement for the `-m gpu` parity tests: it explores one interleaving and no memory-model effects.
@@ -10,6 +10,15 @@ import pytest
 import oracle_py as O
 import _kernel_emu as E
 from workloads import T0, adversarial_batch, bench_requests, extreme_batch, key_hashes, make_clock, zipf_ids
+
+
+# Both evaluation paths run the same bodies: "pipeline" = k_group / k_rank / k_eval / k_finish (what gub_submit* launches for a single
+# table), "fused" = the persistent cooperative kernel k_batch (what rings launch; here on a 6-CTA grid, so most batches take rounds).
+both_paths = pytest.mark.parametrize("path", ["pipeline", "fused"])
+
+
+def Tab(path, capacity, **kw):
+    return E.EmuTable(capacity, fused=(path == "fused"), **kw)
 
 
 @pytest.fixture(scope="module")
@@ -43,12 +52,13 @@ def _check_state(G, tab, pool):
             assert int(s["algorithm"]) == 0 and int(s["remaining"]) == it.remaining_i and int(s["status"]) == it.status
 
 
+@both_paths
 @pytest.mark.parametrize("seed,n_keys,n", [(0, 3, 1500), (1, 40, 3000), (2, 2500, 3000), (3, 1, 700)])
-def test_adversarial_batches_match_oracle(G, seed, n_keys, n):
+def test_adversarial_batches_match_oracle(G, seed, n_keys, n, path):
     """Every behaviour bit, both algorithms, parameter changes mid-run, time steps that expire items: few keys exercise the
     non-uniform (segment) path of k_finish, many keys the singleton path of k_rank."""
     rng = np.random.default_rng(100 + seed)
-    tab, pool = E.EmuTable(1 << 13, max_batch=2048), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, 1 << 13, max_batch=2048), O.Pool(now_ms=T0)
     now = T0
     for step in range(3):
         now += int(rng.choice([0, 1, 900, 70000]))
@@ -58,66 +68,11 @@ def test_adversarial_batches_match_oracle(G, seed, n_keys, n):
     _check_state(G, tab, pool)
 
 
-def test_table_free_build_variant(G):
-    """GUB_EARLY_SINGLES=0: k_rank never touches the table, everything is evaluated in k_eval and repeated keys are written back by
-    k_finish from commit records (the variant that lets two batches overlap).  Not the default build; kept working here."""
-    rng = np.random.default_rng(11)
-    tab, pool = E.EmuTable(1 << 13, max_batch=2048, early_singles=0), O.Pool(now_ms=T0)
-    for step, n_keys in enumerate([3, 0, 2500, 0, 40]):
-        now = T0 + 800 * step
-        pool.set_now(now)
-        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
-        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
-    _check_state(G, tab, pool)
-
-
-@pytest.mark.parametrize("early_singles", [1, 0])
-def test_group_onepass_build_variant(G, early_singles):
-    """GUB_GROUP_ONEPASS=1 (experimental, off by default until measured): one barrier instead of eight warp turns in k_group;
-    local ranks must come out the same, including for the colliding-key fold."""
-    rng = np.random.default_rng(5)
-    tab, pool = E.EmuTable(1 << 13, max_batch=2048, early_singles=early_singles, onepass=1), O.Pool(now_ms=T0)
-    for step, n_keys in enumerate([3, 0, 2500, 40, 0, 1]):
-        now = T0 + 700 * step
-        pool.set_now(now)
-        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
-        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
-    _check_state(G, tab, pool)
-    # keys colliding in the grouping table (see test_fuzz_with_frequent_grouping_collisions)
-    krng = np.random.default_rng(4)
-    tags = krng.integers(0, 1 << 24, 48).astype(np.uint64)
-    newk = (tags[krng.integers(0, len(tags), 8000)] << np.uint64(40)) | krng.integers(2, 1 << 40, 8000).astype(np.uint64)
-    tab, pool = E.EmuTable(1 << 13, max_batch=1024, early_singles=early_singles, onepass=1), O.Pool(now_ms=T0)
-    rng = np.random.default_rng(904)
-    for step in range(2):
-        reqs = adversarial_batch(rng, 3000, 2500, T0).astype(G.REQ_DTYPE)
-        reqs["key_xxh64"] = newk[(reqs["key_xxh64"] % np.uint64(len(newk))).astype(np.int64)]
-        reqs["key_fnv1"] = (reqs["key_xxh64"] * np.uint64(0x9E3779B97F4A7C15)) | np.uint64(0x100)
-        _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"collisions, step {step}")
-    _check_state(G, tab, pool)
-
-
-@pytest.mark.parametrize("onepass", [0, 1])
-def test_rank_class_sort_build_variant(G, onepass):
-    """GUB_RANK_CLASS_SORT=1 (experimental, off by default until measured): k_rank deals a block's requests to its threads by class
-    (single token / single leaky / member of a repeated key); alone and together with GUB_GROUP_ONEPASS."""
-    rng = np.random.default_rng(5)
-    tab, pool = E.EmuTable(1 << 13, max_batch=2048, onepass=onepass, class_sort=1), O.Pool(now_ms=T0)
-    for step, n_keys in enumerate([3, 0, 2500, 40, 0, 1]):
-        now = T0 + 700 * step
-        pool.set_now(now)
-        reqs = adversarial_batch(rng, 2500, n_keys, now) if n_keys else bench_requests(zipf_ids(rng, 2500, 800, 1.1), now)
-        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"step {step}")
-    for n in (1, 33, 255, 257, 2049):  # ragged tails and the max_batch chunking
-        reqs = adversarial_batch(rng, n, 50, now)
-        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"n={n}")
-    _check_state(G, tab, pool)
-
-
-def test_zipf_uniform_runs_use_the_rank_path(G):
+@both_paths
+def test_zipf_uniform_runs_use_the_rank_path(G, path):
     """The bench workload's shape: identical requests per key, heavy repeats — run_to_rank per member, no non-uniform groups."""
     rng = np.random.default_rng(7)
-    tab, pool = E.EmuTable(1 << 13), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, 1 << 13), O.Pool(now_ms=T0)
     for step in range(3):
         now = T0 + 400 * step
         pool.set_now(now)
@@ -128,9 +83,10 @@ def test_zipf_uniform_runs_use_the_rank_path(G):
     _check_state(G, tab, pool)
 
 
-def test_numeric_extremes(G):
+@both_paths
+def test_numeric_extremes(G, path):
     rng = np.random.default_rng(31)
-    tab, pool = E.EmuTable(1 << 12), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, 1 << 12), O.Pool(now_ms=T0)
     for step in range(2):
         now = T0 + 1000 * step
         pool.set_now(now)
@@ -139,9 +95,10 @@ def test_numeric_extremes(G):
     _check_state(G, tab, pool)
 
 
-def test_many_segments_force_the_serial_walk(G):
+@both_paths
+def test_many_segments_force_the_serial_walk(G, path):
     rng = np.random.default_rng(77)
-    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
     n = 1200
     reqs = np.zeros(n, dtype=G.REQ_DTYPE)
     xx, fv = key_hashes([1] * n, name="hot")
@@ -159,8 +116,9 @@ def test_many_segments_force_the_serial_walk(G):
     _check_state(G, tab, pool)
 
 
-def test_token_reset_flipflop(G):
-    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+@both_paths
+def test_token_reset_flipflop(G, path):
+    tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
     n = 300
     reqs = np.zeros(n, dtype=G.REQ_DTYPE)
     xx, fv = key_hashes([7] * n, name="flip")
@@ -171,9 +129,10 @@ def test_token_reset_flipflop(G):
     _check_state(G, tab, pool)
 
 
-def test_ragged_sizes_and_chunking(G):
+@both_paths
+def test_ragged_sizes_and_chunking(G, path):
     rng = np.random.default_rng(5)
-    tab, pool = E.EmuTable(1 << 12, max_batch=1024), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, 1 << 12, max_batch=1024), O.Pool(now_ms=T0)
     assert len(tab.submit(np.zeros(0, dtype=G.REQ_DTYPE), make_clock(T0), O.HRESP_DTYPE)) == 0
     for n in (1, 2, 31, 32, 33, 255, 257, 1023, 1024, 1025, 2500):  # the last two cross the max_batch chunking
         reqs = adversarial_batch(rng, n, 50, T0)
@@ -181,8 +140,9 @@ def test_ragged_sizes_and_chunking(G):
     _check_state(G, tab, pool)
 
 
-def test_sentinel_hashes_table_full_and_sweep(G):
-    tab, pool = E.EmuTable(4096), O.Pool(now_ms=T0)
+@both_paths
+def test_sentinel_hashes_table_full_and_sweep(G, path):
+    tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
     reqs = np.zeros(8, dtype=G.REQ_DTYPE)
     reqs["key_xxh64"] = [0, 1, 2, 3, 0, 1, 2, 3]
     reqs["key_fnv1"] = [10 << 8, 11 << 8, 12 << 8, 13 << 8, 10 << 8, 11 << 8, 12 << 8, 13 << 8]
@@ -190,7 +150,7 @@ def test_sentinel_hashes_table_full_and_sweep(G):
     _cmp(tab.submit(reqs, make_clock(T0), O.HRESP_DTYPE), pool.submit_hashed(reqs))
     # a table far too small for the batch: the reference's LRU would evict (lrucache.go:98,138-149) and still answer every request;
     # so do we: keys whose probe window is full are parked and placed, with eviction, before the next batch reads the table
-    small = E.EmuTable(64)
+    small = Tab(path, 64)
     n = 1500
     reqs = np.zeros(n, dtype=G.REQ_DTYPE)
     xx, fv = key_hashes(np.arange(n), name="full")
@@ -242,9 +202,10 @@ def test_epoch_wrap_with_mixed_groups(G):
     assert c["requests"] == 6000 and c["mixed_groups"] <= 50
 
 
-def test_compact_records_expand_like_the_full_ones(G):
+@both_paths
+def test_compact_records_expand_like_the_full_ones(G, path):
     rng = np.random.default_rng(61)
-    a, b, pool = E.EmuTable(1 << 13), E.EmuTable(1 << 13), O.Pool(now_ms=T0)
+    a, b, pool = Tab(path, 1 << 13), Tab(path, 1 << 13), O.Pool(now_ms=T0)
     for n_sets in (2, 32, 33):  # <= 32 sets travel in the kernel arguments (k_expand_inline), more by pointer (k_expand)
         now = T0 + n_sets
         pool.set_now(now)
@@ -331,8 +292,7 @@ def test_mailbox_routing_kernels_match_per_shard_oracles(G, world):
             _cmp(got[r], want[r], f"step {step} shard {r}")
 
 
-@pytest.mark.parametrize("early_singles", [1, 0])
-def test_keys_colliding_in_the_grouping_table(G, early_singles):
+def test_keys_colliding_in_the_grouping_table(G):
     """Two different keys that share the batch-wide grouping entry (same home position and the same 24-bit tag = top bits of the
     XXH64): they are grouped as one run, found different from the representative, and walked key by key in k_finish.  When both
     have requests in the same block, k_group has to fold their fragments into one (merge_colliding_fragments) — this test found
@@ -349,7 +309,7 @@ def test_keys_colliding_in_the_grouping_table(G, early_singles):
     assert len(same) > 0
     ka, kb = keys[order[same[0]]], keys[order[same[0] + 1]]
     assert ka != kb
-    tab, pool = E.EmuTable(4096, max_batch=max_batch, early_singles=early_singles), O.Pool(now_ms=T0)
+    tab, pool = E.EmuTable(4096, max_batch=max_batch), O.Pool(now_ms=T0)
     for step in range(3):
         now = T0 + step
         pool.set_now(now)
@@ -392,7 +352,8 @@ def test_colliding_keys_in_few_long_segments(G):
     _check_state(G, tab, pool)
 
 
-def test_probe_window_wraps_and_skips_tombstones(G):
+@both_paths
+def test_probe_window_wraps_and_skips_tombstones(G, path):
     """Keys whose home slot is at the very end of a small table (the linear probe wraps to slot 0), expiring at different times:
     after a sweep the survivors are found behind tombstones and new keys reuse the freed slots."""
     cap = 256
@@ -400,7 +361,7 @@ def test_probe_window_wraps_and_skips_tombstones(G):
     cand = rng.integers(2, 1 << 62, 200000).astype(np.uint64) | (np.uint64(0xFF) << np.uint64(56))  # home = (key * cap) >> 64 = 255
     keys = np.unique(cand)[:60]
     assert np.all((keys >> np.uint64(56)) == 255)
-    tab, pool = E.EmuTable(cap), O.Pool(now_ms=T0)
+    tab, pool = Tab(path, cap), O.Pool(now_ms=T0)
 
     def batch(ks, now, duration):
         r = np.zeros(len(ks), dtype=G.REQ_DTYPE)
@@ -419,14 +380,14 @@ def test_probe_window_wraps_and_skips_tombstones(G):
     _check_state(G, tab, pool)
 
 
-@pytest.mark.parametrize("seed,n_keys,early_singles", [(0, 2500, 1), (4, 2500, 0), (5, 1200, 1)])
-def test_fuzz_with_frequent_grouping_collisions(G, seed, n_keys, early_singles):
+@pytest.mark.parametrize("seed,n_keys", [(0, 2500), (5, 1200)])
+def test_fuzz_with_frequent_grouping_collisions(G, seed, n_keys):
     """Adversarial traffic over a key space with only 48 distinct 24-bit tags and a 4096-entry grouping table: several pairs (and
     triples) of different keys share a group entry in every batch, inside and across blocks."""
     rng, krng = np.random.default_rng(900 + seed), np.random.default_rng(seed)
     tags = krng.integers(0, 1 << 24, 48).astype(np.uint64)
     newk = (tags[krng.integers(0, len(tags), 8000)] << np.uint64(40)) | krng.integers(2, 1 << 40, 8000).astype(np.uint64)
-    tab, pool = E.EmuTable(1 << 13, max_batch=1024, early_singles=early_singles), O.Pool(now_ms=T0)
+    tab, pool = E.EmuTable(1 << 13, max_batch=1024), O.Pool(now_ms=T0)
     now = T0
     for step in range(3):
         now += int(rng.choice([0, 1, 900]))

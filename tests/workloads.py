@@ -112,10 +112,9 @@ def bench_batch(rng, n, n_keys, created_at, zipf_s=None, mixed=False, perm_seed=
 _ZIPF_CACHE = {}
 
 
-def zipf_ids(rng, n, n_keys, s, perm_seed=12345):
-    """Bounded Zipf(s) over ranks 1..n_keys: exact inverse CDF for the first 2^20 ranks (cumulative table), the
-    midpoint-rule continuous tail beyond; then rank -> id through a fixed multiplicative permutation (so hot keys are
-    spread over the id space)."""
+def zipf_ranks(rng, n, n_keys, s):
+    """Bounded Zipf(s) over ranks 0..n_keys-1 (0 = hottest): exact inverse CDF for the first 2^20 ranks (cumulative table), the
+    midpoint-rule continuous tail beyond."""
     M = min(n_keys, 1 << 20)
     key = (n_keys, s)
     if key not in _ZIPF_CACHE:
@@ -132,10 +131,19 @@ def zipf_ids(rng, n, n_keys, s, perm_seed=12345):
         a = 1.0 - s
         x = ((u[in_tail] - head[-1]) * a + (M + 0.5) ** a) ** (1.0 / a)  # invert the tail integral
         rank[in_tail] = np.clip(np.floor(x + 0.5).astype(np.int64) - 1, M, n_keys - 1)
-    rank = np.minimum(rank, n_keys - 1)
+    return np.minimum(rank, n_keys - 1)
+
+
+def spread_ranks(rank, n_keys, perm_seed=12345):
+    """rank -> id through a fixed multiplicative permutation (so hot keys are spread over the id space)."""
     mult = 0x9E3779B97F4A7C15
     with np.errstate(over="ignore"):
         return ((rank.astype(np.uint64) * np.uint64(mult) + np.uint64(perm_seed)) % np.uint64(n_keys)).astype(np.int64)
+
+
+def zipf_ids(rng, n, n_keys, s, perm_seed=12345):
+    """Bounded Zipf(s) key ids: zipf_ranks() spread over the id space by spread_ranks()."""
+    return spread_ranks(zipf_ranks(rng, n, n_keys, s), n_keys, perm_seed)
 
 
 # ---- vectorised hashing of the BASELINE.md synthetic keys -----------------------------------------------------
