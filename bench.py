@@ -255,37 +255,43 @@ def run_reference(args):
 
 # ---- DRAM traffic of k_batch, measured by ncu on this very workload (a sub-process of the default run) ------------------
 def measure_traffic(args):
+    """{kernel: DRAM bytes per launch} for the batch kernels of this workload, by running this script's --traffic-probe under ncu."""
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu) or os.environ.get("GUB_BENCH_NO_NCU"):
         return None
     with tempfile.TemporaryDirectory() as d:
         log = os.path.join(d, "traffic.csv")
         cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--cache-control", "none",
-               "--profile-from-start", "off", "-k", "regex:k_batch", "--csv", "--log-file", log,
+               "--profile-from-start", "off", "-k", "regex:k_(group|rank|eval|finish|batch)", "--csv", "--log-file", log,
                sys.executable, os.path.abspath(__file__), "--traffic-probe", "--keys", str(args.keys), "--zipf", str(args.zipf), "--pool", str(args.pool)]
         try:
-            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300, check=False)
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, check=False, text=True)
             import csv
             with open(log) as f:
                 rows = [r for r in csv.reader(f) if len(r) > 5]
-            hdr = next(r for r in rows if "Metric Name" in r)
-            im, iv, iu = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-            rd, wr, n = 0.0, 0.0, 0
+            hdr = next((r for r in rows if "Metric Name" in r), None)
+            if hdr is None:
+                return {"error": "ncu produced no metric rows: " + (res.stdout or "")[-300:]}
+            ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+            per = {}
             for r in rows:
-                if r is hdr or len(r) <= max(im, iv, iu) or r[im] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if r is hdr or len(r) <= max(ik, im, iv, iu) or r[im] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     continue
-                v = float(r[iv].replace(",", ""))
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
+                name = r[ik].split("(")[0].split("::")[-1]
+                v = float(r[iv].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
+                e = per.setdefault(name, {"read": 0.0, "write": 0.0, "launches": 0})
                 if r[im] == "dram__bytes_read.sum":
-                    rd += v * scale; n += 1
+                    e["read"] += v; e["launches"] += 1
                 else:
-                    wr += v * scale
-            if n == 0:
-                return {"error": "ncu reported no k_batch launch"}
-            return {"dram_read_bytes_per_launch": rd / n, "dram_write_bytes_per_launch": wr / n, "launches": n,
-                    "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none over warm steps of this workload (a sub-process of this run)"}
+                    e["write"] += v
+            if not per:
+                return {"error": "ncu reported no batch kernel launch"}
+            out = {k: {"dram_read_bytes_per_launch": e["read"] / e["launches"], "dram_write_bytes_per_launch": e["write"] / e["launches"], "launches": e["launches"]}
+                   for k, e in per.items()}
+            out["how"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none over warm steps of this workload (a sub-process of this run)"
+            return out
         except Exception as ex:
-            return {"error": str(ex)}
+            return {"error": repr(ex)}
 
 
 # ---- this repo's arm --------------------------------------------------------------------------------------------
@@ -669,25 +675,48 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the batch kernel
+    # ---- roofline of the dominant kernel of the evaluation path
     peak, peak_src = load_peaks()
     launches = max(prof["launches"], 1)
-    k_ms = prof["k_group_ms"] / launches  # the first timing slot brackets the whole launch of k_batch
     st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
-    algo_bytes = float(ALGO_BYTES_PER_DECISION * BATCH)
-    achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    multi_req, multi_keys = st["repeated_requests"], st["repeated_keys"]
+    fused_path = os.environ.get("GUB_PATH") == "fused" or p2p is not None
+    if fused_path:
+        kms = {"k_batch": prof["k_group_ms"] / launches}  # the first timing slot brackets the whole launch of k_batch
+        alg = {"k_batch": float(ALGO_BYTES_PER_DECISION * BATCH)}
+    else:
+        kms = {k: prof[k + "_ms"] / launches for k in ("k_group", "k_rank", "k_eval", "k_finish")}
+        # SURVEY 8d's 224 B per decision (64 slot read + 64 slot write-back + 64 request + 32 response), split by where the pipeline
+        # moves them: a key seen once is done entirely in k_rank; a member of a repeated key has its request read in
+        # k_rank (uniformity) and again, with its response written, in k_eval; a repeated key's slot is read once (k_rank, into the
+        # snapshot) and written back once (k_eval); k_group reads every request's 8-byte key hash.
+        alg = {"k_group": 8.0 * BATCH,
+               "k_rank": ALGO_BYTES_PER_DECISION * st["singles"] + 64.0 * multi_req + 64.0 * multi_keys,
+               "k_eval": (64.0 + 32.0) * multi_req + 64.0 * multi_keys,
+               "k_finish": 0.0}
+    dom = max(kms, key=kms.get)
+    k_ms = kms[dom]
+    path_ms = sum(kms.values())
+    achieved = alg[dom] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
     if N == 1 and p2p is None and not args.no_traffic:
         traffic = measure_traffic(args)
-    dram = (traffic["dram_read_bytes_per_launch"] + traffic["dram_write_bytes_per_launch"]) if traffic and "error" not in traffic else None
-    roofline = {"bound": "hbm", "kernel": "k_batch", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": dram, "traffic_detail": traffic, "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
+    dram = None
+    if traffic and "error" not in traffic and dom in traffic:
+        dram = traffic[dom]["dram_read_bytes_per_launch"] + traffic[dom]["dram_write_bytes_per_launch"]
+    dram_path = sum(v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"] for k, v in traffic.items() if isinstance(v, dict)) \
+        if traffic and "error" not in traffic else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": dram, "traffic_detail": traffic, "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg,
                 "bytes_per_decision": ALGO_BYTES_PER_DECISION,
                 "fractions": {
-                    # (1) SURVEY 8d: 224 B x decisions / step time (launch gaps included)
+                    # (1) SURVEY 8d: 224 B x decisions / step time (kernels of consecutive batches overlap; launch gaps included)
                     "survey_8d_over_step_time": ALGO_BYTES_PER_DECISION * BATCH / (ms / args.steps * 1e-3) / 1e9 / peak,
-                    # (2) what the kernel really moved through DRAM / kernel time
+                    # ... and over the sum of the kernels' own times (no overlap credited)
+                    "survey_8d_over_kernel_time_sum": ALGO_BYTES_PER_DECISION * BATCH / (path_ms * 1e-3) / 1e9 / peak if path_ms > 0 else None,
+                    # (2) what the dominant kernel really moved through DRAM / its time; and the whole path's DRAM bytes / step time
                     "measured_dram_over_kernel_time": (dram / (k_ms * 1e-3) / 1e9 / peak) if dram and k_ms > 0 else None,
+                    "measured_dram_path_over_step_time": (dram_path / (ms / args.steps * 1e-3) / 1e9 / peak) if dram_path else None,
                 }}
     # (3) north_star's "HBM-random-access roofline": the measured random 64-byte read-modify-write rate of this device over this very
     # table; the batch's distinct-slot traffic (128 B x distinct keys per batch) as a fraction of it
@@ -709,7 +738,9 @@ def run_b200(args):
                          + ("" if r["keys"] == n_keys else f" (of {n_keys:,}: host memory bounds the CPU table)")
                          + f", from key strings (XXH64 + FNV-1 inside the timed call), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
 
-    per_step_launches = 1 if p2p is None else (3 + (4 if is_global else 0))  # k_batch (+ k_p2p_route, k_p2p_collect; GLOBAL: two queue kernels on either side)
+    # single table: k_group, k_rank, k_eval, k_finish (or k_batch alone with GUB_PATH=fused); ring: k_p2p_route, k_batch, k_p2p_collect (+ two queue
+    # kernels on either side with GLOBAL)
+    per_step_launches = (1 if fused_path else 4) if p2p is None else (3 + (4 if is_global else 0))
     if is_global:
         workload = (f"BASELINE config 5: {n_keys:,} keys, {global_hot:,} GLOBAL hot keys (the top of the Zipf ranking), Zipf s={args.zipf}, {N}xB200, GLOBAL sync tick "
                     f"every {tick_every} steps (~{args.tick_ms:.0f} ms of wall clock): hits to owners over the NVLink mailboxes, UpdatePeerGlobal items by NCCL all-gather")

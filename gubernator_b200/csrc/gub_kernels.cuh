@@ -47,7 +47,6 @@ constexpr int MAX_PROBE = 512;       // window [home, home + MAX_PROBE): inserts
 constexpr int GROUP_THREADS = 256;   // requests per block in k_group / k_rank (a "fragment" is one key's members in one block)
 constexpr int GROUP_SLOTS = 512;     // shared-memory table entries per block (load factor <= 0.5)
 constexpr int MIXED_THREADS = 256;
-constexpr int MAX_SEG = 96;          // uniform segments of a non-uniform group planned in parallel; more => serial walk
 constexpr int MAX_PIECES = 16;
 
 struct __align__(64) Slot { uint64_t w[8]; };
@@ -750,19 +749,21 @@ __global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_eval(cons
 }
 
 // ---- kernel 4: runs whose requests differ ---------------------------------------------------------------------------
+// A group whose requests differ is a sequence of SEGMENTS (runs of identical requests).  It is taken in chunks of MIXED_CHUNK
+// members (rank order: `order`): the block finds the chunk's segment starts in parallel and stages each segment's request in shared
+// memory; thread 0 then FOLDS the segments in order — one closed-form run_to_rank() per segment, keeping the bucket state ENTERING
+// each — and every member evaluates run_to_rank(entering state, request, rank within the segment) by itself.  A chunk that is
+// mostly one-request runs (more than MIXED_SEGS segments), or a segment whose request can never settle, is applied one request
+// at a time by thread 0.  The slot is opened once and written once for the whole group (thread 0 carries the cursor).
+constexpr uint32_t MIXED_CHUNK = 1024, MIXED_SEGS = 256;
 struct MixedShared {
   uint32_t nseg;
-  uint32_t np;
-  uint32_t covered;
-  uint32_t seg[MAX_SEG];
-  Piece pieces[MAX_PIECES];
+  uint32_t seg[MIXED_SEGS + 1];     // first member (offset in the chunk) of every segment, ascending; seg[nseg] = members in the chunk
+  uint32_t raw[MIXED_SEGS];         // the starts as found (any order)
+  uint8_t kind[MIXED_SEGS];         // 1: applied one by one by the folding thread
+  gub_req shape[MIXED_SEGS];        // the segment's request
+  Bucket state[MIXED_SEGS];         // bucket entering the segment
 };
-
-// A group is taken in chunks of MIXED_CHUNK members: per chunk the runs of identical requests (segments) are found in parallel; up
-// to MAX_SEG of them are planned one by one by thread 0 (closed forms) and evaluated by everybody; a chunk with more segments than
-// that is mostly one-request runs, where planning buys nothing: thread 0 applies its requests one after another.  The slot is
-// opened once and written once for the whole group (thread 0 carries the cursor across chunks).
-constexpr uint32_t MIXED_CHUNK = 4096;
 
 __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Tally& t) {
   const uint32_t tid = threadIdx.x;
@@ -778,80 +779,69 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
     __syncthreads();
     if (tid == 0) S.nseg = 0;
     __syncthreads();
-    // segment boundaries: ranks whose request differs from the previous member's (the chunk's first member starts one)
-    for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
+    for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {  // segment starts: ranks whose request differs from the previous member's
       bool boundary = (k == 0);
       if (!boundary) {
         const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
         boundary = !req_same(a, b);
       }
-      if (boundary) { const uint32_t q = atomicAdd(&S.nseg, 1u); if (q < (uint32_t)MAX_SEG) S.seg[q] = k; }
+      if (boundary) { const uint32_t q = atomicAdd(&S.nseg, 1u); if (q < MIXED_SEGS) S.raw[q] = k; }
     }
     __syncthreads();
     const uint32_t nseg = S.nseg;
-    if (nseg > (uint32_t)MAX_SEG) {  // mostly one-request runs: applied one by one
-      if (tid == 0) {
+    const bool planned = nseg <= MIXED_SEGS;
+    if (planned) {  // rank sort of the starts, and the segments' requests into shared memory
+      for (uint32_t q = tid; q < nseg; q += MIXED_THREADS) {
+        const uint32_t v = S.raw[q];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < nseg; j++) r += S.raw[j] < v ? 1u : 0u;
+        S.seg[r] = v;
+        S.shape[r] = load_req(A.reqs + ord[v]);
+      }
+      if (tid == 0) S.seg[nseg] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {  // the fold
+      const uint32_t steps = planned ? nseg : 1u;
 #pragma unroll 1
-        for (uint32_t j = 0; j < cnt; j++) {
-          const uint32_t i = ord[j];
-          const gub_req rq = load_req(A.reqs + i);
+      for (uint32_t sgi = 0; sgi < steps; sgi++) {
+        const uint32_t lo = planned ? S.seg[sgi] : 0u, hi = planned ? S.seg[sgi + 1] : cnt;
+        gub_req rq = planned ? S.shape[sgi] : load_req(A.reqs + ord[0]);
+        const bool closed_form = planned && req_regular(rq);
+        if (planned) S.kind[sgi] = closed_form ? 0 : 1;
+#pragma unroll 1
+        for (uint32_t k = lo; k < hi; k++) {  // closed form: one pass for the whole segment; else one pass per request
+          if (!closed_form && k > lo) rq = load_req(A.reqs + ord[k]);
           const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-          if (!open || key != ck || tag != ct) {
+          if (!open || key != ck || tag != ct) {  // (the key only changes when two keys share a group entry)
             if (open) close_slot(A, cur, t);
             open_slot(A, cur, key, tag);
             open = true; ck = key; ct = tag;
           }
           Delta d = {0, 0, 0};
+          if (closed_form) {
+            S.state[sgi] = cur.b;
+            run_to_rank(cur.b, rq, hi - lo - 1, A.clk, d);
+            t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+            break;
+          }
           const gub_resp r = apply_one(cur.b, rq, A.clk, d);
           t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-          store_resp(A.out + i, r);
+          store_resp(A.out + ord[k], r);
         }
-        atomicAdd(A.counters + C_SERIAL, 1ull);
       }
-      continue;
-    }
-    if (tid == 0) {  // tiny insertion sort of the segment starts
-      for (uint32_t a = 1; a < nseg; a++) {
-        const uint32_t v = S.seg[a];
-        int b = (int)a - 1;
-        while (b >= 0 && S.seg[b] > v) { S.seg[b + 1] = S.seg[b]; b--; }
-        S.seg[b + 1] = v;
-      }
+      if (!planned) atomicAdd(A.counters + C_SERIAL, 1ull);
     }
     __syncthreads();
-    // per segment: thread 0 plans, everybody evaluates
-#pragma unroll 1
-    for (uint32_t sgi = 0; sgi < nseg; sgi++) {
-      const uint32_t lo = S.seg[sgi], hi = (sgi + 1 < nseg) ? S.seg[sgi + 1] : cnt, m = hi - lo;
-      if (tid == 0) {
-        const gub_req rq = load_req(A.reqs + ord[lo]);
-        const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-        if (!open || key != ck || tag != ct) {
-          if (open) close_slot(A, cur, t);
-          open_slot(A, cur, key, tag);
-          open = true; ck = key; ct = tag;
-        }
+    if (planned) {  // every member of a closed-form segment answers for itself
+      for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
+        uint32_t lo = 0, hi = nseg;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (S.seg[mid] <= k) lo = mid; else hi = mid; }
+        if (S.kind[lo]) continue;
+        Bucket b = S.state[lo];
         Delta d = {0, 0, 0};
-        uint32_t np = 0;
-        const uint32_t covered = plan_run(cur.b, rq, m, A.clk, d, S.pieces, MAX_PIECES, &np);
-        t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-        // ranks the piece buffer could not hold (no regular regime, e.g. RESET_REMAINING flip-flops): walk them
-        for (uint32_t k = covered; k < m; k++) {
-          Delta d2 = {0, 0, 0};
-          const gub_resp rr = apply_one(cur.b, rq, A.clk, d2);
-          t.over += d2.over; t.hit += d2.hit; t.miss += d2.miss;
-          store_resp(A.out + ord[lo + k], rr);
-        }
-        S.np = np; S.covered = covered;
+        store_resp(A.out + ord[k], run_to_rank(b, S.shape[lo], k - S.seg[lo], A.clk, d));
       }
-      __syncthreads();
-      const uint32_t np = S.np, covered = S.covered;
-      for (uint32_t k = tid; k < covered; k += MIXED_THREADS) {
-        uint32_t pi = 0;
-        while (pi + 1 < np && S.pieces[pi + 1].start <= k) pi++;
-        store_resp(A.out + ord[lo + k], eval_piece(S.pieces[pi], k));
-      }
-      __syncthreads();
     }
   }
   if (tid == 0 && open) close_slot(A, cur, t);
