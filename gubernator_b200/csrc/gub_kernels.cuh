@@ -63,7 +63,7 @@ __host__ __device__ inline uint32_t aux_count(unsigned long long w) { return (ui
 __host__ __device__ inline uint32_t aux_epoch(unsigned long long w) { return (uint32_t)(w >> 48); }
 __host__ __device__ inline uint32_t aux_tag(unsigned long long w) { return (uint32_t)((w >> 24) & 0xFFFFFFull); }
 
-struct BatchCtr { uint32_t n_mixed, order_bump, _pad0, _pad1; };
+struct BatchCtr { uint32_t n_mixed, order_bump, next_mixed, _pad1; };
 
 // Items whose insert found the probe window full are parked here and placed — evicting the entry of the window that expires first,
 // like the reference's LRU would have evicted (lrucache.go:98,138-149) — before the next batch reads the table.
@@ -639,10 +639,9 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
 }
 
 
-#ifndef GUB_EVAL_MINBLOCKS
-#define GUB_EVAL_MINBLOCKS 2  // resident blocks per SM the register budget of k_rank / k_eval is sized for
-#endif
-__global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_rank(const BatchArgs A) {
+// (Register budget: 2 resident blocks per SM, ~123 registers.  Capping at 80 / 64 registers for 3 / 4 blocks spills and is slower:
+// 37.3 / 39.8 vs 33.0 us per step, profiles/r02_call9_bench_mb{3,4}.json.)
+__global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
   const uint32_t i = partition_by_algorithm(A.reqs, n);
@@ -654,7 +653,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_rank(cons
   pdl_release();
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
-    nxt->n_mixed = 0; nxt->order_bump = 0;
+    nxt->n_mixed = 0; nxt->order_bump = 0; nxt->next_mixed = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
@@ -708,7 +707,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_rank(cons
 }
 
 // ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
-__global__ void __launch_bounds__(GROUP_THREADS, GUB_EVAL_MINBLOCKS) k_eval(const BatchArgs A) {
+__global__ void __launch_bounds__(GROUP_THREADS, 2) k_eval(const BatchArgs A) {
   const uint32_t n = batch_n(A);
   const uint32_t i = partition_by_algorithm(A.reqs, n);
   Tally t = {0, 0, 0, 0, 0};
@@ -855,7 +854,13 @@ __global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A) 
   pdl_release();
   const BatchCtr ctr = A.ctr[A.epoch & 1];
   if (ctr.n_mixed == 0) return;
-  for (uint32_t g = blockIdx.x; g < ctr.n_mixed; g += gridDim.x) {
+  // groups differ a lot in size (a hot key's group has thousands of members): blocks pull the next one when they are done
+  __shared__ uint32_t s_next;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(&A.ctr[A.epoch & 1].next_mixed, 1u);
+    __syncthreads();
+    const uint32_t g = s_next;
+    if (g >= ctr.n_mixed) break;
     mixed_group(A, A.mixed_ent[g], S, t);
     __syncthreads();
   }
