@@ -95,7 +95,13 @@ void emu_destroy(void* tv) {
 }
 
 void emu_set_finish_cap(uint32_t blocks) { g_finish_cap = blocks ? blocks : 148u; }
-void emu_set_epoch(void* tv, uint32_t epoch) { static_cast<EmuTable*>(tv)->epoch = epoch; }
+// Test hook: jump to an arbitrary epoch.  A real sequence alternates parity, and k_rank resets the other parity's allocator for the
+// next batch; a jump may keep the parity, so hand over clean allocators like the launcher does at the wrap.
+void emu_set_epoch(void* tv, uint32_t epoch) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  t->epoch = epoch;
+  std::memset(t->ctr, 0, 2 * sizeof(BatchCtr));
+}
 
 void emu_set_fused(uint32_t on) { g_fused = on; }
 void emu_set_grid(void* tv, uint32_t grid) { static_cast<EmuTable*>(tv)->grid = grid ? grid : 6u; }
