@@ -296,6 +296,9 @@ def measure_traffic(args):
 
 # ---- this repo's arm --------------------------------------------------------------------------------------------
 def run_b200(args):
+    if os.environ.get("GUB_BENCH_WATCHDOG"):  # diagnostic: dump every thread's Python stack and exit if the run takes longer than this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["GUB_BENCH_WATCHDOG"]), exit=True)
     import torch
     import gubernator_b200 as g
     import oracle_py as O
@@ -315,6 +318,12 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     N = world
+    t_start = time.perf_counter()
+
+    def progress(what):  # stderr, every rank: where a multi-GPU run is when something stalls
+        if os.environ.get("GUB_BENCH_PROGRESS"):
+            sys.stderr.write(f"[bench rank {rank} +{time.perf_counter() - t_start:7.1f}s] {what}\n")
+            sys.stderr.flush()
     n_keys = args.keys
     is_global = args.workload == "global"
     global_hot = n_keys // 100 if is_global else 0  # config 5: 1 % of the keys carry Behavior_GLOBAL, the top of the Zipf ranking
@@ -375,14 +384,18 @@ def run_b200(args):
             reqs["behavior"] = np.where(ids < global_hot, O.GLOBAL | O.REQ_IS_OWNER, O.REQ_IS_OWNER).astype(np.uint32)
         n = len(reqs)
         if n:
-            d_chunk[:n].copy_(torch.from_numpy(reqs.view(np.uint8).reshape(n, 64)), non_blocking=False)
+            # (the routing kernel reads d_chunk on the ingest stream: the copy of the next chunk must queue behind it)
+            with torch.cuda.stream(ingest if ingest is not None else torch.cuda.current_stream()):
+                d_chunk[:n].copy_(torch.from_numpy(reqs.view(np.uint8).reshape(n, 64)), non_blocking=False)
         if p2p is None:
             tab.submit_device(d_chunk.data_ptr(), n, clk0, d_chunk_out.data_ptr(), stream)
         else:
             ring_step(d_chunk, n, clk0, d_chunk_out)
+    progress(f"fill enqueued ({n_fill_steps} steps)")
     torch.cuda.synchronize()
     t_fill = time.perf_counter() - t_fill
     c0 = tab.counters()
+    progress("fill done")
 
     # ---- pre-generated batch pool, resident in HBM
     pool_n = max(2, args.pool)
@@ -442,7 +455,9 @@ def run_b200(args):
     tw = time.perf_counter()
     for b in range(args.warmup):
         one_step(b)
+    progress("warm-up enqueued")
     barrier()
+    progress("warm-up done")
     if is_global:
         per_step = (time.perf_counter() - tw) / max(args.warmup, 1)
         t_ps = torch.tensor([per_step], device=dev, dtype=torch.float64)
@@ -459,7 +474,9 @@ def run_b200(args):
         if tick_every and (b + 1) % tick_every == 0:
             do_tick(args.warmup + b)
     ev1.record()
+    progress("timed steps enqueued")
     barrier()
+    progress("timed steps done")
     ms = ev0.elapsed_time(ev1)
     clocks_info = sampler.stop() if rank == 0 else None
     if dist is not None:
@@ -482,15 +499,25 @@ def run_b200(args):
         d_qo = torch.zeros((hot, 32), dtype=torch.uint8, device=dev)
         ring_step(d_q, hot, clk_of(args.warmup + args.steps), d_qo)
         torch.cuda.synchronize()
-        mine = d_qo.view(torch.int64).reshape(hot, 4).clone()
-        same = True
+        mine = d_qo.view(torch.int64).reshape(hot, 4).clone()  # per key: status | err << 32, limit, remaining, reset_time
+        token = torch.from_numpy((q["algorithm"] == 0)).to(dev)
+        conv = {"hot_keys_checked": hot, "token_keys": int(token.sum().item())}
         if dist is not None:
             ref = mine.clone()
             dist.broadcast(ref, src=0)
-            ok = torch.tensor([int(torch.equal(ref, mine))], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            same = bool(ok.item())
-        convergence = {"hot_keys_checked": hot, "all_shards_agree": same}
+            # TestGlobalBehavior's check (functional_test.go:1816-1821, TOKEN_BUCKET): every peer reports the same status and remaining
+            tok_bad = ((ref[:, 0] != mine[:, 0]) | (ref[:, 2] != mine[:, 2])) & token
+            # leaky replicas are installed from an int64 Remaining (UpdatePeerGlobals, gubernator.go:443: float64(g.Status.Remaining)) with
+            # UpdatedAt = the receiver's now, so a replica may trail its owner by the fraction of a token the owner has leaked since
+            lk_diff = (ref[:, 2] - mine[:, 2]).abs() * (~token)
+            cst = torch.stack([tok_bad.sum(), lk_diff.max(), (lk_diff > 0).sum(), (ref != mine).any(dim=1).sum()]).to(torch.int64)
+            dist.all_reduce(cst, op=dist.ReduceOp.MAX)
+            conv.update({"token_keys_differing_max_over_shards": int(cst[0].item()), "leaky_remaining_max_abs_diff": int(cst[1].item()),
+                         "leaky_keys_differing_max_over_shards": int(cst[2].item()), "keys_with_any_field_differing": int(cst[3].item()),
+                         "all_shards_agree": bool(cst[0].item() == 0 and cst[1].item() <= 1)})
+        else:
+            conv["all_shards_agree"] = True
+        convergence = conv
 
     # ---- informational: one C-ABI call with 4 x 65 536 requests (one launch, four rounds inside the kernel)
     big = None
@@ -537,6 +564,7 @@ def run_b200(args):
                               "over_limit_fraction": (ca["over_limit"] - cb["over_limit"]) / max(1, ca["requests"] - cb["requests"])}
 
     # ---- per-kernel timing leg (separate from the number above: the events perturb the pipeline)
+    progress("profiling leg")
     tab.set_profiling(True)
     prof_steps = min(args.steps, 200)
     for b in range(prof_steps):
@@ -554,6 +582,7 @@ def run_b200(args):
         torch.cuda.profiler.stop()
 
     # ---- phase trace of the batch kernel (diagnostic): per-CTA %globaltimer stamps of one launch
+    progress("trace legs")
     phase_trace = None
     try:
         tab.set_trace(True)
@@ -572,8 +601,48 @@ def run_b200(args):
     except Exception as ex:
         phase_trace = {"error": str(ex)}
 
+    # ---- time stamps of the four pipeline kernels (diagnostic): one isolated batch, then the last of six back to back
+    if os.environ.get("GUB_PATH") != "fused":
+        try:
+            tab.set_trace(True)
+            base_b = args.warmup + args.steps + prof_steps + 80
+            names = ["k_group", "k_rank", "k_eval", "k_finish"]
+
+            def summarise(raw):
+                live = raw[:, :, 0] > 0
+                t0 = int(raw[0][live[0], 0].min())
+                out = {}
+                for k in range(4):
+                    r = raw[k][live[k]].astype(np.int64)
+                    if not len(r):
+                        continue
+                    rel = np.where(r > 0, (r - t0) / 1e3, np.nan)
+                    out[names[k]] = {"blocks": int(len(r)), "first_entry_us": round(float(np.nanmin(rel[:, 0])), 2),
+                                     "median_us": [None if np.all(np.isnan(rel[:, m])) else round(float(np.nanmedian(rel[:, m])), 2) for m in range(8)],
+                                     "max_us": [None if np.all(np.isnan(rel[:, m])) else round(float(np.nanmax(rel[:, m])), 2) for m in range(8)]}
+                return out
+            for b in range(3):
+                one_step(base_b + b)
+            torch.cuda.synchronize()
+            tab.get_ktrace(reset=True)
+            one_step(base_b + 3)
+            torch.cuda.synchronize()
+            iso = summarise(tab.get_ktrace(reset=True))
+            for b in range(6):
+                one_step(base_b + 4 + b)
+            torch.cuda.synchronize()
+            piped = summarise(tab.get_ktrace(reset=True))
+            phase_trace = {"marks": "0 entry, 1 after griddepcontrol.wait, 2..5 kernel-specific (k_group: keys in table / local ranks / - / fragment joined; "
+                                    "k_rank: entry read / base rank / snapshot stored / single answered; k_eval: entry read / member answered), 6 work done, 7 exit; "
+                                    "us since the first k_group block entered; latest stamp per block",
+                           "isolated_batch": iso, "six_back_to_back_latest": piped}
+            tab.set_trace(False)
+        except Exception as ex:
+            phase_trace = {"error": str(ex)}
+
     # ---- end-to-end leg from key strings in pinned host memory (N == 1: the public host API; N > 1: pinned H2D + ring step + D2H)
     e2e = None
+    progress("end-to-end leg")
     if not args.no_e2e:
         depth = 4
         e2e_steps = args.steps
@@ -662,6 +731,7 @@ def run_b200(args):
             e2e = {"value": N * BATCH * e2e_steps / dt, "unit": "decisions/s", "h2d_bytes_per_step": N * BATCH * 64, "d2h_bytes_per_step": N * BATCH * 32,
                    "api": "pinned H2D of 64-byte pre-hashed records + gub_p2p_step (route / evaluate out of the mailboxes / collect) + D2H per step"}
 
+    progress("legs done")
     c1 = tab.counters()
     ring_error = None
     if p2p is not None:
@@ -680,7 +750,7 @@ def run_b200(args):
     launches = max(prof["launches"], 1)
     st = {k: float(np.mean([s[k] for s in stats])) for k in stats[0]}
     multi_req, multi_keys = st["repeated_requests"], st["repeated_keys"]
-    fused_path = os.environ.get("GUB_PATH") == "fused" or p2p is not None
+    fused_path = os.environ.get("GUB_PATH") == "fused"
     if fused_path:
         kms = {"k_batch": prof["k_group_ms"] / launches}  # the first timing slot brackets the whole launch of k_batch
         alg = {"k_batch": float(ALGO_BYTES_PER_DECISION * BATCH)}
@@ -738,9 +808,10 @@ def run_b200(args):
                          + ("" if r["keys"] == n_keys else f" (of {n_keys:,}: host memory bounds the CPU table)")
                          + f", from key strings (XXH64 + FNV-1 inside the timed call), oracle worker-pool port on {r['cores']} threads, {r['seconds']:.1f} s timed"}
 
-    # single table: k_group, k_rank, k_eval, k_finish (or k_batch alone with GUB_PATH=fused); ring: k_p2p_route, k_batch, k_p2p_collect (+ two queue
-    # kernels on either side with GLOBAL)
-    per_step_launches = (1 if fused_path else 4) if p2p is None else (3 + (4 if is_global else 0))
+    # single table: k_group, k_rank, k_eval, k_finish (or k_batch alone with GUB_PATH=fused); ring: k_p2p_route, k_seg_wait, the four batch
+    # kernels per pass (one pass covers min(N x 65 536, 262 144) requests), k_seg_publish, k_p2p_collect (+ two queue kernels on either side with GLOBAL)
+    ring_passes = -(-N * BATCH // min(N * BATCH, 262144))
+    per_step_launches = (1 if fused_path else 4) if p2p is None else ((3 if fused_path else 4 + 4 * ring_passes) + (4 if is_global else 0))
     if is_global:
         workload = (f"BASELINE config 5: {n_keys:,} keys, {global_hot:,} GLOBAL hot keys (the top of the Zipf ranking), Zipf s={args.zipf}, {N}xB200, GLOBAL sync tick "
                     f"every {tick_every} steps (~{args.tick_ms:.0f} ms of wall clock): hits to owners over the NVLink mailboxes, UpdatePeerGlobal items by NCCL all-gather")
@@ -748,7 +819,8 @@ def run_b200(args):
         workload = "BASELINE config 3: 100M keys, Zipf s=1.1, TOKEN/LEAKY 50/50, 1xB200"
     else:
         workload = (f"BASELINE config 4: 100M keys sharded over {N}xB200 by replicated_hash (fnv1, 512 replicas), Zipf s=1.1; routing kernel stores the records into the owners' "
-                    "NVLink mailboxes, the batch kernel evaluates out of them" + ("" if args.no_route_overlap else "; routing of step e+1 overlaps evaluation of step e (two streams)"))
+                    "NVLink mailboxes, the batch kernels evaluate out of them and store the responses into the sources' mailboxes"
+                    + ("" if args.no_route_overlap else "; routing, evaluation and collect of consecutive steps overlap (ingest stream + the ring's own evaluation and collect streams)"))
     line = {
         "metric": "rate-limit decisions/sec", "value": value, "unit": "decisions/s", "n_gpus": N, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

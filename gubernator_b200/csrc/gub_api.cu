@@ -87,6 +87,7 @@ struct gub_table {
   gub::OvfItem* ovf = nullptr;
   gub::InvIndex inv{};                // CacheItem.InvalidAt side index
   unsigned long long* trace = nullptr; // per-CTA phase timestamps of the last k_batch launch (gub_set_trace)
+  unsigned long long* ktrace = nullptr; // pipeline kernels: [4][KT_BLOCKS][KT_MARKS] latest time stamps (gub_set_trace / gub_get_ktrace)
   unsigned long long* counters = nullptr;
   // ordering between streams that touch the shared scratch
   cudaEvent_t last_done = nullptr;
@@ -209,9 +210,17 @@ int launch_fused(gub_table* t, const gub::FArgs& A, uint64_t total_hint, cudaStr
   return 0;
 }
 
+// Ring mode: the batch is the concatenation of mailbox segments (see BatchArgs::nseg).
+struct SegDesc {
+  uint32_t nseg = 0;
+  const uint32_t* seg_off = nullptr;
+  const gub_req* reqs[gub::MAX_SHARDS] = {};
+  gub_resp* out[gub::MAX_SHARDS] = {};
+};
+
 // One batch (<= max_batch requests) through the four-kernel pipeline, chained with programmatic dependent launch.
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
-                 const uint32_t* n_dev = nullptr, uint32_t n_off = 0) {
+                 const uint32_t* n_dev = nullptr, uint32_t n_off = 0, const SegDesc* seg = nullptr) {
   gub_table::Scratch& sc = t->scr;
   if (sc.epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
     CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), st));
@@ -222,11 +231,17 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   }
   sc.epoch++;
   gub::BatchArgs A;
+  std::memset(&A, 0, sizeof A);
+  if (seg) {
+    A.nseg = seg->nseg; A.seg_off = seg->seg_off;
+    for (uint32_t k = 0; k < seg->nseg; k++) { A.seg_reqs[k] = seg->reqs[k]; A.seg_out[k] = seg->out[k]; }
+  }
   A.table = t->table; A.capacity = t->capacity; A.reqs = d_reqs; A.out = d_out; A.n = n; A.n_dev = n_dev; A.n_off = n_off; A.epoch = sc.epoch;
   A.aux = sc.aux; A.aux_mask = t->aux_entries - 1; A.presence = sc.presence; A.fragsize = sc.fragsize;
   A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = sc.ent; A.meta = sc.meta; A.rank = sc.rank;
   A.commit = sc.commit; A.order = sc.order; A.mixed_ent = sc.mixed_ent; A.ctr = sc.ctr;
   A.counters = t->counters; A.ovf = t->ovf; A.ovf_count = &t->ctl->ovf_count; A.inv = t->inv;
+  A.ktrace = t->ktrace;
   A.clk = *clk;
   const uint32_t blocks = (n + 255) / 256;
   cudaEvent_t* pe = nullptr;
@@ -239,14 +254,25 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
     t->prof_pending++;
     CK(cudaEventRecord(pe[0], st));
   }
-  CK(launch_k(t, gub::k_group, blocks, gub::GROUP_THREADS, st, A));
-  if (pe) CK(cudaEventRecord(pe[1], st));
-  CK(launch_k(t, gub::k_rank, blocks, gub::GROUP_THREADS, st, A));
-  if (pe) CK(cudaEventRecord(pe[2], st));
-  CK(launch_k(t, gub::k_eval, blocks, gub::GROUP_THREADS, st, A));
-  if (pe) CK(cudaEventRecord(pe[3], st));
-  // non-uniform groups, one block each (grid-stride; normally none: the blocks return at once)
-  CK(launch_k(t, gub::k_finish, std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2)), gub::MIXED_THREADS, st, A));
+  const uint32_t fin_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
+  if (seg) {
+    CK(launch_k(t, gub::k_group<true>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[1], st));
+    CK(launch_k(t, gub::k_rank<true>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[2], st));
+    CK(launch_k(t, gub::k_eval<true>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[3], st));
+    CK(launch_k(t, gub::k_finish<true>, fin_blocks, gub::MIXED_THREADS, st, A));
+  } else {
+    CK(launch_k(t, gub::k_group<false>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[1], st));
+    CK(launch_k(t, gub::k_rank<false>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[2], st));
+    CK(launch_k(t, gub::k_eval<false>, blocks, gub::GROUP_THREADS, st, A));
+    if (pe) CK(cudaEventRecord(pe[3], st));
+    // non-uniform groups, one block each (grid-stride; normally none: the blocks return at once)
+    CK(launch_k(t, gub::k_finish<false>, fin_blocks, gub::MIXED_THREADS, st, A));
+  }
   if (pe) CK(cudaEventRecord(pe[4], st));
   CK(cudaGetLastError());
   return 0;
@@ -325,6 +351,34 @@ gub_item from_dev(const gub::DevItem& d) {
   return it;
 }
 
+// Per-batch scratch of the four-kernel pipeline for batches of up to B requests (replaces what was there: the device must be idle).
+int alloc_scratch(gub_table* t, uint32_t B) {
+  auto& sc = t->scr;
+  void* old[] = {sc.aux, sc.ent, sc.meta, sc.rank, sc.order, sc.mixed_ent, sc.presence, sc.fragsize, sc.commit, sc.ctr};
+  for (void* p : old) if (p) cudaFree(p);
+  sc = gub_table::Scratch();
+  B = std::max<uint32_t>(1024u, std::min<uint32_t>(B, 262144u));
+  B = (B + 255u) & ~255u;
+  t->max_batch = B;
+  t->aux_entries = next_pow2((uint64_t)B * 4);
+  t->max_blocks = (B / gub::GROUP_THREADS + 127u) & ~127u;  // fragment-size row per group entry; a multiple of 128 blocks = 4 presence words (16-byte loads)
+  t->pres_words = t->max_blocks / 32;
+  struct { void** p; size_t bytes; } want[] = {
+      {(void**)&sc.aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry)},
+      {(void**)&sc.presence, (size_t)t->aux_entries * t->pres_words * 4},
+      {(void**)&sc.fragsize, (size_t)t->aux_entries * t->max_blocks},
+      {(void**)&sc.commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2)},
+      {(void**)&sc.ent, (size_t)B * 4}, {(void**)&sc.meta, (size_t)B * 4}, {(void**)&sc.rank, (size_t)B * 4}, {(void**)&sc.order, (size_t)B * 4},
+      {(void**)&sc.mixed_ent, ((size_t)B / 2 + 1) * 4}, {(void**)&sc.ctr, 2 * sizeof(gub::BatchCtr)},
+  };
+  for (auto& w : want) {
+    cudaError_t e = cudaMalloc(w.p, w.bytes);
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc(batch scratch): ") + cudaGetErrorString(e));
+    CK(cudaMemset(*w.p, 0, w.bytes));
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -338,7 +392,7 @@ void gub_destroy(gub_table* t) {
   cudaDeviceSynchronize();
   trace_dump(t);
   void* ptrs[] = {t->table, t->counters, t->d_scalar, t->d_ring_pts, t->d_ring_peers, t->d_ring_lut, t->d_owner, t->d_tile_counts,
-                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf, t->trace, t->inv.e};
+                  t->gaux, t->gpres, t->gfrag, t->gmembers, t->ctl, t->ovf, t->trace, t->ktrace, t->inv.e};
   for (void* p : ptrs) if (p) cudaFree(p);
   {
     auto& sc = t->scr;
@@ -382,10 +436,6 @@ int gub_create(const gub_config* cfg, gub_table** out) {
   if (t->max_batch < 1024) t->max_batch = 1024;
   if (t->max_batch > 262144u) t->max_batch = 262144u;
   t->max_batch = (t->max_batch + 255u) & ~255u;
-  const uint32_t B = t->max_batch;
-  t->aux_entries = next_pow2((uint64_t)B * 4);
-  t->max_blocks = (B / gub::GROUP_THREADS + 31u) & ~31u;  // fragment-size row per group entry (multiple of 32 bytes)
-  t->pres_words = t->max_blocks / 32;
 #define ALLOC(ptr, bytes)                                                    \
   do {                                                                       \
     cudaError_t e__ = cudaMalloc((void**)&(ptr), (bytes));                   \
@@ -397,19 +447,7 @@ int gub_create(const gub_config* cfg, gub_table** out) {
     cudaMemset((ptr), 0, (bytes));                                           \
   } while (0)
   ALLOC(t->table, t->capacity * sizeof(gub::Slot));
-  {
-    auto& sc = t->scr;
-    ALLOC(sc.aux, (size_t)t->aux_entries * sizeof(gub::AuxEntry));
-    ALLOC(sc.presence, (size_t)t->aux_entries * t->pres_words * 4);
-    ALLOC(sc.fragsize, (size_t)t->aux_entries * t->max_blocks);
-    ALLOC(sc.commit, (size_t)t->aux_entries * 6 * sizeof(ulonglong2));
-    ALLOC(sc.ent, (size_t)B * 4);
-    ALLOC(sc.meta, (size_t)B * 4);
-    ALLOC(sc.rank, (size_t)B * 4);
-    ALLOC(sc.order, (size_t)B * 4);
-    ALLOC(sc.mixed_ent, ((size_t)B / 2 + 1) * 4);
-    ALLOC(sc.ctr, 2 * sizeof(gub::BatchCtr));
-  }
+  if (alloc_scratch(t, t->max_batch)) { gub_destroy(t); return -1; }
   t->num_sms = std::min<int>(prop.multiProcessorCount, gub::FB_MAX_GRID);
   if (const char* e = getenv("GUB_PATH")) t->fused = std::string(e) == "fused";
   if (const char* e = getenv("GUB_COOP")) t->coop = std::atoi(e) != 0;
@@ -800,10 +838,29 @@ int gub_set_trace(gub_table* t, int on) {
   if (on && !t->trace) {
     CK(cudaMalloc(&t->trace, (size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS * 8));
     CK(cudaMemset(t->trace, 0, (size_t)gub::FB_MAX_GRID * gub::FB_TRACE_MARKS * 8));
+    CK(cudaMalloc(&t->ktrace, (size_t)4 * gub::KT_BLOCKS * gub::KT_MARKS * 8));
+    CK(cudaMemset(t->ktrace, 0, (size_t)4 * gub::KT_BLOCKS * gub::KT_MARKS * 8));
   } else if (!on && t->trace) {
     cudaFree(t->trace);
     t->trace = nullptr;
+    if (t->ktrace) cudaFree(t->ktrace);
+    t->ktrace = nullptr;
   }
+  return 0;
+}
+
+/* Diagnostic: the pipeline kernels' time stamps since the last reset: out[(kernel * 1024 + block) * 8 + mark] = latest %globaltimer
+ * (ns) at which a warp of the block — or, for the role marks, a thread in that role — passed the mark; 0 = never.  kernel:
+ * 0 k_group, 1 k_rank, 2 k_eval, 3 k_finish. */
+int gub_get_ktrace(gub_table* t, uint64_t* out /* 4 x 1024 x 8 */, int reset) {
+  if (!t || !out) return fail("gub_get_ktrace: null argument");
+  std::lock_guard<std::mutex> lk(t->mu);
+  if (!t->ktrace) return fail("gub_get_ktrace: tracing is off");
+  CK(cudaSetDevice(t->device));
+  CK(cudaDeviceSynchronize());
+  const size_t bytes = (size_t)4 * gub::KT_BLOCKS * gub::KT_MARKS * 8;
+  CK(cudaMemcpy(out, t->ktrace, bytes, cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(t->ktrace, 0, bytes));
   return 0;
 }
 int gub_get_trace(gub_table* t, double* max_us /* 12 */, double* mean_us /* 12 */) {
@@ -1137,6 +1194,13 @@ struct gub_p2p {
   bool connected = false;
   uint32_t* error = nullptr;       // device flag: a bounded wait gave up (a peer died)
   uint32_t* ticket = nullptr;      // [2] tile ticket / tiles done of the routing kernel
+  // gub_p2p_step_streams: evaluation and collect run on streams of our own, so that neither the caller's stream nor the next step's
+  // evaluation ever queues behind a wait for the slowest peer
+  cudaStream_t s_eval = nullptr, s_collect = nullptr;
+  cudaEvent_t ev_fork = nullptr;   // scratch event for one-off stream-to-stream ordering
+  cudaStream_t last_ingest = nullptr;
+  bool own_streams_used = false;
+  uint32_t* seg_off = nullptr;     // [MAX_SHARDS + 1] prefix sums of this step's mailbox segments (k_seg_wait -> the batch kernels)
   // Routing scratch, preallocated (nothing is allocated or freed inside a step) and double-buffered by step parity: with a
   // separate ingest stream the routing of step e+1 runs while step e is still being evaluated and collected.
   struct Route {
@@ -1190,10 +1254,13 @@ void gub_p2p_destroy(gub_p2p* p) {
   cudaSetDevice(p->t->device);
   cudaDeviceSynchronize();
   for (uint32_t r = 0; r < p->world; r++) if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
-  void* ptrs[] = {p->block, p->error, p->ticket, p->g_reqs, p->g_resps, p->g_items, p->g_gather, p->g_count, p->g_counts_all};
+  void* ptrs[] = {p->block, p->error, p->ticket, p->seg_off, p->g_reqs, p->g_resps, p->g_items, p->g_gather, p->g_count, p->g_counts_all};
   for (void* q : ptrs) if (q) cudaFree(q);
   if (p->h_counts) cudaFreeHost(p->h_counts);
   if (p->phase_ev) cudaEventDestroy(p->phase_ev);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->s_eval) cudaStreamDestroy(p->s_eval);
+  if (p->s_collect) cudaStreamDestroy(p->s_collect);
   for (auto& r : p->rt) {
     void* rp[] = {r.tile_agg, r.counts, r.perm, r.true_owner};
     for (void* q : rp) if (q) cudaFree(q);
@@ -1215,6 +1282,16 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t c
     std::lock_guard<std::mutex> lk(t->mu);
     if (ensure_ring(t, ring)) return -1;  // upload the ring now: a step never allocates or synchronises the device
   }
+  if (!t->fused) {
+    // An owner evaluates what all `world` sources send it in a step: up to world x cap records, normally about cap.  Size the
+    // pipeline's scratch so that a step is one pass where it can be (<= 262 144 requests per pass; more passes beyond that).
+    const uint32_t want = (uint32_t)std::min<uint64_t>((uint64_t)world * cap, 262144u);
+    std::lock_guard<std::mutex> lk(t->mu);
+    if (t->max_batch < want) {
+      CK(cudaDeviceSynchronize());
+      if (alloc_scratch(t, want)) return -1;
+    }
+  }
   gub_p2p* p = new gub_p2p();
   p->t = t; p->ring = ring; p->world = world; p->rank = rank; p->cap = cap;
   p->block_bytes = p2p_req_bytes(world, cap) + p2p_resp_bytes(world, cap) + (size_t)4 * world * 8;
@@ -1224,6 +1301,11 @@ int gub_p2p_create(gub_table* t, const gub_ring* ring, uint32_t rank, uint32_t c
   if (e == cudaSuccess) e = cudaMemset(p->error, 0, 4);
   if (e == cudaSuccess) e = cudaMalloc(&p->ticket, 8);
   if (e == cudaSuccess) e = cudaMemset(p->ticket, 0, 8);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_eval, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_collect, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(&p->seg_off, (gub::MAX_SHARDS + 1) * 4);
+  if (e == cudaSuccess) e = cudaMemset(p->seg_off, 0, (gub::MAX_SHARDS + 1) * 4);
   const size_t agg = ((size_t)cap / gub::RT_THREADS + 1) * gub::MAX_SHARDS;
   for (auto& r : p->rt) {
     if (e == cudaSuccess) e = cudaMalloc(&r.tile_agg, agg * 8);
@@ -1326,8 +1408,38 @@ int p2p_route(gub_p2p* p, gub_p2p::Route* rt, const gub::P2PArgs& A, const gub_r
   return 0;
 }
 
+// The owner side of a step.  Default: the four-kernel pipeline reading the mailbox segments in place — k_seg_wait (one warp waits
+// for the sources' flags and writes the segment offsets), the batch kernels in ring mode (responses stored straight into the
+// sources' response mailboxes), k_seg_publish (response flags).  GUB_PATH=fused: one launch of the persistent kernel instead.
 int p2p_evaluate(gub_p2p* p, const gub::P2PArgs& A, const gub_clock* clk, cudaStream_t st) {
   gub_table* t = p->t;
+  if (!t->fused) {
+    const uint32_t par = p->epoch & 1u;
+    SegDesc sd;
+    sd.nseg = p->world; sd.seg_off = p->seg_off;
+    for (uint32_t s = 0; s < p->world; s++) {
+      sd.reqs[s] = A.peers[p->rank].req_mb + ((size_t)par * p->world + s) * p->cap;   // what source s stored into our mailbox
+      sd.out[s] = A.peers[s].resp_mb + ((size_t)par * p->world + p->rank) * p->cap;   // NVLink stores into source s's response mailbox
+    }
+    gub::k_seg_wait<<<1, 32, 0, st>>>(A, p->seg_off);
+    // GLOBAL requests evaluated here as owner go to the updates queue (gubernator.go:604-606, global.go:80-84).  The queue kernels
+    // read the request mailboxes, so they run BEFORE the response flags go out: once a source has its answers it may route the
+    // step after next into the same mailbox half.
+    if (p->updates_q && gq_accumulate_segments(p, A, st)) return -1;
+    const uint64_t total = (uint64_t)p->world * p->cap;
+    for (uint64_t off = 0; off < total; off += t->max_batch) {
+      const uint32_t m = (uint32_t)std::min<uint64_t>(t->max_batch, total - off);
+      if (launch_chunk(t, nullptr, m, clk, nullptr, st, p->seg_off + p->world, (uint32_t)off, &sd)) return -1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, gub::k_seg_publish, A));
+    return 0;
+  }
   gub::FArgs F;
   fused_base_args(t, clk, F);
   const uint32_t par = p->epoch & 1u;
@@ -1390,7 +1502,7 @@ int p2p_phase_evaluate(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
   if (order_after_last(t, st)) return -1;
   if (p2p_evaluate(p, A, clk, st)) return -1;
   t->last_stream = st; t->last_pending = true;
-  if (p->updates_q) {  // GLOBAL requests just evaluated as owner (gubernator.go:604-606, global.go:80-84)
+  if (p->updates_q && t->fused) {  // GLOBAL requests just evaluated as owner (gubernator.go:604-606, global.go:80-84); the pipeline path queues them itself
     if (gq_accumulate_segments(p, A, st)) return -1;
   }
   return 0;
@@ -1420,9 +1532,31 @@ extern "C" {
 int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream, void* stream) {
   if (p2p_step_check(p, d_reqs, n, clk, d_out)) return -1;
   cudaStream_t st = (cudaStream_t)stream, si = (cudaStream_t)ingest_stream;
-  if (p2p_phase_route(p, d_reqs, n, si, st)) return -1;
-  if (p2p_phase_evaluate(p, clk, st)) return -1;
-  return p2p_phase_collect(p, n, d_out, si, st);
+  // Default: routing on the ingest stream, evaluation and collect on `stream`.  GUB_RING_STREAMS=3 (experimental) moves the evaluation
+  // and the collect — which waits for the slowest owner — onto streams of the ring's own, so that step e+1 is evaluated while step e's
+  // answers travel; on 2 x B200 that variant ran the timed loop but stalled under the per-kernel profiling events (profiles/README.md).
+  static const int own_streams = [] { const char* e = getenv("GUB_RING_STREAMS"); return e ? std::atoi(e) : 2; }();
+  if (si != st && own_streams < 3) {
+    if (p2p_phase_route(p, d_reqs, n, si, st)) return -1;
+    if (p2p_phase_evaluate(p, clk, st)) return -1;
+    return p2p_phase_collect(p, n, d_out, si, st);
+  }
+  if (si == st) {  // one stream: the three phases in stream order
+    if (p2p_phase_route(p, d_reqs, n, si, st)) return -1;
+    if (p2p_phase_evaluate(p, clk, st)) return -1;
+    return p2p_phase_collect(p, n, d_out, si, st);
+  }
+  // Two caller streams: routing on the ingest stream; the owner-side evaluation on our own evaluation stream (it synchronises with
+  // the peers through the mailbox flags, not through the caller's streams); the collect — which waits for the slowest owner — on our
+  // collect stream; `stream` then waits for the collect only.  Step e+1 is routed and evaluated while step e's answers travel.
+  if (p2p_phase_route(p, d_reqs, n, si, p->s_collect)) return -1;
+  if (p2p_phase_evaluate(p, clk, p->s_eval)) return -1;
+  CK(cudaEventRecord(p->ev_fork, st));                 // d_out is ours to write once everything queued on `stream` so far is done
+  CK(cudaStreamWaitEvent(p->s_collect, p->ev_fork, 0));
+  if (p2p_phase_collect(p, n, d_out, si, p->s_collect)) return -1;
+  CK(cudaStreamWaitEvent(st, p->rt[p->epoch & 1u].step_done, 0));
+  p->last_ingest = si; p->own_streams_used = true;
+  return 0;
 }
 
 }  // extern "C"
@@ -1623,6 +1757,14 @@ int tick_phase_a(gub_p2p* p, cudaStream_t st) {
   gub_table* t = p->t;
   std::lock_guard<std::mutex> lk(t->mu);
   CK(cudaSetDevice(t->device));
+  if (p->own_streams_used) {  // the steps' queue updates and evaluations ran on other streams: the tick comes after all of them
+    cudaStream_t others[3] = {p->last_ingest, p->s_eval, p->s_collect};
+    for (cudaStream_t o : others) {
+      if (o == st) continue;
+      CK(cudaEventRecord(p->ev_fork, o));
+      CK(cudaStreamWaitEvent(st, p->ev_fork, 0));
+    }
+  }
   CK(cudaMemsetAsync(p->g_count, 0, 16, st));
   gub::k_gq_drain<<<148, 256, 0, st>>>(p->hits_q->q, p->g_reqs, p->gcap, p->g_count + 0, 0u);
   p->epoch++;
@@ -1642,7 +1784,7 @@ int tick_phase_b(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
   if (order_after_last(t, st)) return -1;
   if (p2p_evaluate(p, A, clk, st)) return -1;
   t->last_stream = st; t->last_pending = true;
-  if (gq_accumulate_segments(p, A, st)) return -1;
+  if (t->fused && gq_accumulate_segments(p, A, st)) return -1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -1662,10 +1804,7 @@ int tick_phase_c(gub_p2p* p, const gub_clock* clk, cudaStream_t st) {
     p->seq += (uint64_t)1 << 32;
   }
   gub::k_gq_drain<<<148, 256, 0, st>>>(p->updates_q->q, p->g_reqs, p->gcap, p->g_count + 1, 1u);
-  gub::FArgs F;
-  fused_base_args(t, clk, F);
-  F.seg[0].reqs = p->g_reqs; F.seg[0].out = p->g_resps; F.seg[0].n = p->gcap; F.seg[0].n_dev = p->g_count + 1; F.nseg = 1;
-  if (launch_fused(t, F, 0, st)) return -1;
+  if (launch_batch(t, p->g_reqs, p->gcap, clk, p->g_resps, st, p->g_count + 1)) return -1;  // (either kernel path; the count lives on the device)
   gub::k_make_updates<<<(p->gcap + 255) / 256, 256, 0, st>>>(p->g_reqs, p->g_resps, p->gcap, p->g_count + 1, p->g_items, p->g_count + 2);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(p->h_counts, p->g_count, 16, cudaMemcpyDeviceToHost, st));

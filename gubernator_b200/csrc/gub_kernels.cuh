@@ -48,6 +48,7 @@ constexpr int GROUP_THREADS = 256;   // requests per block in k_group / k_rank (
 constexpr int GROUP_SLOTS = 512;     // shared-memory table entries per block (load factor <= 0.5)
 constexpr int MIXED_THREADS = 256;
 constexpr int MAX_PIECES = 16;
+constexpr int MAX_SHARDS = 16;       // GPUs of one ring (= most mailbox segments a batch is made of)
 
 struct __align__(64) Slot { uint64_t w[8]; };
 
@@ -100,8 +101,19 @@ struct BatchArgs {
   OvfItem* ovf;            // [OVF_CAP] parked inserts
   uint32_t* ovf_count;
   InvIndex inv;            // CacheItem.InvalidAt side index
+  // Ring mode (gub_p2p): the batch is the concatenation, in source order, of `nseg` mailbox segments filled by the ring's shards over
+  // NVLink; request g of the batch is seg_reqs[s][g - seg_off[s]] and its response goes to seg_out[s][g - seg_off[s]] (the source's
+  // response mailbox: peer memory).  seg_off (device, nseg + 1 prefix sums) is written by k_seg_wait once every source's flag has
+  // arrived; n_dev points at seg_off[nseg].  nseg == 0: one dense array (reqs / out).
+  uint32_t nseg;
+  const uint32_t* seg_off;
+  const gub_req* seg_reqs[MAX_SHARDS];
+  gub_resp* seg_out[MAX_SHARDS];
+  unsigned long long* ktrace;  // optional (diagnostic, gub_set_trace): [4 kernels][KT_BLOCKS][KT_MARKS] latest %globaltimer at which a warp / a thread in a role passed a mark
   gub_clock clk;
 };
+constexpr int KT_MARKS = 8, KT_BLOCKS = 1024;
+enum { KT_ENTRY = 0, KT_WAITED, KT_M2, KT_M3, KT_M4, KT_M5, KT_WORK_DONE, KT_EXIT };
 
 __device__ __forceinline__ uint64_t remap_key(uint64_t k) { return k < 2 ? k + 2 : k; }
 
@@ -128,6 +140,21 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #endif
 
 
+// Diagnostic time stamps (see BatchArgs::ktrace).  `dep`: a value the stamp must wait for (a load's result).  all = every calling thread
+// stamps (marks inside divergent role code), else lane 0 of each warp.
+#if defined(GUB_EMULATE)
+#define KT(A, kernel, mark, dep, all) do { } while (0)
+#else
+__device__ __forceinline__ void kt_stamp(unsigned long long* ktrace, int kernel, int mark, uint32_t dep, bool all) {
+  if (ktrace && (all || (threadIdx.x & 31) == 0) && blockIdx.x < 1024u) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : "r"(dep) : "memory");
+    atomicMax(&ktrace[((size_t)kernel * 1024u + blockIdx.x) * 8u + (uint32_t)mark], t);
+  }
+}
+#define KT(A, kernel, mark, dep, all) kt_stamp((A).ktrace, kernel, mark, (uint32_t)(dep), all)
+#endif
+
 // system-scope release / acquire on flags other GPUs (or the host) poll
 #if defined(GUB_EMULATE)
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { *p = v; }
@@ -149,6 +176,24 @@ __device__ __forceinline__ void slot_load(const Slot* s, ulonglong2& a, ulonglon
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s);
   a = __ldcg(p); b = __ldcg(p + 1); c = __ldcg(p + 2); d = __ldcg(p + 3);  // 4 x 128-bit, L2-only (no reuse in L1)
 }
+// A 16-byte L2 load the compiler may neither drop nor sink towards its first use: k_rank / k_eval issue every role's first loads before
+// any role waits for one (inside divergent role code the waits of different roles would otherwise add up instead of overlapping).
+#if defined(GUB_EMULATE)
+__device__ __forceinline__ ulonglong2 ldcg_pinned(const ulonglong2* p) { return *p; }
+__device__ __forceinline__ uint4 ldcg_pinned(const uint4* p) { return *p; }
+#else
+__device__ __forceinline__ ulonglong2 ldcg_pinned(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldcg_pinned(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+#endif
+
 __device__ __forceinline__ void bucket_from(Bucket& bk, const ulonglong2& a, const ulonglong2& b, const ulonglong2& c, const ulonglong2& d) {
   bk.key = a.x; bk.tag = a.y >> 8; bk.flags = (uint32_t)(a.y & 0xFF);
   bk.limit = (int64_t)b.x; bk.duration = (int64_t)b.y; bk.rem = c.x; bk.stamp = (int64_t)c.y;
@@ -197,13 +242,14 @@ __device__ __forceinline__ void apply_invalid_at(const InvIndex& I, Bucket& b, b
 
 // Looks `key` up.  On a hit the slot is loaded into cur.b.  On a miss cur.b is an empty (not live) bucket and cur.slot
 // is the first reusable slot (tombstone or empty) seen, if any.
-__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag) {
+// (The home slot's four words arrive in a..d: callers that know the key early issue that load ahead of other work.)
+__device__ __forceinline__ void cursor_open_preloaded(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag, ulonglong2 a, ulonglong2 b,
+                                                      ulonglong2 c, ulonglong2 d) {
   uint64_t idx = __umul64hi(key, cap);
   cur.home = idx; cur.found = false; cur.slot = -1;
 #pragma unroll 1
   for (int p = 0; p < MAX_PROBE; p++) {
-    ulonglong2 a, b, c, d;
-    slot_load(table + idx, a, b, c, d);
+    if (p > 0) slot_load(table + idx, a, b, c, d);
     if (a.x == key && (a.y >> 8) == tag) {
       bucket_from(cur.b, a, b, c, d);
       cur.old = cur.b; cur.slot = (int64_t)idx; cur.found = true;
@@ -216,6 +262,11 @@ __device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint
   cur.b.key = key; cur.b.tag = tag; cur.b.flags = 0; cur.b.limit = 0; cur.b.duration = 0; cur.b.rem = 0; cur.b.stamp = 0;
   cur.b.burst = 0; cur.b.expire = 0;
   cur.old = cur.b;
+}
+__device__ __forceinline__ void cursor_open(Cursor& cur, const Slot* table, uint64_t cap, uint64_t key, uint64_t tag) {
+  ulonglong2 a, b, c, d;
+  slot_load(table + __umul64hi(key, cap), a, b, c, d);
+  cursor_open_preloaded(cur, table, cap, key, tag, a, b, c, d);
 }
 
 // Writes cur.b back.  Returns false when a new key needed a slot and the probe window had none (table full).
@@ -267,8 +318,14 @@ __device__ __forceinline__ void snap_store(ulonglong2* sp, const Cursor& c, uint
   __stcg(sp + 4, make_ulonglong2((uint64_t)c.b.flags | ((uint64_t)(c.found ? 1u : 0u) << 32), (uint64_t)c.slot));
   __stcg(sp + 5, make_ulonglong2(c.home, (uint64_t)who));
 }
+__device__ __forceinline__ uint32_t snap_unpack(const ulonglong2& a, const ulonglong2& b, const ulonglong2& d, const ulonglong2& e, const ulonglong2& f,
+                                                const ulonglong2& g, Cursor& c);
 __device__ __forceinline__ uint32_t snap_load(const ulonglong2* sp, Cursor& c) {
   const ulonglong2 a = __ldcg(sp + 0), b = __ldcg(sp + 1), d = __ldcg(sp + 2), e = __ldcg(sp + 3), f = __ldcg(sp + 4), g = __ldcg(sp + 5);
+  return snap_unpack(a, b, d, e, f, g, c);
+}
+__device__ __forceinline__ uint32_t snap_unpack(const ulonglong2& a, const ulonglong2& b, const ulonglong2& d, const ulonglong2& e, const ulonglong2& f,
+                                                const ulonglong2& g, Cursor& c) {
   c.b.key = a.x; c.b.tag = a.y; c.b.limit = (int64_t)b.x; c.b.duration = (int64_t)b.y; c.b.rem = d.x; c.b.stamp = (int64_t)d.y;
   c.b.burst = (int64_t)e.x; c.b.expire = (int64_t)e.y; c.b.flags = (uint32_t)(f.x & 0xFFFFFFFFull); c.found = (f.x >> 32) != 0;
   c.slot = (int64_t)f.y; c.home = g.x; c.old = c.b;
@@ -349,6 +406,59 @@ __device__ __forceinline__ void store_resp(gub_resp* p, const gub_resp& r) {
   __stcs(q + 1, make_ulonglong2((uint64_t)r.remaining, (uint64_t)r.reset_time));
 }
 
+__device__ __forceinline__ gub_req load_req_cg(const gub_req* p) {  // records other GPUs stored into this GPU's memory: L2 is the point of coherence
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+  ulonglong2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), d = __ldcg(q + 3);
+  gub_req r;
+  r.key_xxh64 = a.x; r.key_fnv1 = a.y; r.hits = (int64_t)b.x; r.limit = (int64_t)b.y; r.duration = (int64_t)c.x;
+  r.burst = (int64_t)c.y; r.created_at = (int64_t)d.x; r.algorithm = (uint32_t)(d.y & 0xFFFFFFFFull); r.behavior = (uint32_t)(d.y >> 32);
+  return r;
+}
+
+// Where request i of this launch lives and where its response goes.  SEG = false: the dense arrays of BatchArgs.  SEG = true (ring
+// mode): the batch is a concatenation of mailbox segments; the segment table sits in shared memory (io_open).
+struct SegShared { const gub_req* req[MAX_SHARDS]; gub_resp* out[MAX_SHARDS]; uint32_t off[MAX_SHARDS + 1]; uint32_t nseg; };
+template <bool SEG>
+struct Io {
+  const BatchArgs& A;
+  const SegShared* S;
+  __device__ __forceinline__ uint32_t seg_of(uint32_t g) const { uint32_t s = 0; while (s + 1 < S->nseg && g >= S->off[s + 1]) s++; return s; }
+  __device__ __forceinline__ const gub_req* req(uint32_t i) const {
+    if constexpr (!SEG) { return A.reqs + i; }
+    else { const uint32_t g = A.n_off + i, s = seg_of(g); return S->req[s] + (g - S->off[s]); }
+  }
+  __device__ __forceinline__ gub_resp* resp(uint32_t i) const {
+    if constexpr (!SEG) { return A.out + i; }
+    else { const uint32_t g = A.n_off + i, s = seg_of(g); return S->out[s] + (g - S->off[s]); }
+  }
+  __device__ __forceinline__ gub_req load(uint32_t i) const {
+    if constexpr (!SEG) return load_req(A.reqs + i); else return load_req_cg(req(i));
+  }
+  __device__ __forceinline__ uint64_t key(uint32_t i) const {
+    if constexpr (!SEG) return __ldg(&A.reqs[i].key_xxh64); else return __ldcg(&req(i)->key_xxh64);
+  }
+  __device__ __forceinline__ uint32_t algorithm(uint32_t i) const {
+    if constexpr (!SEG) return __ldg(&A.reqs[i].algorithm); else return __ldcg(&req(i)->algorithm);
+  }
+};
+// Block-wide (SEG: fills the shared segment table and contains a barrier; seg_off must be final, i.e. k_seg_wait has completed).
+template <bool SEG>
+__device__ __forceinline__ Io<SEG> io_open(const BatchArgs& A) {
+  if constexpr (SEG) {
+    __shared__ SegShared s_seg;
+#pragma unroll
+    for (int k = 0; k < MAX_SHARDS; k++) {  // static indices: a dynamic index into the kernel parameters would copy them to local memory
+      if (threadIdx.x == (uint32_t)k && (uint32_t)k < A.nseg) { s_seg.req[k] = A.seg_reqs[k]; s_seg.out[k] = A.seg_out[k]; }
+    }
+    if (threadIdx.x <= A.nseg) s_seg.off[threadIdx.x] = __ldcg(A.seg_off + threadIdx.x);
+    if (threadIdx.x == 0) s_seg.nseg = A.nseg;
+    __syncthreads();
+    return Io<SEG>{A, &s_seg};
+  } else {
+    return Io<SEG>{A, nullptr};
+  }
+}
+
 // Counter deltas are summed per block in shared memory first: a grid-wide atomicAdd per warp on five fixed addresses
 // serialises in L2 and costs more than the probes themselves.
 __device__ __forceinline__ void tally_flush_block(const Tally& t, unsigned long long* counters) {
@@ -378,34 +488,6 @@ __device__ __forceinline__ void open_slot(const BatchArgs& A, Cursor& cur, uint6
   apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
 }
 __device__ __forceinline__ void close_slot(const BatchArgs& A, Cursor& cur, Tally& t) { close_or_park(cur, A.table, A.capacity, A.ovf, A.ovf_count, t); }
-
-// Applies the requests reqs[idx[0..cnt)] (ascending batch order) one after another, keeping the current key's slot in
-// registers and switching slots only when the key changes (it never does unless two keys collide on the 24-bit group tag).
-template <typename IdxFn>
-__device__ __forceinline__ void serial_walk(const BatchArgs& A, uint32_t cnt, IdxFn idx_of, Tally& t) {
-  Cursor cur;
-  bool open = false;
-  uint64_t ck = 0, ct = 0;
-  uint32_t i_next = idx_of(0);
-  gub_req rq_next = load_req(A.reqs + i_next);
-#pragma unroll 1
-  for (uint32_t j = 0; j < cnt; j++) {
-    const uint32_t i = i_next;
-    const gub_req rq = rq_next;
-    if (j + 1 < cnt) { i_next = idx_of(j + 1); rq_next = load_req(A.reqs + i_next); }  // overlap the next request's load with this update
-    const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
-    if (!open || key != ck || tag != ct) {
-      if (open) close_slot(A, cur, t);
-      open_slot(A, cur, key, tag);
-      open = true; ck = key; ct = tag;
-    }
-    Delta d = {0, 0, 0};
-    const gub_resp r = apply_one(cur.b, rq, A.clk, d);
-    t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-    store_resp(A.out + i, r);
-  }
-  if (open) close_slot(A, cur, t);
-}
 
 // ---- kernel 1: group the batch by key, rank members inside each block --------------------------------------------
 // Joins `c` members to the batch-wide group of `key`; returns the entry position.  *claimed = this call created the entry.
@@ -466,6 +548,7 @@ __device__ void merge_colliding_fragments(const BatchArgs& A, const uint32_t* s_
   if (valid && s_tlocal[threadIdx.x] != 0xFFFFu) { local = s_tlocal[threadIdx.x]; sp = s_tsp[threadIdx.x]; }
 }
 
+template <bool SEG>
 __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   __shared__ unsigned long long s_key[GROUP_SLOTS];
   __shared__ uint32_t s_cnt[GROUP_SLOTS];  // members of the key in this block
@@ -476,11 +559,15 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   // warp turns with a barrier each: 31.7 vs 40.5 us per 65 536-request step, profiles/r02_ab_round1_switches.json.)
   __shared__ __align__(16) uint8_t s_wcnt[GROUP_SLOTS][GROUP_THREADS / 32];
   static_assert(sizeof(s_wcnt) == GROUP_THREADS * sizeof(uint4), "one 16-byte store per thread clears it");
-  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
+  __shared__ uint32_t s_seen[GROUP_SLOTS];  // group entries joined by this block's fragments (entry + 1): two fragments in one entry = a conflict
+  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; s_seen[k] = 0u; }
   if (threadIdx.x == 0) s_conflict = 0u;
   reinterpret_cast<uint4*>(&s_wcnt[0][0])[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+  KT(A, 0, KT_ENTRY, 0, false);
   pdl_wait();
   pdl_release();
+  KT(A, 0, KT_WAITED, 0, false);
+  const Io<SEG> io = io_open<SEG>(A);
   __syncthreads();
   // Inserts a previous batch could not place (probe window full) are placed now, with eviction: this kernel never reads the table
   // and the previous batch is complete, so nothing can observe a half-moved entry.
@@ -498,7 +585,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   uint64_t key = 0;
   unsigned long long first = 0;
   if (valid) {
-    key = remap_key(__ldg(&A.reqs[i].key_xxh64));  // never 0
+    key = remap_key(io.key(i));  // never 0
     first = __ldcg(&A.aux[aux_home(A, key)].word);  // consumed much later, by the fragment's first member only
     prefetch_l2(A.table + __umul64hi(key, A.capacity));  // the slot k_rank / k_eval will probe
     sp = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 55);  // top 9 bits -> GROUP_SLOTS
@@ -509,6 +596,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
       sp = (sp + 1) & (GROUP_SLOTS - 1);
     }
   }
+  KT(A, 0, KT_M2, sp, false);  // keys loaded and entered into the block's table
   __syncthreads();
   uint32_t local = 0;
   {
@@ -525,6 +613,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
       if (local == 0) s_cnt[sp] = total;
     }
     __syncthreads();
+    KT(A, 0, KT_M3, local, false);  // local ranks known
   }
   // the first member of each fragment joins the batch-wide group
   if (valid && local == 0) {
@@ -532,18 +621,28 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     bool claimed;
     const uint32_t pos = aux_join(A, key, c, first, &claimed);
     if (claimed) { A.aux[pos].rep = i; A.aux[pos].flags = 0; }
-    const uint32_t bit = 1u << (blockIdx.x & 31);
-    const uint32_t was = atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], bit);
+    // the block's presence bit: nobody waits for this atomic (its old value is not needed: conflicts are found in shared memory)
+    atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
     A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(c - 1);
     s_pos[sp] = pos;
-    if (was & bit) s_conflict = 1u;  // the bitmap is clean between batches: another fragment of this block is in this entry already
+    uint32_t h = (pos * 2654435761u) >> 23;  // 9 bits
+#pragma unroll 1
+    for (;;) {
+      const uint32_t old = atomicCAS(&s_seen[h], 0u, pos + 1u);
+      if (old == 0u) break;
+      if (old == pos + 1u) { s_conflict = 1u; break; }  // another fragment of this block is in this entry already
+      h = (h + 1u) & (GROUP_SLOTS - 1);
+    }
+    KT(A, 0, KT_M4, pos, true);  // a fragment has joined its group
   }
+  KT(A, 0, KT_WORK_DONE, 0, false);
   __syncthreads();
   if (s_conflict) merge_colliding_fragments(A, s_pos, valid, sp, local);  // block-uniform, next to never taken
   if (valid) {
     A.ent[i] = s_pos[sp];
     A.meta[i] = (sp << 16) | local;
   }
+  KT(A, 0, KT_EXIT, 0, false);
 }
 
 // ---- kernel 2: singletons are evaluated; members of repeated keys get their rank and check uniformity ------------
@@ -572,42 +671,55 @@ __device__ __forceinline__ uint32_t masked_sum32(const uint4& lo, const uint4& h
   return acc;
 }
 
+// pres_words == 8 (a batch of up to 65 536 requests): p0 / p1 = the group's eight presence words, loaded by the caller
+__device__ __forceinline__ uint32_t fragment_base8(const BatchArgs& A, uint32_t pos, uint32_t b, const uint4& p0, const uint4& p1) {
+  const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
+  const uint32_t last = b >> 5, keep = (1u << (b & 31)) - 1u;
+  uint32_t base = 0;
+  uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+  uint32_t any = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) { bits[w] = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u); any += __popc(bits[w]); }
+  if (any == 0) return 0;
+  if (any <= 2) {  // the common case: a couple of earlier fragments
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      uint32_t x = bits[w];
+      while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
+    }
+    return base;
+  }
+  uint4 lo[8], hi[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    if (bits[w]) { lo[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
+  }
+#pragma unroll
+  for (int w = 0; w < 8; w++) if (bits[w]) base += masked_sum32(lo[w], hi[w], bits[w]);
+  return base;
+}
+
 __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t pos, uint32_t b) {
   const uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
   const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
   const uint32_t last = b >> 5, keep = (1u << (b & 31)) - 1u;
   uint32_t base = 0;
-  if (A.pres_words == 8) {  // max_batch = 65536
-    const uint4 p0 = __ldcg(reinterpret_cast<const uint4*>(pres)), p1 = __ldcg(reinterpret_cast<const uint4*>(pres) + 1);
-    uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    uint32_t any = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) { bits[w] = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u); any += __popc(bits[w]); }
-    if (any == 0) return 0;
-    if (any <= 2) {  // the common case: a couple of earlier fragments
-#pragma unroll
-      for (int w = 0; w < 8; w++) {
-        uint32_t x = bits[w];
-        while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
-      }
-      return base;
-    }
-    uint4 lo[8], hi[8];
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      if (bits[w]) { lo[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
-    }
-#pragma unroll
-    for (int w = 0; w < 8; w++) if (bits[w]) base += masked_sum32(lo[w], hi[w], bits[w]);
-    return base;
-  }
+  // other batch sizes (rings evaluate up to 262 144 requests = 1024 blocks per launch): four bitmap words per round trip
+  // (pres_words is a multiple of 4: gub_create)
+  const uint32_t nq = (last >> 2) + 1;
 #pragma unroll 1
-  for (uint32_t w = 0; w <= last; w++) {
-    uint32_t bits = __ldcg(pres + w);
-    if (w == last) bits &= keep;
-    if (!bits) continue;
-    const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)), hi = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16));
-    base += masked_sum32(lo, hi, bits);
+  for (uint32_t q = 0; q < nq; q++) {
+    const uint4 pv = __ldcg(reinterpret_cast<const uint4*>(pres) + q);
+    uint32_t bits[4] = {pv.x, pv.y, pv.z, pv.w};
+    uint4 lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t w = q * 4 + (uint32_t)k;
+      bits[k] = w < last ? bits[k] : (w == last ? (bits[k] & keep) : 0u);
+      if (bits[k]) { lo[k] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[k] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (bits[k]) base += masked_sum32(lo[k], hi[k], bits[k]);
   }
   return base;
 }
@@ -615,13 +727,14 @@ __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t p
 // Which request each thread of a 256-thread block evaluates: the block's token-bucket requests first, then its leaky-bucket
 // ones (stable), so that all but one warp run a single algorithm's code path instead of both.  Only reads the 4-byte
 // algorithm field, so it can run in the prologue ahead of pdl_wait().
-__device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, uint32_t n) {
+template <bool SEG>
+__device__ __forceinline__ uint32_t partition_by_algorithm(const Io<SEG>& io, uint32_t n) {
   __shared__ uint16_t s_perm[GROUP_THREADS];
   __shared__ uint32_t s_cnt3[GROUP_THREADS / 32][3];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t i = blockIdx.x * GROUP_THREADS + tid;
   uint32_t cls = 2;
-  if (i < n) { const uint32_t a = __ldg(&reqs[i].algorithm); cls = a < 2u ? a : 2u; }
+  if (i < n) { const uint32_t a = io.algorithm(i); cls = a < 2u ? a : 2u; }
   const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1), b2 = ~(b0 | b1);
   if (lane == 0) { s_cnt3[warp][0] = __popc(b0); s_cnt3[warp][1] = __popc(b1); s_cnt3[warp][2] = __popc(b2); }
   __syncthreads();
@@ -641,97 +754,134 @@ __device__ __forceinline__ uint32_t partition_by_algorithm(const gub_req* reqs, 
 
 // (Register budget: 2 resident blocks per SM, ~123 registers.  Capping at 80 / 64 registers for 3 / 4 blocks spills and is slower:
 // 37.3 / 39.8 vs 33.0 us per step, profiles/r02_call9_bench_mb{3,4}.json.)
+template <bool SEG>
 __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
+  const Io<SEG> io = io_open<SEG>(A);  // (ring mode: the segment table was final before k_group started)
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
-  const uint32_t i = partition_by_algorithm(A.reqs, n);
+  const uint32_t i = partition_by_algorithm(io, n);
   Tally t = {0, 0, 0, 0, 0};
   const bool valid = i < n;
   gub_req rq;
-  if (valid) rq = load_req(A.reqs + i);  // the records were complete before k_group started: safe ahead of the wait
+  if (valid) rq = io.load(i);  // the records were complete before k_group started: safe ahead of the wait
+  KT(A, 1, KT_ENTRY, (uint32_t)rq.hits, false);  // (request in registers)
   pdl_wait();
   pdl_release();
+  KT(A, 1, KT_WAITED, 0, false);
   if (blockIdx.x == 0 && threadIdx.x == 0) {  // reset the other parity's allocator for the next batch (nobody is using it now)
     BatchCtr* nxt = A.ctr + ((A.epoch + 1) & 1);
     nxt->n_mixed = 0; nxt->order_bump = 0; nxt->next_mixed = 0;
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
-  uint32_t pos = 0, cnt = 0, sp = 0, local = 0;
+  // Roles: `single` (a key seen once — most keys) is evaluated right here; `leader` (first member of a repeated key's fragment in this
+  // block) computes the fragment's base rank, and the leader holding rank 0 parks the slot as found for its siblings; every member
+  // of a repeated key compares itself with the group's representative.  A warp holds all roles at once, and inside divergent role
+  // code the memory waits of different roles add up — so every role's first loads are ISSUED here, before any role consumes one.
+  uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
+  uint64_t key = 0;
   if (valid) {
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
-    const uint64_t key = remap_key(rq.key_xxh64);
+    key = remap_key(rq.key_xxh64);
     sp = m >> 16; local = m & 0xFFFFu;
     cnt = aux_count(e.x);
-    const uint32_t rep = (uint32_t)(e.y & 0xFFFFFFFFull);
-    if (cnt > 1) {
-      // uniformity does not need the rank: start the representative's load before anything that waits
-      bool mixed = !req_regular(rq);
-      gub_req rr;
-      const bool cmp = !mixed && i != rep;
-      if (cmp) rr = load_req(A.reqs + rep);
-      if (local == 0) {
-        const uint32_t base = fragment_base(A, pos, blockIdx.x);
-        s_base[sp] = base;
-        if (base == 0) {  // rank 0 of the run: look the key up once for everybody
-          Cursor cur;
-          open_slot(A, cur, key, rq.key_fnv1 >> 8);
-          snap_store(A.commit + (size_t)pos * 6, cur, i);
-        }
-      }
-      if (cmp) mixed = !req_same(rq, rr);
-      if (mixed) {
-        const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
-        if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
-          BatchCtr* ctr = A.ctr + (A.epoch & 1);
-          A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
-          A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
-        }
-      }
-    } else if (cnt == 1) {  // a key seen once — most keys: evaluated right here (its slot was prefetched into L2 by k_group)
-      A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+    rep = (uint32_t)(e.y & 0xFFFFFFFFull);
+  }
+  KT(A, 1, KT_M2, cnt, false);  // group entries read
+  const bool single = valid && cnt == 1, member = valid && cnt > 1, leader = member && local == 0;
+  bool mixed = member && !req_regular(rq);
+  const bool cmp = member && !mixed && i != rep;
+  const bool fast_base = A.pres_words == 8;
+  ulonglong2 h0, h1, h2, h3;  // the home slot: singles, and leaders in case they turn out to hold rank 0 (prefetched into L2 by k_group)
+  uint4 p0, p1;               // leaders: the group's presence bitmap
+  gub_req rr;                 // members: the representative
+  if (single || leader) {
+    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(A.table + __umul64hi(key, A.capacity));
+    h0 = ldcg_pinned(hp); h1 = ldcg_pinned(hp + 1); h2 = ldcg_pinned(hp + 2); h3 = ldcg_pinned(hp + 3);
+  }
+  if (leader && fast_base) {
+    const uint4* pp = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * 8u);
+    p0 = ldcg_pinned(pp); p1 = ldcg_pinned(pp + 1);
+  }
+  if (cmp) rr = io.load(rep);
+  // ---- consume
+  if (single) {
+    A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
+    Cursor cur;
+    cursor_open_preloaded(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, h0, h1, h2, h3);
+    apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
+    Delta d = {0, 0, 0};
+    const gub_resp r = apply_one(cur.b, rq, A.clk, d);
+    close_slot(A, cur, t);
+    t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+    store_resp(io.resp(i), r);
+    KT(A, 1, KT_M5, r.status, true);  // a key seen once answered
+  }
+  if (leader) {
+    const uint32_t base = fast_base ? fragment_base8(A, pos, blockIdx.x, p0, p1) : fragment_base(A, pos, blockIdx.x);
+    s_base[sp] = base;
+    KT(A, 1, KT_M3, base, true);  // a fragment's base rank
+    if (base == 0) {  // rank 0 of the run: the slot as found, for everybody
       Cursor cur;
-      open_slot(A, cur, key, rq.key_fnv1 >> 8);
-      Delta d = {0, 0, 0};
-      const gub_resp r = apply_one(cur.b, rq, A.clk, d);
-      close_slot(A, cur, t);
-      t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-      store_resp(A.out + i, r);
+      cursor_open_preloaded(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, h0, h1, h2, h3);
+      apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
+      snap_store(A.commit + (size_t)pos * 6, cur, i);
+      KT(A, 1, KT_M4, (uint32_t)cur.b.flags, true);  // a run's snapshot stored
     }
   }
+  if (cmp) mixed = !req_same(rq, rr);
+  if (mixed) {
+    const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
+    if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
+      BatchCtr* ctr = A.ctr + (A.epoch & 1);
+      A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
+      A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
+    }
+  }
+  KT(A, 1, KT_WORK_DONE, 0, false);
   __syncthreads();
-  if (valid && cnt > 1) A.rank[i] = s_base[sp] + local;
+  if (valid) A.rank[i] = cnt > 1 ? s_base[sp] + local : 0xFFFFFFFFu;  // (0xFFFFFFFF: not a member of a repeated key — k_eval has nothing to do)
   tally_flush_block(t, A.counters);
+  KT(A, 1, KT_EXIT, 0, false);
 }
 
 // ---- kernel 3: every request of a uniform run evaluates its own rank ------------------------------------------------
+template <bool SEG>
 __global__ void __launch_bounds__(GROUP_THREADS, 2) k_eval(const BatchArgs A) {
+  const Io<SEG> io = io_open<SEG>(A);
   const uint32_t n = batch_n(A);
-  const uint32_t i = partition_by_algorithm(A.reqs, n);
+  const uint32_t i = partition_by_algorithm(io, n);
   Tally t = {0, 0, 0, 0, 0};
   uint32_t dup = 0;
   gub_req rq;
-  if (i < n) rq = load_req(A.reqs + i);  // safe ahead of the wait (see k_rank)
+  if (i < n) rq = io.load(i);  // safe ahead of the wait (see k_rank)
+  KT(A, 2, KT_ENTRY, (uint32_t)rq.hits, false);
   pdl_wait();
   pdl_release();
-  if (i < n) {
+  KT(A, 2, KT_WAITED, 0, false);
+  const uint32_t rank = i < n ? A.rank[i] : 0xFFFFFFFFu;
+  if (rank != 0xFFFFFFFFu) {  // a member of a repeated key (k_rank answered the others)
     const uint32_t pos = A.ent[i];
-    const uint32_t rank = A.rank[i];             // garbage for keys seen once: not used
     const AuxEntry* e = &A.aux[pos];
-    const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
+    // the group entry and the run's snapshot depend on `pos` only: one round trip for both
+    const ulonglong2* sp = A.commit + (size_t)pos * 6;
+    const ulonglong2 ev = ldcg_pinned(reinterpret_cast<const ulonglong2*>(e));
+    const ulonglong2 s0 = ldcg_pinned(sp), s1 = ldcg_pinned(sp + 1), s2 = ldcg_pinned(sp + 2), s3 = ldcg_pinned(sp + 3), s4 = ldcg_pinned(sp + 4),
+                     s5 = ldcg_pinned(sp + 5);  // the slot as k_rank found it (the last rank may already be writing the table)
     const uint32_t cnt = aux_count(ev.x);
-    const bool mixed = cnt > 1 && ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
-    if (cnt > 1 && rank == 0) {  // hand the presence bitmap back clean
+    KT(A, 2, KT_M2, cnt, true);  // group entry read
+    const bool mixed = ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
+    if (rank == 0) {  // hand the presence bitmap back clean
       uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
       for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
     }
     if (mixed) {
       A.order[__ldcg(&e->gbase) + rank] = i;
-    } else if (cnt > 1) {
+    } else {
       Cursor cur;
-      snap_load(A.commit + (size_t)pos * 6, cur);  // the slot as k_rank found it (the last rank may already be writing the table)
+      snap_unpack(s0, s1, s2, s3, s4, s5, cur);
       Delta d = {0, 0, 0};
       const gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
       if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
@@ -739,12 +889,15 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_eval(const BatchArgs A) {
         close_slot(A, cur, t);
         dup = 1;
       }
-      store_resp(A.out + i, r);
+      store_resp(io.resp(i), r);
+      KT(A, 2, KT_M3, r.status, true);  // a member of a uniform run answered
     }
   }
+  KT(A, 2, KT_WORK_DONE, 0, false);
   dup = __reduce_add_sync(0xFFFFFFFFu, dup);
   if ((threadIdx.x & 31) == 0 && dup) atomicAdd(A.counters + C_DUP_GROUPS, (unsigned long long)dup);
   tally_flush_block(t, A.counters);
+  KT(A, 2, KT_EXIT, 0, false);
 }
 
 // ---- kernel 4: runs whose requests differ ---------------------------------------------------------------------------
@@ -764,53 +917,67 @@ struct MixedShared {
   Bucket state[MIXED_SEGS];         // bucket entering the segment
 };
 
-__device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Tally& t) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t total = aux_count(__ldcg(&A.aux[pos].word));
-  const uint32_t* ord_all = A.order + __ldcg(&A.aux[pos].gbase);
-  Cursor cur;
-  bool open = false;
-  uint64_t ck = 0, ct = 0;
+__device__ __forceinline__ Bucket bucket_from_lane(const Bucket& b, uint32_t src) {
+  Bucket r;
+  r.key = __shfl_sync(0xFFFFFFFFu, (unsigned long long)b.key, src); r.tag = __shfl_sync(0xFFFFFFFFu, (unsigned long long)b.tag, src);
+  r.limit = (int64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)b.limit, src); r.duration = (int64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)b.duration, src);
+  r.rem = __shfl_sync(0xFFFFFFFFu, (unsigned long long)b.rem, src); r.stamp = (int64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)b.stamp, src);
+  r.burst = (int64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)b.burst, src); r.expire = (int64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)b.expire, src);
+  r.flags = __shfl_sync(0xFFFFFFFFu, b.flags, src);
+  return r;
+}
+
+// Applies one segment to b: a closed form for the whole segment (the state entering it is kept for the members), else request by
+// request with the responses stored right away.
+template <bool SEG>
+__device__ __forceinline__ void fold_segment(const BatchArgs& A, const Io<SEG>& io, MixedShared& S, const uint32_t* ord, uint32_t sgi, Bucket& b, Delta& d) {
+  const uint32_t lo = S.seg[sgi], hi = S.seg[sgi + 1];
+  gub_req rq = S.shape[sgi];
+  const bool closed_form = req_regular(rq);
+  S.kind[sgi] = closed_form ? 0 : 1;
+  if (closed_form) {
+    S.state[sgi] = b;
+    run_to_rank(b, rq, hi - lo - 1, A.clk, d);
+    return;
+  }
 #pragma unroll 1
-  for (uint32_t c0 = 0; c0 < total; c0 += MIXED_CHUNK) {
-    const uint32_t* ord = ord_all + c0;
-    const uint32_t cnt = min(MIXED_CHUNK, total - c0);
-    __syncthreads();
-    if (tid == 0) S.nseg = 0;
-    __syncthreads();
-    for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {  // segment starts: ranks whose request differs from the previous member's
-      bool boundary = (k == 0);
-      if (!boundary) {
-        const gub_req a = load_req(A.reqs + ord[k]), b = load_req(A.reqs + ord[k - 1]);
-        boundary = !req_same(a, b);
-      }
-      if (boundary) { const uint32_t q = atomicAdd(&S.nseg, 1u); if (q < MIXED_SEGS) S.raw[q] = k; }
-    }
-    __syncthreads();
-    const uint32_t nseg = S.nseg;
-    const bool planned = nseg <= MIXED_SEGS;
-    if (planned) {  // rank sort of the starts, and the segments' requests into shared memory
-      for (uint32_t q = tid; q < nseg; q += MIXED_THREADS) {
-        const uint32_t v = S.raw[q];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < nseg; j++) r += S.raw[j] < v ? 1u : 0u;
-        S.seg[r] = v;
-        S.shape[r] = load_req(A.reqs + ord[v]);
-      }
-      if (tid == 0) S.seg[nseg] = cnt;
-    }
-    __syncthreads();
-    if (tid == 0) {  // the fold
+  for (uint32_t k = lo; k < hi; k++) {
+    if (k > lo) rq = io.load(ord[k]);
+    store_resp(io.resp(ord[k]), apply_one(b, rq, A.clk, d));
+  }
+}
+
+// The fold of one chunk, by warp 0.  A hot key whose requests differ (clients asking for different `hits`) is a long sequence of
+// segments, and applying them is inherently sequential — but most segments of such a key leave the bucket where it was (over the
+// limit: a fixed point).  So the warp SPECULATES: the segments are dealt to the lanes in contiguous ranges and every lane folds its
+// range starting from the state E entering the first range not yet final.  Lanes up to and including the first one whose range
+// moves the state (exit != E) started from the right state, so their results are exact; that lane's exit becomes the new E and the
+// lanes behind it fold again.  One pass when nothing moves (the usual case for a key that is over its limit), at worst one pass per
+// lane (the cost of the sequential fold).  Chunks whose segments do not all carry the chunk's first key (two keys sharing a group
+// entry) and chunks with too many segments are folded by lane 0 alone, request by request where it has to be.
+template <bool SEG>
+__device__ void fold_chunk(const BatchArgs& A, const Io<SEG>& io, MixedShared& S, const uint32_t* ord, uint32_t cnt, bool planned, Cursor& cur,
+                                        bool& open, uint64_t& ck, uint64_t& ct, Tally& t) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nseg = planned ? S.nseg : 0u;
+  bool one_key = planned;
+  if (planned) {
+    bool other = false;
+    for (uint32_t q = lane; q < nseg; q += 32) other |= S.shape[q].key_xxh64 != S.shape[0].key_xxh64 || S.shape[q].key_fnv1 != S.shape[0].key_fnv1;
+    one_key = !__any_sync(0xFFFFFFFFu, other);
+  }
+  if (!one_key) {  // lane 0 alone, keeping the slot of the current key in registers
+    if (lane == 0) {
       const uint32_t steps = planned ? nseg : 1u;
 #pragma unroll 1
       for (uint32_t sgi = 0; sgi < steps; sgi++) {
         const uint32_t lo = planned ? S.seg[sgi] : 0u, hi = planned ? S.seg[sgi + 1] : cnt;
-        gub_req rq = planned ? S.shape[sgi] : load_req(A.reqs + ord[0]);
+        gub_req rq = planned ? S.shape[sgi] : io.load(ord[0]);
         const bool closed_form = planned && req_regular(rq);
         if (planned) S.kind[sgi] = closed_form ? 0 : 1;
 #pragma unroll 1
         for (uint32_t k = lo; k < hi; k++) {  // closed form: one pass for the whole segment; else one pass per request
-          if (!closed_form && k > lo) rq = load_req(A.reqs + ord[k]);
+          if (!closed_form && k > lo) rq = io.load(ord[k]);
           const uint64_t key = remap_key(rq.key_xxh64), tag = rq.key_fnv1 >> 8;
           if (!open || key != ck || tag != ct) {  // (the key only changes when two keys share a group entry)
             if (open) close_slot(A, cur, t);
@@ -826,11 +993,95 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
           }
           const gub_resp r = apply_one(cur.b, rq, A.clk, d);
           t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-          store_resp(A.out + ord[k], r);
+          store_resp(io.resp(ord[k]), r);
         }
       }
       if (!planned) atomicAdd(A.counters + C_SERIAL, 1ull);
     }
+    return;
+  }
+  if (lane == 0) {
+    const uint64_t key = remap_key(S.shape[0].key_xxh64), tag = S.shape[0].key_fnv1 >> 8;
+    if (!open || key != ck || tag != ct) {
+      if (open) close_slot(A, cur, t);
+      open_slot(A, cur, key, tag);
+      open = true; ck = key; ct = tag;
+    }
+  }
+  Bucket E = bucket_from_lane(cur.b, 0);
+  const uint32_t per = (nseg + 31u) / 32u;
+  const uint32_t s0 = min(lane * per, nseg), s1 = min(s0 + per, nseg);
+  uint32_t first = 0;  // lanes below `first` are final
+#pragma unroll 1
+  for (;;) {
+    Bucket b = E;
+    Delta d = {0, 0, 0};
+    if (lane >= first) {
+#pragma unroll 1
+      for (uint32_t sgi = s0; sgi < s1; sgi++) fold_segment(A, io, S, ord, sgi, b, d);
+    }
+    const uint32_t moved = __ballot_sync(0xFFFFFFFFu, lane >= first && !bucket_equal(b, E));
+    const uint32_t J = moved ? (uint32_t)__ffs((int)moved) - 1u : 32u;  // lanes first..J started from the state that really enters their range
+    if (lane >= first && lane <= J) { t.over += d.over; t.hit += d.hit; t.miss += d.miss; }
+    if (J >= 32u) break;       // nothing moved: E is also the state leaving the chunk
+    E = bucket_from_lane(b, J);
+    first = J + 1u;
+    if (first >= 32u) break;   // lane 31 was exact
+  }
+  if (lane == 0) cur.b = E;
+}
+
+template <bool SEG>
+__device__ void mixed_group(const BatchArgs& A, const Io<SEG>& io, uint32_t pos, MixedShared& S, Tally& t) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t total = aux_count(__ldcg(&A.aux[pos].word));
+  const uint32_t* ord_all = A.order + __ldcg(&A.aux[pos].gbase);
+  Cursor cur;
+  bool open = false;
+  uint64_t ck = 0, ct = 0;
+#pragma unroll 1
+  for (uint32_t c0 = 0; c0 < total; c0 += MIXED_CHUNK) {
+    const uint32_t* ord = ord_all + c0;
+    const uint32_t cnt = min(MIXED_CHUNK, total - c0);
+    __syncthreads();
+    if (tid == 0) S.nseg = 0;
+    __syncthreads();
+    // segment starts: ranks whose request differs from the previous member's.  Every member loads its own request once; the previous
+    // member's comes from the lane below (lane 0 loads it itself), so a chunk costs two dependent round trips per 256 members.
+#pragma unroll 1
+    for (uint32_t k0 = 0; k0 < cnt; k0 += MIXED_THREADS) {
+      const uint32_t k = k0 + tid;
+      const bool live = k < cnt;
+      const uint32_t lane = tid & 31;
+      gub_req a, b;
+      if (live) a = io.load(ord[k]);
+      if (live && lane == 0 && k > 0) b = io.load(ord[k - 1]);
+      gub_req up;  // the request of the lane below
+      up.key_xxh64 = __shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.key_xxh64, 1); up.key_fnv1 = __shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.key_fnv1, 1);
+      up.hits = (int64_t)__shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.hits, 1); up.limit = (int64_t)__shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.limit, 1);
+      up.duration = (int64_t)__shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.duration, 1); up.burst = (int64_t)__shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.burst, 1);
+      up.created_at = (int64_t)__shfl_up_sync(0xFFFFFFFFu, (unsigned long long)a.created_at, 1);
+      up.algorithm = __shfl_up_sync(0xFFFFFFFFu, a.algorithm, 1); up.behavior = __shfl_up_sync(0xFFFFFFFFu, a.behavior, 1);
+      if (live) {
+        const bool boundary = k == 0 || !req_same(a, lane == 0 ? b : up);
+        if (boundary) { const uint32_t q = atomicAdd(&S.nseg, 1u); if (q < MIXED_SEGS) S.raw[q] = k; }
+      }
+    }
+    __syncthreads();
+    const uint32_t nseg = S.nseg;
+    const bool planned = nseg <= MIXED_SEGS;
+    if (planned) {  // rank sort of the starts, and the segments' requests into shared memory
+      for (uint32_t q = tid; q < nseg; q += MIXED_THREADS) {
+        const uint32_t v = S.raw[q];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < nseg; j++) r += S.raw[j] < v ? 1u : 0u;
+        S.seg[r] = v;
+        S.shape[r] = io.load(ord[v]);
+      }
+      if (tid == 0) S.seg[nseg] = cnt;
+    }
+    __syncthreads();
+    if (tid < 32) fold_chunk(A, io, S, ord, cnt, planned, cur, open, ck, ct, t);  // warp 0 (thread 0 carries the group's cursor)
     __syncthreads();
     if (planned) {  // every member of a closed-form segment answers for itself
       for (uint32_t k = tid; k < cnt; k += MIXED_THREADS) {
@@ -839,7 +1090,7 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
         if (S.kind[lo]) continue;
         Bucket b = S.state[lo];
         Delta d = {0, 0, 0};
-        store_resp(A.out + ord[k], run_to_rank(b, S.shape[lo], k - S.seg[lo], A.clk, d));
+        store_resp(io.resp(ord[k]), run_to_rank(b, S.shape[lo], k - S.seg[lo], A.clk, d));
       }
     }
   }
@@ -847,13 +1098,20 @@ __device__ void mixed_group(const BatchArgs& A, uint32_t pos, MixedShared& S, Ta
 }
 
 // Non-uniform groups, one block each (grid-stride).  A launch with nothing to finish — the usual case — returns at once.
-__global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A) {
+template <bool SEG>
+#if !defined(GUB_FINISH_MIN_BLOCKS)
+#define GUB_FINISH_MIN_BLOCKS 2  // 128 registers (the segment fold spills a little): an empty k_finish block must fit next to a k_eval / k_rank block
+#endif
+__global__ void __launch_bounds__(MIXED_THREADS, GUB_FINISH_MIN_BLOCKS) k_finish(const BatchArgs A) {
   __shared__ MixedShared S;
   Tally t = {0, 0, 0, 0, 0};
+  KT(A, 3, KT_ENTRY, 0, false);
   pdl_wait();
   pdl_release();
+  KT(A, 3, KT_WAITED, 0, false);
   const BatchCtr ctr = A.ctr[A.epoch & 1];
   if (ctr.n_mixed == 0) return;
+  const Io<SEG> io = io_open<SEG>(A);
   // groups differ a lot in size (a hot key's group has thousands of members): blocks pull the next one when they are done
   __shared__ uint32_t s_next;
   for (;;) {
@@ -861,7 +1119,7 @@ __global__ void __launch_bounds__(MIXED_THREADS, 2) k_finish(const BatchArgs A) 
     __syncthreads();
     const uint32_t g = s_next;
     if (g >= ctr.n_mixed) break;
-    mixed_group(A, A.mixed_ent[g], S, t);
+    mixed_group(A, io, A.mixed_ent[g], S, t);
     __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1084,7 +1342,6 @@ __global__ void __launch_bounds__(256) k_random_rmw(Slot* table, uint64_t cap, u
 // Owner of a key = first ring point >= FNV-1(key), wrapping (replicated_hash.go:104-119).  Stable partition of the
 // batch by owner: per-tile counts -> exclusive scan over (owner, tile) -> ordered scatter.
 constexpr int ROUTE_TILE = 1024;  // requests per block
-constexpr int MAX_SHARDS = 16;
 
 __device__ __forceinline__ uint32_t ring_owner(const uint64_t* pts, const int32_t* peers, uint32_t npts, uint64_t h) {
   uint32_t lo = 0, hi = npts;

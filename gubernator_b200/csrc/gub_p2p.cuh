@@ -236,6 +236,34 @@ __global__ void __launch_bounds__(256) k_p2p_collect(const P2PArgs P, const uint
   }
 }
 
+// ---- the owner side of a step on the four-kernel pipeline ------------------------------------------------------------------
+// k_seg_wait: one warp waits for every source's flag (count of records it stored into our mailbox for this epoch) and writes the
+// prefix sums the batch kernels index the mailbox segments with (BatchArgs::seg_off; seg_off[world] = requests of the step).  A
+// tiny kernel of its own, so that no SM is held by spinning CTAs while the peers are still routing: the batch kernels that follow
+// find everything in place.  A source that never shows up (bounded wait) counts as empty and raises the ring's error flag.
+__global__ void __launch_bounds__(32) k_seg_wait(const P2PArgs P, uint32_t* seg_off) {
+  __shared__ uint32_t cnt[MAX_SHARDS];
+  if (threadIdx.x < P.world) {
+    const unsigned long long v = wait_flag(&P.peers[P.rank].req_flag[(size_t)(P.epoch & 1u) * P.world + threadIdx.x], P.epoch, P.error);
+    cnt[threadIdx.x] = min((uint32_t)(v & 0xFFFFFFFFull), P.cap);
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0;
+    for (uint32_t s = 0; s < P.world; s++) { seg_off[s] = a; a += cnt[s]; }
+    seg_off[P.world] = a;
+  }
+}
+// k_seg_publish: every response of the step has been stored into the sources' response mailboxes by the batch kernels before this
+// one starts (stream order; griddepcontrol.wait when launched programmatically): tell every source.
+__global__ void __launch_bounds__(32) k_seg_publish(const P2PArgs P) {
+  pdl_wait();
+  if (threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(&P.peers[threadIdx.x].resp_flag[(size_t)(P.epoch & 1u) * P.world + P.rank], (unsigned long long)P.epoch << 32);
+  }
+}
+
 // With n == 0 nothing is scattered, but the owners still wait for our flags.
 __global__ void k_p2p_publish_empty(const P2PArgs P) {
   if (threadIdx.x < P.world)

@@ -36,7 +36,7 @@ EXPORTS = ["gub_create", "gub_destroy", "gub_last_error", "gub_abi_version", "gu
            "gub_gq_destroy", "gub_gq_accumulate_device", "gub_gq_drain_device", "gub_make_updates_device", "gub_add_items_device",
            "gub_route_owner_device", "gub_route_global_device", "gub_p2p_create", "gub_p2p_destroy", "gub_p2p_export", "gub_p2p_connect",
            "gub_p2p_connect_local", "gub_p2p_step", "gub_p2p_step_streams", "gub_p2p_status", "gub_p2p_enable_global", "gub_nccl_unique_id",
-           "gub_p2p_nccl_init", "gub_p2p_nccl_init_local", "gub_global_tick", "gub_gq_dropped", "gub_set_sweep", "gub_set_trace", "gub_get_trace", "gub_get_trace_raw", "gub_keys_layout", "gub_submit_keys_async", "gub_global_tick_local_all", "gub_p2p_step_local_all"]
+           "gub_p2p_nccl_init", "gub_p2p_nccl_init_local", "gub_global_tick", "gub_gq_dropped", "gub_set_sweep", "gub_set_trace", "gub_get_trace", "gub_get_trace_raw", "gub_get_ktrace", "gub_keys_layout", "gub_submit_keys_async", "gub_global_tick_local_all", "gub_p2p_step_local_all"]
 
 
 class Config(C.Structure):
@@ -122,6 +122,7 @@ def lib():
         L.gub_set_trace.argtypes = [vp, i32]
         L.gub_get_trace.argtypes = [vp, vp, vp]
         L.gub_get_trace_raw.argtypes = [vp, vp]
+        L.gub_get_ktrace.argtypes = [vp, vp, i32]
         L.gub_submit_keys_async.argtypes = [vp, vp, sz, sz, vp, sz, i64, vp, vp, C.POINTER(C.c_int)]
         L.gub_keys_layout.argtypes = [sz, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         _lib = L
@@ -327,6 +328,12 @@ class Table:
     def get_trace_raw(self):
         raw = np.zeros((256, 12), dtype=np.uint64)
         _check(lib().gub_get_trace_raw(self._h, raw.ctypes.data), "gub_get_trace_raw")
+        return raw
+
+    def get_ktrace(self, reset=True):
+        """Pipeline kernels' time stamps [kernel 0..3][block][mark 0..7] in ns (0 = never), see gub_get_ktrace."""
+        raw = np.zeros((4, 1024, 8), dtype=np.uint64)
+        _check(lib().gub_get_ktrace(self._h, raw.ctypes.data, 1 if reset else 0), "gub_get_ktrace")
         return raw
 
     def set_profiling(self, on):

@@ -225,6 +225,11 @@ int gub_set_sweep(gub_table* t, uint32_t slots_per_cta);
 int gub_set_trace(gub_table* t, int on);
 int gub_get_trace(gub_table* t, double* max_us /* 12 */, double* mean_us /* 12 */);
 int gub_get_trace_raw(gub_table* t, uint64_t* out /* 256 CTAs x 12 marks, ns; 0 = CTA not launched */);
+/* The same for the four-kernel pipeline (also switched by gub_set_trace): out[(kernel * 1024 + block) * 8 + mark] = the latest
+ * %globaltimer (ns) at which a warp of the block — for marks 2..5 inside role code: a thread in that role — passed the mark since the
+ * last reset, 0 = never.  kernel: 0 k_group, 1 k_rank, 2 k_eval, 3 k_finish; marks: 0 entry (request loaded), 1 after
+ * griddepcontrol.wait, 6 work done (before the block's last barrier), 7 exit; 2..5 per kernel (gub_kernels.cuh). */
+int gub_get_ktrace(gub_table* t, uint64_t* out /* 4 x 1024 x 8 */, int reset);
 
 /* Diagnostic: random 64-byte read-modify-write rate of the device over the table's own slots (contents unchanged), in GB/s
  * moved (64 B read + 64 B written per access): the "HBM random access" ceiling bench.py reports the path against. */

@@ -145,8 +145,10 @@ def unroute(resps, perm):
 class EmuP2PCluster:
     """W shards in one process stepping through gub_p2p_step's kernels phase by phase (see kernel_emu_harness.cpp)."""
 
-    def __init__(self, world, cap, capacity_slots, pts, peers, max_batch=4096, finish_cap=148):
+    def __init__(self, world, cap, capacity_slots, pts, peers, max_batch=4096, finish_cap=148, fused=False):
+        """fused: owners evaluate with the persistent kernel k_batch (GUB_PATH=fused) instead of the pipeline in ring mode."""
         self.world = world
+        self.fused = bool(fused)
         self._L = lib()
         self._finish_cap = finish_cap
         pts, peers = np.ascontiguousarray(pts, dtype=np.uint64), np.ascontiguousarray(peers, dtype=np.int32)
@@ -160,10 +162,12 @@ class EmuP2PCluster:
         op = (C.c_void_p * self.world)(*[o.ctypes.data for o in outs])
         n = np.array([len(b) for b in batches], dtype=np.uint32)
         self._L.emu_set_finish_cap(self._finish_cap)
+        self._L.emu_set_fused(1 if self.fused else 0)
         try:
             rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op, 0, None)
         finally:
             self._L.emu_set_finish_cap(148)
+            self._L.emu_set_fused(0)
         assert rc == 0, "a mailbox flag wait timed out"
         return [o[:len(b)] for o, b in zip(outs, batches)]
 

@@ -237,6 +237,9 @@ inline unsigned __shfl_sync(unsigned, unsigned v, unsigned src) {
 inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned delta) {
   return emu::warp_collective(v, [delta, v](emu::Warp& w, unsigned lane) { return lane >= delta ? (unsigned)w.val[lane - delta] : v; });
 }
+inline unsigned long long __shfl_up_sync(unsigned, unsigned long long v, unsigned delta) {
+  return emu::warp_collective(v, [delta, v](emu::Warp& w, unsigned lane) { return lane >= delta ? w.val[lane - delta] : v; });
+}
 inline unsigned __ballot_sync(unsigned, bool pred) {
   return emu::warp_collective(pred ? 1ull : 0ull, [](emu::Warp& w, unsigned) {
     unsigned m = 0;

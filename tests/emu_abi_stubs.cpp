@@ -9,6 +9,6 @@ NOT_EMULATED(gub_route_owner_device) NOT_EMULATED(gub_route_global_device) NOT_E
 NOT_EMULATED(gub_p2p_connect) NOT_EMULATED(gub_p2p_connect_local) NOT_EMULATED(gub_p2p_step) NOT_EMULATED(gub_p2p_step_streams)
 NOT_EMULATED(gub_p2p_status) NOT_EMULATED(gub_p2p_enable_global) NOT_EMULATED(gub_nccl_unique_id) NOT_EMULATED(gub_p2p_nccl_init) NOT_EMULATED(gub_p2p_nccl_init_local)
 NOT_EMULATED(gub_global_tick) NOT_EMULATED(gub_global_tick_local_all) NOT_EMULATED(gub_p2p_step_local_all) NOT_EMULATED(gub_gq_dropped) NOT_EMULATED(gub_set_sweep)
-NOT_EMULATED(gub_set_trace) NOT_EMULATED(gub_get_trace) NOT_EMULATED(gub_get_trace_raw) NOT_EMULATED(gub_keys_layout) NOT_EMULATED(gub_submit_keys_async)
+NOT_EMULATED(gub_set_trace) NOT_EMULATED(gub_get_trace) NOT_EMULATED(gub_get_trace_raw) NOT_EMULATED(gub_get_ktrace) NOT_EMULATED(gub_keys_layout) NOT_EMULATED(gub_submit_keys_async)
 extern "C" void gub_gq_destroy() {}
 extern "C" void gub_p2p_destroy() {}

@@ -50,7 +50,7 @@ struct EmuTable {  // what gub_create allocates (gub_api.cu), one scratch set
   uint32_t grid = 6, sweep_chunk = 0;
 };
 
-uint32_t g_fused = 0;  // emu_set_fused(1): the persistent kernel k_batch instead of the four-kernel pipeline (rings always use it)
+uint32_t g_fused = 0;  // emu_set_fused(1): the persistent kernel k_batch instead of the four-kernel pipeline (single tables and rings alike)
 
 }  // namespace
 
@@ -64,7 +64,7 @@ void* emu_create(uint64_t capacity_slots, uint32_t max_batch) {
   B = (B + 255u) & ~255u;
   t->max_batch = B;
   t->aux_entries = next_pow2((uint64_t)B * 4);
-  t->max_blocks = (B / GROUP_THREADS + 31u) & ~31u;
+  t->max_blocks = (B / GROUP_THREADS + 127u) & ~127u;
   t->pres_words = t->max_blocks / 32;
   t->table = zalloc<Slot>(capacity_slots);
   t->aux = zalloc<AuxEntry>(t->aux_entries);
@@ -129,6 +129,45 @@ static int submit_fused(EmuTable* t, const FSeg* segs, uint32_t nseg, uint32_t f
 
 // launch_batch / launch_chunk / launch_finish of gub_api.cu, minus streams.  n_dev != nullptr: the batch size is *n_dev (<= n), as in
 // gub_submit_device_n.
+struct EmuSegs {  // ring mode (SegDesc of gub_api.cu)
+  uint32_t nseg = 0;
+  const uint32_t* seg_off = nullptr;
+  const gub_req* reqs[MAX_SHARDS] = {};
+  gub_resp* out[MAX_SHARDS] = {};
+};
+
+// launch_chunk of gub_api.cu, minus streams
+static void submit_chunk(EmuTable* t, const gub_req* reqs, uint32_t m, const uint32_t* n_dev, uint32_t n_off, const gub_clock* clk, gub_resp* out, const EmuSegs* seg) {
+  if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); std::memset(t->ctr, 0, 2 * sizeof(BatchCtr)); t->epoch = 0; }
+  t->epoch++;
+  BatchArgs A;
+  std::memset(&A, 0, sizeof A);
+  if (seg) {
+    A.nseg = seg->nseg; A.seg_off = seg->seg_off;
+    for (uint32_t k = 0; k < seg->nseg; k++) { A.seg_reqs[k] = seg->reqs[k]; A.seg_out[k] = seg->out[k]; }
+  }
+  A.table = t->table; A.capacity = t->capacity; A.reqs = reqs; A.out = out; A.n = m; A.n_dev = n_dev; A.n_off = n_off; A.epoch = t->epoch;
+  A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
+  A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank;
+  A.commit = t->commit; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
+  A.counters = t->counters; A.ovf = t->ovf; A.ovf_count = &t->ctl->ovf_count; A.inv = t->inv;
+  A.clk = *clk;
+  const uint32_t blocks = (m + 255) / 256;
+  const uint32_t fin = std::min<uint32_t>(g_finish_cap, std::max<uint32_t>(1u, m / 2));  // gub_api.cu caps the grid at 148
+  if (seg) {
+    emu::launch(k_group<true>, blocks, GROUP_THREADS, A);
+    emu::launch(k_rank<true>, blocks, GROUP_THREADS, A);
+    emu::launch(k_eval<true>, blocks, GROUP_THREADS, A);
+    emu::launch(k_finish<true>, fin, MIXED_THREADS, A);
+  } else {
+    emu::launch(k_group<false>, blocks, GROUP_THREADS, A);
+    emu::launch(k_rank<false>, blocks, GROUP_THREADS, A);
+    emu::launch(k_eval<false>, blocks, GROUP_THREADS, A);
+    emu::launch(k_finish<false>, fin, MIXED_THREADS, A);
+  }
+}
+
+// launch_batch of gub_api.cu.  n_dev != nullptr: the batch size is *n_dev (<= n), as in gub_submit_device_n.
 static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_t* n_dev, const gub_clock* clk, gub_resp* out) {
   if (g_fused) {
     FSeg sg;
@@ -138,21 +177,7 @@ static int submit_impl(EmuTable* t, const gub_req* reqs, size_t n, const uint32_
   }
   for (size_t off = 0; off < n; off += t->max_batch) {
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
-    if (t->epoch >= 65535u) { std::memset(t->aux, 0, (size_t)t->aux_entries * sizeof(AuxEntry)); std::memset(t->ctr, 0, 2 * sizeof(BatchCtr)); t->epoch = 0; }
-    t->epoch++;
-    BatchArgs A;
-    std::memset(&A, 0, sizeof A);
-    A.table = t->table; A.capacity = t->capacity; A.reqs = reqs + off; A.out = out + off; A.n = m; A.n_dev = n_dev; A.n_off = (uint32_t)off; A.epoch = t->epoch;
-    A.aux = t->aux; A.aux_mask = t->aux_entries - 1; A.presence = t->presence; A.fragsize = t->fragsize;
-    A.pres_words = t->pres_words; A.max_blocks = t->max_blocks; A.ent = t->ent; A.meta = t->meta; A.rank = t->rank;
-    A.commit = t->commit; A.order = t->order; A.mixed_ent = t->mixed_ent; A.ctr = t->ctr;
-    A.counters = t->counters; A.ovf = t->ovf; A.ovf_count = &t->ctl->ovf_count; A.inv = t->inv;
-    A.clk = *clk;
-    const uint32_t blocks = (m + 255) / 256;
-    emu::launch(k_group, blocks, GROUP_THREADS, A);
-    emu::launch(k_rank, blocks, GROUP_THREADS, A);
-    emu::launch(k_eval, blocks, GROUP_THREADS, A);
-    emu::launch(k_finish, std::min<uint32_t>(g_finish_cap, std::max<uint32_t>(1u, m / 2)), MIXED_THREADS, A);  // gub_api.cu caps the grid at 148
+    submit_chunk(t, reqs + off, m, n_dev, (uint32_t)off, clk, out + off, nullptr);
   }
   return 0;
 }
@@ -281,7 +306,7 @@ struct EmuP2P {
   struct Rank {
     P2PView view;
     unsigned long long* tile_agg;
-    uint32_t *error, *counts, *perm, *ticket;
+    uint32_t *error, *counts, *perm, *ticket, *seg_off;
     uint8_t* true_owner;
   };
   std::vector<Rank> ranks;
@@ -307,7 +332,7 @@ void* emu_p2p_create(uint32_t world, uint32_t cap, uint64_t capacity_slots, uint
     k2.view.resp_flag = zalloc<unsigned long long>((size_t)2 * world);
     k2.tile_agg = zalloc<unsigned long long>(((size_t)cap / RT_THREADS + 1) * MAX_SHARDS);
     k2.error = zalloc<uint32_t>(1); k2.counts = zalloc<uint32_t>(MAX_SHARDS); k2.perm = zalloc<uint32_t>(cap); k2.ticket = zalloc<uint32_t>(2);
-    k2.true_owner = zalloc<uint8_t>(cap);
+    k2.true_owner = zalloc<uint8_t>(cap); k2.seg_off = zalloc<uint32_t>(MAX_SHARDS + 1);
     p->ranks.push_back(k2);
   }
   return p;
@@ -339,6 +364,23 @@ int emu_p2p_step(void* pv, const gub_req* const* reqs, const uint32_t* n, const 
   }
   const uint32_t par = p->epoch & 1u;
   for (uint32_t r = 0; r < p->world; r++) {  // phase 2
+    if (!g_fused) {  // p2p_evaluate's default: k_seg_wait, the pipeline in ring mode (as many passes as world x cap takes), k_seg_publish
+      EmuTable* t = p->tabs[r];
+      EmuSegs sd;
+      sd.nseg = p->world; sd.seg_off = p->ranks[r].seg_off;
+      for (uint32_t s = 0; s < p->world; s++) {
+        sd.reqs[s] = args[r].peers[r].req_mb + ((size_t)par * p->world + s) * p->cap;
+        sd.out[s] = args[r].peers[s].resp_mb + ((size_t)par * p->world + r) * p->cap;
+      }
+      emu::launch(k_seg_wait, 1u, 32u, args[r], p->ranks[r].seg_off);
+      const uint64_t total = (uint64_t)p->world * p->cap;
+      for (uint64_t off = 0; off < total; off += t->max_batch) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(t->max_batch, total - off);
+        submit_chunk(t, nullptr, m, p->ranks[r].seg_off + p->world, (uint32_t)off, clk, nullptr, &sd);
+      }
+      emu::launch(k_seg_publish, 1u, 32u, args[r]);
+      continue;
+    }
     FSeg segs[MAX_SHARDS];
     unsigned long long* rflags[MAX_SHARDS];
     std::memset(segs, 0, sizeof segs);

@@ -16,6 +16,14 @@ from workloads import T0, key_hashes
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+def owner_kernel_path(request, monkeypatch):
+    """Owners evaluate their mailboxes with the four-kernel pipeline in ring mode (default) or with the persistent kernel k_batch
+    (GUB_PATH=fused); read when a table is created."""
+    monkeypatch.setenv("GUB_PATH", request.param)
+    return request.param
+
+
 class GpuCluster:
     def __init__(self, world, now_ms, capacity=1 << 14):
         import torch

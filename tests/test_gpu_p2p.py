@@ -12,6 +12,14 @@ from workloads import T0, adversarial_batch, bench_requests, zipf_ids
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["pipeline", "fused"])
+def owner_kernel_path(request, monkeypatch):
+    """Owners evaluate their mailboxes with the four-kernel pipeline in ring mode (default) or with the persistent kernel k_batch
+    (GUB_PATH=fused); read when a table is created."""
+    monkeypatch.setenv("GUB_PATH", request.param)
+    return request.param
+
 SIZES = [[3000, 1, 0, 8192, 5], [2000, 0, 0, 8192, 700], [1, 4000, 0, 100, 8192], [8192, 0, 0, 7, 300]]
 
 

@@ -117,6 +117,37 @@ def test_many_segments_force_the_serial_walk(G, path):
 
 
 @both_paths
+@pytest.mark.parametrize("algorithm", [0, 1])
+def test_hot_key_with_differing_hits_many_segments(G, path, algorithm):
+    """A hot key whose clients ask for different `hits`: hundreds of segments (runs of identical requests) per chunk of the group.
+    The segment fold speculates that a range of segments leaves the bucket unchanged (true once the key is over its limit) and falls
+    back, range by range, where the state moves: first batch walks the limit down (every range moves the state), later batches
+    sit at the fixed point, the last one mixes in Hits = 0 queries, a limit change and negative hits (state moves again mid-way)."""
+    rng = np.random.default_rng(5 + algorithm)
+    tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
+    n = 3000
+    xx, fv = key_hashes([3] * n, name="hothetero")
+    for b in range(4):
+        now = T0 + 7 * b
+        reqs = np.zeros(n, dtype=G.REQ_DTYPE)
+        reqs["key_xxh64"], reqs["key_fnv1"] = xx, fv
+        run = np.repeat(np.arange(n // 4 + 1), rng.integers(1, 9, n // 4 + 1))[:n]     # runs of 1..8 identical requests
+        hits_of_run = rng.choice([1, 2, 3], run.max() + 1)
+        reqs["hits"] = hits_of_run[run]
+        reqs["limit"] = 4000 if b < 2 else 3000; reqs["duration"] = 60000; reqs["created_at"] = now
+        reqs["algorithm"] = algorithm; reqs["behavior"] = G.native.REQ_IS_OWNER
+        if b == 3:
+            odd = rng.random(n) < 0.03
+            reqs["hits"] = np.where(odd, rng.choice([0, -5, 1 << 20], n), reqs["hits"])
+            reqs["limit"] = np.where(rng.random(n) < 0.01, 3500, reqs["limit"])
+        pool.set_now(now)
+        _cmp(tab.submit(reqs, make_clock(now), O.HRESP_DTYPE), pool.submit_hashed(reqs), f"batch {b}")
+    if path == "pipeline":
+        assert tab.counters()["mixed_groups"] >= 4
+    _check_state(G, tab, pool)
+
+
+@both_paths
 def test_token_reset_flipflop(G, path):
     tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
     n = 300
@@ -254,8 +285,9 @@ def test_route_kernels_partition_stably_by_ring_owner(G, world):
         assert np.array_equal(back["remaining"][order], np.arange(n))
 
 
+@both_paths
 @pytest.mark.parametrize("world", [1, 2, 4])
-def test_mailbox_routing_kernels_match_per_shard_oracles(G, world):
+def test_mailbox_routing_kernels_match_per_shard_oracles(G, world, path):
     """gub_p2p.cuh (partition + stores into the owners' mailboxes, gather, device-side batch size, responses back, un-route)
     for W shards in one process: every response equals what one oracle per shard gives when it applies the records of source 0
     (in index order), then source 1, ... — the order tests/test_gpu_p2p.py checks on the GPU."""
@@ -264,7 +296,8 @@ def test_mailbox_routing_kernels_match_per_shard_oracles(G, world):
     for a in shard_addresses(world):
         oring.add(a)
     pts, peers = oring.points()
-    cl = E.EmuP2PCluster(world, cap=2048, capacity_slots=1 << 13, pts=pts, peers=peers, max_batch=2048, finish_cap=3)  # inbox > max_batch: chunked
+    cl = E.EmuP2PCluster(world, cap=2048, capacity_slots=1 << 13, pts=pts, peers=peers, max_batch=2048, finish_cap=3,
+                         fused=(path == "fused"))  # inbox > max_batch: the pipeline takes it in several passes
     sim = [O.Pool(workers=2, cache_size=10**7, now_ms=T0) for _ in range(world)]
     sizes = [[900, 1, 0, 2048, 5], [600, 0, 0, 2048, 300], [1, 1500, 0, 100, 2048], [2048, 0, 0, 7, 300]]
     for step in range(5):
