@@ -176,24 +176,6 @@ __device__ __forceinline__ void slot_load(const Slot* s, ulonglong2& a, ulonglon
   const ulonglong2* p = reinterpret_cast<const ulonglong2*>(s);
   a = __ldcg(p); b = __ldcg(p + 1); c = __ldcg(p + 2); d = __ldcg(p + 3);  // 4 x 128-bit, L2-only (no reuse in L1)
 }
-// A 16-byte L2 load the compiler may neither drop nor sink towards its first use: k_rank / k_eval issue every role's first loads before
-// any role waits for one (inside divergent role code the waits of different roles would otherwise add up instead of overlapping).
-#if defined(GUB_EMULATE)
-__device__ __forceinline__ ulonglong2 ldcg_pinned(const ulonglong2* p) { return *p; }
-__device__ __forceinline__ uint4 ldcg_pinned(const uint4* p) { return *p; }
-#else
-__device__ __forceinline__ ulonglong2 ldcg_pinned(const ulonglong2* p) {
-  ulonglong2 v;
-  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint4 ldcg_pinned(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-#endif
-
 __device__ __forceinline__ void bucket_from(Bucket& bk, const ulonglong2& a, const ulonglong2& b, const ulonglong2& c, const ulonglong2& d) {
   bk.key = a.x; bk.tag = a.y >> 8; bk.flags = (uint32_t)(a.y & 0xFF);
   bk.limit = (int64_t)b.x; bk.duration = (int64_t)b.y; bk.rem = c.x; bk.stamp = (int64_t)c.y;
@@ -559,8 +541,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
   // warp turns with a barrier each: 31.7 vs 40.5 us per 65 536-request step, profiles/r02_ab_round1_switches.json.)
   __shared__ __align__(16) uint8_t s_wcnt[GROUP_SLOTS][GROUP_THREADS / 32];
   static_assert(sizeof(s_wcnt) == GROUP_THREADS * sizeof(uint4), "one 16-byte store per thread clears it");
-  __shared__ uint32_t s_seen[GROUP_SLOTS];  // group entries joined by this block's fragments (entry + 1): two fragments in one entry = a conflict
-  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; s_seen[k] = 0u; }
+  for (uint32_t k = threadIdx.x; k < GROUP_SLOTS; k += GROUP_THREADS) { s_key[k] = 0ull; s_cnt[k] = 0u; }
   if (threadIdx.x == 0) s_conflict = 0u;
   reinterpret_cast<uint4*>(&s_wcnt[0][0])[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
   KT(A, 0, KT_ENTRY, 0, false);
@@ -621,19 +602,12 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_group(const BatchArgs A) {
     bool claimed;
     const uint32_t pos = aux_join(A, key, c, first, &claimed);
     if (claimed) { A.aux[pos].rep = i; A.aux[pos].flags = 0; }
-    // the block's presence bit: nobody waits for this atomic (its old value is not needed: conflicts are found in shared memory)
-    atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], 1u << (blockIdx.x & 31));
+    const uint32_t bit = 1u << (blockIdx.x & 31);
+    const uint32_t was = atomicOr(&A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)], bit);
     A.fragsize[(size_t)pos * A.max_blocks + blockIdx.x] = (uint8_t)(c - 1);
     s_pos[sp] = pos;
-    uint32_t h = (pos * 2654435761u) >> 23;  // 9 bits
-#pragma unroll 1
-    for (;;) {
-      const uint32_t old = atomicCAS(&s_seen[h], 0u, pos + 1u);
-      if (old == 0u) break;
-      if (old == pos + 1u) { s_conflict = 1u; break; }  // another fragment of this block is in this entry already
-      h = (h + 1u) & (GROUP_SLOTS - 1);
-    }
-    KT(A, 0, KT_M4, pos, true);  // a fragment has joined its group
+    if (was & bit) s_conflict = 1u;  // the bitmap is clean between batches: another fragment of this block is in this entry already
+    KT(A, 0, KT_M4, was, true);  // a fragment has joined its group
   }
   KT(A, 0, KT_WORK_DONE, 0, false);
   __syncthreads();
@@ -671,39 +645,35 @@ __device__ __forceinline__ uint32_t masked_sum32(const uint4& lo, const uint4& h
   return acc;
 }
 
-// pres_words == 8 (a batch of up to 65 536 requests): p0 / p1 = the group's eight presence words, loaded by the caller
-__device__ __forceinline__ uint32_t fragment_base8(const BatchArgs& A, uint32_t pos, uint32_t b, const uint4& p0, const uint4& p1) {
-  const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
-  const uint32_t last = b >> 5, keep = (1u << (b & 31)) - 1u;
-  uint32_t base = 0;
-  uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-  uint32_t any = 0;
-#pragma unroll
-  for (int w = 0; w < 8; w++) { bits[w] = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u); any += __popc(bits[w]); }
-  if (any == 0) return 0;
-  if (any <= 2) {  // the common case: a couple of earlier fragments
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      uint32_t x = bits[w];
-      while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
-    }
-    return base;
-  }
-  uint4 lo[8], hi[8];
-#pragma unroll
-  for (int w = 0; w < 8; w++) {
-    if (bits[w]) { lo[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
-  }
-#pragma unroll
-  for (int w = 0; w < 8; w++) if (bits[w]) base += masked_sum32(lo[w], hi[w], bits[w]);
-  return base;
-}
-
 __device__ __forceinline__ uint32_t fragment_base(const BatchArgs& A, uint32_t pos, uint32_t b) {
   const uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
   const uint8_t* row = A.fragsize + (size_t)pos * A.max_blocks;
   const uint32_t last = b >> 5, keep = (1u << (b & 31)) - 1u;
   uint32_t base = 0;
+  if (A.pres_words == 8) {  // max_batch = 65536
+    const uint4 p0 = __ldcg(reinterpret_cast<const uint4*>(pres)), p1 = __ldcg(reinterpret_cast<const uint4*>(pres) + 1);
+    uint32_t bits[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { bits[w] = ((uint32_t)w < last) ? bits[w] : ((uint32_t)w == last ? (bits[w] & keep) : 0u); any += __popc(bits[w]); }
+    if (any == 0) return 0;
+    if (any <= 2) {  // the common case: a couple of earlier fragments
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        uint32_t x = bits[w];
+        while (x) { const uint32_t k = __ffs(x) - 1; x &= x - 1; base += (uint32_t)row[w * 32 + k] + 1u; }
+      }
+      return base;
+    }
+    uint4 lo[8], hi[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      if (bits[w]) { lo[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32)); hi[w] = __ldcg(reinterpret_cast<const uint4*>(row + w * 32 + 16)); }
+    }
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (bits[w]) base += masked_sum32(lo[w], hi[w], bits[w]);
+    return base;
+  }
   // other batch sizes (rings evaluate up to 262 144 requests = 1024 blocks per launch): four bitmap words per round trip
   // (pres_words is a multiple of 4: gub_create)
   const uint32_t nq = (last >> 2) + 1;
@@ -759,6 +729,10 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
   __shared__ uint32_t s_base[GROUP_SLOTS];
   const Io<SEG> io = io_open<SEG>(A);  // (ring mode: the segment table was final before k_group started)
   const uint32_t n = batch_n(A);  // written at least two kernels ago: safe ahead of the wait, like the records
+  // A launch is sized for the most the batch can hold (ring mode: what all sources could send); blocks beyond the batch leave at once —
+  // before the wait, so that they do not keep the register file from the blocks that have work (two resident blocks per SM).  Block 0
+  // always stays: a grid whose blocks all skipped the wait would complete before its predecessor and break the chain of waits.
+  if (blockIdx.x != 0 && blockIdx.x * GROUP_THREADS >= n) return;
   const uint32_t i = partition_by_algorithm(io, n);
   Tally t = {0, 0, 0, 0, 0};
   const bool valid = i < n;
@@ -774,75 +748,57 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_rank(const BatchArgs A) {
     atomicAdd(A.counters + C_REQUESTS, (unsigned long long)n);
     atomicAdd(A.counters + C_BATCHES, 1ull);
   }
-  // Roles: `single` (a key seen once — most keys) is evaluated right here; `leader` (first member of a repeated key's fragment in this
-  // block) computes the fragment's base rank, and the leader holding rank 0 parks the slot as found for its siblings; every member
-  // of a repeated key compares itself with the group's representative.  A warp holds all roles at once, and inside divergent role
-  // code the memory waits of different roles add up — so every role's first loads are ISSUED here, before any role consumes one.
-  uint32_t pos = 0, cnt = 0, sp = 0, local = 0, rep = 0;
-  uint64_t key = 0;
+  uint32_t pos = 0, cnt = 0, sp = 0, local = 0;
   if (valid) {
     pos = A.ent[i];
     const uint32_t m = A.meta[i];
     const ulonglong2 e = __ldcg(reinterpret_cast<const ulonglong2*>(&A.aux[pos]));
-    key = remap_key(rq.key_xxh64);
+    const uint64_t key = remap_key(rq.key_xxh64);
     sp = m >> 16; local = m & 0xFFFFu;
     cnt = aux_count(e.x);
-    rep = (uint32_t)(e.y & 0xFFFFFFFFull);
-  }
-  KT(A, 1, KT_M2, cnt, false);  // group entries read
-  const bool single = valid && cnt == 1, member = valid && cnt > 1, leader = member && local == 0;
-  bool mixed = member && !req_regular(rq);
-  const bool cmp = member && !mixed && i != rep;
-  const bool fast_base = A.pres_words == 8;
-  ulonglong2 h0, h1, h2, h3;  // the home slot: singles, and leaders in case they turn out to hold rank 0 (prefetched into L2 by k_group)
-  uint4 p0, p1;               // leaders: the group's presence bitmap
-  gub_req rr;                 // members: the representative
-  if (single || leader) {
-    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(A.table + __umul64hi(key, A.capacity));
-    h0 = ldcg_pinned(hp); h1 = ldcg_pinned(hp + 1); h2 = ldcg_pinned(hp + 2); h3 = ldcg_pinned(hp + 3);
-  }
-  if (leader && fast_base) {
-    const uint4* pp = reinterpret_cast<const uint4*>(A.presence + (size_t)pos * 8u);
-    p0 = ldcg_pinned(pp); p1 = ldcg_pinned(pp + 1);
-  }
-  if (cmp) rr = io.load(rep);
-  // ---- consume
-  if (single) {
-    A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
-    Cursor cur;
-    cursor_open_preloaded(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, h0, h1, h2, h3);
-    apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
-    Delta d = {0, 0, 0};
-    const gub_resp r = apply_one(cur.b, rq, A.clk, d);
-    close_slot(A, cur, t);
-    t.over += d.over; t.hit += d.hit; t.miss += d.miss;
-    store_resp(io.resp(i), r);
-    KT(A, 1, KT_M5, r.status, true);  // a key seen once answered
-  }
-  if (leader) {
-    const uint32_t base = fast_base ? fragment_base8(A, pos, blockIdx.x, p0, p1) : fragment_base(A, pos, blockIdx.x);
-    s_base[sp] = base;
-    KT(A, 1, KT_M3, base, true);  // a fragment's base rank
-    if (base == 0) {  // rank 0 of the run: the slot as found, for everybody
+    KT(A, 1, KT_M2, cnt, true);  // group entry read
+    const uint32_t rep = (uint32_t)(e.y & 0xFFFFFFFFull);
+    if (cnt > 1) {
+      // uniformity does not need the rank: start the representative's load before anything that waits
+      bool mixed = !req_regular(rq);
+      gub_req rr;
+      const bool cmp = !mixed && i != rep;
+      if (cmp) rr = io.load(rep);
+      if (local == 0) {
+        const uint32_t base = fragment_base(A, pos, blockIdx.x);
+        s_base[sp] = base;
+        KT(A, 1, KT_M3, base, true);  // a fragment's base rank
+        if (base == 0) {  // rank 0 of the run: look the key up once for everybody
+          Cursor cur;
+          open_slot(A, cur, key, rq.key_fnv1 >> 8);
+          snap_store(A.commit + (size_t)pos * 6, cur, i);
+          KT(A, 1, KT_M4, (uint32_t)cur.b.flags, true);  // a run's snapshot stored
+        }
+      }
+      if (cmp) mixed = !req_same(rq, rr);
+      if (mixed) {
+        const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
+        if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
+          BatchCtr* ctr = A.ctr + (A.epoch & 1);
+          A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
+          A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
+        }
+      }
+    } else if (cnt == 1) {  // a key seen once — most keys: evaluated right here (its slot was prefetched into L2 by k_group)
+      A.presence[(size_t)pos * A.pres_words + (blockIdx.x >> 5)] = 0;  // hand the bitmap back clean (this block's bit is the only one)
       Cursor cur;
-      cursor_open_preloaded(cur, A.table, A.capacity, key, rq.key_fnv1 >> 8, h0, h1, h2, h3);
-      apply_invalid_at(A.inv, cur.b, cur.found, A.clk.now_ms);
-      snap_store(A.commit + (size_t)pos * 6, cur, i);
-      KT(A, 1, KT_M4, (uint32_t)cur.b.flags, true);  // a run's snapshot stored
-    }
-  }
-  if (cmp) mixed = !req_same(rq, rr);
-  if (mixed) {
-    const uint32_t old = atomicOr(&A.aux[pos].flags, AUX_NONUNIFORM);
-    if (!(old & AUX_NONUNIFORM)) {  // first to notice: reserve the group's region of `order` and list the group
-      BatchCtr* ctr = A.ctr + (A.epoch & 1);
-      A.aux[pos].gbase = atomicAdd(&ctr->order_bump, cnt);
-      A.mixed_ent[atomicAdd(&ctr->n_mixed, 1u)] = pos;
+      open_slot(A, cur, key, rq.key_fnv1 >> 8);
+      Delta d = {0, 0, 0};
+      const gub_resp r = apply_one(cur.b, rq, A.clk, d);
+      close_slot(A, cur, t);
+      t.over += d.over; t.hit += d.hit; t.miss += d.miss;
+      store_resp(io.resp(i), r);
+      KT(A, 1, KT_M5, r.status, true);  // a key seen once answered
     }
   }
   KT(A, 1, KT_WORK_DONE, 0, false);
   __syncthreads();
-  if (valid) A.rank[i] = cnt > 1 ? s_base[sp] + local : 0xFFFFFFFFu;  // (0xFFFFFFFF: not a member of a repeated key — k_eval has nothing to do)
+  if (valid && cnt > 1) A.rank[i] = s_base[sp] + local;
   tally_flush_block(t, A.counters);
   KT(A, 1, KT_EXIT, 0, false);
 }
@@ -852,6 +808,7 @@ template <bool SEG>
 __global__ void __launch_bounds__(GROUP_THREADS, 2) k_eval(const BatchArgs A) {
   const Io<SEG> io = io_open<SEG>(A);
   const uint32_t n = batch_n(A);
+  if (blockIdx.x != 0 && blockIdx.x * GROUP_THREADS >= n) return;  // (see k_rank)
   const uint32_t i = partition_by_algorithm(io, n);
   Tally t = {0, 0, 0, 0, 0};
   uint32_t dup = 0;
@@ -861,27 +818,23 @@ __global__ void __launch_bounds__(GROUP_THREADS, 2) k_eval(const BatchArgs A) {
   pdl_wait();
   pdl_release();
   KT(A, 2, KT_WAITED, 0, false);
-  const uint32_t rank = i < n ? A.rank[i] : 0xFFFFFFFFu;
-  if (rank != 0xFFFFFFFFu) {  // a member of a repeated key (k_rank answered the others)
+  if (i < n) {
     const uint32_t pos = A.ent[i];
+    const uint32_t rank = A.rank[i];             // garbage for keys seen once: not used
     const AuxEntry* e = &A.aux[pos];
-    // the group entry and the run's snapshot depend on `pos` only: one round trip for both
-    const ulonglong2* sp = A.commit + (size_t)pos * 6;
-    const ulonglong2 ev = ldcg_pinned(reinterpret_cast<const ulonglong2*>(e));
-    const ulonglong2 s0 = ldcg_pinned(sp), s1 = ldcg_pinned(sp + 1), s2 = ldcg_pinned(sp + 2), s3 = ldcg_pinned(sp + 3), s4 = ldcg_pinned(sp + 4),
-                     s5 = ldcg_pinned(sp + 5);  // the slot as k_rank found it (the last rank may already be writing the table)
+    const ulonglong2 ev = __ldcg(reinterpret_cast<const ulonglong2*>(e));
     const uint32_t cnt = aux_count(ev.x);
     KT(A, 2, KT_M2, cnt, true);  // group entry read
-    const bool mixed = ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
-    if (rank == 0) {  // hand the presence bitmap back clean
+    const bool mixed = cnt > 1 && ((uint32_t)(ev.y >> 32) & AUX_NONUNIFORM) != 0;
+    if (cnt > 1 && rank == 0) {  // hand the presence bitmap back clean
       uint32_t* pres = A.presence + (size_t)pos * A.pres_words;
       for (uint32_t w = 0; w < A.pres_words; w++) pres[w] = 0;
     }
     if (mixed) {
       A.order[__ldcg(&e->gbase) + rank] = i;
-    } else {
+    } else if (cnt > 1) {
       Cursor cur;
-      snap_unpack(s0, s1, s2, s3, s4, s5, cur);
+      snap_load(A.commit + (size_t)pos * 6, cur);  // the slot as k_rank found it (the last rank may already be writing the table)
       Delta d = {0, 0, 0};
       const gub_resp r = run_to_rank(cur.b, rq, rank, A.clk, d);
       if (rank == cnt - 1) {  // I hold the run's final state and its total counter deltas
