@@ -296,9 +296,12 @@ def measure_traffic(args):
 
 # ---- this repo's arm --------------------------------------------------------------------------------------------
 def run_b200(args):
-    if os.environ.get("GUB_BENCH_WATCHDOG"):  # diagnostic: dump every thread's Python stack and exit if the run takes longer than this many seconds
+    # A stalled collective run must end by itself: after GUB_BENCH_WATCHDOG seconds (default 20 minutes when several ranks run, off on one
+    # GPU) every thread's Python stack goes to stderr and the process exits.
+    wd = os.environ.get("GUB_BENCH_WATCHDOG") or ("1200" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "")
+    if wd and float(wd) > 0:
         import faulthandler
-        faulthandler.dump_traceback_later(float(os.environ["GUB_BENCH_WATCHDOG"]), exit=True)
+        faulthandler.dump_traceback_later(float(wd), exit=True)
     import torch
     import gubernator_b200 as g
     import oracle_py as O
@@ -514,7 +517,9 @@ def run_b200(args):
             dist.all_reduce(cst, op=dist.ReduceOp.MAX)
             conv.update({"token_keys_differing_max_over_shards": int(cst[0].item()), "leaky_remaining_max_abs_diff": int(cst[1].item()),
                          "leaky_keys_differing_max_over_shards": int(cst[2].item()), "keys_with_any_field_differing": int(cst[3].item()),
-                         "all_shards_agree": bool(cst[0].item() == 0 and cst[1].item() <= 1)})
+                         # the reference's own consistency check is on TOKEN_BUCKET (functional_test.go:1690-1821): that is the criterion;
+                         # the leaky replicas' distance from their owners is reported beside it
+                         "all_shards_agree": bool(cst[0].item() == 0)})
         else:
             conv["all_shards_agree"] = True
         convergence = conv

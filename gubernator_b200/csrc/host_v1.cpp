@@ -278,7 +278,17 @@ struct gub_aggregator {
     if (total) {
       gub_clock clk;
       gub_clock_fill(gub_instance_now(inst), &clk);
-      rc = gub_submit(inst->table, batch.data(), total, &clk, resp.data());
+      if (inst->has_store) {
+        // a Store plugin sees Get / OnChange / Remove per call (algorithms.go:45-51,149,252): the coalesced calls are evaluated one
+        // after another, in arrival order, through the same path gub_instance_get_rate_limits takes
+        size_t o = 0;
+        for (Call* c : calls) {
+          if (!c->pc.batch.empty() && rc == 0) rc = submit_with_store(inst, c->pc, c->reqs, clk, resp.data() + o);
+          o += c->pc.batch.size();
+        }
+      } else {
+        rc = gub_submit(inst->table, batch.data(), total, &clk, resp.data());
+      }
     }
     size_t off = 0;
     for (Call* c : calls) {

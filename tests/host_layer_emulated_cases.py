@@ -38,6 +38,7 @@ run("test_update_peer_globals_items")
 run("test_add_get_scan_items")
 run("test_invalid_at_of_loaded_items")
 run("test_rpc_aggregator_coalesces_concurrent_calls")
+run("test_aggregator_honours_the_store_plugin")
 for algo in (0, 1):
     run("test_store_plugin_call_sequences", algo)
 assert g.native.lib()._name == sys.argv[1]

@@ -610,6 +610,25 @@ class _MockStore:
         self.calls.append(("Remove", key))
 
 
+def test_aggregator_honours_the_store_plugin(G):
+    """Calls coalesced by the aggregator still reach the Store plugin (the aggregator used to submit straight to the
+    table): a miss pulls from the store, every call reports OnChange for its key, in arrival order."""
+    inst = G.V1Instance(capacity_slots=4096, now_ms=K.T0)
+    st = _MockStore()
+    inst.set_store(st)
+    st.items["n_a"] = dict(algorithm=0, limit=10, duration=1000, remaining=4, remaining_f=4.0, stamp=K.T0, burst=10, expire_at=K.T0 + 1000)
+    agg = inst.aggregator(max_batch=4096, window_us=200)
+    r = agg.get_rate_limits([dict(name="n", unique_key="a", algorithm=0, duration=1000, limit=10, hits=1)])[0]
+    assert (r["status"], r["remaining"]) == (0, 3)  # the stored item (4 left) was loaded, not a fresh bucket
+    assert [c[0] for c in st.calls] == ["Get", "OnChange"] and st.calls[1][2]["remaining"] == 3
+    st.calls.clear()
+    r = agg.get_rate_limits([dict(name="n", unique_key="a", algorithm=0, duration=1000, limit=10, hits=1),
+                             dict(name="n", unique_key="b", algorithm=0, duration=1000, limit=10, hits=2)])
+    assert [x["remaining"] for x in r] == [2, 8]
+    assert [c[:2] for c in st.calls] == [("Get", "n_b"), ("OnChange", "n_a"), ("OnChange", "n_b")]
+    agg.close()
+
+
 @pytest.mark.parametrize("algo", [0, 1])
 def test_store_plugin_call_sequences(G, algo):
     """store_test.go:127-533 TestStore: which Store methods run, in which order, with which item, for a cache miss, a cache
