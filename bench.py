@@ -25,6 +25,7 @@ Prints ONE JSON line (rank 0).
 import argparse
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -277,7 +278,8 @@ def measure_traffic(args):
             for r in rows:
                 if r is hdr or len(r) <= max(ik, im, iv, iu) or r[im] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     continue
-                name = r[ik].split("(")[0].split("::")[-1]
+                m = re.search(r"k_(group|rank|eval|finish|batch)", r[ik])  # "void gub::k_rank<0>(gub::BatchArgs)" -> k_rank
+                name = m.group(0) if m else r[ik].split("(")[0].split("::")[-1]
                 v = float(r[iv].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
                 e = per.setdefault(name, {"read": 0.0, "write": 0.0, "launches": 0})
                 if r[im] == "dram__bytes_read.sum":
