@@ -526,8 +526,9 @@ def _fake_g(G):
                                  native=G.native, clock_fill=G.clock_fill)
 
 
-@pytest.mark.parametrize("name", ["test_keys_colliding_in_the_grouping_table", "test_compact_requests_equal_full_records",
-                                  "test_random_access_probe_leaves_table_unchanged"])
+# (test_compact_requests_equal_full_records and test_random_access_probe_leaves_table_unchanged run the same way — a minute of
+# fibers between them; test_compact_records_expand_like_the_full_ones above covers the compact path at emulator size)
+@pytest.mark.parametrize("name", ["test_keys_colliding_in_the_grouping_table"])
 def test_gpu_test_bodies_on_the_emulator(G, name):
     """The GPU tests added after this round's last GPU run (any other function of tests/test_gpu_parity.py that only uses the Table
     surface above can be run the same way)."""
