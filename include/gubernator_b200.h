@@ -307,11 +307,14 @@ int gub_route_global_device(gub_table* t, const gub_ring* ring, uint32_t self, c
  * (replaces gubernator.go:257-283 peer forwarding + peer_client.go:284 batching + global.go inside one NVSwitch domain)
  * One gub_p2p per shard (GPU): one process per GPU (gub_p2p_export / gub_p2p_connect swap cudaIpc handles), or all shards in
  * one process like the reference daemon (gub_p2p_connect_local enables peer access between the devices).
- * gub_p2p_step = three launches:
+ * gub_p2p_step:
  *   k_p2p_route   partitions the ingest batch by owning shard (replicated_hash.go:104-119, stable: per-key order survives) and
  *                 stores every 64-byte record straight into the owner's mailbox; the last tile publishes the per-owner counts;
- *   k_batch       the owner's batch kernel waits for the W flags, evaluates straight out of the mailboxes (segment order = source
- *                 rank, then source index) and stores every 32-byte response into the source's response mailbox; publishes;
+ *   on the owner  k_seg_wait (one warp waits for the W flags, bounded) -> the four batch kernels in ring mode: they read the W mailbox
+ *                 segments in place (segment order = source rank, then source index) and store every 32-byte response straight into
+ *                 the source's response mailbox -> k_seg_publish (response flags).  (GUB_PATH=fused: one launch of the persistent
+ *                 kernel k_batch instead.)  gub_p2p_create sizes the table's batch scratch for min(world x cap, 262 144) requests
+ *                 per pass;
  *   k_p2p_collect the source waits for the owners' flags and puts the responses back in request order.
  * Collective: every shard of the ring must call gub_p2p_step the same number of times.  n <= cap. */
 typedef struct gub_p2p gub_p2p;
@@ -324,7 +327,8 @@ int gub_p2p_connect_local(gub_p2p* p, gub_p2p* const* peers /* world pointers, s
 int gub_p2p_step(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* stream);
 /* Same step on two streams: the routing kernel (partition + NVLink stores into the owners' mailboxes) runs on
  * `ingest_stream`, the stream d_reqs was produced on; evaluation, response return and collect run on `stream`,
- * where d_out becomes valid.  Routing touches no bucket state, so the routing of step e+1 overlaps the evaluation of step
+ * where d_out becomes valid (GUB_RING_STREAMS=3, experimental: evaluation and collect on streams of the ring's own, `stream` only
+ * waits for the collect).  Routing touches no bucket state, so the routing of step e+1 overlaps the evaluation of step
  * e (the reference overlaps forwarding and evaluation the same way: peer_client.go:284 runs in its own goroutine). */
 int gub_p2p_step_streams(gub_p2p* p, const gub_req* d_reqs, size_t n, const gub_clock* clk, gub_resp* d_out, void* ingest_stream,
                          void* stream);
