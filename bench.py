@@ -254,6 +254,33 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def parse_traffic_csv(path):
+    """{kernel: DRAM read / write bytes per launch} from an `ncu --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum` log."""
+    import csv
+    with open(path) as f:
+        rows = [r for r in csv.reader(f) if len(r) > 5]
+    hdr = next((r for r in rows if "Metric Name" in r), None)
+    if hdr is None:
+        return {"error": "ncu produced no metric rows"}
+    ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    per = {}
+    for r in rows:
+        if r is hdr or len(r) <= max(ik, im, iv, iu) or r[im] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            continue
+        m = re.search(r"k_(group|rank|eval|finish|batch)", r[ik])  # "void gub::k_rank<0>(gub::BatchArgs)" -> k_rank
+        name = m.group(0) if m else r[ik].split("(")[0].split("::")[-1]
+        v = float(r[iv].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
+        e = per.setdefault(name, {"read": 0.0, "write": 0.0, "launches": 0})
+        if r[im] == "dram__bytes_read.sum":
+            e["read"] += v; e["launches"] += 1
+        else:
+            e["write"] += v
+    if not per:
+        return {"error": "ncu reported no batch kernel launch"}
+    return {k: {"dram_read_bytes_per_launch": e["read"] / e["launches"], "dram_write_bytes_per_launch": e["write"] / e["launches"], "launches": e["launches"]}
+            for k, e in per.items()}
+
+
 # ---- DRAM traffic of k_batch, measured by ncu on this very workload (a sub-process of the default run) ------------------
 def measure_traffic(args):
     """{kernel: DRAM bytes per launch} for the batch kernels of this workload, by running this script's --traffic-probe under ncu."""
@@ -267,29 +294,10 @@ def measure_traffic(args):
                sys.executable, os.path.abspath(__file__), "--traffic-probe", "--keys", str(args.keys), "--zipf", str(args.zipf), "--pool", str(args.pool)]
         try:
             res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300, check=False, text=True)
-            import csv
-            with open(log) as f:
-                rows = [r for r in csv.reader(f) if len(r) > 5]
-            hdr = next((r for r in rows if "Metric Name" in r), None)
-            if hdr is None:
-                return {"error": "ncu produced no metric rows: " + (res.stdout or "")[-300:]}
-            ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-            per = {}
-            for r in rows:
-                if r is hdr or len(r) <= max(ik, im, iv, iu) or r[im] not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    continue
-                m = re.search(r"k_(group|rank|eval|finish|batch)", r[ik])  # "void gub::k_rank<0>(gub::BatchArgs)" -> k_rank
-                name = m.group(0) if m else r[ik].split("(")[0].split("::")[-1]
-                v = float(r[iv].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
-                e = per.setdefault(name, {"read": 0.0, "write": 0.0, "launches": 0})
-                if r[im] == "dram__bytes_read.sum":
-                    e["read"] += v; e["launches"] += 1
-                else:
-                    e["write"] += v
-            if not per:
-                return {"error": "ncu reported no batch kernel launch"}
-            out = {k: {"dram_read_bytes_per_launch": e["read"] / e["launches"], "dram_write_bytes_per_launch": e["write"] / e["launches"], "launches": e["launches"]}
-                   for k, e in per.items()}
+            out = parse_traffic_csv(log)
+            if "error" in out:
+                out["error"] += ": " + (res.stdout or "")[-300:]
+                return out
             out["how"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none over warm steps of this workload (a sub-process of this run)"
             return out
         except Exception as ex:
