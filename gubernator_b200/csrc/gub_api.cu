@@ -166,7 +166,9 @@ cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cuda
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+  // With per-kernel profiling on, an event record sits between consecutive kernels: they are launched plainly then (full stream
+  // order; griddepcontrol.* are no-ops without the attribute) rather than as programmatic dependents of "the previous kernel".
+  cfg.attrs = attr; cfg.numAttrs = (t->pdl && !t->prof) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, A);
 }
 
@@ -1436,7 +1438,7 @@ int p2p_evaluate(gub_p2p* p, const gub::P2PArgs& A, const gub_clock* clk, cudaSt
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = t->pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (t->pdl && !t->prof) ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, gub::k_seg_publish, A));
     return 0;
   }
