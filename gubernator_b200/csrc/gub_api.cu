@@ -160,7 +160,7 @@ void trace_dump(gub_table* t) {
 // Launches one batch kernel, with programmatic stream serialization when enabled (the kernels call griddepcontrol.wait
 // before touching anything an earlier kernel produced; without the attribute that instruction is a no-op).
 template <typename K>
-cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cudaStream_t st, const gub::BatchArgs& A) {
+cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cudaStream_t st, const gub::BatchArgs& A, bool plain = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -168,7 +168,8 @@ cudaError_t launch_k(gub_table* t, K kernel, uint32_t grid, uint32_t block, cuda
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   // With per-kernel profiling on, an event record sits between consecutive kernels: they are launched plainly then (full stream
   // order; griddepcontrol.* are no-ops without the attribute) rather than as programmatic dependents of "the previous kernel".
-  cfg.attrs = attr; cfg.numAttrs = (t->pdl && !t->prof) ? 1 : 0;
+  // `plain`: the stream's previous operation is not a kernel of this chain (the memsets at the epoch wrap): full stream order.
+  cfg.attrs = attr; cfg.numAttrs = (t->pdl && !t->prof && !plain) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, A);
 }
 
@@ -224,7 +225,9 @@ struct SegDesc {
 int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_clock* clk, gub_resp* d_out, cudaStream_t st,
                  const uint32_t* n_dev = nullptr, uint32_t n_off = 0, const SegDesc* seg = nullptr) {
   gub_table::Scratch& sc = t->scr;
+  bool wrapped = false;
   if (sc.epoch >= 65535u) {  // 16-bit epoch tags wrapped: clear the grouping table so stale tags cannot alias
+    wrapped = true;
     CK(cudaMemsetAsync(sc.aux, 0, (size_t)t->aux_entries * sizeof(gub::AuxEntry), st));
     // 65535 -> 1 keeps the parity: the batch after the wrap reuses ctr[1], which k_rank (it only resets the OTHER parity) left
     // holding batch 65535's allocators.  Clear both.
@@ -258,7 +261,7 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   }
   const uint32_t fin_blocks = std::min<uint32_t>(148u, std::max<uint32_t>(1u, n / 2));
   if (seg) {
-    CK(launch_k(t, gub::k_group<true>, blocks, gub::GROUP_THREADS, st, A));
+    CK(launch_k(t, gub::k_group<true>, blocks, gub::GROUP_THREADS, st, A, wrapped));
     if (pe) CK(cudaEventRecord(pe[1], st));
     CK(launch_k(t, gub::k_rank<true>, blocks, gub::GROUP_THREADS, st, A));
     if (pe) CK(cudaEventRecord(pe[2], st));
@@ -266,7 +269,7 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
     if (pe) CK(cudaEventRecord(pe[3], st));
     CK(launch_k(t, gub::k_finish<true>, fin_blocks, gub::MIXED_THREADS, st, A));
   } else {
-    CK(launch_k(t, gub::k_group<false>, blocks, gub::GROUP_THREADS, st, A));
+    CK(launch_k(t, gub::k_group<false>, blocks, gub::GROUP_THREADS, st, A, wrapped));
     if (pe) CK(cudaEventRecord(pe[1], st));
     CK(launch_k(t, gub::k_rank<false>, blocks, gub::GROUP_THREADS, st, A));
     if (pe) CK(cudaEventRecord(pe[2], st));
