@@ -79,6 +79,10 @@ struct gub_table {
   bool coop = true;                   // cooperative launch (co-residency of the grid guaranteed by the driver)
   int num_sms = 0;
   uint32_t sweep_chunk = 0;           // slots every CTA sweeps per batch (incremental expiry sweep), 0 = off
+  // the four-kernel pipeline's incremental sweep: every SWEEP_EVERY batches one slice of the table is swept between two batches
+  // (k_sweep on the batch's stream: nothing else touches the table then); the whole table once every ~65 536 batches
+  uint32_t since_sweep = 0;
+  uint64_t sweep_cursor = 0;
   gub::GEntry* gaux = nullptr;
   uint32_t* gpres = nullptr;
   unsigned long long* gfrag = nullptr;
@@ -283,6 +287,22 @@ int launch_chunk(gub_table* t, const gub_req* d_reqs, uint32_t n, const gub_cloc
   return 0;
 }
 
+// The pipeline's share of the capacity policy (lrucache.go:115 frees expired items lazily on access; a table slot whose key never
+// comes back would stay occupied for ever): every SWEEP_EVERY batches, 1/64 of the table is swept on the batch's stream, after the
+// batch — removed / expired entries become tombstones, which inserts reuse.  (The persistent kernel sweeps a few slots per batch
+// itself.)  Off with gub_set_sweep(t, 0) / GUB_SWEEP=0.
+constexpr uint32_t SWEEP_EVERY = 1024;
+int maybe_sweep(gub_table* t, const gub_clock* clk, cudaStream_t st) {
+  if (!t->sweep_chunk || ++t->since_sweep < SWEEP_EVERY) return 0;
+  t->since_sweep = 0;
+  const uint64_t slice = (t->capacity + 63) / 64;
+  const uint64_t lo = t->sweep_cursor, hi = std::min<uint64_t>(t->capacity, lo + slice);
+  t->sweep_cursor = hi >= t->capacity ? 0 : hi;
+  gub::k_sweep<<<148 * 4, 256, 0, st>>>(t->table, lo, hi, clk->now_ms, t->counters + gub::C_SWEPT);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // Table-touching work from different caller streams must be ordered.  The common case (same stream as last time) costs
 // nothing; only a change of stream records an event on the old stream and makes the new one wait for it.
 int order_after_last(gub_table* t, cudaStream_t st) {
@@ -313,6 +333,7 @@ int launch_batch(gub_table* t, const gub_req* d_reqs, size_t n, const gub_clock*
     const uint32_t m = (uint32_t)std::min<size_t>(t->max_batch, n - off);
     if (launch_chunk(t, d_reqs + off, m, clk, d_out + off, st, n_dev, (uint32_t)off)) return -1;
   }
+  if (maybe_sweep(t, clk, st)) return -1;
   t->last_stream = st; t->last_pending = true;
   return 0;
 }
@@ -790,7 +811,7 @@ int gub_sweep(gub_table* t, int64_t now_ms, size_t* removed) {
   CK(cudaSetDevice(t->device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemset(t->d_scalar, 0, 8));
-  gub::k_sweep<<<148 * 8, 256>>>(t->table, t->capacity, now_ms, t->d_scalar);
+  gub::k_sweep<<<148 * 8, 256>>>(t->table, (uint64_t)0, t->capacity, now_ms, t->d_scalar);
   CK(cudaDeviceSynchronize());
   unsigned long long r = 0;
   CK(cudaMemcpy(&r, t->d_scalar, 8, cudaMemcpyDeviceToHost));
@@ -1443,7 +1464,7 @@ int p2p_evaluate(gub_p2p* p, const gub::P2PArgs& A, const gub_clock* clk, cudaSt
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = (t->pdl && !t->prof) ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, gub::k_seg_publish, A));
-    return 0;
+    return maybe_sweep(t, clk, st);
   }
   gub::FArgs F;
   fused_base_args(t, clk, F);

@@ -1262,9 +1262,10 @@ __global__ void k_scan(const Slot* table, uint64_t cap, DevItem* out, unsigned l
 }
 
 // Frees slots whose item is gone (removed, or ExpireAt < now): the batch path only ever marks them not-live.
-__global__ void k_sweep(Slot* table, uint64_t cap, int64_t now_ms, unsigned long long* removed) {
+// (slots [lo, hi): gub_sweep takes the whole table; the library's incremental sweep a slice at a time, between batches.)
+__global__ void k_sweep(Slot* table, uint64_t lo, uint64_t hi, int64_t now_ms, unsigned long long* removed) {
   unsigned long long mine = 0;
-  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t s = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += (uint64_t)gridDim.x * blockDim.x) {
     const ulonglong2 a = __ldcs(reinterpret_cast<const ulonglong2*>(table + s));
     if (a.x > KEY_TOMB) {
       bool dead = !(a.y & F_LIVE);

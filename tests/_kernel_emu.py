@@ -40,6 +40,7 @@ def lib():
         L.emu_counters.argtypes = [vp, vp]; L.emu_counters.restype = None
         L.emu_scan.argtypes = [vp, vp, u64]; L.emu_scan.restype = u64
         L.emu_sweep.argtypes = [vp, i64]; L.emu_sweep.restype = u64
+        L.emu_sweep_range.argtypes = [vp, u64, u64, i64]; L.emu_sweep_range.restype = u64
         L.emu_random_rmw.argtypes = [vp, u64]; L.emu_random_rmw.restype = None
         L.emu_hash_keys.argtypes = [vp, vp, u32, vp, vp]; L.emu_hash_keys.restype = None
         L.emu_route.argtypes = [vp, u32, vp, vp, u32, u32, vp, vp, vp, vp]; L.emu_route.restype = None
@@ -100,6 +101,9 @@ class EmuTable:
 
     def sweep(self, now_ms):
         return int(self._L.emu_sweep(self._h, int(now_ms)))
+
+    def sweep_range(self, lo, hi, now_ms):
+        return int(self._L.emu_sweep_range(self._h, int(lo), int(hi), int(now_ms)))
 
     def random_rmw(self, accesses):
         self._L.emu_random_rmw(self._h, int(accesses))

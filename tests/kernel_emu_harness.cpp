@@ -237,7 +237,14 @@ void emu_random_rmw(void* tv, uint64_t accesses) {
 uint64_t emu_sweep(void* tv, int64_t now_ms) {
   EmuTable* t = static_cast<EmuTable*>(tv);
   unsigned long long removed = 0;
-  emu::launch(k_sweep, 4u, 256u, t->table, t->capacity, now_ms, &removed);
+  emu::launch(k_sweep, 4u, 256u, t->table, (uint64_t)0, t->capacity, now_ms, &removed);
+  return removed;
+}
+// maybe_sweep of gub_api.cu: one slice [lo, hi) of the table (the pipeline's incremental sweep, between batches)
+uint64_t emu_sweep_range(void* tv, uint64_t lo, uint64_t hi, int64_t now_ms) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  unsigned long long removed = 0;
+  emu::launch(k_sweep, 4u, 256u, t->table, lo, std::min<uint64_t>(hi, t->capacity), now_ms, &removed);
   return removed;
 }
 

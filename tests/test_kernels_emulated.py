@@ -147,6 +147,28 @@ def test_hot_key_with_differing_hits_many_segments(G, path, algorithm):
     _check_state(G, tab, pool)
 
 
+def test_sweep_in_slices_equals_one_sweep(G):
+    """The pipeline's incremental sweep (gub_api.cu maybe_sweep: one slice of the table between batches) frees exactly what one
+    whole-table sweep frees, and the table keeps answering like the oracle afterwards (expired keys are misses either way)."""
+    rng = np.random.default_rng(9)
+    cap = 1 << 12
+    tabs, pool = [Tab("pipeline", cap), Tab("pipeline", cap)], O.Pool(now_ms=T0)
+    reqs = bench_requests(rng.permutation(1500), T0).astype(G.REQ_DTYPE)
+    reqs["duration"] = np.where(np.arange(1500) % 3 == 0, 50, 60000)  # a third of the keys expire at T0 + 50
+    want = pool.submit_hashed(reqs)
+    for t in tabs:
+        _cmp(t.submit(reqs, make_clock(T0), O.HRESP_DTYPE), want)
+    now = T0 + 1000
+    whole = tabs[0].sweep(now)
+    parts = sum(tabs[1].sweep_range(lo, lo + cap // 8, now) for lo in range(0, cap, cap // 8))
+    assert whole == parts == 500
+    pool.set_now(now)
+    reqs["created_at"] = now
+    want = pool.submit_hashed(reqs)
+    for t in tabs:
+        _cmp(t.submit(reqs, make_clock(now), O.HRESP_DTYPE), want)
+
+
 @both_paths
 def test_token_reset_flipflop(G, path):
     tab, pool = Tab(path, 4096), O.Pool(now_ms=T0)
