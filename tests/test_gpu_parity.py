@@ -2,6 +2,8 @@
 
 Bit-exact on every response field (integer work; the leaky bucket's float64 state is compared through its int64
 projections in responses and bit-for-bit in the table scan)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -468,6 +470,28 @@ def test_epoch_wrap(G):
         if b in checkpoints:
             torch.cuda.synchronize()
             _cmp(d_out.cpu().numpy().reshape(-1).view(G.RESP_DTYPE), want, f"batch {b}")
+
+
+def test_scheduled_sweep_between_batches(G):
+    """The library's incremental sweep on the pipeline path (every 1024 batches 1/64 of the table, k_sweep on the batch's stream):
+    with keys that expire while the clock advances, 2200 batches trigger it twice; every response still equals the oracle's (an
+    expired key is a miss with or without the sweep) and entries were reclaimed."""
+    rng = np.random.default_rng(23)
+    tab = G.Table(1 << 10, max_batch=1024)  # 64 slices of 16 slots: sweeps 1 and 2 cover slots 0..31
+    tab.set_sweep(1)
+    pool = O.Pool(now_ms=T0)
+    swept_before = tab.counters()["swept"]
+    for b in range(2200):
+        now = T0 + 40 * b
+        pool.set_now(now)
+        reqs = bench_requests(rng.integers(0, 300, 48), now)
+        reqs["duration"] = 100  # expires after 100 ms: most resident keys are dead by the time a slice is swept
+        got = tab.submit(reqs, G.clock_fill(now))
+        want = pool.submit_hashed(reqs)
+        if b % 97 == 0 or b > 2040:
+            _cmp(got, want, f"batch {b}")
+    if os.environ.get("GUB_PATH") != "fused":
+        assert tab.counters()["swept"] > swept_before
 
 
 def test_invalid_at_of_loaded_items(G):
