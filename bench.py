@@ -455,7 +455,9 @@ def run_b200(args):
     def do_tick(b):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        st = p2p.tick(clk_of(b), T0 + 1 + b, stream)
+        # (the receivers' "now" — UpdatedAt / CreatedAt of the installed replicas — in the clock domain of the requests' created_at,
+        # which cycles with the batch pool; the kernels' expiry clock clk_of(b) keeps advancing)
+        st = p2p.tick(clk_of(b), T0 + 1 + (b % pool_n), stream)
         e1.record()
         torch.cuda.synchronize()
         st["ms"] = e0.elapsed_time(e1)
@@ -505,7 +507,9 @@ def run_b200(args):
         do_tick(args.warmup + args.steps)
         do_tick(args.warmup + args.steps)
         hot = min(global_hot, BATCH)
-        q = bench_requests(np.arange(hot, dtype=np.int64), T0 + 1 + args.warmup + args.steps, dtype=g.REQ_DTYPE)
+        # created_at of the query = the installed replicas' "now" (same clock domain as the traffic: a query stamped seconds ahead of
+        # every request's created_at would credit the owners' leaky buckets tokens their freshly installed replicas do not see)
+        q = bench_requests(np.arange(hot, dtype=np.int64), T0 + 1 + ((args.warmup + args.steps) % pool_n), dtype=g.REQ_DTYPE)
         q["hits"] = 0
         q["behavior"] = np.uint32(O.GLOBAL | O.REQ_IS_OWNER)
         d_q = torch.from_numpy(q.view(np.uint8).reshape(hot, 64)).to(dev)

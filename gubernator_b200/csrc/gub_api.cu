@@ -1156,26 +1156,6 @@ int gub_make_updates_device(gub_table* t, const gub_req* d_queries, const gub_re
   return 0;
 }
 
-__global__ void k_add_items_pub(gub::Slot* table, uint64_t cap, const gub_item* items, uint32_t n, int64_t now_ms, unsigned long long* counters, gub::InvIndex inv) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const gub_item it = items[i];
-  if (it.algorithm != GUB_TOKEN_BUCKET && it.algorithm != GUB_LEAKY_BUCKET) return;
-  gub::Cursor cur;
-  const uint64_t key = gub::remap_key(it.key_xxh64), tag = it.key_fnv1 >> 8;
-  gub::cursor_open(cur, table, cap, key, tag);
-  const bool leaky = it.algorithm == GUB_LEAKY_BUCKET;
-  cur.b.key = key; cur.b.tag = tag;
-  cur.b.flags = gub::F_LIVE | (leaky ? gub::F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? gub::F_OVER : 0u) | (it.invalid_at != 0 ? gub::F_INVALID_AT : 0u);
-  if (it.invalid_at != 0) gub::inv_store(inv, key, tag, it.invalid_at);
-  cur.b.limit = it.limit; cur.b.duration = it.duration;
-  cur.b.rem = leaky ? gub::f2bits(it.remaining_f) : (uint64_t)it.remaining;
-  cur.b.stamp = now_ms; cur.b.burst = leaky ? it.burst : 0; cur.b.expire = it.expire_at;
-  uint32_t ins = 0;
-  if (!gub::cursor_close(cur, table, cap, ins)) atomicAdd(counters + gub::C_FULL, 1ull);
-  if (ins) atomicAdd(counters + gub::C_INSERTS, (unsigned long long)ins);
-}
-
 int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_t now_ms, void* stream) {
   if (!t || (n && !d_items)) return fail("gub_add_items_device: null argument");
   if (n == 0) return 0;
@@ -1183,7 +1163,7 @@ int gub_add_items_device(gub_table* t, const gub_item* d_items, size_t n, int64_
   CK(cudaSetDevice(t->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (order_after_last(t, st)) return -1;
-  k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters, t->inv);
+  gub::k_add_items_pub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t->table, t->capacity, d_items, (uint32_t)n, now_ms, t->counters, t->inv);
   CK(cudaGetLastError());
   t->last_stream = st; t->last_pending = true;
   return 0;
@@ -1860,7 +1840,7 @@ int tick_install_local(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* in
     const gub_p2p* q = p->local_peers[r];
     const uint32_t k = std::min(q->h_counts[2], q->gcap);
     if (!k) continue;
-    k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, q->g_items, k, now_ms, t->counters, t->inv);
+    gub::k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, q->g_items, k, now_ms, t->counters, t->inv);
     *installed += k;
     p->tick_bytes += (uint64_t)k * sizeof(gub_item);
   }
@@ -1887,7 +1867,7 @@ int tick_install_nccl(gub_p2p* p, int64_t now_ms, cudaStream_t st, uint64_t* ins
     for (uint32_t r = 0; r < p->world; r++) {
       const uint32_t k = std::min(all[r], p->gcap);
       if (r == p->rank || !k) continue;  // "Exclude ourselves from the update" (global.go:263-265)
-      k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters, t->inv);
+      gub::k_add_items_pub<<<(k + 255) / 256, 256, 0, st>>>(t->table, t->capacity, p->g_gather + (size_t)r * pad, k, now_ms, t->counters, t->inv);
       *installed += k;
     }
     CK(cudaGetLastError());

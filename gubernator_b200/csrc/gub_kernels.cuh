@@ -1226,6 +1226,30 @@ __global__ void k_add_items(Slot* table, uint64_t cap, const DevItem* items, uin
   if (ins) atomicAdd(counters + C_INSERTS, (unsigned long long)ins);
 }
 
+// UpdatePeerGlobals (gubernator.go:425-459): install the owners' UpdatePeerGlobal items (public gub_item records, as built by
+// k_make_updates) as this shard's replicas: token {Status, Limit, Duration, Remaining, CreatedAt = now}, leaky {Remaining =
+// float64(status.Remaining), Limit, Duration, Burst = Limit, UpdatedAt = now}, ExpireAt = the status' ResetTime.
+__global__ void k_add_items_pub(Slot* table, uint64_t cap, const gub_item* items, uint32_t n, int64_t now_ms, unsigned long long* counters, InvIndex inv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const gub_item it = items[i];
+  if (it.algorithm != GUB_TOKEN_BUCKET && it.algorithm != GUB_LEAKY_BUCKET) return;
+  Cursor cur;
+  const uint64_t key = remap_key(it.key_xxh64), tag = it.key_fnv1 >> 8;
+  cursor_open(cur, table, cap, key, tag);
+  const bool leaky = it.algorithm == GUB_LEAKY_BUCKET;
+  cur.b.key = key; cur.b.tag = tag;
+  cur.b.flags = F_LIVE | (leaky ? F_LEAKY : 0u) | ((!leaky && it.status == GUB_OVER_LIMIT) ? F_OVER : 0u) | (it.invalid_at != 0 ? F_INVALID_AT : 0u);
+  if (it.invalid_at != 0) inv_store(inv, key, tag, it.invalid_at);
+  cur.b.limit = it.limit; cur.b.duration = it.duration;
+  cur.b.rem = leaky ? f2bits(it.remaining_f) : (uint64_t)it.remaining;
+  cur.b.stamp = now_ms; cur.b.burst = leaky ? it.burst : 0; cur.b.expire = it.expire_at;
+  uint32_t ins = 0;
+  if (!cursor_close(cur, table, cap, ins)) atomicAdd(counters + C_FULL, 1ull);
+  if (ins) atomicAdd(counters + C_INSERTS, (unsigned long long)ins);
+}
+
+
 __global__ void k_get_items(const Slot* table, uint64_t cap, const uint64_t* keys, const uint64_t* fnv, uint32_t n, int64_t now_ms,
                             DevItem* out, uint8_t* found, InvIndex inv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,6 +52,7 @@ def lib():
         L.emu_p2p_create.argtypes = [u32, u32, u64, u32, vp, vp, u32]; L.emu_p2p_create.restype = vp
         L.emu_p2p_table.argtypes = [vp, u32]; L.emu_p2p_table.restype = vp
         L.emu_p2p_step.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+        L.emu_install_updates.argtypes = [vp, vp, u32, i64]; L.emu_install_updates.restype = None
         assert L.emu_counter_count() == len(COUNTER_NAMES)
         _libs["L"] = L
     return _libs["L"]
@@ -110,7 +111,8 @@ class EmuTable:
 
     def __del__(self):
         try:
-            self._L.emu_destroy(self._h)
+            if getattr(self, "_owned", True):  # (a handle borrowed from an EmuP2PCluster belongs to the cluster)
+                self._L.emu_destroy(self._h)
         except Exception:
             pass
 
@@ -153,27 +155,42 @@ class EmuP2PCluster:
         """fused: owners evaluate with the persistent kernel k_batch (GUB_PATH=fused) instead of the pipeline in ring mode."""
         self.world = world
         self.fused = bool(fused)
+        self.capacity_slots = int(capacity_slots)
         self._L = lib()
         self._finish_cap = finish_cap
         pts, peers = np.ascontiguousarray(pts, dtype=np.uint64), np.ascontiguousarray(peers, dtype=np.int32)
         self._h = self._L.emu_p2p_create(world, cap, int(capacity_slots), int(max_batch), pts.ctypes.data, peers.ctypes.data, len(pts))
 
-    def step(self, batches, clk, resp_dtype):
-        """batches: one request array per shard (what that shard ingests); returns one response array per shard."""
+    def step(self, batches, clk, resp_dtype, global_mode=False):
+        """batches: one request array per shard (what that shard ingests); returns one response array per shard.  global_mode (after
+        gub_p2p_enable_global): GLOBAL requests a shard does not own stay with it; also returns every request's ring owner."""
         batches = [np.ascontiguousarray(b) for b in batches]
         outs = [np.zeros(max(len(b), 1), dtype=resp_dtype) for b in batches]
+        owners = [np.zeros(max(len(b), 1), dtype=np.uint8) for b in batches]
         rp = (C.c_void_p * self.world)(*[b.ctypes.data if len(b) else None for b in batches])
         op = (C.c_void_p * self.world)(*[o.ctypes.data for o in outs])
+        wp = (C.c_void_p * self.world)(*[o.ctypes.data for o in owners])
         n = np.array([len(b) for b in batches], dtype=np.uint32)
         self._L.emu_set_finish_cap(self._finish_cap)
         self._L.emu_set_fused(1 if self.fused else 0)
         try:
-            rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op, 0, None)
+            rc = self._L.emu_p2p_step(self._h, rp, n.ctypes.data, clk.ctypes.data, op, 1 if global_mode else 0, wp if global_mode else None)
         finally:
             self._L.emu_set_finish_cap(148)
             self._L.emu_set_fused(0)
         assert rc == 0, "a mailbox flag wait timed out"
-        return [o[:len(b)] for o, b in zip(outs, batches)]
+        res = [o[:len(b)] for o, b in zip(outs, batches)]
+        return (res, [o[:len(b)] for o, b in zip(owners, batches)]) if global_mode else res
+
+    def table(self, rank):
+        """The shard's table as an EmuTable-like handle (submit / scan on it go through the single-table path)."""
+        t = EmuTable.__new__(EmuTable)
+        t._L, t._h, t.fused, t._owned, t.capacity = self._L, self._L.emu_p2p_table(self._h, rank), self.fused, False, self.capacity_slots
+        return t
+
+    def install(self, rank, items, now_ms):
+        items = np.ascontiguousarray(items)
+        self._L.emu_install_updates(self._L.emu_p2p_table(self._h, rank), items.ctypes.data if len(items) else None, len(items), int(now_ms))
 
 
 class EmuGq:

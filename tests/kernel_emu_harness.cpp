@@ -302,6 +302,12 @@ uint32_t emu_make_updates(const gub_req* queries, const gub_resp* resps, uint32_
   return count;
 }
 
+// UpdatePeerGlobals: install UpdatePeerGlobal items as replicas (k_add_items_pub: gub_add_items_device / the tick's install phase)
+void emu_install_updates(void* tv, const gub_item* items, uint32_t n, int64_t now_ms) {
+  EmuTable* t = static_cast<EmuTable*>(tv);
+  if (n) emu::launch(k_add_items_pub, (n + 255) / 256, 256u, t->table, t->capacity, items, n, now_ms, t->counters, t->inv);
+}
+
 // ---- gub_p2p_step for W shards living in one process, phase by phase: every shard scatters, then every shard gathers,
 // evaluates and returns responses, then every shard un-routes.  The flag waits of the real kernels find their flags already
 // published, so the spin loops fall through; what is exercised is the mailbox indexing, the (source rank, source index) order at

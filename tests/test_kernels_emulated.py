@@ -634,3 +634,97 @@ def test_global_queue_overflow_drops_whole_keys(G):
     got = q.drain(G.REQ_DTYPE, as_status_query=False)
     assert len(got) == 64 and len(set(got["key_xxh64"].tolist())) == 64
     assert np.all(got["hits"] == 6) and np.all(got["limit"] == 9)
+
+
+def test_global_flow_on_bench_like_traffic_matches_the_cluster_model(G):
+    """BASELINE config 5 in small: two shards, the hot keys (top of the Zipf ranking) carry GLOBAL, both algorithms, the clock
+    advances 35 ms per step (limit 100 per 60 s: a leaky token per 600 ms), a sync tick after warm-up and two at the end.  The
+    whole flow runs on the emulated kernels — routing with GLOBAL requests kept on the non-owner, the ring-mode pipeline, the hits /
+    updates queues, status queries, k_make_updates, replica install — orchestrated like gub_global_tick, and is compared with the
+    oracle cluster model (tests/global_model.py): every response of every step, and the answers of both shards to a Hits = 0 query
+    on every hot key after the quiesced ticks."""
+    import importlib.util
+    import os
+    from global_model import OracleCluster
+    from gubernator_b200.sharded import shard_addresses
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    W, n_keys, per_step, steps, dt = 2, 200000, 4096, 60, 35
+    hot = n_keys // 100
+    oring = O.Ring(0, 512)
+    for a in shard_addresses(W):
+        oring.add(a)
+    pts, peers = oring.points()
+    cl = E.EmuP2PCluster(W, cap=per_step, capacity_slots=1 << 16, pts=pts, peers=peers, max_batch=W * per_step)
+    model = OracleCluster(W, T0)
+    hits_q = [E.EmuGq(capacity=1 << 13, keep_latest=False) for _ in range(W)]
+    upd_q = [E.EmuGq(capacity=1 << 13, keep_latest=True) for _ in range(W)]
+    rngs = [np.random.default_rng(900 + r) for r in range(W)]
+    seq = [0]
+
+    def evaluated_at(g, batches, owners):
+        """The records shard g evaluated in a global-mode step, in evaluation order (source rank, then source index)."""
+        parts = []
+        for s_, b in enumerate(batches):
+            is_global = (b["behavior"] & O.GLOBAL) != 0
+            dest = np.where(is_global & (owners[s_] != s_), s_, owners[s_])
+            sel = dest == g
+            ev = b[sel].copy()
+            local = (is_global & (owners[s_] != s_))[sel]
+            ev["behavior"][local] = (ev["behavior"][local] | O.NO_BATCHING) & ~np.uint32(O.GLOBAL | O.REQ_IS_OWNER)
+            parts.append(ev)
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=G.REQ_DTYPE)
+
+    def step(batches, now):
+        clk = make_clock(now)
+        got, owners = cl.step(batches, clk, O.HRESP_DTYPE, global_mode=True)
+        owners = [o.astype(np.int64) for o in owners]
+        for r in range(W):
+            hits_q[r].accumulate(batches[r], owners[r].astype(np.uint8), r, seq[0] << 32)
+            upd_q[r].accumulate(evaluated_at(r, batches, owners), None, r, seq[0] << 32)
+        seq[0] += 1
+        return got
+
+    def tick(now):
+        clk = make_clock(now)
+        recs = [hits_q[r].drain(G.REQ_DTYPE, False, cap=1 << 13) for r in range(W)]       # phase A: hits to their owners ...
+        cl.step(recs, clk, O.HRESP_DTYPE)                                                   # ... evaluated there (phase B)
+        owners = [np.array([oring.get_by_hash(int(h)) for h in b["key_fnv1"]], dtype=np.int64) for b in recs]
+        for g in range(W):
+            ev = np.concatenate([recs[s_][owners[s_] == g] for s_ in range(W)])
+            upd_q[g].accumulate(ev, None, g, seq[0] << 32)
+        seq[0] += 1
+        for g in range(W):                                                                  # phase C + install
+            q = upd_q[g].drain(G.REQ_DTYPE, True, cap=1 << 13)
+            if not len(q):
+                continue
+            resp = cl.table(g).submit(q, clk, O.HRESP_DTYPE)
+            items = E.make_updates(q, resp, G.ITEM_DTYPE)
+            for p_ in range(W):
+                if p_ != g:
+                    cl.install(p_, items, now)
+
+    def batch(r, now):
+        return bench.gen_batch(rngs[r], per_step, n_keys, now, 1.1, G.REQ_DTYPE, global_hot=hot)[0]
+    now = T0
+    for b in range(steps):
+        now = T0 + 1 + dt * b
+        batches = [batch(r, now) for r in range(W)]
+        got, want = step(batches, now), model.step([x.astype(O.HREQ_DTYPE) for x in batches], now)
+        for r in range(W):
+            _cmp(got[r], want[r], f"step {b} shard {r}")
+        if b == 4:
+            tick(now); model.tick(now)
+    tick(now); model.tick(now)
+    tick(now); model.tick(now)
+    q = bench_requests(np.arange(hot, dtype=np.int64), now).astype(G.REQ_DTYPE)
+    q["hits"] = 0
+    q["behavior"] = np.uint32(O.GLOBAL | O.REQ_IS_OWNER)
+    got = step([q.copy() for _ in range(W)], now)
+    want = model.step([q.astype(O.HREQ_DTYPE) for _ in range(W)], now)
+    for r in range(W):
+        _cmp(got[r], want[r], f"convergence query shard {r}")
+    tok = q["algorithm"] == 0
+    assert np.array_equal(got[0][tok], got[1][tok])  # the reference's own consistency check (functional_test.go:1816-1821)
