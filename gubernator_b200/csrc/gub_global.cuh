@@ -139,6 +139,8 @@ __global__ void k_gq_drain(Gq q, gub_req* out, uint32_t out_cap, uint32_t* out_c
       if (as_status_query) { e.hits = 0; e.behavior &= ~(uint32_t)GUB_REQ_IS_OWNER; }
       else e.behavior |= (uint32_t)(GUB_BEHAVIOR_DRAIN_OVER_LIMIT | GUB_REQ_IS_OWNER);
       out[k] = e;
+    } else if (q.dropped) {
+      atomicAdd(q.dropped, 1ull);  // more keys in one sync window than a tick carries (the mailbox capacity): counted, not silent
     }
     gub_req z = {};
     q.slots[pos] = z;
