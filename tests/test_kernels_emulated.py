@@ -636,7 +636,8 @@ def test_global_queue_overflow_drops_whole_keys(G):
     assert np.all(got["hits"] == 6) and np.all(got["limit"] == 9)
 
 
-def test_global_flow_on_bench_like_traffic_matches_the_cluster_model(G):
+@both_paths
+def test_global_flow_on_bench_like_traffic_matches_the_cluster_model(G, path):
     """BASELINE config 5 in small: two shards, the hot keys (top of the Zipf ranking) carry GLOBAL, both algorithms, the clock
     advances 35 ms per step (limit 100 per 60 s: a leaky token per 600 ms), a sync tick after warm-up and two at the end.  The
     whole flow runs on the emulated kernels — routing with GLOBAL requests kept on the non-owner, the ring-mode pipeline, the hits /
@@ -651,13 +652,14 @@ def test_global_flow_on_bench_like_traffic_matches_the_cluster_model(G):
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    W, n_keys, per_step, steps, dt = 2, 200000, 4096, 60, 35
+    W, n_keys, per_step, dt = 2, 200000, 4096, 35
+    steps = 60 if path == "pipeline" else 14  # (a persistent-kernel step costs several times the fibers)
     hot = n_keys // 100
     oring = O.Ring(0, 512)
     for a in shard_addresses(W):
         oring.add(a)
     pts, peers = oring.points()
-    cl = E.EmuP2PCluster(W, cap=per_step, capacity_slots=1 << 16, pts=pts, peers=peers, max_batch=W * per_step)
+    cl = E.EmuP2PCluster(W, cap=per_step, capacity_slots=1 << 16, pts=pts, peers=peers, max_batch=W * per_step, fused=(path == "fused"))
     model = OracleCluster(W, T0)
     hits_q = [E.EmuGq(capacity=1 << 13, keep_latest=False) for _ in range(W)]
     upd_q = [E.EmuGq(capacity=1 << 13, keep_latest=True) for _ in range(W)]
